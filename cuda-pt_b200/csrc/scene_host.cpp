@@ -1,0 +1,422 @@
+// scene_host.cpp — .cpts container IO, scene validation and the derived
+// device-ready arrays (precomputed triangles, packed normals/uvs, pair-node
+// BVH re-layout).  Host-only C++.
+#include "scene_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+
+namespace cptb {
+
+namespace {
+
+struct FileCloser {
+    FILE *fp;
+    ~FileCloser() {
+        if (fp)
+            fclose(fp);
+    }
+};
+
+template <typename T> void read_into(FILE *fp, const CptsSection &s, std::vector<T> &dst, const char *what) {
+    if (s.elem_size != sizeof(T))
+        throw std::runtime_error(std::string("cpts: section '") + what + "' has unexpected element size");
+    dst.resize(s.count);
+    if (s.count && fread(dst.data(), sizeof(T), s.count, fp) != s.count)
+        throw std::runtime_error(std::string("cpts: truncated section '") + what + "'");
+}
+
+void skip_pad(FILE *fp, uint64_t bytes) {
+    const uint64_t pad = (16 - bytes % 16) % 16;
+    if (pad)
+        fseek(fp, long(pad), SEEK_CUR);
+}
+
+struct SectionWriter {
+    FILE *fp;
+    uint32_t n = 0;
+    void put(const char *name, const void *data, uint32_t elem, uint64_t count) {
+        CptsSection s{};
+        strncpy(s.name, name, sizeof(s.name) - 1);
+        s.elem_size = elem;
+        s.count = count;
+        fwrite(&s, sizeof(s), 1, fp);
+        const uint64_t bytes = uint64_t(elem) * count;
+        if (bytes)
+            fwrite(data, 1, bytes, fp);
+        static const char zeros[16] = {0};
+        const uint64_t pad = (16 - bytes % 16) % 16;
+        if (pad)
+            fwrite(zeros, 1, pad, fp);
+        ++n;
+    }
+};
+
+// IEEE binary32 -> binary16, round to nearest even (what __float2half does on the device,
+// reference: src/core/vec2_half.cuh:44-46 via scene.cu:1213-1220)
+uint16_t float_to_half_rn(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x7F800000u) // inf / nan
+        return uint16_t(sign | 0x7C00u | (x > 0x7F800000u ? 0x0200u | ((x >> 13) & 0x3FFu) : 0u));
+    if (x >= 0x477FF000u) // rounds to >= 65520 -> inf
+        return uint16_t(sign | 0x7C00u);
+    if (x < 0x33000001u) // rounds to zero (<= 2^-25)
+        return uint16_t(sign);
+    int exp = int(x >> 23) - 127;
+    uint32_t man = (x & 0x7FFFFFu) | 0x800000u;
+    int shift;
+    uint32_t half_exp;
+    if (exp < -14) { // subnormal half
+        shift = 13 + (-14 - exp);
+        half_exp = 0;
+    } else {
+        shift = 13;
+        half_exp = uint32_t(exp + 15) << 10;
+    }
+    uint32_t half_man = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (half_man & 1u)))
+        half_man++;
+    // for normals half_man still carries the implicit bit (0x400): adding folds a mantissa carry into the exponent
+    uint32_t out = (exp < -14) ? half_man : (half_exp + (half_man - 0x400u));
+    return uint16_t(sign | out);
+}
+
+} // namespace
+
+void load_cpts(const std::string &path, HostScene &out) {
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp)
+        throw std::runtime_error("cpts: cannot open '" + path + "'");
+    FileCloser closer{fp};
+    CptsHeader h{};
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, CPTS_MAGIC, 8) != 0)
+        throw std::runtime_error("cpts: bad magic in '" + path + "'");
+    out = HostScene();
+    std::vector<CptsTexDesc> tex_desc;
+    std::vector<float> tex_data;
+    for (uint32_t i = 0; i < h.n_sections; i++) {
+        CptsSection s{};
+        if (fread(&s, sizeof(s), 1, fp) != 1)
+            throw std::runtime_error("cpts: truncated section table");
+        s.name[sizeof(s.name) - 1] = 0;
+        const std::string name = s.name;
+        const uint64_t bytes = uint64_t(s.elem_size) * s.count;
+        auto vec3_of = [&](const char *prefix, std::array<std::vector<F3>, 3> &dst) {
+            for (int k = 0; k < 3; k++)
+                if (name == std::string(prefix) + char('0' + k)) {
+                    read_into(fp, s, dst[k], s.name);
+                    return true;
+                }
+            return false;
+        };
+        if (name == "config") {
+            std::vector<int32_t> v;
+            read_into(fp, s, v, "config");
+            if (v.size() != CPTS_CFG_COUNT)
+                throw std::runtime_error("cpts: config section has wrong length");
+            std::copy(v.begin(), v.end(), out.config);
+        } else if (name == "camera") {
+            std::vector<float> v;
+            read_into(fp, s, v, "camera");
+            if (v.size() != CPTS_CAM_COUNT)
+                throw std::runtime_error("cpts: camera section has wrong length");
+            std::copy(v.begin(), v.end(), out.camera);
+        } else if (name == "nodes")
+            read_into(fp, s, out.nodes, "nodes");
+        else if (name == "cache_nodes")
+            read_into(fp, s, out.cache_nodes, "cache_nodes");
+        else if (name == "obj_idxs")
+            read_into(fp, s, out.obj_idxs, "obj_idxs");
+        else if (vec3_of("v", out.verts) || vec3_of("n", out.norms)) {
+        } else if (name == "uv0")
+            read_into(fp, s, out.uvs[0], "uv0");
+        else if (name == "uv1")
+            read_into(fp, s, out.uvs[1], "uv1");
+        else if (name == "uv2")
+            read_into(fp, s, out.uvs[2], "uv2");
+        else if (name == "objects")
+            read_into(fp, s, out.objects, "objects");
+        else if (name == "emitter_prims")
+            read_into(fp, s, out.emitter_prims, "emitter_prims");
+        else if (name == "bsdfs")
+            read_into(fp, s, out.bsdfs, "bsdfs");
+        else if (name == "emitters")
+            read_into(fp, s, out.emitters, "emitters");
+        else if (name == "cie_xyz")
+            read_into(fp, s, out.cie_xyz, "cie_xyz");
+        else if (name == "d65_spd")
+            read_into(fp, s, out.d65_spd, "d65_spd");
+        else if (name == "tex_desc")
+            read_into(fp, s, tex_desc, "tex_desc");
+        else if (name == "tex_data")
+            read_into(fp, s, tex_data, "tex_data");
+        else
+            fseek(fp, long(bytes), SEEK_CUR); // unknown section: forward compatible
+        skip_pad(fp, bytes);
+    }
+    for (const auto &d : tex_desc) {
+        HostTexture t;
+        t.width = d.width, t.height = d.height, t.channels = d.channels;
+        const uint64_t n = uint64_t(d.width) * d.height * d.channels;
+        if (d.offset + n > tex_data.size())
+            throw std::runtime_error("cpts: texture data out of range");
+        t.texels.assign(tex_data.begin() + d.offset, tex_data.begin() + d.offset + n);
+        out.textures.push_back(std::move(t));
+    }
+    validate_scene(out);
+}
+
+void save_cpts(const HostScene &sc, const std::string &path) {
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp)
+        throw std::runtime_error("cpts: cannot create '" + path + "'");
+    FileCloser closer{fp};
+    CptsHeader h{};
+    memcpy(h.magic, CPTS_MAGIC, 8);
+    fwrite(&h, sizeof(h), 1, fp);
+    SectionWriter w{fp};
+    w.put("config", sc.config, 4, CPTS_CFG_COUNT);
+    w.put("camera", sc.camera, 4, CPTS_CAM_COUNT);
+    w.put("nodes", sc.nodes.data(), 16, sc.nodes.size());
+    w.put("cache_nodes", sc.cache_nodes.data(), 16, sc.cache_nodes.size());
+    w.put("obj_idxs", sc.obj_idxs.data(), 4, sc.obj_idxs.size());
+    const char *vn[3] = {"v0", "v1", "v2"}, *nn[3] = {"n0", "n1", "n2"}, *tn[3] = {"uv0", "uv1", "uv2"};
+    for (int k = 0; k < 3; k++) {
+        w.put(vn[k], sc.verts[k].data(), 12, sc.verts[k].size());
+        w.put(nn[k], sc.norms[k].data(), 12, sc.norms[k].size());
+        w.put(tn[k], sc.uvs[k].data(), 8, sc.uvs[k].size());
+    }
+    w.put("objects", sc.objects.data(), 16, sc.objects.size());
+    w.put("emitter_prims", sc.emitter_prims.data(), 4, sc.emitter_prims.size());
+    w.put("bsdfs", sc.bsdfs.data(), sizeof(CptsBsdf), sc.bsdfs.size());
+    w.put("emitters", sc.emitters.data(), sizeof(CptsEmitter), sc.emitters.size());
+    if (!sc.cie_xyz.empty()) {
+        w.put("cie_xyz", sc.cie_xyz.data(), 16, sc.cie_xyz.size());
+        w.put("d65_spd", sc.d65_spd.data(), 4, sc.d65_spd.size());
+    }
+    if (!sc.textures.empty()) {
+        std::vector<CptsTexDesc> desc;
+        std::vector<float> data;
+        for (const auto &t : sc.textures) {
+            CptsTexDesc d{};
+            d.width = t.width, d.height = t.height, d.channels = t.channels;
+            d.offset = data.size();
+            data.insert(data.end(), t.texels.begin(), t.texels.end());
+            desc.push_back(d);
+        }
+        w.put("tex_desc", desc.data(), sizeof(CptsTexDesc), desc.size());
+        w.put("tex_data", data.data(), 4, data.size());
+    }
+    h.n_sections = w.n;
+    fseek(fp, 0, SEEK_SET);
+    fwrite(&h, sizeof(h), 1, fp);
+}
+
+void validate_scene(const HostScene &sc) {
+    auto fail = [](const std::string &m) { throw std::runtime_error("scene: " + m); };
+    const size_t P = sc.verts[0].size();
+    if (sc.width() <= 0 || sc.height() <= 0)
+        fail("film size must be positive");
+    if (uint64_t(sc.width()) * sc.height() > (1u << 24))
+        fail("film larger than the 24-bit pixel index limit of the reference (wavefront_pt.cu:49)");
+    if (P == 0)
+        fail("no primitives");
+    for (int k = 0; k < 3; k++)
+        if (sc.verts[k].size() != P || sc.norms[k].size() != P || sc.uvs[k].size() != P)
+            fail("vertex / normal / uv arrays differ in length");
+    if (sc.obj_idxs.size() != P)
+        fail("obj_idxs length differs from primitive count");
+    if (sc.nodes.empty() || sc.nodes.size() % 2)
+        fail("BVH required (path_tracer.cu:73-75)");
+    if (sc.cache_nodes.size() > 255)
+        fail("more than 255 cached nodes");
+    if (sc.objects.empty())
+        fail("no objects");
+    if (sc.bsdfs.empty() || sc.bsdfs.size() > 48)
+        fail("BSDF count must be in [1,48] (scene.cu:28-29)");
+    if (sc.emitters.empty() || sc.emitters.size() > 9)
+        fail("emitter table must hold the null emitter plus at most 8 emitters");
+    for (const auto &b : sc.bsdfs)
+        if (b.type == CPTS_BSDF_DISPERSION && (sc.cie_xyz.size() != 471 || sc.d65_spd.size() != 531))
+            fail("dispersion BSDF needs the CIE XYZ (471) and D65 (531) spectral tables (sections cie_xyz / d65_spd); "
+                 "the XML loader does not carry them");
+    for (int32_t w : sc.obj_idxs) {
+        if (w < 0)
+            fail("sphere primitives are not supported (reference default build is TRIANGLE_ONLY, defines.cuh:26)");
+        if (size_t(w & 0x000fffff) >= sc.objects.size())
+            fail("primitive references an unknown object");
+    }
+    for (const auto &o : sc.objects) {
+        const int bsdf = o.bsdf_emitter >> 16;
+        int em = o.bsdf_emitter & 0xFFFF;
+        em = (em ^ 0x8000) - 0x8000;
+        if (bsdf < 0 || size_t(bsdf) >= sc.bsdfs.size())
+            fail("object references an unknown BSDF");
+        if (em < 0 || size_t(em) >= sc.emitters.size())
+            fail("object references an unknown emitter");
+        if (em > 0 && (o.prim_num <= 0 || size_t(o.prim_offset) + o.prim_num > sc.emitter_prims.size()))
+            fail("emitter object primitive range outside emitter_prims");
+    }
+    for (int32_t p : sc.emitter_prims)
+        if (p < 0 || size_t(p) >= P)
+            fail("emitter_prims entry out of range");
+    for (const auto &e : sc.emitters)
+        if (e.obj_ref >= int(sc.objects.size()))
+            fail("emitter bound to an unknown object");
+    // leaf ranges
+    const int N = sc.num_nodes();
+    for (int k = 0; k < N; k++) {
+        int32_t base, cnt;
+        memcpy(&base, &sc.nodes[2 * k].w, 4);
+        memcpy(&cnt, &sc.nodes[2 * k + 1].w, 4);
+        if (cnt > 0 && (base < 0 || size_t(base) + cnt > P))
+            fail("BVH leaf primitive range out of bounds");
+        if (cnt < 0 && k - cnt > N)
+            fail("BVH skip offset runs past the node array");
+        if (cnt == 0)
+            fail("BVH node with zero primitive count");
+    }
+}
+
+void build_triangles(const HostScene &sc, std::vector<F4> &tris) {
+    const size_t P = sc.verts[0].size();
+    tris.resize(3 * P);
+    for (size_t i = 0; i < P; i++) {
+        const F3 a = sc.verts[0][i], b = sc.verts[1][i], c = sc.verts[2][i];
+        // plain fp32 products and differences, no contraction (host code of the reference is built without FMA)
+        const volatile float d1x = b.x - a.x, d1y = b.y - a.y, d1z = b.z - a.z;
+        const volatile float d2x = c.x - a.x, d2y = c.y - a.y, d2z = c.z - a.z;
+        const volatile float p0 = d1y * d2z, p1 = d1z * d2y, p2 = d2x * d1z, p3 = d1x * d2z, p4 = d1x * d2y, p5 = d2x * d1y;
+        const float a20 = p0 - p1, a21 = p2 - p3, a22 = p4 - p5;
+        tris[3 * i + 0] = F4{a.x, a.y, a.z, a20};
+        tris[3 * i + 1] = F4{d1x, d1y, d1z, a21};
+        tris[3 * i + 2] = F4{d2x, d2y, d2z, a22};
+    }
+}
+
+void build_normals_uvs(const HostScene &sc, std::vector<F4> &norms, std::vector<U4> &uvs) {
+    const size_t P = sc.verts[0].size();
+    norms.resize(3 * P);
+    uvs.resize(P);
+    for (size_t i = 0; i < P; i++) {
+        for (int k = 0; k < 3; k++) {
+            const F3 n = sc.norms[k][i];
+            norms[3 * i + k] = F4{n.x, n.y, n.z, 0.f};
+        }
+        auto pack = [](F2 uv) { return uint32_t(float_to_half_rn(uv.x)) | (uint32_t(float_to_half_rn(uv.y)) << 16); };
+        uvs[i] = U4{pack(sc.uvs[0][i]), pack(sc.uvs[1][i]), pack(sc.uvs[2][i]), 0u};
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair-node layout
+// ------------------------------------------------------------------------------------------------
+void build_pair_layout(const HostScene &sc, PairLayout &out) {
+    const int N = sc.num_nodes();
+    out = PairLayout();
+    auto node_cnt = [&](int k) {
+        int32_t c;
+        memcpy(&c, &sc.nodes[2 * k + 1].w, 4);
+        return c;
+    };
+    auto node_base = [&](int k) {
+        int32_t b;
+        memcpy(&b, &sc.nodes[2 * k].w, 4);
+        return b;
+    };
+    auto subtree = [&](int k) { return node_cnt(k) < 0 ? -node_cnt(k) : 1; };
+    auto as_float = [](int32_t v) {
+        float f;
+        memcpy(&f, &v, 4);
+        return f;
+    };
+    constexpr int kMaxLeaf = (1 << (31 - 26)) - 1; // 5-bit count
+    constexpr int kBaseMask = (1 << 26) - 1;
+
+    // emits a child record {min,ref}{max,end}
+    struct Child {
+        F4 lo, hi;
+    };
+    auto new_node = [&]() {
+        const int idx = int(out.wnodes.size() / 4);
+        out.wnodes.resize(out.wnodes.size() + 4, F4{0, 0, 0, 0});
+        return idx;
+    };
+    const Child empty_child{F4{1e30f, 1e30f, 1e30f, as_float(~0)}, F4{-1e30f, -1e30f, -1e30f, as_float(0)}};
+
+    // leaf child (possibly a chain of pair nodes when the primitive count exceeds the 5-bit field;
+    // every link repeats the leaf's own box so the set of tested primitives is unchanged)
+    std::function<Child(int, int, int)> leaf_child = [&](int k, int base, int cnt) -> Child {
+        const F4 lo = sc.nodes[2 * k], hi = sc.nodes[2 * k + 1];
+        Child c;
+        if (cnt <= kMaxLeaf) {
+            if (base > kBaseMask)
+                throw std::runtime_error("pair layout: primitive index exceeds 26 bits");
+            const int32_t ref = ~int32_t(base | (cnt << 26));
+            c.lo = F4{lo.x, lo.y, lo.z, as_float(ref)};
+            c.hi = F4{hi.x, hi.y, hi.z, as_float(k + 1)};
+            return c;
+        }
+        out.oversize_leaves++;
+        const int idx = new_node();
+        const Child a = leaf_child(k, base, kMaxLeaf), b = leaf_child(k, base + kMaxLeaf, cnt - kMaxLeaf);
+        out.wnodes[4 * idx + 0] = a.lo, out.wnodes[4 * idx + 1] = a.hi;
+        out.wnodes[4 * idx + 2] = b.lo, out.wnodes[4 * idx + 3] = b.hi;
+        c.lo = F4{lo.x, lo.y, lo.z, as_float(idx)};
+        c.hi = F4{hi.x, hi.y, hi.z, as_float(k + 1)};
+        return c;
+    };
+
+    auto contained = [&](int child, int parent) {
+        const F4 cl = sc.nodes[2 * child], ch = sc.nodes[2 * child + 1], pl = sc.nodes[2 * parent], ph = sc.nodes[2 * parent + 1];
+        return cl.x >= pl.x && cl.y >= pl.y && cl.z >= pl.z && ch.x <= ph.x && ch.y <= ph.y && ch.z <= ph.z;
+    };
+
+    // explicit stack: (reference node k, slot to fill = pair node index * 2 + child id, depth)
+    struct Item {
+        int k, slot, depth;
+    };
+    std::vector<Item> todo;
+    const int root_pair = new_node();
+    out.root = root_pair;
+    out.wnodes[4 * root_pair + 2] = empty_child.lo;
+    out.wnodes[4 * root_pair + 3] = empty_child.hi;
+    todo.push_back(Item{0, root_pair * 2, 1});
+    while (!todo.empty()) {
+        const Item it = todo.back();
+        todo.pop_back();
+        out.max_depth = std::max(out.max_depth, it.depth);
+        const int pair_idx = it.slot >> 1, which = it.slot & 1;
+        Child c;
+        if (node_cnt(it.k) > 0) {
+            c = leaf_child(it.k, node_base(it.k), node_cnt(it.k));
+        } else {
+            const int idx = new_node();
+            const F4 lo = sc.nodes[2 * it.k], hi = sc.nodes[2 * it.k + 1];
+            c.lo = F4{lo.x, lo.y, lo.z, as_float(idx)};
+            c.hi = F4{hi.x, hi.y, hi.z, as_float(it.k + subtree(it.k))};
+            const int left = it.k + 1, right = left + subtree(left);
+            if (right >= N || right >= it.k + subtree(it.k))
+                throw std::runtime_error("pair layout: malformed skip offsets");
+            if (!contained(left, it.k))
+                out.nesting_violations++;
+            if (!contained(right, it.k))
+                out.nesting_violations++;
+            // push right first so the left subtree is laid out next (DFS order => parent/child locality)
+            todo.push_back(Item{right, idx * 2 + 1, it.depth + 1});
+            todo.push_back(Item{left, idx * 2 + 0, it.depth + 1});
+        }
+        out.wnodes[4 * pair_idx + 2 * which + 0] = c.lo;
+        out.wnodes[4 * pair_idx + 2 * which + 1] = c.hi;
+    }
+}
+
+} // namespace cptb

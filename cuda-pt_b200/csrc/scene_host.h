@@ -1,0 +1,82 @@
+// scene_host.h — host-side flat scene (what the reference's `Scene` hands to a
+// renderer constructor; reference: src/core/scene.cuh:49-107) and the helpers
+// that turn it into device-ready arrays.  Pure C++ (no CUDA calls) so that the
+// loader, the .cpts reader/writer and the BVH re-layout can be unit-tested on
+// a CPU-only box.
+#pragma once
+#include "cpts_format.h"
+
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace cptb {
+
+struct F3 {
+    float x, y, z;
+};
+struct F2 {
+    float x, y;
+};
+struct F4 {
+    float x, y, z, w;
+};
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+struct HostTexture {
+    int width = 0, height = 0, channels = 4;
+    std::vector<float> texels;
+};
+
+struct HostScene {
+    int32_t config[CPTS_CFG_COUNT] = {0};
+    float camera[CPTS_CAM_COUNT] = {0};
+    std::vector<F4> nodes;       // 2 per node
+    std::vector<U4> cache_nodes; // fp16 near-root nodes
+    std::vector<int32_t> obj_idxs;
+    std::array<std::vector<F3>, 3> verts, norms;
+    std::array<std::vector<F2>, 3> uvs;
+    std::vector<CptsObject> objects;
+    std::vector<int32_t> emitter_prims;
+    std::vector<CptsBsdf> bsdfs;
+    std::vector<CptsEmitter> emitters; // [0] = null emitter
+    std::vector<HostTexture> textures;
+    std::vector<F4> cie_xyz;    // 471 samples, 360..830 nm (only present when a dispersion BSDF needs it)
+    std::vector<float> d65_spd; // 531 samples, 300..830 nm
+
+    int width() const { return config[CPTS_CFG_WIDTH]; }
+    int height() const { return config[CPTS_CFG_HEIGHT]; }
+    int num_nodes() const { return int(nodes.size() / 2); }
+    int num_prims() const { return int(verts[0].size()); }
+};
+
+// ---- .cpts container (include/cpts_format.h) ----
+void load_cpts(const std::string &path, HostScene &out); // throws std::runtime_error
+void save_cpts(const HostScene &scene, const std::string &path);
+
+// ---- XML scene loader (scene format v1.2; reference behaviour: src/impl/scene.cu:937-1192) ----
+void load_xml(const std::string &path, HostScene &out); // throws std::runtime_error
+
+// consistency checks shared by both loaders; throws on malformed scenes
+void validate_scene(const HostScene &scene);
+
+// ---- device-ready derived arrays ----
+// 48 B precomputed-adjoint triangles {v0,a20}{e1,a21}{e2,a22} (reference: src/core/aos.cuh:134-164)
+void build_triangles(const HostScene &scene, std::vector<F4> &tris);
+// 3 x {n.xyz,0} per primitive and packed half uvs (reference: aos.cuh:248-262, vec2_half.cuh:160-170)
+void build_normals_uvs(const HostScene &scene, std::vector<F4> &norms, std::vector<U4> &uvs);
+
+// Pair-node re-layout for ordered traversal (see traverse.cuh).  Returns the root reference.
+struct PairLayout {
+    std::vector<F4> wnodes; // 4 per inner node
+    int root = 0;
+    int max_depth = 0;
+    int nesting_violations = 0; // child boxes that are not contained in their parent's box
+    int oversize_leaves = 0;
+};
+void build_pair_layout(const HostScene &scene, PairLayout &out);
+
+} // namespace cptb

@@ -1,0 +1,246 @@
+// traverse.cuh — BVH traversal for the wavefront kernels.
+//
+// Two interchangeable back-ends produce the reference's hit set:
+//
+//  * `closest_hit_dfs` / `occluded_dfs`: the reference's own stackless
+//    skip-offset DFS over its 32 B linear nodes (reference:
+//    src/renderer/tracing_func.cuh:44-99,117-181).  Kept as the strict
+//    comparison mode (CPTB200_TRAVERSAL=dfs) and for tiny scenes.
+//
+//  * `closest_hit_ordered` / `occluded_ordered`: near-child-first traversal with
+//    a short per-thread stack over "pair nodes" (both children's boxes in one
+//    64 B record, built by bvh_relayout.cpp from the SAME tree, boxes and leaf
+//    ranges).  Every box keeps the reference's fp32 bounds and is tested with
+//    the reference's slab arithmetic (src/core/aabb.cuh:58-65), so the set of
+//    leaves whose primitives get tested is the same; only the visiting order
+//    changes (DESIGN.md §"Why ordered traversal is parity-safe").
+//
+// Both honour the reference's cached near-root phase: up to 255 fp16 nodes in
+// shared memory choose the DFS index at which global traversal starts, and
+// everything that precedes that index in DFS order is skipped
+// (tracing_func.cuh:124-142; SURVEY.md App. A.9 — including the round-to-nearest
+// fp16 bounds quirk).
+#pragma once
+#include "pt_device.cuh"
+
+namespace cptb {
+
+// slab test, same fma/min/max structure as AABB::intersect (aabb.cuh:58-65, vec3.cuh:263-276)
+PT_DEV bool slab_test(float minx, float miny, float minz, float maxx, float maxy, float maxz, V3 inv_d, V3 o_div,
+                      float &t_near) {
+    const float ax = fmaf(minx, inv_d.x, -o_div.x), ay = fmaf(miny, inv_d.y, -o_div.y), az = fmaf(minz, inv_d.z, -o_div.z);
+    const float bx = fmaf(maxx, inv_d.x, -o_div.x), by = fmaf(maxy, inv_d.y, -o_div.y), bz = fmaf(maxz, inv_d.z, -o_div.z);
+    const float min_x = ax < bx ? ax : bx, max_x = ax < bx ? bx : ax;
+    const float min_y = ay < by ? ay : by, max_y = ay < by ? by : ay;
+    const float min_z = az < bz ? az : bz, max_z = az < bz ? bz : az;
+    t_near = fmaxf(min_x, fmaxf(min_y, min_z));
+    const float t_far = fminf(max_x, fminf(max_y, max_z));
+    return (t_far > t_near) && (t_far > 0);
+}
+
+// cached fp16 phase: returns the DFS node index at which global traversal starts, or `miss_value`
+// when no cached frontier node is intersected (bvh.cuh:182-251, tracing_func.cuh:53-65,128-140)
+PT_DEV int cached_entry(const uint4 *__restrict__ s_cached, int cache_num, V3 inv_d, V3 o_div, float limit, int miss_value) {
+    int node_idx = miss_value;
+    float t_near = 0;
+    for (int i = 0; i < cache_num;) {
+        const uint4 c = s_cached[i];
+        const float2 xx = __half22float2(*reinterpret_cast<const __half2 *>(&c.x));
+        const float2 yy = __half22float2(*reinterpret_cast<const __half2 *>(&c.y));
+        const float2 zz = __half22float2(*reinterpret_cast<const __half2 *>(&c.z));
+        bool hit = slab_test(xx.x, yy.x, zz.x, xx.y, yy.y, zz.y, inv_d, o_div, t_near) && t_near < limit;
+        const int all_offset = int(c.w & 0xFFu), gmem_index = int((c.w >> 8) & 0x00FFFFFFu);
+        const int increment = (!hit) * all_offset + int(hit && all_offset != 1);
+        hit = hit && all_offset == 1;
+        i = hit ? cache_num : (i + increment);
+        node_idx = hit ? gmem_index : node_idx;
+    }
+    return node_idx;
+}
+
+struct Hit {
+    float t, u, v;
+    int prim;     // -1: miss
+    int obj_word; // raw per-primitive object word
+};
+
+// ---------------------------------------------------------------------------------------------
+// strict mode: reference DFS
+// ---------------------------------------------------------------------------------------------
+PT_DEV Hit closest_hit_dfs(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
+    Hit h{kMaxDist, 0.f, 0.f, -1, 0};
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    int node_idx = cached_entry(s_cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+    float t_near = 0;
+    while (node_idx < sc.num_nodes) {
+        const float4 lo = __ldg(sc.nodes + 2 * node_idx), hi = __ldg(sc.nodes + 2 * node_idx + 1);
+        const int beg = __float_as_int(lo.w);
+        int end = __float_as_int(hi.w);
+        const bool hit = slab_test(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, inv_d, o_div, t_near) && t_near < h.t;
+        node_idx += (!hit) * (end < 0 ? -end : 1) + int(hit);
+        end = hit ? end + beg : 0;
+        for (int idx = beg; idx < end; idx++) {
+            float u, v;
+            const float dist = hit_triangle(sc.tris, idx, o, d, u, v, __int_as_float(0x7f800000));
+            const bool valid = dist > kEps && dist < h.t;
+            h.t = valid ? dist : h.t;
+            h.u = valid ? u : h.u;
+            h.v = valid ? v : h.v;
+            h.prim = valid ? idx : h.prim;
+        }
+    }
+    if (h.prim >= 0)
+        h.obj_word = __ldg(sc.obj_idxs + h.prim);
+    return h;
+}
+
+// true == unoccluded
+PT_DEV bool unoccluded_dfs(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist) {
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    int node_idx = cached_entry(s_cached, sc.num_cache, inv_d, o_div, max_dist, sc.num_nodes);
+    float t_near = 0;
+    while (node_idx < sc.num_nodes) {
+        const float4 lo = __ldg(sc.nodes + 2 * node_idx), hi = __ldg(sc.nodes + 2 * node_idx + 1);
+        const int beg = __float_as_int(lo.w);
+        int end = __float_as_int(hi.w);
+        const bool hit = slab_test(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, inv_d, o_div, t_near) && t_near < max_dist;
+        node_idx += (!hit) * (end < 0 ? -end : 1) + int(hit);
+        end = hit ? end + beg : 0;
+        for (int idx = beg; idx < end; idx++) {
+            float u, v;
+            const float dist = hit_triangle(sc.tris, idx, o, d, u, v, max_dist);
+            if (dist > kEps)
+                return false;
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ordered mode: pair nodes + per-thread stack
+//   pair node (4 x float4): {c0.min, ref0} {c0.max, end0} {c1.min, ref1} {c1.max, end1}
+//   ref >= 0 : index of an inner pair node;  ref < 0 : leaf, ~ref = prim_base | (prim_count << 26)
+//   end      : one past the last reference-DFS node index inside that child's subtree
+// ---------------------------------------------------------------------------------------------
+constexpr int kStackSize = 48;
+constexpr int kLeafCountShift = 26;
+constexpr int kLeafBaseMask = (1 << kLeafCountShift) - 1;
+
+PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
+    Hit h{kMaxDist, 0.f, 0.f, -1, 0};
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int sp = 0;
+    int cur = sc.wroot;
+    const float inf = __int_as_float(0x7f800000);
+    while (true) {
+        if (cur >= 0) {
+            const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
+                         b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+            float t0, t1;
+            const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < h.t &&
+                            __float_as_int(a1.w) > start;
+            const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < h.t &&
+                            __float_as_int(b1.w) > start;
+            const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+            if (h0 && h1) {
+                const bool swap = t1 < t0;
+                stack_ref[sp] = swap ? r0 : r1;
+                stack_t[sp] = swap ? t0 : t1;
+                ++sp;
+                cur = swap ? r1 : r0;
+                continue;
+            }
+            if (h0 || h1) {
+                cur = h0 ? r0 : r1;
+                continue;
+            }
+        } else {
+            const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+            for (int idx = base; idx < base + cnt; idx++) {
+                float u, v;
+                const float dist = hit_triangle(sc.tris, idx, o, d, u, v, inf);
+                const bool valid = dist > kEps && dist < h.t;
+                h.t = valid ? dist : h.t;
+                h.u = valid ? u : h.u;
+                h.v = valid ? v : h.v;
+                h.prim = valid ? idx : h.prim;
+            }
+        }
+        // pop the next entry that can still beat the current closest hit
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] < h.t) {
+                cur = stack_ref[sp];
+                found = true;
+                break;
+            }
+        }
+        if (!found)
+            break;
+    }
+    if (h.prim >= 0)
+        h.obj_word = __ldg(sc.obj_idxs + h.prim);
+    return h;
+}
+
+PT_DEV bool unoccluded_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist) {
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, max_dist, sc.num_nodes);
+    if (start >= sc.num_nodes)
+        return true;
+    int stack_ref[kStackSize];
+    int sp = 0;
+    int cur = sc.wroot;
+    while (true) {
+        if (cur >= 0) {
+            const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
+                         b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+            float t0, t1;
+            const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < max_dist &&
+                            __float_as_int(a1.w) > start;
+            const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < max_dist &&
+                            __float_as_int(b1.w) > start;
+            const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+            if (h0 && h1) {
+                stack_ref[sp++] = r1;
+                cur = r0;
+                continue;
+            }
+            if (h0 || h1) {
+                cur = h0 ? r0 : r1;
+                continue;
+            }
+        } else {
+            const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+            for (int idx = base; idx < base + cnt; idx++) {
+                float u, v;
+                const float dist = hit_triangle(sc.tris, idx, o, d, u, v, max_dist);
+                if (dist > kEps)
+                    return false;
+            }
+        }
+        if (sp == 0)
+            break;
+        cur = stack_ref[--sp];
+    }
+    return true;
+}
+
+template <bool ORDERED> PT_DEV Hit closest_hit(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
+    if constexpr (ORDERED)
+        return closest_hit_ordered(sc, s_cached, o, d);
+    else
+        return closest_hit_dfs(sc, s_cached, o, d);
+}
+template <bool ORDERED> PT_DEV bool unoccluded(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist) {
+    if constexpr (ORDERED)
+        return unoccluded_ordered(sc, s_cached, o, d, max_dist);
+    else
+        return unoccluded_dfs(sc, s_cached, o, d, max_dist);
+}
+
+} // namespace cptb

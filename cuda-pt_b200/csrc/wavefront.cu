@@ -1,0 +1,890 @@
+// wavefront.cu — the per-bounce wavefront path-tracing hot path as sm_100a kernels.
+//
+// Pipeline for one batch of S samples over P = W*H pixels (slots = S*P paths in flight):
+//
+//   k_raygen      camera ray + primary closest hit, payload init, hit paths -> queue[0]
+//   for bounce b: k_shade  (NEE shadow ray + MIS + emission + BSDF sample)  over queue[b]
+//                 k_trace  (closest hit + interaction + miss/envmap + Russian roulette),
+//                          survivors are compacted into queue[b+1] with warp ballots
+//   k_splat       NaN scrub, ordered per-sample accumulation, running mean, gamma, Welford variance
+//
+// This replaces the reference's raygen_primary_hit_shader / fused_ray_bounce_shader /
+// fused_closesthit_shader / radiance_splat (src/pt_impl/wavefront_pt.cu:71-314,476-503) and its
+// host loop with thrust::sort + lower_bound + D2H count per bounce
+// (src/pt_impl/wf_path_tracer.cu:175-230).  Differences that matter on B200:
+//   * no host synchronisation inside a batch: queue sizes stay in device memory, every kernel is a
+//     persistent grid (k x 148 SMs) whose warps pull 32-path chunks with one atomic per chunk;
+//   * compaction is fused into k_trace's epilogue (ballot + popc prefix, one atomic per warp);
+//     the image is indexed by path slot, so processing order never changes pixel values;
+//   * S samples are in flight at once (180 GB HBM3e) so late bounces still fill 148 SMs;
+//   * near-child-first traversal over a re-laid-out copy of the SAME tree (traverse.cuh).
+#include "traverse.cuh"
+#include "wavefront.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+
+namespace cptb {
+
+#define CUDA_OK(expr)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t err__ = (expr);                                                                                    \
+        if (err__ != cudaSuccess) {                                                                                    \
+            char buf__[512];                                                                                           \
+            snprintf(buf__, sizeof(buf__), "CUDA error %s at %s:%d (%s)", cudaGetErrorString(err__), __FILE__,         \
+                     __LINE__, #expr);                                                                                 \
+            throw std::runtime_error(buf__);                                                                           \
+        }                                                                                                              \
+    } while (0)
+
+constexpr int kBlock = 128;
+
+struct PathState {
+    float4 *ray_o; // o.xyz, hit_t
+    float4 *ray_d; // d.xyz, tag bits
+    float4 *thp;
+    float4 *L;
+    float4 *isect; // n.xyz, half2 uv
+    uint2 *rng;
+    float *pdf;
+};
+
+struct BatchParams {
+    int W, H, P, S, first_accum, seed_offset;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_cached_nodes(const DevScene &sc, uint4 *s_cached) {
+    for (int i = threadIdx.x; i < sc.num_cache; i += blockDim.x)
+        s_cached[i] = sc.cache_nodes[i];
+    __syncthreads();
+}
+
+// one atomic per warp chunk; returns the chunk index
+__device__ __forceinline__ int warp_next_chunk(int *counter, int lane) {
+    int v = 0;
+    if (lane == 0)
+        v = atomicAdd(counter, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+// warp-aggregated append (ballot + popc prefix); must be called by the full warp
+__device__ __forceinline__ void warp_push(uint32_t *queue, int *count, bool pred, uint32_t value, int lane) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0)
+        return;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader)
+        base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred)
+        queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__device__ __forceinline__ V4 null_or_env(const DevScene &sc, V3 dir) {
+    // c_emitter[envmap_id]->eval_le(&ray.d): envmap_id == 0 selects the null emitter -> (0,0,0,1)
+    if (sc.envmap_id > 0)
+        return emitter_eval(sc.emitters[sc.envmap_id], dir, make_float4(0, 0, 0, 0), false);
+    return mk4(0, 0, 0, 1);
+}
+
+// CompactedObjInfo::solid_angle_pdf (object.cuh:51-56): the quotient is formed in double (1e-4 is a double
+// literal) and rounded to float by the return type
+__device__ __forceinline__ float solid_angle_pdf(float inv_area, V3 normal, V3 incid, float min_depth) {
+    return inv_area * min_depth * min_depth / max(fabsf(dot(incid, normal)), 1e-4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_raygen — reference: raygen_primary_hit_shader (wavefront_pt.cu:71-133)
+// one warp = one 8x4 pixel tile of one sample
+// ------------------------------------------------------------------------------------------------
+template <bool ORDERED>
+__global__ void __launch_bounds__(kBlock)
+    k_raygen(DevScene sc, CameraPOD cam, PathState st, BatchParams bp, uint32_t *q_out, int *q_count, int *work) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = (bp.W + 7) >> 3, tiles_y = (bp.H + 3) >> 2, tiles = tiles_x * tiles_y;
+    const int total = tiles * bp.S;
+    for (int task = warp_next_chunk(work, lane); task < total; task = warp_next_chunk(work, lane)) {
+        const int s = task / tiles, tile = task - s * tiles;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int px = (tx << 3) + (lane & 7), py = (ty << 2) + (lane >> 3);
+        const bool inside = px < bp.W && py < bp.H;
+        bool hit_any = false;
+        uint32_t slot = 0;
+        if (inside) {
+            const int gidx = px + py * bp.W;
+            slot = uint32_t(s) * uint32_t(bp.P) + uint32_t(gidx);
+            Rng rng;
+            rng.seed(gidx, bp.seed_offset + (bp.first_accum + s) * kSeedScaler);
+            V3 o, d;
+            camera_ray(cam, px, py, rng, o, d);
+            st.thp[slot] = make_float4(1, 1, 1, 1);
+            st.pdf[slot] = 1.f;
+            st.rng[slot] = make_uint2(rng.d0, rng.d1);
+            const Hit h = closest_hit<ORDERED>(sc, s_cached, o, d);
+            uint32_t tag = 0;
+            V4 L = mk4(0, 0, 0, 1);
+            if (h.prim >= 0) {
+                tag = TAG_ACTIVE | TAG_HIT | uint32_t(h.prim);
+                st.isect[slot] = make_interaction(sc, h.prim, h.u, h.v);
+                hit_any = true;
+            } else {
+                L = null_or_env(sc, d);
+            }
+            st.L[slot] = to_f4(L);
+            st.ray_o[slot] = make_float4(o.x, o.y, o.z, h.t);
+            st.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
+        }
+        warp_push(q_out, q_count, hit_any, slot, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shade — reference: fused_ray_bounce_shader (wavefront_pt.cu:213-314)
+// ------------------------------------------------------------------------------------------------
+template <bool ORDERED>
+__global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
+                                                  const int *__restrict__ q_count, int *work,
+                                                  unsigned long long *shadow_counter, int secondary_bounce) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    unsigned int local_shadow = 0;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        if (i >= count)
+            continue;
+        const uint32_t slot = queue[i];
+        V4 thp = from_f4(st.thp[slot]), rdc = from_f4(st.L[slot]);
+        const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+        const uint2 rs = st.rng[slot];
+        Rng rng{rs.x, rs.y};
+        const float4 it = st.isect[slot];
+        V3 o = xyz(ro), d = xyz(rd);
+        const float hit_t = ro.w;
+        uint32_t tag = __float_as_uint(rd.w);
+
+        int object_id = __ldg(sc.obj_idxs + (tag & TAG_INDEX));
+        object_id = object_id >= 0 ? object_id : -object_id - 1;
+        const ObjectPOD ob = sc.objects[object_id];
+        const int material_id = ob.bsdf_emitter >> 16;
+        const int emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+        const Material &mat = sc.mats[material_id];
+
+        float direct_pdf = 1;
+        // ---- pick an emitter (tracing_func.cuh:210-225)
+        int num = sc.num_emitters;
+        num -= emitter_id > 0 && num > 1;
+        uint32_t emit_id = (rng.next_u32() % uint32_t(num)) + 1;
+        emit_id += emit_id >= uint32_t(emitter_id) && emitter_id > 0;
+        direct_pdf = 1.f / float(num);
+        emit_id = emit_id * uint32_t(emitter_id == 0 || num > 1);
+        const EmitterPOD &em = sc.emitters[emit_id];
+        // ---- pick a primitive on it (object.cuh:45-49, wavefront_pt.cu:254-259)
+        const ObjectPOD eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
+        direct_pdf *= eo.inv_area;
+        int emit_prim = int(rng.next_u32() % uint32_t(eo.prim_num)) + eo.prim_offset;
+        emit_prim = __ldg(sc.emitter_prims + emit_prim);
+
+        const V3 hit_pos = advance(o, d, hit_t);
+        o = hit_pos;
+        V4 direct_comp = mk4(0, 0, 0, 1);
+        V3 sd = emitter_sample(sc, em, hit_pos, xyz(it), direct_comp, direct_pdf, rng.next2d(), emit_prim) - hit_pos;
+        float emit_len_mis = length(sd);
+        sd *= __frcp_rn(emit_len_mis);
+        // ---- NEE shadow ray + MIS (wavefront_pt.cu:273-289)
+        if (emit_id != 0) {
+            ++local_shadow;
+            if (unoccluded<ORDERED>(sc, s_cached, hit_pos, sd, emit_len_mis - kEps)) {
+                emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
+                rdc += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
+                       (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+            }
+        }
+        // ---- emission with MIS against light sampling (wavefront_pt.cu:291-302, object.cuh:51-56)
+        float pdf = st.pdf[slot],
+              emission_weight = pdf / (pdf + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, hit_t) *
+                                                 (emitter_id > 0) * secondary_bounce * ((tag & TAG_DELTA) == 0));
+        const V4 L = (thp * emitter_eval(sc.emitters[emitter_id], d, it, true)) * emission_weight + rdc;
+        st.L[slot] = to_f4(L);
+
+        // ---- sample the next direction (wavefront_pt.cu:304-312)
+        int lobe = LOBE_NONE;
+        d = bsdf_sample(sc, mat, d, it, thp, pdf, rng, lobe);
+        tag &= ~TAG_DELTA;
+        tag |= uint32_t((lobe & LOBE_SPECULAR) > 0) << 30;
+
+        st.thp[slot] = to_f4(thp);
+        st.rng[slot] = make_uint2(rng.d0, rng.d1);
+        st.ray_o[slot] = make_float4(o.x, o.y, o.z, hit_t);
+        st.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
+        st.pdf[slot] = pdf;
+    }
+    // per-warp ray statistics (Mrays/s accounting)
+    for (int off = 16; off > 0; off >>= 1)
+        local_shadow += __shfl_down_sync(0xffffffffu, local_shadow, off);
+    if (lane == 0 && local_shadow)
+        atomicAdd(shadow_counter, (unsigned long long)local_shadow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_trace — reference: fused_closesthit_shader (wavefront_pt.cu:141-207) + the sort/lower_bound
+// compaction of wf_path_tracer.cu:197-202
+// ------------------------------------------------------------------------------------------------
+template <bool ORDERED>
+__global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
+                                                  const int *__restrict__ q_count, int *work, uint32_t *q_next,
+                                                  int *q_next_count, int bounce) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        bool alive = false;
+        uint32_t slot = 0;
+        if (i < count) {
+            slot = queue[i];
+            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            const V3 o = xyz(ro), d = xyz(rd);
+            uint32_t tag = __float_as_uint(rd.w) & 0xd0000000u; // reset(): clear hit flag and hit index
+            const Hit h = closest_hit<ORDERED>(sc, s_cached, o, d);
+            V4 thp = from_f4(st.thp[slot]);
+            if (h.prim >= 0) {
+                tag |= TAG_HIT | TAG_ACTIVE | uint32_t(h.prim);
+                st.isect[slot] = make_interaction(sc, h.prim, h.u, h.v);
+                alive = true;
+                const float max_value = max3(thp);
+                if (bounce >= kRRBounce && max_value < kRRThreshold) {
+                    const uint2 rs = st.rng[slot];
+                    Rng rng{rs.x, rs.y};
+                    const bool survive = rng.next1d() < max_value && max_value > kThpEps;
+                    alive = survive;
+                    if (!survive)
+                        tag &= ~TAG_ACTIVE;
+                    thp *= survive ? 1.f / max_value : 0.f;
+                    st.thp[slot] = to_f4(thp);
+                    st.rng[slot] = make_uint2(rng.d0, rng.d1);
+                }
+            } else {
+                V4 L = from_f4(st.L[slot]);
+                L += thp * null_or_env(sc, d);
+                st.L[slot] = to_f4(L);
+                tag &= ~TAG_ACTIVE;
+            }
+            st.ray_o[slot].w = h.t;
+            st.ray_d[slot].w = __uint_as_float(tag);
+        }
+        warp_push(q_next, q_next_count, alive, slot, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_splat — reference: radiance_splat (wavefront_pt.cu:476-503), estimate_variance
+// (tracing_func.cuh:194-208), Vec4::gamma_corr (vec4.cuh:213-217)
+// samples of a batch are added in sample order, so the fp32 sum is the one the reference produces
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_splat(const float4 *__restrict__ Lbuf, float4 *__restrict__ image,
+                                               float4 *__restrict__ out, float *__restrict__ var, int P, int S,
+                                               int first_accum, int write_output, int gamma) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        V4 acc = from_f4(image[p]);
+        float variance = var ? var[p] : 0.f;
+        for (int s = 0; s < S; s++) {
+            V4 L = from_f4(Lbuf[size_t(s) * P + p]);
+            L = bad_rgb(L) ? mk4(0, 0, 0, 1) : L;
+            if (var) {
+                const int accum_cnt = first_accum + s;
+                float cur_val = (L.x + L.y + L.z) * 0.33333333f, old_mean = (acc.x + acc.y + acc.z) * 0.33333333f,
+                      new_mean = old_mean + cur_val, rcp_cnt = 1.f / float(accum_cnt);
+                old_mean = accum_cnt > 1 ? old_mean / float(accum_cnt - 1) : 0;
+                new_mean *= rcp_cnt;
+                variance = (float(accum_cnt - 1) * variance + (cur_val - old_mean) * (cur_val - new_mean)) * rcp_cnt;
+            }
+            acc += L;
+        }
+        image[p] = to_f4(acc);
+        if (var)
+            var[p] = variance;
+        if (write_output) {
+            V4 o = acc;
+            o *= 1.f / float(first_accum + S - 1);
+            if (gamma)
+                o = mk4(powf(fmaxf(0.f, o.x), 1.f / 2.2f), powf(fmaxf(0.f, o.y), 1.f / 2.2f),
+                        powf(fmaxf(0.f, o.z), 1.f / 2.2f));
+            out[p] = to_f4(o);
+        }
+    }
+}
+
+// folds the per-bounce queue sizes of a finished batch into the cumulative ray statistics
+__global__ void k_fold_stats(const int *__restrict__ q_counts, int traced_bounces, int shaded_bounces,
+                             unsigned long long *stats) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long closest = 0, shaded = 0;
+        for (int b = 0; b < shaded_bounces; b++)
+            shaded += (unsigned long long)q_counts[b];
+        for (int b = 0; b < traced_bounces; b++)
+            closest += (unsigned long long)q_counts[b];
+        stats[0] += closest;
+        stats[2] += shaded;
+    }
+}
+
+// derived material / emitter parameters are computed on the device with the same math functions the
+// reference uses inside its device-side constructors (virtual_funcs.cu:85-98, bsdf_plastic.cu:25-36,
+// fresnel.cuh:62-75, cuda_utils.cuh:115-120, emitter.cuh:349-353)
+__device__ float roughness_to_alpha_dev(float roughness) {
+    roughness = fmaxf(roughness, 1e-3f);
+    float x = logf(roughness);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+__device__ float diffuse_fresnel_dev(float ior) {
+    const int sample_cnt = 131072;
+    double diff_fresnel = 0.0;
+    float fb = fresnel_simple(ior, 0.0f);
+    for (int i = 1; i <= sample_cnt; i++) {
+        float cos_theta2 = float(i) / sample_cnt;
+        float fa = fresnel_simple(ior, min(sqrtf(cos_theta2), 1.0f));
+        diff_fresnel += double(fa + fb) * (0.5f / sample_cnt);
+        fb = fa;
+    }
+    return float(diff_fresnel);
+}
+__global__ void k_derive_tables(Material *mats, int num_mats, EmitterPOD *ems, int num_ems) {
+    const int i = threadIdx.x;
+    if (i < num_mats) {
+        Material &m = mats[i];
+        if (m.type == MAT_GGX) {
+            m.k_d = make_float4(0, 0, 0, 0);
+            m.k_s = make_float4(roughness_to_alpha_dev(m.raw[0]), roughness_to_alpha_dev(m.raw[1]), 1, 1);
+        } else if (m.type == MAT_PLASTIC || m.type == MAT_PLASTIC_FWD) {
+            m.eta = 1.f / m.raw[0];
+            m.precomp_diff_f = m.type == MAT_PLASTIC ? diffuse_fresnel_dev(m.raw[0]) : 0.f;
+        }
+    }
+    if (i < num_ems && ems[i].type == EM_ENVMAP) {
+        EmitterPOD &e = ems[i];
+        float s, c;
+        sincosf(e.azimuth * 0.5f, &s, &c);
+        Quat yaw{0 * s, 0 * s, 1 * s, c};
+        sincosf(e.zenith * 0.5f, &s, &c);
+        Quat pit{1 * s, 0 * s, 0 * s, c};
+        Quat r = qmul(yaw, pit);
+        e.rot = make_float4(r.x, r.y, r.z, r.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count)
+            CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T> &v) {
+        alloc(v.size());
+        if (!v.empty())
+            CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void release() {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct Renderer::Impl {
+    DevBuf<float4> nodes, tris, norms, wnodes;
+    DevBuf<uint4> cache_nodes, uvs;
+    DevBuf<int> obj_idxs, emitter_prims;
+    DevBuf<ObjectPOD> objects;
+    DevBuf<Material> mats;
+    DevBuf<EmitterPOD> emitters;
+    DevScene dev{};
+    CameraPOD cam{};
+    // path pool
+    DevBuf<float4> ray_o, ray_d, thp, L, isect;
+    DevBuf<uint2> rng;
+    DevBuf<float> pdf;
+    DevBuf<uint32_t> queue[2];
+    DevBuf<int> counters;                 // [0..D] queue sizes, [D+1 ..] work counters
+    DevBuf<unsigned long long> stats;     // closest, shadow, shaded
+    std::vector<cudaTextureObject_t> tex_objs;
+    std::vector<cudaArray_t> tex_arrays;
+    int capacity_samples = 0;
+    int pair_depth = 0, nesting_violations = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    size_t scene_bytes = 0;
+};
+
+static CameraPOD camera_from_floats(const float *c) {
+    CameraPOD cam;
+    cam.R.r0 = V3{c[0], c[1], c[2]};
+    cam.R.r1 = V3{c[3], c[4], c[5]};
+    cam.R.r2 = V3{c[6], c[7], c[8]};
+    cam.t = V3{c[9], c[10], c[11]};
+    cam.inv_focal = c[CPTS_CAM_INV_FOCAL];
+    cam.hw = c[CPTS_CAM_HW];
+    cam.hh = c[CPTS_CAM_HH];
+    cam.sign_x = c[CPTS_CAM_SIGN_X];
+    cam.aperture = c[CPTS_CAM_APERTURE];
+    cam.focal_dist = c[CPTS_CAM_FOCAL_DIST];
+    return cam;
+}
+
+static cudaTextureObject_t make_texture2d(const HostTexture &t, std::vector<cudaArray_t> &arrays) {
+    // reference: src/impl/textures.cu — bilinear, wrap, normalised coordinates
+    cudaChannelFormatDesc desc =
+        t.channels == 4 ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float2>();
+    cudaArray_t arr;
+    CUDA_OK(cudaMallocArray(&arr, &desc, t.width, t.height));
+    const size_t row = size_t(t.width) * t.channels * sizeof(float);
+    CUDA_OK(cudaMemcpy2DToArray(arr, 0, 0, t.texels.data(), row, row, t.height, cudaMemcpyHostToDevice));
+    arrays.push_back(arr);
+    cudaResourceDesc res{};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    cudaTextureObject_t obj = 0;
+    CUDA_OK(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+    return obj;
+}
+
+Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
+    : device_(device), seed_offset_(seed_offset), impl_(new Impl) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("cpt_b200: no CUDA device available (this library has no CPU fallback)");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    num_sms_ = prop.multiProcessorCount;
+    validate_scene(scene);
+    w_ = scene.width();
+    h_ = scene.height();
+    max_depth_ = scene.config[CPTS_CFG_MAX_DEPTH];
+    CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&impl_->ev0));
+    CUDA_OK(cudaEventCreate(&impl_->ev1));
+
+    Impl &m = *impl_;
+    // ---- geometry / BVH
+    {
+        std::vector<float4> tmp(scene.nodes.size());
+        memcpy(tmp.data(), scene.nodes.data(), tmp.size() * sizeof(float4));
+        m.nodes.upload(tmp);
+        std::vector<uint4> ctmp(scene.cache_nodes.size());
+        memcpy(ctmp.data(), scene.cache_nodes.data(), ctmp.size() * sizeof(uint4));
+        m.cache_nodes.upload(ctmp);
+        std::vector<F4> tris, norms;
+        std::vector<U4> uvs;
+        build_triangles(scene, tris);
+        build_normals_uvs(scene, norms, uvs);
+        std::vector<float4> t4(tris.size()), n4(norms.size());
+        memcpy(t4.data(), tris.data(), t4.size() * sizeof(float4));
+        memcpy(n4.data(), norms.data(), n4.size() * sizeof(float4));
+        std::vector<uint4> u4(uvs.size());
+        memcpy(u4.data(), uvs.data(), u4.size() * sizeof(uint4));
+        m.tris.upload(t4);
+        m.norms.upload(n4);
+        m.uvs.upload(u4);
+        PairLayout pl;
+        build_pair_layout(scene, pl);
+        std::vector<float4> w4(pl.wnodes.size());
+        memcpy(w4.data(), pl.wnodes.data(), w4.size() * sizeof(float4));
+        m.wnodes.upload(w4);
+        m.pair_depth = pl.max_depth;
+        m.nesting_violations = pl.nesting_violations;
+        m.dev.wroot = pl.root;
+        if (pl.max_depth + 2 > kStackSize || pl.nesting_violations > 0)
+            traversal_ = TRAVERSAL_DFS; // ordered traversal's preconditions do not hold: use the reference order
+        m.obj_idxs.upload(std::vector<int>(scene.obj_idxs.begin(), scene.obj_idxs.end()));
+        // emitter primitive map is padded like path_tracer.cu:76-87 (zero filled here)
+        std::vector<int> ep(scene.emitter_prims.begin(), scene.emitter_prims.end());
+        ep.resize(std::max<size_t>(ep.size(), size_t(std::max(scene.objects.front().prim_num, 1))), 0);
+        m.emitter_prims.upload(ep);
+        std::vector<ObjectPOD> objs(scene.objects.size());
+        for (size_t i = 0; i < objs.size(); i++)
+            objs[i] = ObjectPOD{scene.objects[i].bsdf_emitter, scene.objects[i].prim_offset, scene.objects[i].prim_num,
+                                scene.objects[i].inv_area};
+        m.objects.upload(objs);
+        m.scene_bytes = (t4.size() + n4.size() + w4.size() + tmp.size()) * sizeof(float4) + u4.size() * sizeof(uint4);
+    }
+    // ---- textures
+    for (const auto &t : scene.textures)
+        m.tex_objs.push_back(make_texture2d(t, m.tex_arrays));
+    auto tex_of = [&](int idx) -> cudaTextureObject_t {
+        return (idx >= 0 && size_t(idx) < m.tex_objs.size()) ? m.tex_objs[idx] : 0;
+    };
+    // ---- materials / emitters
+    {
+        std::vector<Material> mats(scene.bsdfs.size());
+        for (size_t i = 0; i < mats.size(); i++) {
+            const CptsBsdf &b = scene.bsdfs[i];
+            Material mm{};
+            mm.type = b.type;
+            mm.flags = b.flags;
+            mm.k_d = make_float4(b.k_d[0], b.k_d[1], b.k_d[2], b.k_d[3]);
+            mm.k_s = make_float4(b.k_s[0], b.k_s[1], b.k_s[2], b.k_s[3]);
+            mm.k_g = make_float4(b.k_g[0], b.k_g[1], b.k_g[2], b.k_g[3]);
+            if (b.type == CPTS_BSDF_GGX_CONDUCTOR) {
+                for (int k = 0; k < 3; k++)
+                    mm.eta_t[k] = b.extras[k], mm.kk[k] = b.extras[3 + k];
+                mm.raw[0] = b.extras[6], mm.raw[1] = b.extras[7];
+            } else if (b.type == CPTS_BSDF_PLASTIC || b.type == CPTS_BSDF_PLASTIC_FORWARD) {
+                mm.raw[0] = b.extras[0];
+                mm.trans_scaler = b.extras[1];
+                mm.thickness = b.extras[2];
+                mm.penetrable = b.extras[3] != 0.f;
+            } else if (b.type == CPTS_BSDF_DISPERSION) {
+                mm.k_d = make_float4(b.extras[0], b.extras[1], 0, 1);
+            } else if (b.type == CPTS_BSDF_FORWARD) {
+                mm.k_d = mm.k_s = mm.k_g = make_float4(0, 0, 0, 1);
+            }
+            for (int k = 0; k < 5; k++)
+                mm.tex[k] = tex_of(b.tex[k]);
+            mats[i] = mm;
+        }
+        m.mats.upload(mats);
+        std::vector<EmitterPOD> ems(scene.emitters.size());
+        for (size_t i = 0; i < ems.size(); i++) {
+            const CptsEmitter &e = scene.emitters[i];
+            EmitterPOD ee{};
+            ee.type = e.type;
+            ee.obj_ref = e.obj_ref;
+            ee.is_sphere = e.is_sphere;
+            ee.Le = make_float4(e.Le[0], e.Le[1], e.Le[2], e.Le[3]);
+            ee.pos = make_float3(e.pos[0], e.pos[1], e.pos[2]);
+            ee.cos_val = e.cos_val;
+            ee.tex = tex_of(e.tex);
+            ee.scale = e.scale;
+            ee.azimuth = e.azimuth;
+            ee.zenith = e.zenith;
+            ee.rot = make_float4(0, 0, 0, 1);
+            if (e.is_sphere)
+                throw std::runtime_error("cpt_b200: sphere-bound emitters are not supported (TRIANGLE_ONLY build)");
+            if (e.type == CPTS_EMIT_ENVMAP && ee.tex == 0)
+                throw std::runtime_error("cpt_b200: environment map emitter without a texture");
+            ems[i] = ee;
+        }
+        m.emitters.upload(ems);
+        k_derive_tables<<<1, 64, 0, stream_>>>(m.mats.p, int(mats.size()), m.emitters.p, int(ems.size()));
+        CUDA_OK(cudaGetLastError());
+    }
+    m.dev.nodes = m.nodes.p;
+    m.dev.cache_nodes = m.cache_nodes.p;
+    m.dev.obj_idxs = m.obj_idxs.p;
+    m.dev.tris = m.tris.p;
+    m.dev.norms = m.norms.p;
+    m.dev.uvs = m.uvs.p;
+    m.dev.objects = m.objects.p;
+    m.dev.emitter_prims = m.emitter_prims.p;
+    m.dev.mats = m.mats.p;
+    m.dev.emitters = m.emitters.p;
+    m.dev.wnodes = m.wnodes.p;
+    m.dev.num_nodes = scene.num_nodes();
+    m.dev.num_cache = int(scene.cache_nodes.size());
+    m.dev.num_prims = scene.num_prims();
+    m.dev.num_emitters = int(scene.emitters.size()) - 1;
+    m.dev.envmap_id = scene.config[CPTS_CFG_ENVMAP_ID];
+    m.dev.cie = m.dev.d65 = 0;
+    if (!scene.cie_xyz.empty()) {
+        // 1-D array textures, linear filter, clamp, normalised coordinates (reference: src/core/xyz.cuh:60-84)
+        auto make1d = [&](const void *src, size_t count, bool four) {
+            cudaChannelFormatDesc desc = four ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float>();
+            cudaArray_t arr;
+            CUDA_OK(cudaMallocArray(&arr, &desc, count));
+            const size_t bytes = count * (four ? 16 : 4);
+            CUDA_OK(cudaMemcpy2DToArray(arr, 0, 0, src, bytes, bytes, 1, cudaMemcpyHostToDevice));
+            m.tex_arrays.push_back(arr);
+            cudaResourceDesc res{};
+            res.resType = cudaResourceTypeArray;
+            res.res.array.array = arr;
+            cudaTextureDesc td{};
+            td.addressMode[0] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 1;
+            cudaTextureObject_t obj = 0;
+            CUDA_OK(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+            m.tex_objs.push_back(obj);
+            return obj;
+        };
+        m.dev.cie = make1d(scene.cie_xyz.data(), scene.cie_xyz.size(), true);
+        m.dev.d65 = make1d(scene.d65_spd.data(), scene.d65_spd.size(), false);
+    }
+    m.cam = camera_from_floats(scene.camera);
+
+    const size_t P = size_t(w_) * h_;
+    CUDA_OK(cudaMalloc(&d_image_, P * sizeof(float4)));
+    CUDA_OK(cudaMalloc(&d_out_, P * sizeof(float4)));
+    CUDA_OK(cudaMemsetAsync(d_image_, 0, P * sizeof(float4), stream_));
+    CUDA_OK(cudaMemsetAsync(d_out_, 0, P * sizeof(float4), stream_));
+    m.stats.alloc(4);
+    CUDA_OK(cudaMemsetAsync(m.stats.p, 0, 4 * sizeof(unsigned long long), stream_));
+    // default number of samples in flight: ~8M paths, at least 1, at most 64
+    set_samples_in_flight(int(std::min<size_t>(64, std::max<size_t>(1, (size_t(8) << 20) / P))));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+}
+
+Renderer::~Renderer() {
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    for (auto t : impl_->tex_objs)
+        cudaDestroyTextureObject(t);
+    for (auto a : impl_->tex_arrays)
+        cudaFreeArray(a);
+    if (impl_->ev0)
+        cudaEventDestroy(impl_->ev0);
+    if (impl_->ev1)
+        cudaEventDestroy(impl_->ev1);
+    cudaFree(d_image_);
+    cudaFree(d_out_);
+    cudaFree(d_var_);
+    impl_.reset();
+    cudaStreamDestroy(stream_);
+}
+
+void Renderer::set_samples_in_flight(int s) {
+    if (s < 1)
+        throw std::runtime_error("samples_in_flight must be >= 1");
+    const size_t P = size_t(w_) * h_;
+    if (P * size_t(s) >= (size_t(1) << 32))
+        throw std::runtime_error("samples_in_flight * pixels exceeds the 32-bit slot index");
+    s_max_ = s;
+}
+
+void Renderer::enable_variance(bool on) {
+    CUDA_OK(cudaSetDevice(device_));
+    if (on && !d_var_) {
+        CUDA_OK(cudaMalloc(&d_var_, size_t(w_) * h_ * sizeof(float)));
+        CUDA_OK(cudaMemsetAsync(d_var_, 0, size_t(w_) * h_ * sizeof(float), stream_));
+    }
+    variance_on_ = on;
+}
+
+void Renderer::ensure_capacity(int samples) {
+    Impl &m = *impl_;
+    if (samples <= m.capacity_samples && int(m.counters.n) >= 3 * (max_depth_ + 2) + 4)
+        return;
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    const size_t slots = size_t(w_) * h_ * size_t(std::max(samples, m.capacity_samples));
+    m.ray_o.alloc(slots);
+    m.ray_d.alloc(slots);
+    m.thp.alloc(slots);
+    m.L.alloc(slots);
+    m.isect.alloc(slots);
+    m.rng.alloc(slots);
+    m.pdf.alloc(slots);
+    m.queue[0].alloc(slots);
+    m.queue[1].alloc(slots);
+    m.counters.alloc(size_t(3 * (max_depth_ + 2) + 4)); // D+2 queue sizes, then one work counter per launch (<= 2D+1)
+    m.capacity_samples = std::max(samples, m.capacity_samples);
+}
+
+template <bool ORDERED>
+static void launch_pipeline(Renderer::Impl *, cudaStream_t); // (declared for symmetry; real work below)
+
+void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write_output, bool use_variance) {
+    Impl &m = *impl_;
+    CUDA_OK(cudaSetDevice(device_));
+    ensure_capacity(samples);
+    const int P = w_ * h_, D = max_depth_;
+    PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p};
+    BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_};
+    int *q_counts = m.counters.p;          // D + 1 entries
+    int *work = m.counters.p + (D + 2);    // one per launch
+    CUDA_OK(cudaMemsetAsync(m.counters.p, 0, m.counters.n * sizeof(int), stream_));
+    const size_t smem = size_t(m.dev.num_cache) * sizeof(uint4);
+    const int grid = num_sms_ * 8;
+    const bool ordered = traversal_ == TRAVERSAL_ORDERED;
+    CUDA_OK(cudaEventRecord(m.ev0, stream_));
+    int wk = 0;
+    if (ordered)
+        k_raygen<true><<<grid, kBlock, smem, stream_>>>(m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk++);
+    else
+        k_raygen<false><<<grid, kBlock, smem, stream_>>>(m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk++);
+    unsigned long long *shadow_counter = m.stats.p + 1;
+    int launches = 1, traced = 0, shaded = 0;
+    for (int b = 0; b < D; b++) {
+        uint32_t *q_cur = m.queue[b & 1].p, *q_nxt = m.queue[(b + 1) & 1].p;
+        if (ordered)
+            k_shade<true><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, shadow_counter, b > 0);
+        else
+            k_shade<false><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, shadow_counter, b > 0);
+        ++launches, ++shaded;
+        if (b + 1 >= D)
+            break;
+        if (ordered)
+            k_trace<true><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, q_nxt, q_counts + b + 1, b);
+        else
+            k_trace<false><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, q_nxt, q_counts + b + 1, b);
+        ++launches, ++traced;
+    }
+    k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples,
+                                               first_accum, write_output ? 1 : 0, gamma ? 1 : 0);
+    k_fold_stats<<<1, 32, 0, stream_>>>(q_counts, traced, shaded, m.stats.p);
+    launches += 2;
+    CUDA_OK(cudaEventRecord(m.ev1, stream_));
+    CUDA_OK(cudaGetLastError());
+    host_stats_.samples += uint64_t(P) * samples;
+    host_stats_.launches += launches;
+}
+
+const float *Renderer::render_raw(bool gamma) {
+    accum_cnt_++;
+    launch_batch(accum_cnt_, 1, gamma, true, variance_on_);
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
+    host_stats_.device_ms += ms;
+    return reinterpret_cast<const float *>(d_out_);
+}
+
+const float *Renderer::render_batch(int spp, bool gamma) {
+    if (spp <= 0)
+        throw std::runtime_error("render_batch: spp must be positive");
+    int done = 0;
+    while (done < spp) {
+        const int s = std::min(s_max_, spp - done);
+        const bool last = done + s >= spp;
+        launch_batch(accum_cnt_ + 1, s, gamma, last, variance_on_);
+        accum_cnt_ += s;
+        done += s;
+        CUDA_OK(cudaStreamSynchronize(stream_)); // events are reused per batch
+        float ms = 0;
+        cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
+        host_stats_.device_ms += ms;
+    }
+    return reinterpret_cast<const float *>(d_out_);
+}
+
+static inline int to_int_gamma(float x) { // reference: core/cuda_utils.cuh:111-113
+    return int(powf(std::min(std::max(x, 0.f), 1.f), 1.f / 2.1f) * 255.f + .5f);
+}
+static inline int to_int_linear(float x) { return int(std::min(std::max(x, 0.f), 1.f) * 255.f); }
+
+void Renderer::render_offline(int num_iter, bool gamma, uint8_t *rgba8) {
+    // TracerBase::render semantics (wf_path_tracer.cu:107-173): seeds use the 0-based iteration index,
+    // the sum image is exported as 8-bit with the 1/2.1 gamma of host_device.cuh:63-112
+    if (num_iter <= 0)
+        throw std::runtime_error("render_offline: num_iter must be positive");
+    int done = 0;
+    while (done < num_iter) {
+        const int s = std::min(s_max_, num_iter - done);
+        launch_batch(done, s, false, false, false);
+        done += s;
+        CUDA_OK(cudaStreamSynchronize(stream_));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
+        host_stats_.device_ms += ms;
+    }
+    std::vector<float> host(size_t(w_) * h_ * 4);
+    download_accumulator(host.data());
+    const float inv = 1.f / num_iter;
+    for (size_t p = 0; p < size_t(w_) * h_; p++) {
+        for (int c = 0; c < 3; c++)
+            rgba8[4 * p + c] = uint8_t(gamma ? to_int_gamma(host[4 * p + c] * inv) : to_int_linear(host[4 * p + c] * inv));
+        rgba8[4 * p + 3] = 255;
+    }
+}
+
+void Renderer::download_output(float *host) const {
+    CUDA_OK(cudaSetDevice(device_));
+    CUDA_OK(cudaMemcpyAsync(host, d_out_, size_t(w_) * h_ * sizeof(float4), cudaMemcpyDeviceToHost, stream_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+}
+void Renderer::download_accumulator(float *host) const {
+    CUDA_OK(cudaSetDevice(device_));
+    CUDA_OK(cudaMemcpyAsync(host, d_image_, size_t(w_) * h_ * sizeof(float4), cudaMemcpyDeviceToHost, stream_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+}
+void Renderer::download_variance(float *host) const {
+    if (!d_var_)
+        throw std::runtime_error("variance buffer not enabled");
+    CUDA_OK(cudaSetDevice(device_));
+    CUDA_OK(cudaMemcpyAsync(host, d_var_, size_t(w_) * h_ * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+}
+
+void Renderer::download_state(const char *which, void *host) const {
+    const Impl &m = *impl_;
+    const size_t P = size_t(w_) * h_;
+    const std::string k = which;
+    const void *src = nullptr;
+    size_t elem = 16;
+    if (k == "thp") src = m.thp.p;
+    else if (k == "L") src = m.L.p;
+    else if (k == "ray_o") src = m.ray_o.p;
+    else if (k == "ray_d") src = m.ray_d.p;
+    else if (k == "isect") src = m.isect.p;
+    else if (k == "rng") src = m.rng.p, elem = 8;
+    else if (k == "pdf") src = m.pdf.p, elem = 4;
+    if (!src)
+        throw std::runtime_error("download_state: unknown or unallocated array '" + k + "'");
+    CUDA_OK(cudaSetDevice(device_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    CUDA_OK(cudaMemcpy(host, src, P * elem, cudaMemcpyDeviceToHost));
+}
+
+void Renderer::reset() {
+    CUDA_OK(cudaSetDevice(device_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    CUDA_OK(cudaMemsetAsync(d_image_, 0, size_t(w_) * h_ * sizeof(float4), stream_));
+    if (d_var_)
+        CUDA_OK(cudaMemsetAsync(d_var_, 0, size_t(w_) * h_ * sizeof(float), stream_));
+    accum_cnt_ = 0;
+}
+
+void Renderer::update_camera(const float cam[CPTS_CAM_COUNT]) { impl_->cam = camera_from_floats(cam); }
+
+void Renderer::sync() const {
+    CUDA_OK(cudaSetDevice(device_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+}
+
+RenderStats Renderer::stats() {
+    CUDA_OK(cudaSetDevice(device_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CUDA_OK(cudaMemcpy(h, impl_->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    RenderStats s = host_stats_;
+    s.closest_rays = h[0];
+    s.shadow_rays = h[1];
+    s.shaded = h[2];
+    return s;
+}
+
+std::string Renderer::info() const {
+    std::ostringstream os;
+    os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
+       << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
+       << " cached), traversal=" << (traversal_ == TRAVERSAL_ORDERED ? "ordered" : "dfs")
+       << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations
+       << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
+    return os.str();
+}
+
+} // namespace cptb

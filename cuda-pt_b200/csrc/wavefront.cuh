@@ -1,0 +1,88 @@
+// wavefront.cuh — host-side renderer object behind the C-ABI (include/cpt_b200.h).
+//
+// Replaces, for the wavefront path, the reference's
+//   WavefrontPathTracer (src/renderer/wf_path_tracer.cuh, src/pt_impl/wf_path_tracer.cu:36-230)
+//   + PathTracer / TracerBase device-buffer ownership (src/pt_impl/path_tracer.cu:49-112,
+//     src/renderer/tracer_base.cuh:29-160).
+#pragma once
+#include "scene_host.h"
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace cptb {
+
+enum Traversal : int { TRAVERSAL_ORDERED = 0, TRAVERSAL_DFS = 1 };
+
+struct RenderStats {
+    uint64_t samples = 0;      // pixel-samples (primary rays)
+    uint64_t closest_rays = 0; // extension (closest-hit) traversals after the primary one
+    uint64_t shadow_rays = 0;  // NEE any-hit traversals
+    uint64_t shaded = 0;       // path segments shaded
+    uint64_t launches = 0;     // kernels launched
+    double device_ms = 0;      // device time spent in render batches (CUDA events)
+};
+
+class Renderer {
+  public:
+    Renderer(const HostScene &scene, int device, int seed_offset);
+    ~Renderer();
+    Renderer(const Renderer &) = delete;
+    Renderer &operator=(const Renderer &) = delete;
+
+    // one sample per call, like TracerBase::render_raw: returns the device pointer of the running-mean buffer
+    const float *render_raw(bool gamma);
+    // `spp` more samples with several samples in flight; output buffer refreshed at the end
+    const float *render_batch(int spp, bool gamma);
+    // TracerBase::render semantics (0-based seeds, sum image, 8-bit export): fills rgba8 (w*h*4 bytes)
+    void render_offline(int num_iter, bool gamma, uint8_t *rgba8);
+
+    void download_output(float *host_rgba) const; // synchronous D2H of the running-mean buffer
+    void download_variance(float *host) const;
+    void download_accumulator(float *host_rgba) const;
+    // debugging / parity probes: the first W*H entries (sample 0 of the last batch) of a path-state array
+    void download_state(const char *which, void *host) const;
+
+    const float *output_buffer() const { return reinterpret_cast<const float *>(d_out_); }
+    float *accumulator() { return reinterpret_cast<float *>(d_image_); }
+    const float *variance_buffer() const { return d_var_; }
+
+    void reset();
+    void set_seed_offset(int v) { seed_offset_ = v; }
+    void update_camera(const float cam[CPTS_CAM_COUNT]);
+    void set_max_depth(int d) { max_depth_ = d; }
+    void set_samples_in_flight(int s);
+    void set_traversal(int t) { traversal_ = t; }
+    void enable_variance(bool on);
+    void set_accum_count(int c) { accum_cnt_ = c; }
+
+    int width() const { return w_; }
+    int height() const { return h_; }
+    int counter() const { return accum_cnt_; }
+    int device() const { return device_; }
+    int max_depth() const { return max_depth_; }
+    int samples_in_flight() const { return s_max_; }
+    cudaStream_t stream() const { return stream_; }
+    RenderStats stats();
+    std::string info() const;
+    void sync() const;
+
+  private:
+    struct Impl;
+    void launch_batch(int first_accum, int samples, bool gamma, bool write_output, bool use_variance);
+    void ensure_capacity(int samples);
+
+    int device_ = 0, w_ = 0, h_ = 0, seed_offset_ = 0, accum_cnt_ = 0, max_depth_ = 0;
+    int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148;
+    bool variance_on_ = false;
+    cudaStream_t stream_ = nullptr;
+    float4 *d_image_ = nullptr, *d_out_ = nullptr;
+    float *d_var_ = nullptr;
+    std::unique_ptr<Impl> impl_;
+    RenderStats host_stats_;
+};
+
+} // namespace cptb

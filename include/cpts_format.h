@@ -1,0 +1,153 @@
+/*
+ * cpts_format.h — the flat scene container (".cpts") shared by the C-ABI
+ * library, the CPU oracle and the reference harness.
+ *
+ * A .cpts file is the POD image of what the reference's `Scene` object hands
+ * to a renderer constructor (reference: src/core/scene.cuh:49-107 public
+ * fields, consumed by src/renderer/tracer_base.cuh:62-69 and
+ * src/pt_impl/path_tracer.cu:49-99): linear BVH nodes, cached fp16 nodes,
+ * primitive arrays, primitive->object words, compacted object table, emitter
+ * primitive map, plus POD restatements of the device-heap BSDF / Emitter
+ * objects (reference: src/core/virtual_funcs.cuh:28-118) and the camera
+ * (src/core/camera_model.cuh:40-48).
+ *
+ * Layout (little endian):
+ *   CptsHeader
+ *   n_sections x { CptsSection, payload (count*elem_size bytes, padded to 16) }
+ *
+ * Plain C so that C, C++, CUDA and ctypes/numpy readers agree.
+ */
+#ifndef CPTS_FORMAT_H
+#define CPTS_FORMAT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPTS_MAGIC "CPTSCN01"
+
+typedef struct CptsHeader {
+    char magic[8];
+    uint32_t n_sections;
+    uint32_t reserved;
+} CptsHeader;
+
+typedef struct CptsSection {
+    char name[24];      /* zero padded */
+    uint32_t elem_size; /* bytes per element */
+    uint32_t reserved;
+    uint64_t count;     /* number of elements */
+} CptsSection;
+
+/* indices into the "config" section (int32[32]) */
+enum {
+    CPTS_CFG_WIDTH = 0,
+    CPTS_CFG_HEIGHT = 1,
+    CPTS_CFG_SPP = 2,
+    CPTS_CFG_MAX_DEPTH = 3,
+    CPTS_CFG_MAX_DIFFUSE = 4,
+    CPTS_CFG_MAX_SPECULAR = 5,
+    CPTS_CFG_MAX_TRANSMIT = 6,
+    CPTS_CFG_GAMMA = 7,
+    CPTS_CFG_RENDERER = 8, /* reference RendererType: 0 = pt megakernel, 1 = wfpt */
+    CPTS_CFG_NUM_BSDFS = 9,
+    CPTS_CFG_NUM_EMITTERS = 10, /* real emitters; table holds num+1 (index 0 = null emitter) */
+    CPTS_CFG_ENVMAP_ID = 11,
+    CPTS_CFG_NUM_OBJECTS = 12,
+    CPTS_CFG_NUM_PRIMS = 13,
+    CPTS_CFG_NUM_NODES = 14,
+    CPTS_CFG_NUM_CACHE = 15,
+    CPTS_CFG_CACHE_LEVEL = 16,
+    CPTS_CFG_MAX_NODE_NUM = 17,
+    CPTS_CFG_USE_SBVH = 18,
+    CPTS_CFG_COUNT = 32
+};
+
+/* "camera" section: float[18], reference DeviceCamera (camera_model.cuh:40-48) */
+enum {
+    CPTS_CAM_R = 0,          /* 9 floats, row major */
+    CPTS_CAM_T = 9,          /* 3 floats */
+    CPTS_CAM_INV_FOCAL = 12,
+    CPTS_CAM_HW = 13,
+    CPTS_CAM_HH = 14,
+    CPTS_CAM_SIGN_X = 15,
+    CPTS_CAM_APERTURE = 16,
+    CPTS_CAM_FOCAL_DIST = 17,
+    CPTS_CAM_COUNT = 18
+};
+
+/* BSDF types, same numbering as the reference's BSDFType (core/enums.cuh:55-65) */
+enum {
+    CPTS_BSDF_LAMBERTIAN = 0,
+    CPTS_BSDF_SPECULAR = 1,
+    CPTS_BSDF_TRANSLUCENT = 2,
+    CPTS_BSDF_PLASTIC = 3,
+    CPTS_BSDF_PLASTIC_FORWARD = 4,
+    CPTS_BSDF_GGX_CONDUCTOR = 5,
+    CPTS_BSDF_DISPERSION = 6,
+    CPTS_BSDF_FORWARD = 7
+};
+
+/* "bsdfs" section, 128 B per entry. `extras` meaning by type:
+ *   GGX conductor : [0..2] eta_t, [3..5] k, [6] roughness_x, [7] roughness_y (raw, pre roughness_to_alpha)
+ *   plastic(-fwd) : [0] ior, [1] trans_scaler, [2] thickness, [3] penetrable (0/1)
+ *   dispersion    : [0] cauchy A, [1] cauchy B
+ * tex[] = {diffuse, specular, glossy, normal, roughness} indices into the
+ * "tex_desc" section or -1. */
+typedef struct CptsBsdf {
+    int32_t type;
+    int32_t flags;
+    float k_d[4];
+    float k_s[4];
+    float k_g[4];
+    float extras[8];
+    int32_t tex[5];
+    int32_t pad[5];
+} CptsBsdf;
+
+enum {
+    CPTS_EMIT_NULL = 0,
+    CPTS_EMIT_POINT = 1,
+    CPTS_EMIT_AREA = 2,
+    CPTS_EMIT_AREA_SPOT = 3,
+    CPTS_EMIT_ENVMAP = 4
+};
+
+/* "emitters" section, 64 B per entry (entry 0 is the null emitter). */
+typedef struct CptsEmitter {
+    int32_t type;
+    int32_t obj_ref;   /* bound object index, -1 if none */
+    int32_t is_sphere;
+    int32_t tex;       /* index into "tex_desc" or -1 */
+    float Le[4];
+    float pos[3];
+    float cos_val;
+    float scale;
+    float azimuth;     /* radians */
+    float zenith;      /* radians */
+    int32_t pad;
+} CptsEmitter;
+
+/* "objects" section, 16 B per entry: reference CompactedObjInfo (object.cuh:31-65) */
+typedef struct CptsObject {
+    int32_t bsdf_emitter;
+    int32_t prim_offset;
+    int32_t prim_num;
+    float inv_area;
+} CptsObject;
+
+/* "tex_desc" section: one per texture; texels live in "tex_data" (float) at `offset` floats. */
+typedef struct CptsTexDesc {
+    int32_t width;
+    int32_t height;
+    int32_t channels; /* 4 or 2 */
+    int32_t pad;
+    uint64_t offset;
+} CptsTexDesc;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPTS_FORMAT_H */

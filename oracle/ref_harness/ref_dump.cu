@@ -1,0 +1,483 @@
+/*
+ * ref_dump — TEST INFRASTRUCTURE, not product code.
+ *
+ * A thin driver around the UNMODIFIED reference (Enigmatisms/cuda-pt).  It is
+ * compiled by oracle/build_ref.sh against the sources where they lie under
+ * /root/reference and linked into oracle/_ref/ref_dump.  Nothing of the
+ * reference is copied into this repository: this file only calls the
+ * reference's public C++ interface:
+ *     Scene(std::string)                         src/core/scene.cuh:49-107
+ *     WavefrontPathTracer / PathTracer<...>      src/renderer/wf_path_tracer.cuh, path_tracer.cuh
+ *     TracerBase::render_raw / update_camera ... src/renderer/tracer_base.cuh:86-160
+ * exactly the way app/pt_renderer.cu:26-117 and
+ * src/pyrender/python_render.cu:71-148 do.
+ *
+ * Sub-commands
+ *   dump   <xml> <out.cpts>
+ *          load the XML with the reference loader and write the flat scene
+ *          (include/cpts_format.h) that our renderer and the CPU oracle read.
+ *   render <xml> <out_prefix> <mode: wfpt|pt> <seed_offset> <frame,frame,...>
+ *          run render_raw() and save the float RGBA output buffer after the
+ *          listed (1-based) frame counts as <out_prefix>_fNNNN.bin, and the
+ *          scene as <out_prefix>.cpts (same in-process Scene => same BVH /
+ *          emitter primitive order, SURVEY.md §7 "hard parts").
+ *   bench  <xml> <mode> <warmup> <frames> [seed_offset]
+ *          time `frames` render_raw() calls with CUDA events; prints one JSON line.
+ */
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "core/scene.cuh"
+#include "core/xyz.cuh"
+// Debug probe only (`state` sub-command): read the reference's per-path payload pool, which the class keeps
+// private.  The member layout is unchanged; nothing in the reference is modified or re-implemented.
+#define private public
+#include "renderer/wf_path_tracer.cuh"
+#undef private
+
+#include "cpts_format.h"
+
+extern CPT_GPU_CONST Emitter *c_emitter[9];
+extern CPT_GPU_CONST BSDF *c_material[48];
+
+// reads the spectral tables back out of the reference's own device textures at texel centres
+// (linear filtering at a texel centre returns the texel): CIE 1931 XYZ 360-830 nm and D65 300-830 nm,
+// uploaded by ColorSpaceXYZ::init() (src/impl/xyz.cu:808-830).  Run-time extraction, not a source copy.
+__global__ void read_spectral_tables(float4 *cie, float *d65) {
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i < ColorSpaceXYZ::CIE_samples)
+        cie[i] = tex1D<float4>(XYZ.CIE, (float(i) + 0.5f) / float(ColorSpaceXYZ::CIE_samples));
+    if (i < ColorSpaceXYZ::D65_samples)
+        d65[i] = tex1D<float>(XYZ.D65, (float(i) + 0.5f) / float(ColorSpaceXYZ::D65_samples));
+}
+
+namespace {
+
+struct Writer {
+    FILE *fp = nullptr;
+    uint32_t n = 0;
+    explicit Writer(const std::string &path) {
+        fp = fopen(path.c_str(), "wb");
+        if (!fp) {
+            fprintf(stderr, "cannot open %s\n", path.c_str());
+            exit(2);
+        }
+        CptsHeader h{};
+        memcpy(h.magic, CPTS_MAGIC, 8);
+        fwrite(&h, sizeof(h), 1, fp);
+    }
+    void section(const char *name, const void *data, uint32_t elem, uint64_t count) {
+        CptsSection s{};
+        strncpy(s.name, name, sizeof(s.name) - 1);
+        s.elem_size = elem;
+        s.count = count;
+        fwrite(&s, sizeof(s), 1, fp);
+        size_t bytes = size_t(elem) * count;
+        if (bytes)
+            fwrite(data, 1, bytes, fp);
+        static const char zeros[16] = {0};
+        size_t pad = (16 - bytes % 16) % 16;
+        if (pad)
+            fwrite(zeros, 1, pad, fp);
+        ++n;
+    }
+    void close() {
+        CptsHeader h{};
+        memcpy(h.magic, CPTS_MAGIC, 8);
+        h.n_sections = n;
+        fseek(fp, 0, SEEK_SET);
+        fwrite(&h, sizeof(h), 1, fp);
+        fclose(fp);
+    }
+};
+
+// colour attribute grammar of the scene format ("#RRGGBB" | "r, g, b" | "v")
+void parse_color(const char *txt, float out[3]) {
+    std::string v = txt ? txt : "0";
+    if (!v.empty() && v[0] == '#') {
+        unsigned c = 0;
+        sscanf(v.c_str() + 1, "%x", &c);
+        out[0] = float((c >> 16) & 0xFF) / 255.0f;
+        out[1] = float((c >> 8) & 0xFF) / 255.0f;
+        out[2] = float(c & 0xFF) / 255.0f;
+        return;
+    }
+    for (auto &ch : v)
+        if (ch == ',')
+            ch = ' ';
+    std::stringstream ss(v);
+    std::vector<float> vals;
+    float f;
+    while (ss >> f)
+        vals.push_back(f);
+    if (vals.size() >= 3) {
+        out[0] = vals[0], out[1] = vals[1], out[2] = vals[2];
+    } else {
+        out[0] = out[1] = out[2] = vals.empty() ? 0.f : vals[0];
+    }
+}
+
+const tinyxml2::XMLElement *child_named(const tinyxml2::XMLElement *parent, const char *tag,
+                                        std::initializer_list<const char *> names) {
+    for (auto e = parent->FirstChildElement(tag); e; e = e->NextSiblingElement(tag)) {
+        const char *n = e->Attribute("name");
+        if (!n)
+            continue;
+        for (auto want : names)
+            if (strcmp(n, want) == 0)
+                return e;
+    }
+    return nullptr;
+}
+
+int lobe_flags_for(int type) {
+    switch (type) {
+    case BSDFType::Lambertian: return BSDF_DIFFUSE | BSDF_REFLECT;
+    case BSDFType::Specular: return BSDF_SPECULAR | BSDF_REFLECT;
+    case BSDFType::Translucent: return BSDF_SPECULAR | BSDF_TRANSMIT;
+    case BSDFType::Plastic: return BSDF_SPECULAR | BSDF_DIFFUSE | BSDF_REFLECT;
+    case BSDFType::PlasticForward: return BSDF_SPECULAR | BSDF_TRANSMIT | BSDF_REFLECT;
+    case BSDFType::GGXConductor: return BSDF_GLOSSY | BSDF_REFLECT;
+    case BSDFType::Dispersion: return BSDF_DIFFUSE | BSDF_TRANSMIT;
+    default: return BSDF_NONE;
+    }
+}
+
+void dump_scene(const Scene &scene, const std::string &xml_path, const std::string &out_path) {
+    Writer w(out_path);
+
+    int32_t cfg[CPTS_CFG_COUNT] = {0};
+    cfg[CPTS_CFG_WIDTH] = scene.config.width;
+    cfg[CPTS_CFG_HEIGHT] = scene.config.height;
+    cfg[CPTS_CFG_SPP] = scene.config.spp;
+    cfg[CPTS_CFG_MAX_DEPTH] = scene.config.md.max_depth;
+    cfg[CPTS_CFG_MAX_DIFFUSE] = scene.config.md.max_diffuse;
+    cfg[CPTS_CFG_MAX_SPECULAR] = scene.config.md.max_specular;
+    cfg[CPTS_CFG_MAX_TRANSMIT] = scene.config.md.max_tranmit;
+    cfg[CPTS_CFG_GAMMA] = scene.config.gamma_correction;
+    cfg[CPTS_CFG_RENDERER] = int(scene.rdr_type);
+    cfg[CPTS_CFG_NUM_BSDFS] = scene.num_bsdfs;
+    cfg[CPTS_CFG_NUM_EMITTERS] = scene.num_emitters;
+    cfg[CPTS_CFG_ENVMAP_ID] = scene.envmap_id;
+    cfg[CPTS_CFG_NUM_OBJECTS] = int(scene.objects.size());
+    cfg[CPTS_CFG_NUM_PRIMS] = scene.num_prims;
+    cfg[CPTS_CFG_NUM_NODES] = int(scene.nodes.size() >> 1);
+    cfg[CPTS_CFG_NUM_CACHE] = int(scene.cache_nodes.size());
+    cfg[CPTS_CFG_CACHE_LEVEL] = scene.config.bvh.cache_level;
+    cfg[CPTS_CFG_MAX_NODE_NUM] = scene.config.bvh.max_node_num;
+    cfg[CPTS_CFG_USE_SBVH] = scene.config.bvh.use_sbvh;
+    w.section("config", cfg, 4, CPTS_CFG_COUNT);
+
+    static_assert(sizeof(DeviceCamera) == CPTS_CAM_COUNT * sizeof(float), "camera POD size");
+    w.section("camera", scene.cam, 4, CPTS_CAM_COUNT);
+
+    w.section("nodes", scene.nodes.data(), 16, scene.nodes.size());
+    static_assert(sizeof(CompactNode) == 16, "compact node size");
+    w.section("cache_nodes", scene.cache_nodes.data(), 16, scene.cache_nodes.size());
+    w.section("obj_idxs", scene.obj_idxs.data(), 4, scene.obj_idxs.size());
+
+    const char *vnames[3] = {"v0", "v1", "v2"}, *nnames[3] = {"n0", "n1", "n2"},
+               *tnames[3] = {"uv0", "uv1", "uv2"};
+    for (int k = 0; k < 3; k++) {
+        static_assert(sizeof(Vec3) == 12 && sizeof(Vec2) == 8, "vec sizes");
+        w.section(vnames[k], scene.verts_list[k].data(), 12, scene.verts_list[k].size());
+        w.section(nnames[k], scene.norms_list[k].data(), 12, scene.norms_list[k].size());
+        w.section(tnames[k], scene.uvs_list[k].data(), 8, scene.uvs_list[k].size());
+    }
+
+    std::vector<CompactedObjInfo> objs;
+    for (const auto &o : scene.objects)
+        objs.push_back(o.export_gpu());
+    static_assert(sizeof(CompactedObjInfo) == sizeof(CptsObject), "object POD size");
+    w.section("objects", objs.data(), 16, objs.size());
+    w.section("emitter_prims", scene.emitter_prims.data(), 4, scene.emitter_prims.size());
+
+    // ---- BSDF / emitter POD tables: host-side info + a re-read of the XML for
+    // the fields the reference does not keep on the host.
+    tinyxml2::XMLDocument doc;
+    doc.LoadFile(xml_path.c_str());
+    const tinyxml2::XMLElement *root = doc.FirstChildElement("scene");
+
+    std::vector<CptsBsdf> bsdfs(scene.num_bsdfs);
+    const tinyxml2::XMLElement *be = root->FirstChildElement("brdf");
+    for (int i = 0; i < scene.num_bsdfs; i++, be = be->NextSiblingElement("brdf")) {
+        const BSDFInfo &info = scene.bsdf_infos[i];
+        CptsBsdf b{};
+        b.type = info.type;
+        b.flags = lobe_flags_for(info.type);
+        for (int k = 0; k < 5; k++)
+            b.tex[k] = -1;
+        for (int k = 0; k < 4; k++) {
+            b.k_d[k] = info.bsdf.k_d[k];
+            b.k_s[k] = info.bsdf.k_s[k];
+            b.k_g[k] = info.bsdf.k_g[k];
+        }
+        if (info.type == BSDFType::GGXConductor) {
+            const Vec3 eta = METAL_ETA_TS[info.bsdf.mtype], kk = METAL_KS[info.bsdf.mtype];
+            for (int k = 0; k < 3; k++) {
+                b.extras[k] = eta[k];
+                b.extras[3 + k] = kk[k];
+            }
+            b.extras[6] = info.bsdf.roughness_x();
+            b.extras[7] = info.bsdf.roughness_y();
+        } else if (info.type == BSDFType::Plastic || info.type == BSDFType::PlasticForward) {
+            // the loader resets sigma_a (k_g) to (0,0,0,1) before creating the
+            // device object (scene.cu:293), BSDFInfo still holds the XML value
+            b.k_g[0] = b.k_g[1] = b.k_g[2] = 0.f, b.k_g[3] = 1.f;
+            b.extras[0] = info.bsdf.ior();
+            b.extras[1] = info.bsdf.trans_scaler();
+            b.extras[2] = info.bsdf.thickness();
+            bool pen = false;
+            if (auto e = child_named(be, "bool", {"penetrable"}))
+                e->QueryBoolAttribute("value", &pen);
+            b.extras[3] = pen ? 1.f : 0.f;
+        } else if (info.type == BSDFType::Dispersion) {
+            const Vec2 p = DISPERSION_PARAMS[info.bsdf.mtype];
+            b.extras[0] = p.x();
+            b.extras[1] = p.y();
+        }
+        bsdfs[i] = b;
+    }
+    w.section("bsdfs", bsdfs.data(), sizeof(CptsBsdf), bsdfs.size());
+
+    std::vector<CptsEmitter> ems(scene.num_emitters + 1);
+    memset(ems.data(), 0, ems.size() * sizeof(CptsEmitter));
+    ems[0].type = CPTS_EMIT_NULL;
+    ems[0].obj_ref = -1;
+    ems[0].tex = -1;
+    ems[0].Le[3] = 1.f; // Emitter(Vec4(0,0,0)) => w = 1
+    const tinyxml2::XMLElement *ee = root->FirstChildElement("emitter");
+    for (int i = 1; i <= scene.num_emitters; i++, ee = ee->NextSiblingElement("emitter")) {
+        CptsEmitter e{};
+        e.tex = -1;
+        e.obj_ref = -1;
+        std::string type = ee->Attribute("type");
+        float emission[3] = {0, 0, 0}, scaler[3] = {1, 1, 1};
+        if (auto c = child_named(ee, "rgb", {"emission"}))
+            parse_color(c->Attribute("value"), emission);
+        if (auto c = child_named(ee, "rgb", {"scaler"}))
+            parse_color(c->Attribute("value"), scaler);
+        for (int k = 0; k < 3; k++)
+            e.Le[k] = emission[k] * scaler[k];
+        e.Le[3] = 1.f * scaler[0];
+        for (size_t o = 0; o < scene.objects.size(); o++)
+            if (scene.objects[o].emitter_id == i)
+                e.obj_ref = int(o); // last bound shape wins, as in the loader's map
+        const tinyxml2::XMLElement *bind = child_named(ee, "string", {"bind_type"});
+        e.is_sphere = bind && strcmp(bind->Attribute("value"), "sphere") == 0;
+        if (type == "point") {
+            e.type = CPTS_EMIT_POINT;
+            e.obj_ref = -1;
+            if (auto p = child_named(ee, "point", {"center", "pos"})) {
+                p->QueryFloatAttribute("x", &e.pos[0]);
+                p->QueryFloatAttribute("y", &e.pos[1]);
+                p->QueryFloatAttribute("z", &e.pos[2]);
+            }
+        } else if (type == "area") {
+            e.type = CPTS_EMIT_AREA;
+        } else if (type == "area-spot") {
+            e.type = CPTS_EMIT_AREA_SPOT;
+            float ang = 0;
+            e.cos_val = 0.99f;
+            // the loader only looks at the FIRST <float> child
+            const tinyxml2::XMLElement *f = ee->FirstChildElement("float");
+            if (f && f->Attribute("name") &&
+                (!strcmp(f->Attribute("name"), "half-angle") || !strcmp(f->Attribute("name"), "angle"))) {
+                f->QueryFloatAttribute("value", &ang);
+                e.cos_val = cosf(ang * DEG2RAD);
+            }
+        } else if (type == "envmap") {
+            e.type = CPTS_EMIT_ENVMAP;
+            e.obj_ref = -1;
+            e.Le[0] = e.Le[1] = e.Le[2] = 0, e.Le[3] = 1;
+            e.scale = 1.f;
+            float az = 0, ze = 0;
+            if (auto c = child_named(ee, "float", {"scaler"}))
+                c->QueryFloatAttribute("value", &e.scale);
+            if (auto c = child_named(ee, "float", {"azimuth"}))
+                c->QueryFloatAttribute("value", &az);
+            if (auto c = child_named(ee, "float", {"zenith"}))
+                c->QueryFloatAttribute("value", &ze);
+            e.azimuth = az * DEG2RAD;
+            e.zenith = ze * DEG2RAD;
+        }
+        ems[i] = e;
+    }
+    w.section("emitters", ems.data(), sizeof(CptsEmitter), ems.size());
+
+    bool has_dispersion = false;
+    for (const auto &b : bsdfs)
+        has_dispersion |= b.type == CPTS_BSDF_DISPERSION;
+    if (has_dispersion) {
+        float4 *d_cie;
+        float *d_d65;
+        CUDA_CHECK_RETURN(cudaMalloc(&d_cie, sizeof(float4) * ColorSpaceXYZ::CIE_samples));
+        CUDA_CHECK_RETURN(cudaMalloc(&d_d65, sizeof(float) * ColorSpaceXYZ::D65_samples));
+        read_spectral_tables<<<5, 128>>>(d_cie, d_d65);
+        std::vector<float4> cie(ColorSpaceXYZ::CIE_samples);
+        std::vector<float> d65(ColorSpaceXYZ::D65_samples);
+        CUDA_CHECK_RETURN(cudaMemcpy(cie.data(), d_cie, sizeof(float4) * cie.size(), cudaMemcpyDeviceToHost));
+        CUDA_CHECK_RETURN(cudaMemcpy(d65.data(), d_d65, sizeof(float) * d65.size(), cudaMemcpyDeviceToHost));
+        w.section("cie_xyz", cie.data(), 16, cie.size());
+        w.section("d65_spd", d65.data(), 4, d65.size());
+        cudaFree(d_cie);
+        cudaFree(d_d65);
+    }
+    w.close();
+}
+
+std::unique_ptr<TracerBase> make_renderer(const Scene &scene, const std::string &mode) {
+    CUDA_CHECK_RETURN(cudaMemcpyToSymbol(c_material, scene.bsdfs, scene.num_bsdfs * sizeof(BSDF *)));
+    CUDA_CHECK_RETURN(
+        cudaMemcpyToSymbol(c_emitter, scene.emitters, (scene.num_emitters + 1) * sizeof(Emitter *)));
+    std::unique_ptr<TracerBase> r;
+    if (mode == "wfpt")
+        r = std::make_unique<WavefrontPathTracer>(scene);
+    else
+        r = std::make_unique<PathTracer<SingleTileScheduler>>(scene, false);
+    return r;
+}
+
+std::vector<int> parse_int_list(const char *txt) {
+    std::vector<int> out;
+    std::stringstream ss(txt);
+    std::string tok;
+    while (std::getline(ss, tok, ','))
+        if (!tok.empty())
+            out.push_back(atoi(tok.c_str()));
+    return out;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 3) {
+        fprintf(stderr, "usage: ref_dump dump|render|bench ... (see header comment)\n");
+        return 1;
+    }
+    std::string cmd = argv[1], xml = argv[2];
+    CUDA_CHECK_RETURN(cudaFree(nullptr));
+    ColorSpaceXYZ xyz_host;
+    Scene scene(xml);
+    xyz_host.init(); // dispersion tables, as pyrender does (python_render.cu:79-82)
+
+    if (cmd == "dump") {
+        if (argc < 4)
+            return 1;
+        dump_scene(scene, xml, argv[3]);
+        printf("[ref_dump] wrote %s\n", argv[3]);
+        return 0;
+    }
+    if (cmd == "render") {
+        if (argc < 7)
+            return 1;
+        std::string prefix = argv[3], mode = argv[4];
+        int seed_offset = atoi(argv[5]);
+        std::vector<int> frames = parse_int_list(argv[6]);
+        dump_scene(scene, xml, prefix + ".cpts");
+        auto rdr = make_renderer(scene, mode);
+        rdr->initialize_var_buffer();
+        rdr->set_seed_offset(seed_offset);
+        rdr->update_camera(scene.cam);
+        rdr->initialize_output_buffer();
+        const int W = rdr->width(), H = rdr->height();
+        std::vector<float> host(size_t(W) * H * 4), hvar(size_t(W) * H);
+        int last = 0;
+        for (int f : frames)
+            last = std::max(last, f);
+        size_t next = 0;
+        for (int i = 1; i <= last; i++) {
+            const float *dev = rdr->render_raw(scene.config.md, false);
+            if (next < frames.size() && frames[next] == i) {
+                CUDA_CHECK_RETURN(
+                    cudaMemcpy(host.data(), dev, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+                char name[512];
+                snprintf(name, sizeof(name), "%s_%s_f%04d.bin", prefix.c_str(), mode.c_str(), i);
+                FILE *fp = fopen(name, "wb");
+                fwrite(host.data(), sizeof(float), host.size(), fp);
+                fclose(fp);
+                CUDA_CHECK_RETURN(cudaMemcpy(hvar.data(), rdr->get_variance_buffer(),
+                                             hvar.size() * sizeof(float), cudaMemcpyDeviceToHost));
+                snprintf(name, sizeof(name), "%s_%s_var_f%04d.bin", prefix.c_str(), mode.c_str(), i);
+                fp = fopen(name, "wb");
+                fwrite(hvar.data(), sizeof(float), hvar.size(), fp);
+                fclose(fp);
+                printf("[ref_dump] frame %d saved (%dx%d)\n", i, W, H);
+                ++next;
+            }
+        }
+        return 0;
+    }
+    if (cmd == "bench") {
+        if (argc < 6)
+            return 1;
+        std::string mode = argv[3];
+        int warm = atoi(argv[4]), frames = atoi(argv[5]);
+        int seed_offset = argc > 6 ? atoi(argv[6]) : 0;
+        auto rdr = make_renderer(scene, mode);
+        rdr->set_seed_offset(seed_offset);
+        rdr->update_camera(scene.cam);
+        rdr->initialize_output_buffer();
+        for (int i = 0; i < warm; i++)
+            rdr->render_raw(scene.config.md, false);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        CUDA_CHECK_RETURN(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        for (int i = 0; i < frames; i++)
+            rdr->render_raw(scene.config.md, false);
+        cudaEventRecord(e1);
+        CUDA_CHECK_RETURN(cudaDeviceSynchronize());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("{\"ref_bench\": true, \"mode\": \"%s\", \"width\": %d, \"height\": %d, "
+               "\"frames\": %d, \"warmup\": %d, \"total_ms\": %.4f, \"ms_per_frame\": %.5f, "
+               "\"max_depth\": %d, \"num_prims\": %d}\n",
+               mode.c_str(), rdr->width(), rdr->height(), frames, warm, ms, ms / frames,
+               scene.config.md.max_depth, scene.num_prims);
+        return 0;
+    }
+    if (cmd == "state") {
+        // state <xml> <out_prefix> <seed_offset> <max_depth> : one wavefront sample with the depth overridden,
+        // then the raw payload arrays (per pixel: thp, L, ray_o, ray_d, interaction, sampler, pdf)
+        if (argc < 6)
+            return 1;
+        std::string prefix = argv[3];
+        int seed_offset = atoi(argv[4]), depth = atoi(argv[5]);
+        CUDA_CHECK_RETURN(cudaMemcpyToSymbol(c_material, scene.bsdfs, scene.num_bsdfs * sizeof(BSDF *)));
+        CUDA_CHECK_RETURN(
+            cudaMemcpyToSymbol(c_emitter, scene.emitters, (scene.num_emitters + 1) * sizeof(Emitter *)));
+        WavefrontPathTracer rdr(scene);
+        rdr.set_seed_offset(seed_offset);
+        rdr.update_camera(scene.cam);
+        rdr.initialize_output_buffer();
+        MaxDepthParams md = scene.config.md;
+        md.max_depth = depth;
+        rdr.render_raw(md, false);
+        const size_t P = size_t(rdr.width()) * rdr.height();
+        struct Item {
+            const char *name;
+            const void *ptr;
+            size_t elem;
+        } items[] = {{"thp", rdr.payload_buffer.thps, 16},      {"L", rdr.payload_buffer.Ls, 16},
+                     {"ray_o", rdr.payload_buffer.ray_os, 16},  {"ray_d", rdr.payload_buffer.ray_ds, 16},
+                     {"isect", rdr.payload_buffer.interactions, 16}, {"rng", rdr.payload_buffer.samplers, 8},
+                     {"pdf", rdr.payload_buffer.pdfs, 4}};
+        for (auto &it : items) {
+            std::vector<char> host(P * it.elem);
+            CUDA_CHECK_RETURN(cudaMemcpy(host.data(), it.ptr, host.size(), cudaMemcpyDeviceToHost));
+            FILE *fp = fopen((prefix + "_d" + std::to_string(depth) + "_" + it.name + ".bin").c_str(), "wb");
+            fwrite(host.data(), 1, host.size(), fp);
+            fclose(fp);
+        }
+        printf("[ref_dump] payload state written for depth %d\n", depth);
+        return 0;
+    }
+    fprintf(stderr, "unknown sub-command %s\n", cmd.c_str());
+    return 1;
+}
