@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mrays/s of the wavefront path-tracing hot path at 1920x1080 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the unmodified reference on the same box
+
+A "step" is one pass of the hot path over one batch of paths: `--spp-per-step` (default 8) samples of the full
+1080p frame of `scenes/xml/vader_wfpt_1080p.xml` (BASELINE config 1: vader geometry, 320k triangles, 2 area
+lights, thin lens, 16 bounces; the textures / environment map of the upstream scene are not shipped and are
+removed).  rays = primary + closest-hit + shadow traversals, counted on the device.
+
+One JSON line is printed by rank 0.  Keys beyond the base contract:
+  roofline     dominant kernel, algorithmic bytes (SURVEY §8d figures) / CUDA-event time vs the measured HBM peak
+  stages       the same for every kernel of the pipeline
+  cpu_baseline the CPU oracle (a port: the reference has no CPU renderer) timed on a bounded sample (N=1 only)
+  e2e          the same metric through the C-ABI call with HOST buffers (camera H2D + frame D2H every step)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tools")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+# algorithmic bytes per unit of work (the reference's state layout; ours is the same 92 B pool)
+BYTES_PER_UNIT = {"raygen": 100, "shade": 172, "trace": 140, "splat": 64}
+METRIC = "Mrays/s (primary + closest-hit + shadow traversals), wavefront PT, 1920x1080"
+
+
+def pick_scene(arg):
+    if arg:
+        return arg, os.path.basename(arg)
+    vader = os.path.join(ROOT, "scenes", "xml", "vader_wfpt_1080p.xml")
+    if os.path.exists(os.path.join(ROOT, "scenes", "meshes", "vader", "vader.obj")):
+        return vader, "vader_wfpt_1080p.xml"
+    # meshes absent (fresh checkout without the asset copy): the committed cornell scene re-targeted to 1080p
+    return os.path.join(ROOT, "tests", "golden", "ref", "cbox_wfpt_256.cpts"), "cbox_wfpt_256.cpts@1920x1080"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def rays_table():
+    p = os.path.join(ROOT, "profiles", "workload_rays.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def cpu_oracle_rate(scene_cpts, width, height, budget_s=12.0):
+    """Mrays/s of the CPU oracle (OpenMP, all host cores) on a bounded sample: 1 sample of a centred row band."""
+    import oracle
+    sc = oracle.OracleScene(scene_cpts)
+    mid = height // 2
+    t0 = time.perf_counter()
+    _, st = sc.render(1, rows=(mid - 4, mid + 4))
+    dt = max(time.perf_counter() - t0, 1e-3)
+    rows = int(min(height, max(16, 8 * budget_s / dt)))
+    rows -= rows % 2
+    r0 = max(0, mid - rows // 2)
+    t0 = time.perf_counter()
+    _, st = sc.render(1, rows=(r0, r0 + rows))
+    dt = time.perf_counter() - t0
+    return {"value": st["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"1 spp x rows [{r0},{r0 + rows}) of {width}x{height} ({st['samples']} paths, {st['rays']} rays, {dt:.1f} s), "
+                      "oracle/cpt_oracle.cpp with OpenMP; the reference has no CPU renderer",
+            "msamples_per_s": st["samples"] / dt / 1e6, "rays_per_sample": st["rays"] / st["samples"]}
+
+
+def run_reference(args, scene, workload):
+    """--impl reference: the UNMODIFIED reference (its GPU kernels driven by its own host loop: thrust sort +
+    per-bounce D2H count) through oracle/_ref/ref_dump on this box; CPU-oracle port if that binary is unavailable."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S = args.spp_per_step
+    ref_dump = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+    base = {"metric": METRIC, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "impl": "reference",
+            "data": "vader geometry bundled with the reference; textures/envmap not shipped upstream, removed",
+            "config": {"workload": workload, "width": 1920, "height": 1080, "spp_per_step": S, "max_depth": 16}}
+    tbl = rays_table().get(workload)
+    if scene.endswith(".xml") and os.path.exists(ref_dump):
+        try:
+            out = subprocess.run([ref_dump, "bench", scene, "wfpt", str(args.warmup * S), str(args.steps * S)],
+                                 capture_output=True, text=True, timeout=3000, cwd=ROOT)
+            line = [l for l in out.stdout.splitlines() if l.startswith("{\"ref_bench\"")][-1]
+            rb = json.loads(line)
+            rps = tbl["rays_per_sample"] if tbl else None
+            ms_step = rb["ms_per_frame"] * S
+            msamples = rb["width"] * rb["height"] / rb["ms_per_frame"] / 1e3
+            value = msamples * rps if rps else None
+            base.update({"value": value, "ms_per_step": ms_step, "msamples_per_s": msamples,
+                         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "reference",
+                                          "sample": f"{args.steps * S} x WavefrontPathTracer::render_raw (1 spp each) on 1 GPU of this box, "
+                                                    "reference kernels + its host loop (one host thread); rays/sample from "
+                                                    "profiles/workload_rays.json (same scene, counts parity-checked)"},
+                         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "reference_kind": "reference GPU kernels (sm_100a rebuild) + reference host loop"})
+            print(json.dumps(base))
+            return
+        except Exception as e:  # fall through to the CPU port
+            base["reference_error"] = str(e)[:200]
+    import cuda_pt_b200 as cpt
+    sc = cpt.Scene(scene)
+    if not scene.endswith(".xml"):
+        sc.set_film(1920, 1080)
+    tmp = os.path.join(tempfile.gettempdir(), "bench_scene_ref.cpts")
+    sc.save(tmp)
+    cb = cpu_oracle_rate(tmp, 1920, 1080, budget_s=20.0)
+    base.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
+                 "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default=None)
+    ap.add_argument("--spp-per-step", type=int, default=8)
+    ap.add_argument("--traversal", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    scene, workload = pick_scene(args.scene)
+    if args.impl == "reference":
+        run_reference(args, scene, workload)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import cuda_pt_b200 as cpt
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    sc = cpt.Scene(scene)
+    if not scene.endswith(".xml"):
+        sc.set_film(1920, 1080)
+    cfg = sc.config
+    W, H, S, K, Wm = cfg["width"], cfg["height"], args.spp_per_step, args.steps, args.warmup
+    r = cpt.WavefrontRenderer(sc, local_rank, 0)
+    r.set_option("samples_in_flight", S)
+    r.set_option("traversal", args.traversal)
+    r.set_option("kernel_timing", 1)
+    # weak scaling: every rank renders its own K*S sample numbers of the same seed stream
+    r.set_counter(rank * (K + Wm) * S * 2)
+    ext = torch.cuda.ExternalStream(r.stream(), device=dev)
+    acc = cpt.device_tensor(r.accumulator_ptr(), (H, W, 4), local_rank, r)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        r.render_batch(S, False)
+        if world > 1:  # one NCCL reduce of the HDR accumulator per sample batch (ddp_render.py:70-81)
+            total = acc.clone()
+            dist.all_reduce(total)
+            torch.cuda.current_stream(dev).synchronize()
+
+    for _ in range(Wm):
+        step()
+    barrier()
+    st0, kt0 = r.stats(), r.kernel_times()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    t_wall = time.perf_counter()
+    for _ in range(K):
+        step()
+    e1.record(ext)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    st1, kt1 = r.stats(), r.kernel_times()
+    rays = st1["rays"] - st0["rays"]
+    tvec = torch.tensor([ms, float(rays), float(st1["samples"] - st0["samples"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tvec.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tvec.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, rays, samples = float(mx[0]), float(sm[1]), float(sm[2])
+    else:
+        samples = float(tvec[2])
+    value = rays / (ms * 1e-3) / 1e6
+
+    # ---- end-to-end through the C ABI with host buffers: camera in (H2D), frame out (D2H) every step
+    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    cam = sc.camera
+    for _ in range(2):
+        r.update_camera(cam)
+        r.render_to_host(S, False, out=pinned)
+    barrier()
+    s0 = r.stats()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        r.update_camera(cam)
+        r.render_to_host(S, False, out=pinned)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    e2e_rays = float(r.stats()["rays"] - s0["rays"])
+    tv = torch.tensor([t_e2e, e2e_rays], dtype=torch.float64, device=dev)
+    if world > 1:
+        a = tv.clone()
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = tv.clone()
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        t_e2e, e2e_rays = float(a[0]), float(b[1])
+    e2e = {"value": e2e_rays / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 72, "d2h_bytes_per_step": W * H * 16,
+           "ms_per_step": t_e2e / K * 1e3, "timing": "host wall clock around K x (cpt_b200_update_camera + cpt_b200_render_to_host into pinned memory)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline (rank 0's kernels)
+    peak, peak_src = measured_peaks()
+    stages = {}
+    total_kernel_ms = sum(kt1[j]["ms"] - kt0[j]["ms"] for j in kt1)
+    for k in ("raygen", "shade", "trace", "splat"):
+        dms = kt1[k]["ms"] - kt0[k]["ms"]
+        units = kt1[k]["units"] - kt0[k]["units"]
+        n = kt1[k]["launches"] - kt0[k]["launches"]
+        if n == 0 or dms <= 0:
+            continue
+        gbs = units * BYTES_PER_UNIT[k] / (dms * 1e-3) / 1e9
+        stages[k] = {"ms_per_step": dms / K, "launches_per_step": n / K, "units_per_step": units / K,
+                     "bytes_per_unit": BYTES_PER_UNIT[k], "achieved_gbs": gbs, "frac": gbs / peak,
+                     "avg_launch_ms": dms / n, "share_of_step": dms / max(total_kernel_ms, 1e-9)}
+    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = None
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": {"raygen": "k_raygen", "shade": "k_shade", "trace": "k_trace", "splat": "k_splat"}[dom],
+                "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
+                "traffic": traffic, "peak_source": peak_src,
+                "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; BVH/triangle reads are L2-served "
+                        "(scene fits the 126 MB L2) and traversal is latency/issue bound, so the HBM fraction is small by nature"}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        tmp = os.path.join(tempfile.gettempdir(), "bench_scene.cpts")
+        sc.save(tmp)
+        cpu_baseline = cpu_oracle_rate(tmp, W, H)
+
+    out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "vader geometry bundled with the reference (textures/envmap not shipped upstream, removed); fixed seeds",
+           "config": {"workload": workload, "width": W, "height": H, "spp_per_step": S, "max_depth": cfg["max_depth"],
+                      "triangles": cfg["num_prims"], "parallelism": f"sample-split x{world}, 1 NCCL all-reduce of the fp32 accumulator per step" if world > 1 else "1 GPU",
+                      "l2_note": f"path-state pool {S * W * H * 92 / 1e6:.0f} MB per step >> 126 MB L2 (no flush needed)",
+                      "traversal": "ordered pair-node" if args.traversal == 0 else "reference DFS order"},
+           "msamples_per_s": samples / (ms * 1e-3) / 1e6, "rays_per_sample": rays / samples,
+           "gpu_launches": int((st1["launches"] - st0["launches"])), "wall_s": t_wall,
+           "clocks": clk, "e2e": e2e, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

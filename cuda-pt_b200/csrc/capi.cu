@@ -246,6 +246,8 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
             if (value != 0 && value != 1)
                 throw std::runtime_error("traversal must be 0 (ordered) or 1 (dfs)");
             r->impl->set_traversal(int(value));
+        } else if (k == "kernel_timing") {
+            r->impl->set_kernel_timing(value != 0);
         } else if (k == "max_depth") {
             if (value < 0 || value > 64)
                 throw std::runtime_error("max_depth must be in [0,64]");
@@ -279,6 +281,20 @@ int cpt_b200_stats(cpt_b200_renderer *r, uint64_t *stats8) {
         stats8[5] = uint64_t(s.device_ms * 1000.0);
         stats8[6] = stats8[7] = 0;
     });
+}
+
+int cpt_b200_kernel_times(cpt_b200_renderer *r, double *ms4, uint64_t *launches4, uint64_t *units4) {
+    REQUIRE(r);
+    REQUIRE(ms4);
+    const cptb::KernelTimes t = r->impl->kernel_times();
+    for (int i = 0; i < 4; i++) {
+        ms4[i] = t.ms[i];
+        if (launches4)
+            launches4[i] = t.launches[i];
+        if (units4)
+            units4[i] = t.units[i];
+    }
+    return 0;
 }
 
 int cpt_b200_info(const cpt_b200_renderer *r, char *buf, int buf_len) {

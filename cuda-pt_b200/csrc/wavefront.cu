@@ -433,6 +433,11 @@ struct Renderer::Impl {
     int pair_depth = 0, nesting_violations = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     size_t scene_bytes = 0;
+    // optional per-launch timing
+    std::vector<cudaEvent_t> kev;
+    std::vector<int> kev_kind;     // kind of the launch between kev[i] and kev[i+1]
+    std::vector<int> kev_bounce;
+    std::vector<int> h_counts;
 };
 
 static CameraPOD camera_from_floats(const float *c) {
@@ -660,6 +665,8 @@ Renderer::~Renderer() {
         cudaEventDestroy(impl_->ev0);
     if (impl_->ev1)
         cudaEventDestroy(impl_->ev1);
+    for (auto e : impl_->kev)
+        cudaEventDestroy(e);
     cudaFree(d_image_);
     cudaFree(d_out_);
     cudaFree(d_var_);
@@ -722,6 +729,24 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     const bool ordered = traversal_ == TRAVERSAL_ORDERED;
     CUDA_OK(cudaEventRecord(m.ev0, stream_));
     int wk = 0;
+    size_t kev_used = 0;
+    m.kev_kind.clear();
+    m.kev_bounce.clear();
+    auto mark = [&](int kind, int bounce) { // event BEFORE a launch of `kind` (-1: closing event)
+        if (!kernel_timing_)
+            return;
+        if (kev_used == m.kev.size()) {
+            cudaEvent_t e;
+            CUDA_OK(cudaEventCreate(&e));
+            m.kev.push_back(e);
+        }
+        CUDA_OK(cudaEventRecord(m.kev[kev_used++], stream_));
+        if (kind >= 0) {
+            m.kev_kind.push_back(kind);
+            m.kev_bounce.push_back(bounce);
+        }
+    };
+    mark(0, 0);
     if (ordered)
         k_raygen<true><<<grid, kBlock, smem, stream_>>>(m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk++);
     else
@@ -730,6 +755,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     int launches = 1, traced = 0, shaded = 0;
     for (int b = 0; b < D; b++) {
         uint32_t *q_cur = m.queue[b & 1].p, *q_nxt = m.queue[(b + 1) & 1].p;
+        mark(1, b);
         if (ordered)
             k_shade<true><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, shadow_counter, b > 0);
         else
@@ -737,20 +763,40 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         ++launches, ++shaded;
         if (b + 1 >= D)
             break;
+        mark(2, b);
         if (ordered)
             k_trace<true><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, q_nxt, q_counts + b + 1, b);
         else
             k_trace<false><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, q_nxt, q_counts + b + 1, b);
         ++launches, ++traced;
     }
+    mark(3, 0);
     k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples,
                                                first_accum, write_output ? 1 : 0, gamma ? 1 : 0);
+    mark(-1, 0);
     k_fold_stats<<<1, 32, 0, stream_>>>(q_counts, traced, shaded, m.stats.p);
     launches += 2;
     CUDA_OK(cudaEventRecord(m.ev1, stream_));
     CUDA_OK(cudaGetLastError());
     host_stats_.samples += uint64_t(P) * samples;
     host_stats_.launches += launches;
+}
+
+void Renderer::collect_kernel_times(int samples) {
+    // called after the batch's stream sync: fold per-launch event deltas and queue sizes into the totals
+    if (!kernel_timing_)
+        return;
+    Impl &m = *impl_;
+    m.h_counts.resize(size_t(max_depth_) + 2);
+    CUDA_OK(cudaMemcpy(m.h_counts.data(), m.counters.p, m.h_counts.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < m.kev_kind.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, m.kev[i], m.kev[i + 1]);
+        const int kind = m.kev_kind[i];
+        ktimes_.ms[kind] += ms;
+        ktimes_.launches[kind] += 1;
+        ktimes_.units[kind] += (kind == 0 || kind == 3) ? uint64_t(w_) * h_ * samples : uint64_t(m.h_counts[m.kev_bounce[i]]);
+    }
 }
 
 const float *Renderer::render_raw(bool gamma) {
@@ -760,6 +806,7 @@ const float *Renderer::render_raw(bool gamma) {
     float ms = 0;
     cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
     host_stats_.device_ms += ms;
+    collect_kernel_times(1);
     return reinterpret_cast<const float *>(d_out_);
 }
 
@@ -777,6 +824,7 @@ const float *Renderer::render_batch(int spp, bool gamma) {
         float ms = 0;
         cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
         host_stats_.device_ms += ms;
+        collect_kernel_times(s);
     }
     return reinterpret_cast<const float *>(d_out_);
 }

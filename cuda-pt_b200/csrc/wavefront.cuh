@@ -26,6 +26,13 @@ struct RenderStats {
     double device_ms = 0;      // device time spent in render batches (CUDA events)
 };
 
+// per-kernel device time (CUDA events around every launch, only when "kernel_timing" is enabled)
+struct KernelTimes {
+    double ms[4] = {0, 0, 0, 0};         // raygen, shade, trace, splat
+    uint64_t launches[4] = {0, 0, 0, 0};
+    uint64_t units[4] = {0, 0, 0, 0};    // pixel-samples, shaded segments, traced segments, pixel-samples
+};
+
 class Renderer {
   public:
     Renderer(const HostScene &scene, int device, int seed_offset);
@@ -58,6 +65,8 @@ class Renderer {
     void set_traversal(int t) { traversal_ = t; }
     void enable_variance(bool on);
     void set_accum_count(int c) { accum_cnt_ = c; }
+    void set_kernel_timing(bool on) { kernel_timing_ = on; }
+    KernelTimes kernel_times() const { return ktimes_; }
 
     int width() const { return w_; }
     int height() const { return h_; }
@@ -77,7 +86,9 @@ class Renderer {
 
     int device_ = 0, w_ = 0, h_ = 0, seed_offset_ = 0, accum_cnt_ = 0, max_depth_ = 0;
     int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148;
-    bool variance_on_ = false;
+    bool variance_on_ = false, kernel_timing_ = false;
+    KernelTimes ktimes_;
+    void collect_kernel_times(int samples);
     cudaStream_t stream_ = nullptr;
     float4 *d_image_ = nullptr, *d_out_ = nullptr;
     float *d_var_ = nullptr;

@@ -168,6 +168,13 @@ class WavefrontRenderer:
         d["rays"] = d["samples"] + d["closest_rays"] + d["shadow_rays"]
         return d
 
+    def kernel_times(self):
+        """Per-kernel device time (needs set_option("kernel_timing", 1)): {name: (ms, launches, units)}."""
+        ms, ln, un = (C.c_double * 4)(), (C.c_uint64 * 4)(), (C.c_uint64 * 4)()
+        check(lib().cpt_b200_kernel_times(self._h, ms, ln, un))
+        return {k: {"ms": float(ms[i]), "launches": int(ln[i]), "units": int(un[i])}
+                for i, k in enumerate(["raygen", "shade", "trace", "splat"])}
+
     def info(self):
         buf = C.create_string_buffer(1024)
         check(lib().cpt_b200_info(self._h, buf, 1024))

@@ -1,0 +1,945 @@
+/*
+ * cpt_oracle.cpp — CPU restatement of the reference's wavefront path-tracing hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (cuda-pt_b200/, include/) links, imports or
+ * executes this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and there only as the checker / the timed CPU baseline.
+ *
+ * What it restates (reference = Enigmatisms/cuda-pt @ 8ee28d0a, paths relative to /root/reference):
+ *   sampler            src/core/sampler.cuh:28-76
+ *   warps              src/core/sampling.cuh:27-67
+ *   camera             src/core/camera_model.cuh:58-87
+ *   slab / fp16 nodes  src/core/aabb.cuh:58-65, src/core/bvh.cuh:154-251
+ *   traversal          src/renderer/tracing_func.cuh:44-99 (any hit), :117-181 (closest hit)
+ *   triangle test      src/core/primitives.cuh:57-87, layout src/core/aos.cuh:134-164
+ *   interaction        src/core/primitives.cuh:109-123, src/core/aos.cuh:305-319, src/core/vec2_half.cuh:182-186
+ *   frames             src/core/so3.cuh:201-252
+ *   BSDFs              src/bsdf/{lambert,specular,translucent,plastic,ggx_conductor,dispersion,forward}.cuh,
+ *                      src/impl/bsdf_{ggx,plastic,dispersion}.cu, src/bsdf/fresnel.cuh:28-140
+ *   emitters           src/core/emitter.cuh:32-303 (point, area, area-spot; no environment maps here)
+ *   per-bounce logic   src/pt_impl/wavefront_pt.cu:71-314 (raygen, shade, closest-hit + RR), :476-503 (splat),
+ *                      host loop src/pt_impl/wf_path_tracer.cu:175-230, emitter pick tracing_func.cuh:210-225
+ *
+ * It is a TOLERANCE oracle: the reference runs on the GPU with --use_fast_math (approximate
+ * rcp/sqrt/div, flush-to-zero), which cannot be reproduced bit-for-bit on a CPU.
+ * It is pinned against the committed reference frames in tests/golden/ref (same scene dump, same seeds):
+ * per-pixel sample streams are identical, so images agree to ~1e-4 relative L2 at 64 spp apart from
+ * a handful of paths that flip at discrete decisions.  Integer machinery (RNG, keys, emitter picks,
+ * half conversion) is exact and has known-answer tests.
+ */
+#include "cpts_format.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct V3 {
+    float x, y, z;
+};
+struct V4 {
+    float x, y, z, w;
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(float s, V3 a) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+inline V3 operator/(V3 a, V3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline float len2(V3 a) { return dot(a, a); }
+inline V3 normalize(V3 a) { return a * (1.f / std::sqrt(len2(a))); }
+inline V4 operator+(V4 a, V4 b) { return {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+inline V4 operator*(V4 a, V4 b) { return {a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w}; }
+inline V4 operator*(V4 a, float s) { return {a.x * s, a.y * s, a.z * s, a.w * s}; }
+inline V4 operator/(V4 a, V4 b) { return {a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w}; }
+inline V4 operator+(V4 a, float s) { return {a.x + s, a.y + s, a.z + s, a.w + s}; }
+inline V4 v4(float v) { return {v, v, v, v}; }
+inline V4 v4(float v, float a) { return {v, v, v, a}; }
+inline V4 v4(const float *p) { return {p[0], p[1], p[2], p[3]}; }
+inline V4 expxyz(V4 a) { return {std::exp(a.x), std::exp(a.y), std::exp(a.z), 1.f}; }
+
+constexpr float EPS = 1e-3f, THP_EPS = 1e-4f, MAX_DIST = 1e7f, PI = 3.1415926535897f, INV_PI = 1.f / PI;
+constexpr int SEED_SCALER = 11467, RR_BOUNCE = 2;
+constexpr float RR_THRESHOLD = 0.1f;
+enum { LOBE_DIFFUSE = 1, LOBE_SPECULAR = 2, LOBE_GLOSSY = 4, LOBE_REFLECT = 0x10, LOBE_TRANSMIT = 0x20 };
+
+// ---- half helpers -------------------------------------------------------------------------------
+float half_to_float(uint16_t h) {
+    const uint32_t sign = uint32_t(h & 0x8000u) << 16, exp = (h >> 10) & 0x1F, man = h & 0x3FFu;
+    uint32_t out;
+    if (exp == 0) {
+        if (man == 0)
+            out = sign;
+        else {
+            int e = -1;
+            uint32_t m = man;
+            do {
+                ++e;
+                m <<= 1;
+            } while ((m & 0x400u) == 0);
+            out = sign | uint32_t(127 - 15 - e) << 23 | ((m & 0x3FFu) << 13);
+        }
+    } else if (exp == 31)
+        out = sign | 0x7F800000u | (man << 13);
+    else
+        out = sign | (exp + 112) << 23 | (man << 13);
+    float f;
+    memcpy(&f, &out, 4);
+    return f;
+}
+uint16_t float_to_half(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x7F800000u)
+        return uint16_t(sign | 0x7C00u | (x > 0x7F800000u ? 0x0200u : 0u));
+    if (x >= 0x477FF000u)
+        return uint16_t(sign | 0x7C00u);
+    if (x < 0x33000001u)
+        return uint16_t(sign);
+    const int exp = int(x >> 23) - 127;
+    const uint32_t man = (x & 0x7FFFFFu) | 0x800000u;
+    const int shift = exp < -14 ? 13 + (-14 - exp) : 13;
+    uint32_t hm = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (hm & 1u)))
+        hm++;
+    return uint16_t(sign | (exp < -14 ? hm : ((uint32_t(exp + 15) << 10) + (hm - 0x400u))));
+}
+inline float hround(float f) { return half_to_float(float_to_half(f)); }
+
+// ---- sampler (sampler.cuh:36-72) ------------------------------------------------------------------
+struct Rng {
+    uint32_t d0, d1;
+    void seed(int s, int offset) {
+        const unsigned long long v = (unsigned long long)(int)(uint32_t(s) + uint32_t(offset));
+        d0 = uint32_t(v) ^ 0x12345678u;
+        d1 = uint32_t(v >> 32) ^ 0x87654321u;
+    }
+    uint32_t u32() {
+        uint32_t t = d0;
+        t ^= t << 13;
+        t ^= t >> 17;
+        t ^= t << 5;
+        const uint32_t out = t + d1;
+        d1 = d0;
+        d0 = out;
+        return out;
+    }
+    float f() { return float(u32()) * 2.3283064e-10f + (2.3283064e-10f / 2.0f); }
+};
+
+// ---- scene ----------------------------------------------------------------------------------------
+struct Scene {
+    int32_t cfg[CPTS_CFG_COUNT];
+    float cam[CPTS_CAM_COUNT];
+    std::vector<float> nodes;       // 8 floats per node
+    std::vector<uint32_t> cache;    // 4 words per cached node
+    std::vector<int32_t> obj_idxs, emitter_prims;
+    std::vector<float> v[3], n[3], uv[3];
+    std::vector<CptsObject> objects;
+    std::vector<CptsBsdf> bsdfs;
+    std::vector<CptsEmitter> emitters;
+    std::vector<float> tris; // 12 floats per primitive
+    std::vector<float> cie, d65;
+    // derived material parameters (device constructors of the reference)
+    std::vector<float> alpha_x, alpha_y, eta, diff_f;
+    int num_nodes() const { return int(nodes.size() / 8); }
+};
+
+template <typename T> void read_vec(FILE *fp, const CptsSection &s, std::vector<T> &dst) {
+    const size_t bytes = size_t(s.elem_size) * s.count;
+    dst.resize(bytes / sizeof(T));
+    if (bytes && fread(dst.data(), 1, bytes, fp) != bytes)
+        throw std::string("truncated cpts section");
+}
+
+float fresnel_simple(float eta, float ci);
+
+float roughness_to_alpha(float r) { // cuda_utils.cuh:115-120
+    r = std::max(r, 1e-3f);
+    const float x = std::log(r);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+float diffuse_fresnel(float ior) { // fresnel.cuh:62-75
+    const int n = 131072;
+    double acc = 0.0;
+    float fb = fresnel_simple(ior, 0.0f);
+    for (int i = 1; i <= n; i++) {
+        const float c2 = float(i) / n;
+        const float fa = fresnel_simple(ior, std::min(std::sqrt(c2), 1.0f));
+        acc += double(fa + fb) * (0.5f / n);
+        fb = fa;
+    }
+    return float(acc);
+}
+
+Scene *load_scene(const char *path) {
+    FILE *fp = fopen(path, "rb");
+    if (!fp)
+        throw std::string("cannot open ") + path;
+    CptsHeader h{};
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, CPTS_MAGIC, 8) != 0) {
+        fclose(fp);
+        throw std::string("bad cpts magic");
+    }
+    Scene *sc = new Scene();
+    for (uint32_t i = 0; i < h.n_sections; i++) {
+        CptsSection s{};
+        if (fread(&s, sizeof(s), 1, fp) != 1)
+            break;
+        s.name[sizeof(s.name) - 1] = 0;
+        const std::string name = s.name;
+        const size_t bytes = size_t(s.elem_size) * s.count;
+        std::vector<int32_t> ti;
+        std::vector<float> tf;
+        if (name == "config") {
+            read_vec(fp, s, ti);
+            std::copy(ti.begin(), ti.end(), sc->cfg);
+        } else if (name == "camera") {
+            read_vec(fp, s, tf);
+            std::copy(tf.begin(), tf.end(), sc->cam);
+        } else if (name == "nodes")
+            read_vec(fp, s, sc->nodes);
+        else if (name == "cache_nodes")
+            read_vec(fp, s, sc->cache);
+        else if (name == "obj_idxs")
+            read_vec(fp, s, sc->obj_idxs);
+        else if (name == "emitter_prims")
+            read_vec(fp, s, sc->emitter_prims);
+        else if (name == "objects")
+            read_vec(fp, s, sc->objects);
+        else if (name == "bsdfs")
+            read_vec(fp, s, sc->bsdfs);
+        else if (name == "emitters")
+            read_vec(fp, s, sc->emitters);
+        else if (name == "cie_xyz")
+            read_vec(fp, s, sc->cie);
+        else if (name == "d65_spd")
+            read_vec(fp, s, sc->d65);
+        else if (name.size() == 2 && name[0] == 'v' && name[1] >= '0' && name[1] <= '2')
+            read_vec(fp, s, sc->v[name[1] - '0']);
+        else if (name.size() == 2 && name[0] == 'n' && name[1] >= '0' && name[1] <= '2')
+            read_vec(fp, s, sc->n[name[1] - '0']);
+        else if (name.size() == 3 && name[0] == 'u' && name[2] >= '0' && name[2] <= '2')
+            read_vec(fp, s, sc->uv[name[2] - '0']);
+        else
+            fseek(fp, long(bytes), SEEK_CUR);
+        fseek(fp, long((16 - bytes % 16) % 16), SEEK_CUR);
+    }
+    fclose(fp);
+    // precomputed triangles (aos.cuh:134-164)
+    const size_t P = sc->v[0].size() / 3;
+    sc->tris.resize(12 * P);
+    for (size_t i = 0; i < P; i++) {
+        const float *a = &sc->v[0][3 * i], *b = &sc->v[1][3 * i], *c = &sc->v[2][3 * i];
+        const float d1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, d2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+        float *t = &sc->tris[12 * i];
+        t[0] = a[0], t[1] = a[1], t[2] = a[2], t[3] = d1[1] * d2[2] - d1[2] * d2[1];
+        t[4] = d1[0], t[5] = d1[1], t[6] = d1[2], t[7] = d2[0] * d1[2] - d1[0] * d2[2];
+        t[8] = d2[0], t[9] = d2[1], t[10] = d2[2], t[11] = d1[0] * d2[1] - d2[0] * d1[1];
+    }
+    const size_t B = sc->bsdfs.size();
+    sc->alpha_x.assign(B, 0), sc->alpha_y.assign(B, 0), sc->eta.assign(B, 1), sc->diff_f.assign(B, 0);
+    for (size_t i = 0; i < B; i++) {
+        const CptsBsdf &b = sc->bsdfs[i];
+        if (b.type == CPTS_BSDF_GGX_CONDUCTOR) {
+            sc->alpha_x[i] = roughness_to_alpha(b.extras[6]);
+            sc->alpha_y[i] = roughness_to_alpha(b.extras[7]);
+        } else if (b.type == CPTS_BSDF_PLASTIC || b.type == CPTS_BSDF_PLASTIC_FORWARD) {
+            sc->eta[i] = 1.f / b.extras[0];
+            if (b.type == CPTS_BSDF_PLASTIC)
+                sc->diff_f[i] = diffuse_fresnel(b.extras[0]);
+        }
+    }
+    for (const auto &e : sc->emitters)
+        if (e.type == CPTS_EMIT_ENVMAP)
+            throw std::string("oracle: environment maps are not restated");
+    return sc;
+}
+
+// ---- geometry -------------------------------------------------------------------------------------
+inline bool slab(const float *lo, const float *hi, V3 inv_d, V3 o_div, float &t_near) { // aabb.cuh:58-65
+    const float ax = lo[0] * inv_d.x - o_div.x, ay = lo[1] * inv_d.y - o_div.y, az = lo[2] * inv_d.z - o_div.z;
+    const float bx = hi[0] * inv_d.x - o_div.x, by = hi[1] * inv_d.y - o_div.y, bz = hi[2] * inv_d.z - o_div.z;
+    t_near = std::max(std::min(ax, bx), std::max(std::min(ay, by), std::min(az, bz)));
+    const float t_far = std::min(std::max(ax, bx), std::min(std::max(ay, by), std::max(az, bz)));
+    return t_far > t_near && t_far > 0;
+}
+
+int cached_entry(const Scene &sc, V3 inv_d, V3 o_div, float limit, int miss) { // tracing_func.cuh:53-65 / :128-140
+    int node = miss;
+    const int cn = int(sc.cache.size() / 4);
+    for (int i = 0; i < cn;) {
+        const uint32_t *c = &sc.cache[4 * i];
+        const float lo[3] = {half_to_float(c[0] & 0xFFFF), half_to_float(c[1] & 0xFFFF), half_to_float(c[2] & 0xFFFF)};
+        const float hi[3] = {half_to_float(c[0] >> 16), half_to_float(c[1] >> 16), half_to_float(c[2] >> 16)};
+        float tn;
+        bool hit = slab(lo, hi, inv_d, o_div, tn) && tn < limit;
+        const int off = int(c[3] & 0xFF), gidx = int((c[3] >> 8) & 0xFFFFFF);
+        const int inc = (!hit) * off + int(hit && off != 1);
+        hit = hit && off == 1;
+        i = hit ? cn : i + inc;
+        node = hit ? gidx : node;
+    }
+    return node;
+}
+
+inline float hit_tri(const Scene &sc, int idx, V3 o, V3 d, float &u, float &v, float max_range) { // primitives.cuh:57-87
+    const float *t = &sc.tris[12 * idx];
+    const V3 p{o.x - t[0], o.y - t[1], o.z - t[2]};
+    const V3 e1{t[4], t[5], t[6]}, e2{t[8], t[9], t[10]};
+    const V3 t1{e2.y * -d.z + d.y * e2.z, -d.x * e2.z + e2.x * d.z, e2.x * -d.y + d.x * e2.y};
+    const V3 t2{-d.y * e1.z + e1.y * d.z, e1.x * -d.z + d.x * e1.z, -d.x * e1.y + e1.x * d.y};
+    const float det = e1.x * t1.x + e2.x * t2.x - t[3] * d.x, inv = 1.f / det;
+    const float a = dot(t1, p) * inv, b = dot(t2, p) * inv, tt = (t[3] * p.x + t[7] * p.y + t[11] * p.z) * inv;
+    u = a, v = b;
+    return tt * float(a > 0 && b > 0 && a + b < 1 && tt > EPS && tt < max_range);
+}
+
+struct Hit {
+    float t, u, v;
+    int prim;
+};
+Hit closest_hit(const Scene &sc, V3 o, V3 d) { // tracing_func.cuh:117-181
+    Hit h{MAX_DIST, 0, 0, -1};
+    const V3 inv_d{1.f / d.x, 1.f / d.y, 1.f / d.z}, o_div = o * inv_d;
+    int node = cached_entry(sc, inv_d, o_div, MAX_DIST, 0);
+    const int N = sc.num_nodes();
+    while (node < N) {
+        const float *nd = &sc.nodes[8 * node];
+        int32_t beg, end;
+        memcpy(&beg, nd + 3, 4);
+        memcpy(&end, nd + 7, 4);
+        float tn;
+        const bool hit = slab(nd, nd + 4, inv_d, o_div, tn) && tn < h.t;
+        node += (!hit) * (end < 0 ? -end : 1) + int(hit);
+        end = hit ? end + beg : 0;
+        for (int i = beg; i < end; i++) {
+            float u, v;
+            const float dist = hit_tri(sc, i, o, d, u, v, INFINITY);
+            if (dist > EPS && dist < h.t)
+                h = Hit{dist, u, v, i};
+        }
+    }
+    return h;
+}
+bool unoccluded(const Scene &sc, V3 o, V3 d, float max_dist) { // tracing_func.cuh:44-99
+    const V3 inv_d{1.f / d.x, 1.f / d.y, 1.f / d.z}, o_div = o * inv_d;
+    const int N = sc.num_nodes();
+    int node = cached_entry(sc, inv_d, o_div, max_dist, N);
+    while (node < N) {
+        const float *nd = &sc.nodes[8 * node];
+        int32_t beg, end;
+        memcpy(&beg, nd + 3, 4);
+        memcpy(&end, nd + 7, 4);
+        float tn;
+        const bool hit = slab(nd, nd + 4, inv_d, o_div, tn) && tn < max_dist;
+        node += (!hit) * (end < 0 ? -end : 1) + int(hit);
+        end = hit ? end + beg : 0;
+        for (int i = beg; i < end; i++) {
+            float u, v;
+            if (hit_tri(sc, i, o, d, u, v, max_dist) > EPS)
+                return false;
+        }
+    }
+    return true;
+}
+
+struct Isect {
+    V3 n;
+    float u, v; // half-rounded uv
+};
+Isect interaction(const Scene &sc, int prim, float u, float v) { // primitives.cuh:109-123
+    const float w = 1.f - u - v;
+    auto at = [&](int k) { return V3{sc.n[k][3 * prim], sc.n[k][3 * prim + 1], sc.n[k][3 * prim + 2]}; };
+    Isect it;
+    it.n = normalize(at(0) * w + at(1) * u + at(2) * v);
+    const float hw = hround(w), hu = hround(u), hv = hround(v);
+    for (int c = 0; c < 2; c++) {
+        const float a = hround(sc.uv[0][2 * prim + c]), b = hround(sc.uv[1][2 * prim + c]), cc = hround(sc.uv[2][2 * prim + c]);
+        const float r = hround(hround(hround(a * hw) + hround(b * hu)) + hround(cc * hv));
+        (c == 0 ? it.u : it.v) = r;
+    }
+    return it;
+}
+
+// ---- frames (so3.cuh:201-252) -----------------------------------------------------------------------
+struct M3 {
+    V3 r[3];
+};
+M3 frame(V3 to, bool l2w) {
+    V3 axis{l2w ? -to.y : to.y, l2w ? to.x : -to.x, 0.f};
+    M3 R{{{to.z, 0, 0}, {0, to.z, 0}, {0, 0, to.z}}};
+    if (std::fabs(to.z) < 1.f - 1e-5f) {
+        const V3 sk[3] = {{0, -axis.z, axis.y}, {axis.z, 0, -axis.x}, {-axis.y, axis.x, 0}};
+        axis = normalize(axis);
+        const float s = 1.f - to.z, a[3] = {axis.x, axis.y, axis.z};
+        for (int i = 0; i < 3; i++)
+            R.r[i] = R.r[i] + ((axis * a[i]) * s + sk[i]);
+    }
+    return R;
+}
+inline V3 rot(const M3 &m, V3 v) { return {dot(m.r[0], v), dot(m.r[1], v), dot(m.r[2], v)}; }
+inline V3 rot_t(const M3 &m, V3 v) {
+    return {m.r[0].x * v.x + m.r[1].x * v.y + m.r[2].x * v.z, m.r[0].y * v.x + m.r[1].y * v.y + m.r[2].y * v.z,
+            m.r[0].z * v.x + m.r[1].z * v.y + m.r[2].z * v.z};
+}
+inline V3 to_world(V3 n, V3 local) { return rot(frame(n, true), local); }
+// without normal maps eval_normal() reduces to R_w2l^T (0,0,1) (textures.cuh:79-90)
+inline V3 shading_normal(V3 n, M3 *R = nullptr) {
+    const M3 m = frame(n, false);
+    if (R)
+        *R = m;
+    return rot_t(m, V3{0, 0, 1});
+}
+
+// ---- sampling warps (sampling.cuh:27-67) --------------------------------------------------------------
+V3 cos_hemisphere(float ux, float uy, float &pdf) {
+    const float ct = std::sqrt(ux), st = std::sqrt(1.f - ux);
+    pdf = ct * INV_PI;
+    return {std::cos(2.f * uy * PI) * st, std::sin(2.f * uy * PI) * st, ct};
+}
+
+// ---- Fresnel (fresnel.cuh:28-140) -----------------------------------------------------------------------
+float fresnel_simple(float eta, float ci) {
+    eta = ci < 0.f ? 1.f / eta : eta;
+    ci = std::fabs(ci);
+    const float st2 = eta * eta * (1.f - ci * ci);
+    if (st2 >= 1.f)
+        return 1.f;
+    const float ct = std::sqrt(std::max(1.f - st2, 0.f));
+    const float rs = (eta * ci - ct) / (eta * ci + ct), rp = (eta * ct - ci) / (eta * ct + ci);
+    return (rs * rs + rp * rp) * 0.5f;
+}
+inline float sgn(float v) { return float(v > 0.f) - float(v < 0.f); }
+V3 snell(V3 in, V3 n, float &cos_r2, float dn, float ni, float nr) {
+    const float ratio = ni / nr;
+    cos_r2 = float(1.f - (ratio * ratio) * (1. - dn * dn));
+    return normalize(ratio * in - (ratio * dn) * n + (sgn(dn) * std::sqrt(std::fabs(cos_r2))) * n) * float(cos_r2 > 0.f);
+}
+float fresnel_dielectric(float n_in, float n_out, float ci, float cr) {
+    const float a = n_in * ci, b = n_out * ci, c = n_in * cr, d = n_out * cr;
+    const float rs = (a - d) / (a + d), rp = (c - b) / (c + b);
+    return 0.5f * (rs * rs + rp * rp);
+}
+V4 fresnel_conductor(const CptsBsdf &m, float ci) {
+    ci = std::min(std::max(ci, -1.f), 1.f);
+    const float c2 = ci * ci, s2 = 1.f - c2;
+    float out[3];
+    for (int k = 0; k < 3; k++) {
+        const float e2 = m.extras[k] * m.extras[k], k2 = m.extras[3 + k] * m.extras[3 + k];
+        const float t0 = e2 - k2 - s2, a2b2 = std::sqrt(t0 * t0 + 4 * e2 * k2), t1 = a2b2 + c2;
+        const float a = std::sqrt(0.5f * (a2b2 + t0)), t2 = 2.f * ci * a, rs = (t1 - t2) / (t1 + t2);
+        const float t3 = c2 * a2b2 + s2 * s2, t4 = t2 * s2, rp = rs * (t3 - t4) / (t3 + t4);
+        out[k] = 0.5f * (rp + rs);
+    }
+    return {out[0], out[1], out[2], 1.f};
+}
+
+// ---- GGX (bsdf_ggx.cu:25-189) ------------------------------------------------------------------------------
+float ggx_lambda(V3 l, float ax, float ay) {
+    const float c2 = l.z * l.z, ic2 = c2 == 0 ? 0 : 1.f / c2;
+    const float e = (l.x * l.x * ax * ax + l.y * l.y * ay * ay) * ic2;
+    return e == 0 ? 0 : (-1.f + std::sqrt(1.f + e)) * 0.5f;
+}
+float ggx_D(V3 l, float ax, float ay) {
+    const float c2 = l.z * l.z, ic2 = c2 == 0 ? 0 : 1.f / c2;
+    const float e = (l.x * l.x / (ax * ax) + l.y * l.y / (ay * ay)) * ic2;
+    return 1.f / (PI * ax * ay * c2 * c2 * (1 + e) * (1 + e));
+}
+float ggx_G1(V3 l, float ax, float ay) { return 1.f / (1.f + ggx_lambda(l, ax, ay)); }
+float ggx_G(V3 a, V3 b, float ax, float ay) { return 1.f / (1.f + ggx_lambda(a, ax, ay) + ggx_lambda(b, ax, ay)); }
+void ggx_slopes(float ct, float ux, float uy, float &sx, float &sy) {
+    if (ct == 1) {
+        const float r = std::sqrt(ux / (1 - uy));
+        sx = r * std::cos(2.f * uy * PI), sy = r * std::sin(2.f * uy * PI);
+        return;
+    }
+    const float st = std::sqrt(std::max(0.f, 1.f - ct * ct)), tt = st / ct, a = 1.f / tt;
+    const float G1 = 2.f / (1 + std::sqrt(1.f + 1.f / (a * a)));
+    const float A = 2.f * ux / G1 - 1, tmp = std::min(1.f / (A * A - 1.f), 1e9f), B = tt;
+    const float D = std::sqrt(std::max(B * B * tmp * tmp - (A * A - B * B) * tmp, 0.f));
+    const float s1 = B * tmp - D, s2 = B * tmp + D;
+    sx = (A < 0 || s2 > 1.f / tt) ? s1 : s2;
+    const float sign = uy > 0.5f ? 1.f : -1.f;
+    uy = 2.f * (uy - .5f) * sign;
+    const float z = (uy * (uy * (uy * 0.27385f - 0.73369f) + 0.46341f)) /
+                    (uy * (uy * (uy * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+    sy = sign * z * std::sqrt(1.f + sx * sx);
+}
+V3 ggx_sample_wh(V3 li, float ax, float ay, float ux, float uy) {
+    const V3 ws = normalize(V3{li.x * ax, li.y * ay, li.z});
+    float sx, sy;
+    ggx_slopes(ws.z, ux, uy, sx, sy);
+    const float s2 = std::max(1.f - ws.z * ws.z, 0.f), inv = 1.f / std::sqrt(s2);
+    const float cphi = s2 == 0 ? 1 : std::min(std::max(ws.x * inv, -1.f), 1.f),
+                sphi = s2 == 0 ? 0 : std::min(std::max(ws.y * inv, -1.f), 1.f);
+    const float tmp = cphi * sx - sphi * sy;
+    sy = (sphi * sx + cphi * sy) * ay;
+    sx = tmp * ax;
+    return normalize(V3{-sx, -sy, 1.f});
+}
+
+// ---- dispersion colour (bsdf_dispersion.cu:26-44, xyz.cuh:47-57) ------------------------------------------
+float table_lookup(const std::vector<float> &tab, int stride, int comp, float x01) { // linear filter, clamp
+    const int n = int(tab.size()) / stride;
+    float p = x01 * n - 0.5f;
+    p = std::min(std::max(p, 0.f), float(n - 1));
+    const int i0 = int(std::floor(p)), i1 = std::min(i0 + 1, n - 1);
+    const float f = p - i0;
+    return tab[i0 * stride + comp] * (1 - f) + tab[i1 * stride + comp] * f;
+}
+V4 wavelength_rgb(const Scene &sc, float wl) {
+    const float ci = (wl - 360.f) / 471.f, di = (wl - 300.f) / 531.f;
+    const float spd = table_lookup(sc.d65, 1, 0, di) / 22.2175f;
+    const float X = table_lookup(sc.cie, 4, 0, ci) * spd, Y = table_lookup(sc.cie, 4, 1, ci) * spd, Z = table_lookup(sc.cie, 4, 2, ci) * spd;
+    const float r = 3.240479f * X - 1.537150f * Y - 0.498535f * Z, g = -0.969256f * X + 1.875991f * Y + 0.041556f * Z,
+                b = 0.055648f * X - 0.204043f * Y + 1.057311f * Z;
+    // Vec4(r,g,b) has w = 1; the scale constructor too
+    return {std::max(r, 0.f) / 1.4979f, std::max(g, 0.f) / 1.13591f, std::max(b, 0.f) / 1.13159f, 1.f};
+}
+
+// ---- dielectric core (translucent.cuh:43-98); is_radiance is false on this path (base-class default) ------
+V4 dielectric_eval(V3 n, V3 out, V3 in, V4 ks, float eta) {
+    const float dn = dot(in, n), ni = dn < 0 ? 1.f : eta, nr = dn < 0 ? eta : 1.f;
+    float c2 = 0;
+    const V3 ret = normalize(in + n * (-2.f * dn)), refr = snell(in, n, c2, dn, ni, nr);
+    return ks * float((dot(out, ret) > 0.99999f) | (dot(out, refr) > 0.99999f));
+}
+V3 dielectric_sample(V3 in, V3 n, V4 ks, float eta, V4 &thp, Rng &rng, float &pdf, int &lobe) {
+    const float dn = dot(in, n), ni = dn < 0 ? 1.f : eta;
+    float nr = dn < 0 ? eta : 1.f, c2 = 0;
+    const V3 ret = normalize(in + n * (-2.f * dn)), refr = snell(in, n, c2, dn, ni, nr);
+    const bool total = (1.f - (ni * ni) / (nr * nr) * (1.f - dn * dn)) < 0.f;
+    nr = fresnel_dielectric(ni, nr, std::fabs(dn), std::sqrt(std::fabs(c2)));
+    const bool reflect = total || rng.f() < nr;
+    pdf = total ? 1.f : (reflect ? nr : 1.f - nr);
+    lobe = LOBE_SPECULAR | (total || reflect ? LOBE_REFLECT : LOBE_TRANSMIT);
+    thp = thp * ks;
+    return reflect ? ret : refr;
+}
+bool dispersion_wl(const CptsBsdf &m, V3 in, V3 out, V3 n, float &wl) { // dispersion.cuh:70-80
+    const float ci = dot(n, in), co = dot(n, out), si = std::sqrt(1.f - ci * ci), so = std::sqrt(1.f - co * co);
+    const float eta = si > so ? si / so : so / si;
+    wl = std::sqrt(m.extras[1] / std::max(eta - m.extras[0], 1e-5f));
+    return wl > 360.f && wl < 831.f;
+}
+
+// ---- BSDF interface ---------------------------------------------------------------------------------------
+struct Mat {
+    const CptsBsdf *b;
+    float ax, ay, eta, diff_f;
+};
+float bsdf_pdf(const Scene &sc, const Mat &m, V3 nrm, V3 out, V3 in) {
+    const CptsBsdf &b = *m.b;
+    switch (b.type) {
+    case CPTS_BSDF_LAMBERTIAN: return std::max(dot(shading_normal(nrm), out), 0.f) * INV_PI;
+    case CPTS_BSDF_PLASTIC: {
+        const V3 n = shading_normal(nrm);
+        const float dwo = std::fabs(dot(out, n)), dwi = std::fabs(dot(in, n)), Fi = fresnel_simple(m.eta, dwi),
+                    sp = Fi / (Fi + b.extras[1] * (1.f - Fi));
+        const V3 rd = in - n * (2.f * dot(in, n));
+        return dot(rd, out) < 1.f - THP_EPS ? INV_PI * dwo * (1.f - sp) : sp;
+    }
+    case CPTS_BSDF_PLASTIC_FORWARD: {
+        const V3 n = shading_normal(nrm);
+        const float dwi = dot(in, n), Fi = fresnel_simple(m.eta, -dwi), sp = Fi / (Fi + b.extras[1] * (1.f - Fi));
+        const V3 rd = in - n * (2.f * dwi);
+        float p = 0;
+        p = dot(rd, out) < 1.f - THP_EPS ? p : sp;
+        p = dot(in, out) < 1.f - THP_EPS ? p : 1.f - sp;
+        return p;
+    }
+    case CPTS_BSDF_GGX_CONDUCTOR: {
+        M3 R;
+        shading_normal(nrm, &R);
+        const V3 li = -rot(R, in), lo = rot(R, out), wh = normalize(lo + li);
+        const float pv = ggx_D(wh, m.ax, m.ay) * ggx_G1(li, m.ax, m.ay) * (std::fabs(dot(li, wh)) / std::fabs(li.z));
+        return ((li.z > 0) ^ (lo.z > 0)) ? 0 : pv * (1.f / (4.f * dot(wh, li)));
+    }
+    case CPTS_BSDF_DISPERSION: {
+        const V3 n = shading_normal(nrm);
+        float p = 0;
+        if (((dot(n, in) > 0) ^ (dot(n, out) > 0)) == false) {
+            float wl = 0;
+            p = dispersion_wl(b, in, out, n, wl);
+            const float eta = b.extras[0] + b.extras[1] / (wl * wl), F = fresnel_simple(eta, -dot(in, n));
+            p *= (1.f - F) / 471.f;
+        }
+        return p;
+    }
+    case CPTS_BSDF_FORWARD: return float(dot(in, out) == 1.f);
+    default: return 0.f;
+    }
+}
+V4 bsdf_eval(const Scene &sc, const Mat &m, V3 nrm, V3 out, V3 in) {
+    const CptsBsdf &b = *m.b;
+    const V4 kd = v4(b.k_d), ks = v4(b.k_s), kg = v4(b.k_g);
+    switch (b.type) {
+    case CPTS_BSDF_LAMBERTIAN: {
+        const V3 n = shading_normal(nrm);
+        const float ct = dot(n, out), di = dot(n, in);
+        return kd * std::max(0.f, ct) * INV_PI * float((di > 0) ^ (ct > 0));
+    }
+    case CPTS_BSDF_SPECULAR: {
+        const V3 n = shading_normal(nrm), rd = normalize(in + n * (-2.f * dot(in, n)));
+        return ks * float(dot(out, rd) > 0.99999f);
+    }
+    case CPTS_BSDF_TRANSLUCENT: return dielectric_eval(shading_normal(nrm), out, in, ks, b.k_d[0]);
+    case CPTS_BSDF_PLASTIC: {
+        const V3 n = shading_normal(nrm);
+        const float rwo = dot(out, n), rwi = dot(in, n), dwo = std::fabs(rwo), dwi = std::fabs(rwi),
+                    Fi = fresnel_simple(m.eta, dwi), Fo = fresnel_simple(m.eta, dwo);
+        const V3 rd = in - n * (2.f * rwi);
+        V4 brdf = (kd / ((kd * -m.diff_f) + 1.f)) * ((INV_PI * (1.f - Fi) * (1.f - Fo) * m.eta * m.eta) * dwo) *
+                  expxyz(kg * b.extras[2] * (-1.f / dwo - 1.f / dwi));
+        if (!(dot(rd, out) < 1.f - THP_EPS))
+            brdf = brdf + v4(Fi, 1) * ks;
+        return (b.extras[3] > 0 || ((rwo > 0) ^ (rwi > 0))) ? brdf : v4(0, 1);
+    }
+    case CPTS_BSDF_PLASTIC_FORWARD: {
+        const V3 n = shading_normal(nrm);
+        const float dwi = dot(in, n), Fi = fresnel_simple(m.eta, std::fabs(dwi));
+        const V3 rd = in - n * (2.f * dwi);
+        V4 brdf = dot(in, out) < 1.f - THP_EPS
+                      ? v4(0, 1)
+                      : kd * ((1.f - Fi) * (1.f - Fi)) * m.eta * m.eta * expxyz(kg * b.extras[2] * (-2.f / std::fabs(dwi)));
+        brdf = brdf + (dot(rd, out) < 1.f - THP_EPS ? brdf : v4(Fi, 1) * ks);
+        return brdf;
+    }
+    case CPTS_BSDF_GGX_CONDUCTOR: {
+        M3 R;
+        const V3 n = shading_normal(nrm, &R), li = -rot(R, in), lo = rot(R, out);
+        V3 wh = normalize(lo + li);
+        if (!(wh.z > 0))
+            wh = -wh;
+        const V4 F = fresnel_conductor(b, std::fabs(dot(lo, wh)));
+        if ((li.z > 0) ^ (lo.z > 0))
+            return v4(0.f) * kg;
+        const V4 g = F * ggx_D(wh, m.ax, m.ay) * (1.f / (4.f * li.z * lo.z)) * ggx_G(li, lo, m.ax, m.ay);
+        return kg * g * std::max(0.f, dot(out, n));
+    }
+    case CPTS_BSDF_DISPERSION: {
+        const V3 n = shading_normal(nrm);
+        float wl = 0;
+        const bool valid = dispersion_wl(b, in, out, n, wl);
+        const float eta = valid ? b.extras[0] + b.extras[1] / (wl * wl) : b.extras[0];
+        V4 r = dielectric_eval(n, out, in, ks, eta);
+        return r * (valid ? wavelength_rgb(sc, wl) : v4(1.f));
+    }
+    case CPTS_BSDF_FORWARD: return v4(float(dot(in, out) == 1.f), 1);
+    default: return v4(0.f);
+    }
+}
+V3 bsdf_sample(const Scene &sc, const Mat &m, V3 in, V3 nrm, V4 &thp, float &pdf, Rng &rng, int &lobe) {
+    const CptsBsdf &b = *m.b;
+    const V4 kd = v4(b.k_d), ks = v4(b.k_s), kg = v4(b.k_g);
+    switch (b.type) {
+    case CPTS_BSDF_LAMBERTIAN: {
+        const float ux = rng.f(), uy = rng.f();
+        const V3 local = cos_hemisphere(ux, uy, pdf), n = shading_normal(nrm), out = to_world(n, local);
+        thp = thp * kd * float((dot(n, in) > 0) ^ (dot(n, out) > 0));
+        lobe = b.flags;
+        return out;
+    }
+    case CPTS_BSDF_SPECULAR: {
+        const V3 n = shading_normal(nrm);
+        pdf = 1.f;
+        lobe = b.flags;
+        thp = thp * ks;
+        return in - n * (2.f * dot(in, n));
+    }
+    case CPTS_BSDF_TRANSLUCENT: return dielectric_sample(in, shading_normal(nrm), ks, b.k_d[0], thp, rng, pdf, lobe);
+    case CPTS_BSDF_PLASTIC: {
+        const V3 n = shading_normal(nrm);
+        const float rdi = dot(n, in), di = std::fabs(rdi), Fi = fresnel_simple(m.eta, di), sp = Fi / (Fi + b.extras[1] * (1.f - Fi));
+        V3 out;
+        if (rng.f() < sp) {
+            out = in - n * (2.f * dot(in, n));
+            pdf = sp;
+            thp = thp * (v4(Fi / sp, 1) * ks);
+            lobe = LOBE_REFLECT | LOBE_SPECULAR;
+        } else {
+            float dummy;
+            const float ux = rng.f(), uy = rng.f();
+            const V3 local = cos_hemisphere(ux, uy, dummy);
+            const float Fo = fresnel_simple(m.eta, local.z);
+            const V4 lthp = (kd / ((kd * -m.diff_f) + 1.f)) * ((1.f - Fi) * (1.f - Fo) * m.eta * m.eta) *
+                            expxyz(kg * b.extras[2] * (-1.f / local.z - 1.f / di));
+            pdf = INV_PI * local.z * (1.f - sp);
+            thp = thp * (lthp * (1.f / (1.f - sp)));
+            out = to_world(n, local);
+            lobe = LOBE_REFLECT | LOBE_DIFFUSE;
+        }
+        if (!(b.extras[3] > 0 || ((rdi > 0) ^ (dot(out, n) > 0))))
+            thp = v4(0, 1);
+        return out;
+    }
+    case CPTS_BSDF_PLASTIC_FORWARD: {
+        const V3 n = shading_normal(nrm);
+        const float di = dot(n, in), Fi = fresnel_simple(m.eta, std::fabs(di)), sp = Fi / (Fi + b.extras[1] * (1.f - Fi));
+        if (rng.f() < sp) {
+            pdf = sp;
+            thp = thp * (v4(Fi / sp, 1) * ks);
+            lobe = LOBE_REFLECT | LOBE_SPECULAR;
+            return in - n * (2.f * di);
+        }
+        const V4 lthp = kd * ((1.f - Fi) * (1.f - Fi) * m.eta * m.eta) * expxyz(kg * b.extras[2] * (-2.f / std::fabs(di)));
+        pdf = 1.f - sp;
+        thp = thp * (lthp * (1.f / (1.f - sp)));
+        lobe = LOBE_TRANSMIT | LOBE_SPECULAR;
+        return in;
+    }
+    case CPTS_BSDF_GGX_CONDUCTOR: {
+        M3 R;
+        const V3 n = shading_normal(nrm, &R), li = -rot(R, in);
+        const float ux = rng.f(), uy = rng.f();
+        const V3 wh = ggx_sample_wh(li, m.ax, m.ay, ux, uy);
+        const float D = ggx_D(wh, m.ax, m.ay), dim = dot(li, wh);
+        pdf = D * ggx_G1(li, m.ax, m.ay) * std::fabs(dim / li.z);
+        pdf = (pdf > 0 && dim > 0) ? pdf * (1.f / (4.f * dim)) : 0;
+        const V3 lref = wh * (2.f * dim) - li, ref = rot_t(R, lref);
+        const float ci = li.z, co = lref.z;
+        const V4 F = fresnel_conductor(b, std::fabs(dot(lref, wh)));
+        if (ci > 0 && co > 0 && pdf > 0)
+            thp = thp * (kg * (1.f / pdf) * D * ggx_G(li, lref, m.ax, m.ay) * (1.f / (4.f * ci * co)) * F * std::max(dot(n, ref), 0.f));
+        lobe = b.flags;
+        return ref;
+    }
+    case CPTS_BSDF_DISPERSION: {
+        const float wl = rng.f() * 471.f + 360.f, eta = b.extras[0] + b.extras[1] / (wl * wl);
+        const V3 r = dielectric_sample(in, shading_normal(nrm), ks, eta, thp, rng, pdf, lobe);
+        thp = thp * wavelength_rgb(sc, wl);
+        pdf *= 1.f / 471.f;
+        return r;
+    }
+    default:
+        pdf = 1.f;
+        lobe = b.flags;
+        return in;
+    }
+}
+
+// ---- emitters (emitter.cuh) ---------------------------------------------------------------------------------
+V4 emitter_eval(const CptsEmitter &e, V3 inci, V3 n) {
+    if (e.type == CPTS_EMIT_AREA)
+        return dot(inci, n) < 0 ? v4(e.Le) : V4{0, 0, 0, 1};
+    if (e.type == CPTS_EMIT_AREA_SPOT)
+        return dot(inci, n) < -e.cos_val ? v4(e.Le) : V4{0, 0, 0, 1};
+    return {0, 0, 0, 1};
+}
+V3 emitter_sample(const Scene &sc, const CptsEmitter &e, V3 hit, V4 &le, float &pdf, float ux, float uy, int prim) {
+    if (e.type == CPTS_EMIT_POINT) {
+        const V3 p{e.pos[0], e.pos[1], e.pos[2]};
+        le = v4(e.Le) * std::min(1.f / std::max(len2(p - hit), 1e-5f), 1.f);
+        return p;
+    }
+    if (e.type == CPTS_EMIT_AREA || e.type == CPTS_EMIT_AREA_SPOT) {
+        if (!(ux + uy < 1.f))
+            ux = 1.f - ux, uy = 1.f - uy;
+        const float *t = &sc.tris[12 * prim];
+        const V3 p = V3{t[4], t[5], t[6]} * ux + V3{t[8], t[9], t[10]} * uy + V3{t[0], t[1], t[2]};
+        auto at = [&](int k) { return V3{sc.n[k][3 * prim], sc.n[k][3 * prim + 1], sc.n[k][3 * prim + 2]}; };
+        const V3 n = normalize(at(0) * (1.f - ux - uy) + at(1) * ux + at(2) * uy);
+        V3 th = hit - p;
+        pdf *= len2(th);
+        th = normalize(th);
+        const float c = dot(n, th);
+        pdf *= float(c > 0) / c;
+        le = v4(e.Le) * float(e.type == CPTS_EMIT_AREA ? c > 0 : c > e.cos_val);
+        return p;
+    }
+    pdf = 1;
+    le = v4(0.f);
+    return {0, 0, 0};
+}
+
+// ---- one path (wavefront_pt.cu:71-314; loop structure of wf_path_tracer.cu:175-230) ----------------------------
+struct Counts {
+    uint64_t closest = 0, shadow = 0, shaded = 0;
+};
+V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int max_depth, Counts &cnt) {
+    const int W = sc.cfg[CPTS_CFG_WIDTH];
+    Rng rng;
+    rng.seed(px + py * W, int(uint32_t(seed_offset) + uint32_t(accum) * uint32_t(SEED_SCALER)));
+    // camera (camera_model.cuh:58-87)
+    const float *c = sc.cam;
+    const float xp = rng.f() + float(px), yp = rng.f() + float(py);
+    const float nx = (xp - c[CPTS_CAM_HW]) * c[CPTS_CAM_INV_FOCAL] * c[CPTS_CAM_SIGN_X], ny = (c[CPTS_CAM_HH] - yp) * c[CPTS_CAM_INV_FOCAL];
+    const M3 R{{{c[0], c[1], c[2]}, {c[3], c[4], c[5]}, {c[6], c[7], c[8]}}};
+    const V3 T{c[9], c[10], c[11]};
+    V3 o, d = normalize(rot(R, V3{nx, ny, 1.f}));
+    if (c[CPTS_CAM_FOCAL_DIST] == 0) {
+        o = T + V3{c[1], c[4], c[7]} * ny + V3{c[0], c[3], c[6]} * nx;
+        d = normalize(rot(R, V3{0, 0, 1}));
+    } else if (c[CPTS_CAM_APERTURE] > 0) {
+        const V3 focus = T + d * c[CPTS_CAM_FOCAL_DIST];
+        const float ux = rng.f(), uy = rng.f(), r = std::sqrt(ux);
+        const float lx = r * std::cos(2.f * uy * PI) * c[CPTS_CAM_APERTURE], ly = r * std::sin(2.f * uy * PI) * c[CPTS_CAM_APERTURE];
+        o = T + (V3{c[0], c[3], c[6]} * lx + V3{c[1], c[4], c[7]} * ly);
+        d = normalize(focus - o);
+    } else
+        o = T;
+
+    V4 thp{1, 1, 1, 1}, L{0, 0, 0, 1};
+    float pdf = 1.f;
+    bool delta = false;
+    Hit h = closest_hit(sc, o, d);
+    if (h.prim < 0)
+        return L; // null emitter: (0,0,0,1)
+    Isect it = interaction(sc, h.prim, h.u, h.v);
+    const int num_emitters = int(sc.emitters.size()) - 1;
+    for (int bounce = 0; bounce < max_depth; bounce++) {
+        // ---- shade (fused_ray_bounce_shader)
+        cnt.shaded++;
+        int obj_id = sc.obj_idxs[h.prim];
+        obj_id = obj_id >= 0 ? obj_id : -obj_id - 1;
+        const CptsObject &ob = sc.objects[obj_id];
+        const int mat_id = ob.bsdf_emitter >> 16, emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+        const Mat m{&sc.bsdfs[mat_id], sc.alpha_x[mat_id], sc.alpha_y[mat_id], sc.eta[mat_id], sc.diff_f[mat_id]};
+        int num = num_emitters;
+        num -= emitter_id > 0 && num > 1;
+        uint32_t eid = rng.u32() % uint32_t(num) + 1;
+        eid += eid >= uint32_t(emitter_id) && emitter_id > 0;
+        float direct_pdf = 1.f / float(num);
+        eid *= uint32_t(emitter_id == 0 || num > 1);
+        const CptsEmitter &em = sc.emitters[eid];
+        const CptsObject &eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
+        direct_pdf *= eo.inv_area;
+        const uint32_t pick = rng.u32() % uint32_t(eo.prim_num) + uint32_t(eo.prim_offset);
+        const int eprim = pick < sc.emitter_prims.size() ? sc.emitter_prims[pick] : 0;
+        const V3 hit_pos = o + d * h.t;
+        o = hit_pos;
+        V4 direct{0, 0, 0, 1};
+        const float ux = rng.f(), uy = rng.f();
+        V3 sd = emitter_sample(sc, em, hit_pos, direct, direct_pdf, ux, uy, eprim) - hit_pos;
+        const float dist = std::sqrt(len2(sd));
+        sd = sd * (1.f / dist);
+        V4 rdc = L;
+        if (eid != 0) {
+            cnt.shadow++;
+            if (unoccluded(sc, hit_pos, sd, dist - EPS)) {
+                const float mis = direct_pdf + bsdf_pdf(sc, m, it.n, sd, d) * float(em.is_sphere != 0);
+                rdc = rdc + thp * direct * bsdf_eval(sc, m, it.n, sd, d) * (mis > EPS ? 1.f / mis : 0.f);
+            }
+        }
+        const float sa = ob.inv_area * h.t * h.t / std::max(std::fabs(dot(d, shading_normal(it.n))), 1e-4f);
+        const float w = pdf / (pdf + sa * float(emitter_id > 0) * float(bounce > 0) * float(!delta));
+        L = (thp * emitter_eval(sc.emitters[emitter_id], d, it.n)) * w + rdc;
+        int lobe = 0;
+        d = bsdf_sample(sc, m, d, it.n, thp, pdf, rng, lobe);
+        delta = (lobe & LOBE_SPECULAR) != 0;
+        if (bounce + 1 >= max_depth)
+            break;
+        // ---- trace + Russian roulette (fused_closesthit_shader)
+        cnt.closest++;
+        h = closest_hit(sc, o, d);
+        if (h.prim < 0) {
+            L = L + thp * V4{0, 0, 0, 1};
+            break;
+        }
+        it = interaction(sc, h.prim, h.u, h.v);
+        const float mx = std::max(thp.x, std::max(thp.y, thp.z));
+        if (bounce >= RR_BOUNCE && mx < RR_THRESHOLD) {
+            const bool survive = rng.f() < mx && mx > THP_EPS;
+            thp = thp * (survive ? 1.f / mx : 0.f);
+            if (!survive)
+                break;
+        }
+    }
+    return L;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+static thread_local std::string g_err;
+const char *oracle_last_error() { return g_err.c_str(); }
+
+void *oracle_load(const char *path) {
+    try {
+        return load_scene(path);
+    } catch (const std::string &e) {
+        g_err = e;
+        return nullptr;
+    }
+}
+void oracle_free(void *h) { delete static_cast<Scene *>(h); }
+void oracle_config(void *h, int32_t *cfg32) { memcpy(cfg32, static_cast<Scene *>(h)->cfg, sizeof(int32_t) * CPTS_CFG_COUNT); }
+
+/* Adds `spp` samples (accum counters first_accum .. first_accum+spp-1, as render_raw numbers them) to the
+ * running SUM image `sum_rgba` (H*W*4 floats) in sample order with the splat's NaN/Inf scrub
+ * (wavefront_pt.cu:486-487).  max_depth <= 0 uses the scene's.  stats3 (optional): closest, shadow, shaded.
+ * Rows [row0,row1) only (row1 <= 0: all) so that a timing run can take a bounded sample. */
+int oracle_render(void *hs, int first_accum, int spp, int seed_offset, int max_depth, int row0, int row1,
+                  float *sum_rgba, uint64_t *stats3) {
+    Scene &sc = *static_cast<Scene *>(hs);
+    const int W = sc.cfg[CPTS_CFG_WIDTH], H = sc.cfg[CPTS_CFG_HEIGHT];
+    if (max_depth <= 0)
+        max_depth = sc.cfg[CPTS_CFG_MAX_DEPTH];
+    if (row1 <= 0 || row1 > H)
+        row1 = H;
+    uint64_t c0 = 0, c1 = 0, c2 = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c0, c1, c2)
+    for (int y = row0; y < row1; y++) {
+        Counts cnt;
+        for (int x = 0; x < W; x++) {
+            float *dst = sum_rgba + 4 * (size_t(y) * W + x);
+            for (int s = 0; s < spp; s++) {
+                V4 L = trace_path(sc, x, y, first_accum + s, seed_offset, max_depth, cnt);
+                if (std::isnan(L.x) || std::isnan(L.y) || std::isnan(L.z) || std::isinf(L.x) || std::isinf(L.y) || std::isinf(L.z))
+                    L = V4{0, 0, 0, 1};
+                dst[0] += L.x, dst[1] += L.y, dst[2] += L.z, dst[3] += L.w;
+            }
+        }
+        c0 += cnt.closest, c1 += cnt.shadow, c2 += cnt.shaded;
+    }
+    if (stats3)
+        stats3[0] = c0, stats3[1] = c1, stats3[2] = c2;
+    return 0;
+}
+
+/* known-answer helpers */
+void oracle_rng(int seed, int offset, int n, uint32_t *out) {
+    Rng r;
+    r.seed(seed, offset);
+    for (int i = 0; i < n; i++)
+        out[i] = r.u32();
+}
+uint16_t oracle_float_to_half(float f) { return float_to_half(f); }
+float oracle_half_to_float(uint16_t h) { return half_to_float(h); }
+/* closest hit along (o,d): returns primitive index or -1; out4 = {t,u,v,0} */
+int oracle_closest_hit(void *hs, const float *o, const float *d, float *out4) {
+    const Hit h = closest_hit(*static_cast<Scene *>(hs), V3{o[0], o[1], o[2]}, V3{d[0], d[1], d[2]});
+    out4[0] = h.t, out4[1] = h.u, out4[2] = h.v, out4[3] = 0;
+    return h.prim;
+}
+int oracle_unoccluded(void *hs, const float *o, const float *d, float max_dist) {
+    return unoccluded(*static_cast<Scene *>(hs), V3{o[0], o[1], o[2]}, V3{d[0], d[1], d[2]}, max_dist);
+}
+/* brute force over every primitive (no BVH): the traversal's own oracle */
+int oracle_closest_hit_bruteforce(void *hs, const float *o, const float *d, float *out4) {
+    const Scene &sc = *static_cast<Scene *>(hs);
+    Hit h{MAX_DIST, 0, 0, -1};
+    const int P = int(sc.tris.size() / 12);
+    for (int i = 0; i < P; i++) {
+        float u, v;
+        const float t = hit_tri(sc, i, V3{o[0], o[1], o[2]}, V3{d[0], d[1], d[2]}, u, v, INFINITY);
+        if (t > EPS && t < h.t)
+            h = Hit{t, u, v, i};
+    }
+    out4[0] = h.t, out4[1] = h.u, out4[2] = h.v, out4[3] = 0;
+    return h.prim;
+}
+}

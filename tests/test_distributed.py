@@ -1,0 +1,61 @@
+"""world_size-2 gloo test of the multi-GPU host logic (sample split + one sum-reduce of the accumulator).
+The per-rank renderer is stood in for by the CPU oracle: the split / reduce code is the same."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cuda_pt_b200  # noqa: F401  (registers the package)
+from cuda_pt_b200 import distributed as cd
+from conftest import GOLDEN, ROOT
+
+
+def test_sample_range_partitions_exactly():
+    for total in (0, 1, 7, 64, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                base, n = cd.sample_range(total, world, r)
+                seen += list(range(base + 1, base + n + 1))
+            assert seen == list(range(1, total + 1))
+            counts = [cd.sample_range(total, world, r)[1] for r in range(world)]
+            assert max(counts) - min(counts) <= 1
+    with pytest.raises(ValueError):
+        cd.sample_range(4, 2, 2)
+    assert cd.reference_seed_offset(3, 10) == 3 * 4201 + 10
+
+
+def _worker(rank, world, port, total_spp, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import oracle
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    base, n = cd.sample_range(total_spp, world, rank)
+    s = np.zeros((256, 256, 4), np.float32)
+    if n:
+        sc.render(n, first_accum=base + 1, rows=(96, 128), sum_image=s)
+    local_mean = torch.from_numpy(s / max(n, 1))  # what PythonRenderer.render() returns on this rank
+    t = torch.from_numpy(s.copy())
+    cd.reduce_sum_(t)
+    mean, spp = cd.reduce_rendered_image(local_mean, n)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sum.npy"), t.numpy())
+        np.save(os.path.join(out_dir, "mean.npy"), mean.numpy())
+        assert spp == total_spp
+    dist.destroy_process_group()
+
+
+def test_two_rank_sample_split_reproduces_single_process(tmp_path):
+    import oracle
+    total = 5
+    mp.spawn(_worker, args=(2, 29517, total, str(tmp_path)), nprocs=2, join=True)
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    one, _ = sc.render(total, rows=(96, 128))
+    two = np.load(tmp_path / "sum.npy")
+    assert np.allclose(two, one, rtol=1e-6, atol=1e-7)          # same paths, fp32 summation order differs
+    assert np.allclose(np.load(tmp_path / "mean.npy"), one / total, rtol=1e-5, atol=1e-6)

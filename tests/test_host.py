@@ -1,0 +1,186 @@
+"""Host-side logic that needs no GPU: C-ABI surface, scene loaders, container round trips, error behaviour."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cuda_pt_b200 as cpt
+import oracle
+from conftest import GOLDEN, ROOT, SCENES, have_meshes, have_vader
+from cpts import read_cpts
+
+needs_meshes = pytest.mark.skipif(not have_meshes(), reason="scene meshes not present (copied from the reference by build())")
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cpt_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cpt_b200_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    L = C.CDLL(os.path.join(ROOT, "cuda-pt_b200", "libcpt_b200.so"))
+    missing = [n for n in declared if not hasattr(L, n)]
+    assert not missing, missing
+    bound = set(cpt.lib()._signatures)
+    assert set(declared) == bound, (set(declared) ^ bound)
+    assert b"sm_100a" in cpt.lib().cpt_b200_version()
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package or include/ may reference it."""
+    bad = []
+    for base in ("cuda-pt_b200", "include"):
+        for dp, _dn, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"liboracle|cpt_oracle|import oracle|oracle/|tools\.oracle", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_renderer_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sc = cpt.Scene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    with pytest.raises(cpt.CptError, match="no CUDA device"):
+        cpt.WavefrontRenderer(sc, 0, 0)
+
+
+def test_cpts_roundtrip_and_reader(tmp_path):
+    src = os.path.join(GOLDEN, "cbox_mats_256.cpts")
+    sc = cpt.Scene(src)
+    out = str(tmp_path / "copy.cpts")
+    sc.save(out)
+    a, b = read_cpts(src), read_cpts(out)
+    assert set(a) == set(b)
+    for k in a:
+        assert a[k].tobytes() == b[k].tobytes(), k  # bytes: node words hold ints that read as NaN floats
+    cfg = sc.config
+    assert (cfg["width"], cfg["height"], cfg["spp"], cfg["max_depth"], cfg["renderer"]) == (256, 256, 64, 8, 1)
+    assert a["cie_xyz"].shape == (471, 4) and a["d65_spd"].shape == (531,)
+
+
+def test_scene_errors(tmp_path):
+    with pytest.raises(cpt.CptError, match="cannot open"):
+        cpt.Scene(str(tmp_path / "missing.cpts"))
+    bad = tmp_path / "bad.cpts"
+    bad.write_bytes(b"NOTASCENE" * 10)
+    with pytest.raises(cpt.CptError, match="bad magic"):
+        cpt.Scene(str(bad))
+    with pytest.raises(cpt.CptError, match="cannot open scene file"):
+        cpt.Scene(str(tmp_path / "missing.xml"))
+    x = tmp_path / "v.xml"
+    x.write_text('<scene version="1.1"><sensor/></scene>')
+    with pytest.raises(cpt.CptError, match="version"):
+        cpt.Scene(str(x))
+    x.write_text('<scene version="1.2"><sensor><film/></sensor><brdf type="lambertian" id="a"/>'
+                 '<shape type="sphere"><ref type="material" id="a"/></shape></scene>')
+    with pytest.raises(cpt.CptError, match="TRIANGLE_ONLY"):
+        cpt.Scene(str(x))
+    x.write_text('<scene version="1.2"><sensor><film/></sensor><brdf type="lambertian" id="a">'
+                 '<ref type="texture" id="t"/></brdf></scene>')
+    with pytest.raises(cpt.CptError, match="texture"):
+        cpt.Scene(str(x))
+    x.write_text('<scene version="1.2"><sensor></scene>')
+    with pytest.raises(cpt.CptError, match="xml"):
+        cpt.Scene(str(x))
+    # truncated container
+    data = open(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), "rb").read()
+    t = tmp_path / "trunc.cpts"
+    t.write_bytes(data[: len(data) // 2])
+    with pytest.raises(cpt.CptError):
+        cpt.Scene(str(t))
+
+
+@needs_meshes
+def test_xml_loader_matches_reference_loader(tmp_path):
+    """Our XML loader vs the flat scene the reference's loader produced for the same XML: identical camera,
+    configuration, materials, emitters and object table; an equivalent (not identical) BVH."""
+    ours = cpt.Scene(os.path.join(SCENES, "cbox_wfpt_256.xml"))
+    out = str(tmp_path / "ours.cpts")
+    ours.save(out)
+    a, r = read_cpts(out), read_cpts(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    assert np.array_equal(a["camera"].view(np.uint32), r["camera"].view(np.uint32))  # bit-identical DeviceCamera
+    for k in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12):
+        assert a["config"][k] == r["config"][k], k
+    assert np.array_equal(a["bsdfs"][:, :108], r["bsdfs"][:, :108])
+    assert np.array_equal(a["emitters"], r["emitters"])
+    # object table: same materials / emitters / primitive counts / inverse areas (prim_offset differs: no SBVH split)
+    oa, orf = a["objects"].view(np.int32).reshape(-1, 4), r["objects"].view(np.int32).reshape(-1, 4)
+    assert np.array_equal(oa[:, [0, 2, 3]], orf[:, [0, 2, 3]])
+    assert a["config"][13] == 36 and r["config"][13] == 53  # the reference's SBVH duplicates 17 references
+    # same geometry: every triangle of ours appears in the reference's (duplicated) set
+    def tri_set(d):
+        t = np.concatenate([d["v0"], d["v1"], d["v2"]], axis=1)
+        return {tuple(np.round(row, 5)) for row in t}
+    assert tri_set(a) <= tri_set(r)
+    # emitter primitive map points at the light's two triangles
+    light = int(np.nonzero((oa[:, 0] & 0xFFFF) == 1)[0][0])
+    for p in a["emitter_prims"]:
+        assert (a["obj_idxs"][p] & 0xFFFFF) == light
+
+
+@needs_meshes
+def test_xml_loader_bvh_is_a_correct_reference_format_tree(tmp_path):
+    """The BVH our loader emits is traversed by the oracle's restatement of the reference traversal and must find
+    the brute-force closest hit (every BSDF scene: no SBVH, so the cached-phase quirk cannot drop hits...)"""
+    ours = cpt.Scene(os.path.join(SCENES, "cbox_mats_wfpt_256.xml")) if False else cpt.Scene(os.path.join(SCENES, "cbox_wfpt_256.xml"))
+    out = str(tmp_path / "ours.cpts")
+    ours.save(out)
+    sc = oracle.OracleScene(out)
+    rs = np.random.RandomState(3)
+    o = np.array([2.78, 2.73, -8.0], np.float32)
+    for _ in range(600):
+        d = np.array([rs.uniform(-0.35, 0.35), rs.uniform(-0.35, 0.35), 1.0], np.float32)
+        d /= np.linalg.norm(d)
+        p0, h0 = sc.closest_hit(o, d)
+        p1, h1 = sc.closest_hit(o, d, brute=True)
+        assert (p0 < 0) == (p1 < 0)
+        if p1 >= 0:
+            assert h0[0] <= h1[0] * (1 + 1e-6) + 1e-6 and h0[0] >= h1[0] * (1 - 1e-6) - 1e-6
+    d = read_cpts(out)
+    nodes = d["nodes"].reshape(-1, 2, 4)
+    cnt = nodes[:, 1, 3].view(np.int32)
+    base = nodes[:, 0, 3].view(np.int32)
+    leaves = cnt > 0
+    assert cnt[leaves].sum() == d["config"][13]                      # every primitive in exactly one leaf
+    assert cnt[leaves].max() <= d["config"][17]                      # max_node_num honoured
+    assert sorted(base[leaves]) == list(np.cumsum(np.r_[0, cnt[leaves]][:-1]))  # contiguous DFS-ordered ranges
+    assert -cnt[0] == len(cnt)                                       # root skip offset spans the whole tree
+    assert len(d["cache_nodes"]) <= 255
+
+
+@needs_meshes
+def test_render_of_our_loader_scene_matches_reference_statistically(tmp_path):
+    """Oracle on OUR loader's scene vs the reference frame: different BVH and emitter-primitive order give a
+    different noise realisation of the same integrand."""
+    ours = cpt.Scene(os.path.join(SCENES, "cbox_mats_wfpt_256.xml")) if False else cpt.Scene(os.path.join(SCENES, "cbox_wfpt_256.xml"))
+    out = str(tmp_path / "ours.cpts")
+    ours.save(out)
+    s, _ = oracle.OracleScene(out).render(16)
+    ref = np.fromfile(os.path.join(GOLDEN, "cbox_wfpt_256_wfpt_f0064.bin"), dtype=np.float32).reshape(256, 256, 4)
+    m = s / 16
+    # robust block statistics (median luminance per 32x32 block); the blocks showing the tall box and the caustic
+    # it throws on the ceiling are excluded: the reference drops some of that box's triangles (test_oracle.py),
+    # a scene built by our loader does not
+    bm = lambda x: np.median(x[:, :, :3].mean(-1).reshape(8, 32, 8, 32).transpose(0, 2, 1, 3).reshape(8, 8, -1), axis=-1)
+    a, b = bm(m), bm(ref)
+    mask = np.ones((8, 8), bool)
+    mask[1:5, 1:4] = False
+    assert np.abs(a[mask] - b[mask]).max() < 0.05
+    assert abs(a[mask].mean() - b[mask].mean()) < 0.01
+
+
+@pytest.mark.skipif(not have_vader(), reason="vader mesh not present")
+def test_xml_loader_vader_scale():
+    sc = cpt.Scene(os.path.join(SCENES, "vader_wfpt_1080p.xml"))
+    cfg = sc.config
+    assert (cfg["width"], cfg["height"], cfg["spp"], cfg["max_depth"]) == (1920, 1080, 1024, 16)
+    assert cfg["num_prims"] == 320328 and cfg["num_emitters"] == 2 and cfg["num_bsdfs"] == 3
+    assert cfg["num_nodes"] < 2 * cfg["num_prims"] and cfg["num_cache"] == 15
+    cam = sc.camera
+    assert abs(cam[16] - 0.19) < 1e-7 and abs(cam[17] - 5.4) < 1e-6  # thin lens
+    sc.set_film(256, 128)
+    assert sc.config["width"] == 256 and sc.camera[13] == 128.0 and sc.camera[14] == 64.0

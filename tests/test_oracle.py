@@ -1,0 +1,134 @@
+"""CPU oracle: known-answer tests of the exact integer machinery and the pin against the reference's own
+frames (tests/golden/ref, written by the unmodified reference on a B200)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, load_frame, rel_l2
+
+
+def test_rng_known_answers():
+    # TinySampler streams derived from the definition in src/core/sampler.cuh:36-72
+    assert [int(x) for x in oracle.rng_stream(0, 0, 6)] == [0x0EFD9DC6, 0x2819C65C, 0x1999265B, 0xBF330D0E, 0x26601102, 0x6B7B3470]
+    assert [int(x) for x in oracle.rng_stream(11467, 0, 4)] == [0xB88E1763, 0x485F7AC5, 0x0084B8E9, 0xAD03324A]
+    # negative seed + offset sign-extends into the high word
+    assert [int(x) for x in oracle.rng_stream(-5, 0, 3)] == [0x0025F71C, 0x53CED122, 0xB4D66653]
+    assert (oracle.rng_stream(3, 4, 8) == oracle.rng_stream(7, 0, 8)).all()
+    # int32 wrap-around of seed + offset
+    assert (oracle.rng_stream(2**31 - 1, 1, 4) == oracle.rng_stream(-2**31, 0, 4)).all()
+
+
+def test_half_conversion_round_to_nearest_even():
+    L = oracle.lib()
+    table = {0.0: 0x0000, 1.0: 0x3C00, -2.0: 0xC000, 65504.0: 0x7BFF, 65520.0: 0x7C00, 5.9604645e-08: 0x0001,
+             2.9802322e-08: 0x0000, 0.333251953125: 0x3555, 1.00048828125: 0x3C00, 1.00146484375: 0x3C02}
+    for f, h in table.items():
+        assert L.oracle_float_to_half(f) == h, (f, hex(h))
+    for h in (0x0001, 0x03FF, 0x0400, 0x3555, 0x7BFF, 0xC000, 0x8001):
+        assert L.oracle_float_to_half(L.oracle_half_to_float(h)) == h
+    # numpy agrees on a random sweep
+    rs = np.random.RandomState(0)
+    xs = np.concatenate([rs.uniform(-70000, 70000, 2000), rs.normal(0, 1e-4, 2000), rs.normal(0, 1, 2000)]).astype(np.float32)
+    ours = np.array([L.oracle_float_to_half(float(x)) for x in xs], dtype=np.uint16)
+    with np.errstate(over="ignore"):
+        ref = xs.astype(np.float16).view(np.uint16)
+    assert (ours == ref).all()
+
+
+@pytest.mark.parametrize("scene,exact", [("cbox_mats_256.cpts", True), ("cbox_wfpt_256.cpts", False)])
+def test_bvh_traversal_vs_bruteforce(scene, exact):
+    """Stackless skip-offset DFS + cached fp16 phase against a loop over every primitive.
+
+    On the BVH scene the two agree exactly.  On the SBVH cornell scene the reference's cached phase starts global
+    traversal at the FIRST fp16 frontier node the ray enters and never revisits earlier DFS nodes
+    (tracing_func.cuh:124-142), which drops real hits (the triangular holes in the tall box of the reference's
+    own image, tests/golden/ref/cbox_wfpt_256_wfpt_f0064.bin).  That behaviour is part of the parity target, so
+    here it is only bounded: the traversal never invents a closer hit and agrees for most rays."""
+    sc = oracle.OracleScene(os.path.join(GOLDEN, scene))
+    rs = np.random.RandomState(1)
+    o = np.array([2.78, 2.73, -8.0], np.float32)
+    farther = 0
+    n = 1500
+    for _ in range(n):
+        d = np.array([rs.uniform(-0.35, 0.35), rs.uniform(-0.35, 0.35), 1.0], np.float32)
+        d /= np.linalg.norm(d)
+        p0, h0 = sc.closest_hit(o, d)
+        p1, h1 = sc.closest_hit(o, d, brute=True)
+        if exact:
+            assert p0 == p1 and np.array_equal(h0, h1)
+        else:
+            if p1 < 0:  # the ray escapes the scene: both must miss
+                assert p0 < 0
+                continue
+            if p0 < 0 or h0[0] > h1[0]:
+                farther += 1
+            else:
+                assert h0[0] == h1[0]  # same triangle (possibly another SBVH duplicate of it)
+    assert farther <= 0.1 * n
+    if exact:
+        assert farther == 0
+    # occlusion agrees with closest hit
+    for _ in range(200):
+        d = np.array([rs.uniform(-0.3, 0.3), rs.uniform(-0.3, 0.3), 1.0], np.float32)
+        d /= np.linalg.norm(d)
+        p, h = sc.closest_hit(o, d)
+        if p >= 0 and h[0] > 0.1:
+            assert sc.unoccluded(o, d, h[0] * 0.5)
+            if exact:
+                assert not sc.unoccluded(o, d, h[0] * 1.5)
+
+
+@pytest.mark.parametrize("frames", [1, 4, 64])
+def test_oracle_pinned_to_reference_cornell(frames):
+    """BASELINE config C0 (cornell box 256x256, seed 0): same per-pixel sample streams as the reference.
+    The GPU reference uses approximate fast-math, so this is a tolerance pin (bit parity is a GPU test)."""
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    s, st = sc.render(frames)
+    ref = load_frame(f"cbox_wfpt_256_wfpt_f{frames:04d}.bin")
+    mean = s / frames
+    assert rel_l2(mean, ref) < 5e-4
+    d = np.abs(mean[..., :3] - ref[..., :3]).max(-1)
+    assert np.median(d) < 1e-6
+    assert (d > 1e-3 * np.maximum(ref[..., :3].max(-1), 1e-3)).mean() < 5e-3
+    # 6.56 traversals per pixel-sample on this scene
+    assert 6.4 < st["rays"] / st["samples"] < 6.7
+
+
+def test_oracle_seed_offset_and_sample_numbering():
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    s, _ = sc.render(3, seed_offset=7)
+    ref = load_frame("cbox_wfpt_256_s7_wfpt_f0003.bin")
+    assert rel_l2(s / 3, ref) < 5e-4
+    # samples are independent and additive: (1..2) + (3) == (1..3) up to fp32 summation order
+    a, _ = sc.render(2, seed_offset=7)
+    a, _ = sc.render(1, seed_offset=7, first_accum=3, sum_image=a)
+    assert np.allclose(a, s, rtol=1e-6, atol=1e-7)
+    # seed_offset + accum * 11467 is the only seed input: shifting both is the identity
+    b, _ = sc.render(1, seed_offset=7 + 11467, first_accum=1)
+    c, _ = sc.render(1, seed_offset=7, first_accum=2)
+    assert np.array_equal(b, c)
+
+
+def test_oracle_pinned_to_reference_all_materials():
+    """Every BSDF family + point/area emitters.  Glass / dispersion / near-specular GGX paths are
+    ill-conditioned (delta-lobe thresholds, grazing-angle slope sampling), so the pin is on robust statistics."""
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_mats_256.cpts"))
+    s, st = sc.render(16)
+    ref = load_frame("cbox_mats_256_wfpt_f0016.bin")
+    mean = s / 16
+    d = np.abs(mean[..., :3] - ref[..., :3]).max(-1)
+    assert np.median(d) < 1e-6
+    assert (d < 1e-3 * np.maximum(ref[..., :3].max(-1), 1e-2)).mean() > 0.93
+    calm = (ref[..., :3].max(-1) < 2) & (mean[..., :3].max(-1) < 2)
+    assert abs(mean[calm][:, :3].mean() - ref[calm][:, :3].mean()) < 0.02 * ref[calm][:, :3].mean()
+
+
+def test_oracle_rows_subset_matches_full():
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    full, _ = sc.render(2)
+    part, st = sc.render(2, rows=(100, 132))
+    assert np.array_equal(part[100:132], full[100:132])
+    assert not part[:100].any() and not part[132:].any()
+    assert st["samples"] == 32 * 256 * 2
