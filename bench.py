@@ -296,9 +296,12 @@ def main():
         n = kt1[k]["launches"] - kt0[k]["launches"]
         if n == 0 or dms <= 0:
             continue
-        gbs = units * BYTES_PER_UNIT[k] / (dms * 1e-3) / 1e9
+        bpu = BYTES_PER_UNIT[k]
+        if k == "splat":  # one launch folds S samples per pixel: S x 16 B radiance + 48 B accumulator/output per pixel
+            units, bpu = n * W * H, 16 * S + 48
+        gbs = units * bpu / (dms * 1e-3) / 1e9
         stages[k] = {"ms_per_step": dms / K, "launches_per_step": n / K, "units_per_step": units / K,
-                     "bytes_per_unit": BYTES_PER_UNIT[k], "achieved_gbs": gbs, "frac": gbs / peak,
+                     "bytes_per_unit": bpu, "achieved_gbs": gbs, "frac": gbs / peak,
                      "avg_launch_ms": dms / n, "share_of_step": dms / max(total_kernel_ms, 1e-9)}
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")

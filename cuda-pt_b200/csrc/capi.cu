@@ -243,8 +243,8 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
         if (k == "samples_in_flight")
             r->impl->set_samples_in_flight(int(value));
         else if (k == "traversal") {
-            if (value != 0 && value != 1)
-                throw std::runtime_error("traversal must be 0 (ordered) or 1 (dfs)");
+            if (value < 0 || value > 3)
+                throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (while-while) or 3 (warp vote)");
             r->impl->set_traversal(int(value));
         } else if (k == "kernel_timing") {
             r->impl->set_kernel_timing(value != 0);

@@ -126,6 +126,119 @@ constexpr int kStackSize = 48;
 constexpr int kLeafCountShift = 26;
 constexpr int kLeafBaseMask = (1 << kLeafCountShift) - 1;
 
+constexpr int kTraversalDone = 0x7fffffff; // "cur" value meaning: stack exhausted
+
+PT_DEV Hit closest_hit_ww(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
+    Hit h{kMaxDist, 0.f, 0.f, -1, 0};
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int sp = 0;
+    int cur = sc.wroot;
+    const float inf = __int_as_float(0x7f800000);
+    // "while-while": all lanes of a warp descend inner nodes together until each holds a leaf (or is done),
+    // then all test triangles together; keeps the two code paths from alternating lane by lane
+    while (cur != kTraversalDone) {
+        while (cur >= 0 && cur != kTraversalDone) {
+            const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
+                         b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+            float t0, t1;
+            const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < h.t &&
+                            __float_as_int(a1.w) > start;
+            const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < h.t &&
+                            __float_as_int(b1.w) > start;
+            const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+            if (h0 && h1) {
+                const bool swap = t1 < t0;
+                stack_ref[sp] = swap ? r0 : r1;
+                stack_t[sp] = swap ? t0 : t1;
+                ++sp;
+                cur = swap ? r1 : r0;
+            } else if (h0 || h1) {
+                cur = h0 ? r0 : r1;
+            } else {
+                cur = kTraversalDone;
+                while (sp > 0) {
+                    --sp;
+                    if (stack_t[sp] < h.t) {
+                        cur = stack_ref[sp];
+                        break;
+                    }
+                }
+            }
+        }
+        if (cur == kTraversalDone)
+            break;
+        {
+            const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+            for (int idx = base; idx < base + cnt; idx++) {
+                float u, v;
+                const float dist = hit_triangle(sc.tris, idx, o, d, u, v, inf);
+                // equal distances: the reference keeps the first hit in DFS order == the smaller primitive index
+                const bool valid = dist > kEps && (dist < h.t || (dist == h.t && idx < h.prim));
+                h.t = valid ? dist : h.t;
+                h.u = valid ? u : h.u;
+                h.v = valid ? v : h.v;
+                h.prim = valid ? idx : h.prim;
+            }
+        }
+        cur = kTraversalDone;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] < h.t) {
+                cur = stack_ref[sp];
+                break;
+            }
+        }
+    }
+    if (h.prim >= 0)
+        h.obj_word = __ldg(sc.obj_idxs + h.prim);
+    return h;
+}
+
+PT_DEV bool unoccluded_ww(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist) {
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, max_dist, sc.num_nodes);
+    if (start >= sc.num_nodes)
+        return true;
+    int stack_ref[kStackSize];
+    int sp = 0;
+    int cur = sc.wroot;
+    while (cur != kTraversalDone) {
+        while (cur >= 0 && cur != kTraversalDone) {
+            const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
+                         b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+            float t0, t1;
+            const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < max_dist &&
+                            __float_as_int(a1.w) > start;
+            const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < max_dist &&
+                            __float_as_int(b1.w) > start;
+            const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+            if (h0 && h1) {
+                stack_ref[sp++] = r1;
+                cur = r0;
+            } else if (h0 || h1) {
+                cur = h0 ? r0 : r1;
+            } else {
+                cur = sp > 0 ? stack_ref[--sp] : kTraversalDone;
+            }
+        }
+        if (cur == kTraversalDone)
+            break;
+        const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+        for (int idx = base; idx < base + cnt; idx++) {
+            float u, v;
+            const float dist = hit_triangle(sc.tris, idx, o, d, u, v, max_dist);
+            if (dist > kEps)
+                return false;
+        }
+        cur = sp > 0 ? stack_ref[--sp] : kTraversalDone;
+    }
+    return true;
+}
+
+// variant with one inner-or-leaf step per loop iteration (lanes alternate freely between the two paths)
 PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
     Hit h{kMaxDist, 0.f, 0.f, -1, 0};
     const V3 inv_d = rcp3(d), o_div = o * inv_d;
@@ -162,14 +275,14 @@ PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, 
             for (int idx = base; idx < base + cnt; idx++) {
                 float u, v;
                 const float dist = hit_triangle(sc.tris, idx, o, d, u, v, inf);
-                const bool valid = dist > kEps && dist < h.t;
+                // equal distances: the reference keeps the first hit in DFS order == the smaller primitive index
+                const bool valid = dist > kEps && (dist < h.t || (dist == h.t && idx < h.prim));
                 h.t = valid ? dist : h.t;
                 h.u = valid ? u : h.u;
                 h.v = valid ? v : h.v;
                 h.prim = valid ? idx : h.prim;
             }
         }
-        // pop the next entry that can still beat the current closest hit
         bool found = false;
         while (sp > 0) {
             --sp;
@@ -230,17 +343,175 @@ PT_DEV bool unoccluded_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, 
     return true;
 }
 
-template <bool ORDERED> PT_DEV Hit closest_hit(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
-    if constexpr (ORDERED)
-        return closest_hit_ordered(sc, s_cached, o, d);
-    else
-        return closest_hit_dfs(sc, s_cached, o, d);
+// ---------------------------------------------------------------------------------------------
+// "vote" variant: warp-synchronous step scheduler.  Every lane is either at an inner pair node or inside a
+// leaf (one triangle per step).  Each iteration the warp ballots which of the two step kinds more lanes are
+// waiting for and executes only that one, so a single code path runs per iteration at >= 50 % lane
+// utilisation of the lanes still alive, instead of both paths back to back.  Must be called by all 32 lanes
+// (lanes without a ray pass active = false).  Same boxes, same tests, same tie rule as the other ordered modes.
+// ---------------------------------------------------------------------------------------------
+PT_DEV Hit closest_hit_vote(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, bool active) {
+    Hit h{kMaxDist, 0.f, 0.f, -1, 0};
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    const int start = active ? cached_entry(s_cached, sc.num_cache, inv_d, o_div, kMaxDist, 0) : 0;
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int sp = 0;
+    int cur = sc.wroot, ti = 0, te = 0;
+    const float inf = __int_as_float(0x7f800000);
+    while (true) {
+        const bool want_inner = active && ti >= te, want_tri = active && ti < te;
+        const unsigned mi = __ballot_sync(0xffffffffu, want_inner), mt = __ballot_sync(0xffffffffu, want_tri);
+        if ((mi | mt) == 0u)
+            break;
+        int next = kTraversalDone; // set when this lane has to move on to a new node reference
+        bool advance = false;
+        if (__popc(mi) >= __popc(mt)) {
+            if (want_inner) {
+                const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
+                             b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+                float t0, t1;
+                const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < h.t &&
+                                __float_as_int(a1.w) > start;
+                const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < h.t &&
+                                __float_as_int(b1.w) > start;
+                const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+                advance = true;
+                if (h0 && h1) {
+                    const bool swap = t1 < t0;
+                    stack_ref[sp] = swap ? r0 : r1;
+                    stack_t[sp] = swap ? t0 : t1;
+                    ++sp;
+                    next = swap ? r1 : r0;
+                } else if (h0 || h1) {
+                    next = h0 ? r0 : r1;
+                }
+            }
+        } else if (want_tri) {
+            float u, v;
+            const float dist = hit_triangle(sc.tris, ti, o, d, u, v, inf);
+            const bool valid = dist > kEps && (dist < h.t || (dist == h.t && ti < h.prim));
+            h.t = valid ? dist : h.t;
+            h.u = valid ? u : h.u;
+            h.v = valid ? v : h.v;
+            h.prim = valid ? ti : h.prim;
+            ++ti;
+            advance = ti >= te;
+        }
+        if (advance) {
+            if (next == kTraversalDone) { // pop the next entry that can still beat the closest hit
+                while (sp > 0) {
+                    --sp;
+                    if (stack_t[sp] < h.t) {
+                        next = stack_ref[sp];
+                        break;
+                    }
+                }
+            }
+            if (next == kTraversalDone) {
+                active = false;
+            } else if (next < 0) {
+                const int packed = ~next;
+                ti = packed & kLeafBaseMask;
+                te = ti + (packed >> kLeafCountShift);
+            } else {
+                cur = next;
+                ti = te = 0;
+            }
+        }
+    }
+    if (h.prim >= 0)
+        h.obj_word = __ldg(sc.obj_idxs + h.prim);
+    return h;
 }
-template <bool ORDERED> PT_DEV bool unoccluded(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist) {
-    if constexpr (ORDERED)
-        return unoccluded_ordered(sc, s_cached, o, d, max_dist);
+
+PT_DEV bool unoccluded_vote(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist, bool active) {
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    const int start = active ? cached_entry(s_cached, sc.num_cache, inv_d, o_div, max_dist, sc.num_nodes) : sc.num_nodes;
+    bool clear = true;
+    active = active && start < sc.num_nodes;
+    int stack_ref[kStackSize];
+    int sp = 0;
+    int cur = sc.wroot, ti = 0, te = 0;
+    while (true) {
+        const bool want_inner = active && ti >= te, want_tri = active && ti < te;
+        const unsigned mi = __ballot_sync(0xffffffffu, want_inner), mt = __ballot_sync(0xffffffffu, want_tri);
+        if ((mi | mt) == 0u)
+            break;
+        int next = kTraversalDone;
+        bool advance = false;
+        if (__popc(mi) >= __popc(mt)) {
+            if (want_inner) {
+                const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
+                             b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+                float t0, t1;
+                const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < max_dist &&
+                                __float_as_int(a1.w) > start;
+                const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < max_dist &&
+                                __float_as_int(b1.w) > start;
+                const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+                advance = true;
+                if (h0 && h1) {
+                    stack_ref[sp++] = r1;
+                    next = r0;
+                } else if (h0 || h1) {
+                    next = h0 ? r0 : r1;
+                }
+            }
+        } else if (want_tri) {
+            float u, v;
+            const float dist = hit_triangle(sc.tris, ti, o, d, u, v, max_dist);
+            if (dist > kEps) {
+                clear = false;
+                active = false;
+            }
+            ++ti;
+            advance = active && ti >= te;
+        }
+        if (advance) {
+            if (next == kTraversalDone && sp > 0)
+                next = stack_ref[--sp];
+            if (next == kTraversalDone) {
+                active = false;
+            } else if (next < 0) {
+                const int packed = ~next;
+                ti = packed & kLeafBaseMask;
+                te = ti + (packed >> kLeafCountShift);
+            } else {
+                cur = next;
+                ti = te = 0;
+            }
+        }
+    }
+    return clear;
+}
+
+// MODE: 0 ordered (step per iteration), 1 reference DFS order, 2 ordered "while-while", 3 ordered warp-vote scheduler.
+// `active` = this lane carries a ray; MODE 3 is warp-synchronous and must be called by all 32 lanes.
+template <int MODE> PT_DEV Hit closest_hit(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, bool active = true) {
+    if constexpr (MODE == 3)
+        return closest_hit_vote(sc, s_cached, o, d, active);
+    Hit miss{kMaxDist, 0.f, 0.f, -1, 0};
+    if (!active)
+        return miss;
+    if constexpr (MODE == 0)
+        return closest_hit_ordered(sc, s_cached, o, d);
+    else if constexpr (MODE == 1)
+        return closest_hit_dfs(sc, s_cached, o, d);
     else
+        return closest_hit_ww(sc, s_cached, o, d);
+}
+template <int MODE> PT_DEV bool unoccluded(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist, bool active = true) {
+    if constexpr (MODE == 3)
+        return unoccluded_vote(sc, s_cached, o, d, max_dist, active);
+    if (!active)
+        return true;
+    if constexpr (MODE == 0)
+        return unoccluded_ordered(sc, s_cached, o, d, max_dist);
+    else if constexpr (MODE == 1)
         return unoccluded_dfs(sc, s_cached, o, d, max_dist);
+    else
+        return unoccluded_ww(sc, s_cached, o, d, max_dist);
 }
 
 } // namespace cptb

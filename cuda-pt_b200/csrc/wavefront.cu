@@ -34,6 +34,7 @@ namespace cptb {
     do {                                                                                                               \
         cudaError_t err__ = (expr);                                                                                    \
         if (err__ != cudaSuccess) {                                                                                    \
+            cudaGetLastError(); /* clear the non-sticky error so that later calls do not re-report it */              \
             char buf__[512];                                                                                           \
             snprintf(buf__, sizeof(buf__), "CUDA error %s at %s:%d (%s)", cudaGetErrorString(err__), __FILE__,         \
                      __LINE__, #expr);                                                                                 \
@@ -105,7 +106,7 @@ __device__ __forceinline__ float solid_angle_pdf(float inv_area, V3 normal, V3 i
 // k_raygen — reference: raygen_primary_hit_shader (wavefront_pt.cu:71-133)
 // one warp = one 8x4 pixel tile of one sample
 // ------------------------------------------------------------------------------------------------
-template <bool ORDERED>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock)
     k_raygen(DevScene sc, CameraPOD cam, PathState st, BatchParams bp, uint32_t *q_out, int *q_count, int *work) {
     extern __shared__ uint4 s_cached[];
@@ -120,17 +121,19 @@ __global__ void __launch_bounds__(kBlock)
         const bool inside = px < bp.W && py < bp.H;
         bool hit_any = false;
         uint32_t slot = 0;
+        V3 o{0, 0, 0}, d{0, 0, 1};
         if (inside) {
             const int gidx = px + py * bp.W;
             slot = uint32_t(s) * uint32_t(bp.P) + uint32_t(gidx);
             Rng rng;
             rng.seed(gidx, bp.seed_offset + (bp.first_accum + s) * kSeedScaler);
-            V3 o, d;
             camera_ray(cam, px, py, rng, o, d);
             st.thp[slot] = make_float4(1, 1, 1, 1);
             st.pdf[slot] = 1.f;
             st.rng[slot] = make_uint2(rng.d0, rng.d1);
-            const Hit h = closest_hit<ORDERED>(sc, s_cached, o, d);
+        }
+        const Hit h = closest_hit<MODE>(sc, s_cached, o, d, inside); // all 32 lanes call (warp-synchronous modes)
+        if (inside) {
             uint32_t tag = 0;
             V4 L = mk4(0, 0, 0, 1);
             if (h.prim >= 0) {
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kBlock)
 // ------------------------------------------------------------------------------------------------
 // k_shade — reference: fused_ray_bounce_shader (wavefront_pt.cu:213-314)
 // ------------------------------------------------------------------------------------------------
-template <bool ORDERED>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
                                                   const int *__restrict__ q_count, int *work,
                                                   unsigned long long *shadow_counter, int secondary_bounce) {
@@ -162,73 +165,86 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
     unsigned int local_shadow = 0;
     for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
         const int i = chunk * 32 + lane;
-        if (i >= count)
-            continue;
-        const uint32_t slot = queue[i];
-        V4 thp = from_f4(st.thp[slot]), rdc = from_f4(st.L[slot]);
-        const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
-        const uint2 rs = st.rng[slot];
-        Rng rng{rs.x, rs.y};
-        const float4 it = st.isect[slot];
-        V3 o = xyz(ro), d = xyz(rd);
-        const float hit_t = ro.w;
-        uint32_t tag = __float_as_uint(rd.w);
+        const bool valid = i < count;
+        // ---- part 1 (per lane): load the path, pick an emitter + primitive, sample it, set up the shadow ray
+        uint32_t slot = 0, tag = 0, emit_id = 0;
+        V4 thp = mk4(0, 0, 0, 0), rdc = thp, direct_comp = mk4(0, 0, 0, 1);
+        V3 o{0, 0, 0}, d{0, 0, 1}, hit_pos{0, 0, 0}, sd{0, 0, 1};
+        float4 it = make_float4(0, 0, 1, 0);
+        float hit_t = 0, direct_pdf = 1, emit_len_mis = 1;
+        Rng rng{0, 0};
+        int material_id = 0, emitter_id = 0;
+        ObjectPOD ob{0, 0, 1, 0.f};
+        if (valid) {
+            slot = queue[i];
+            thp = from_f4(st.thp[slot]);
+            rdc = from_f4(st.L[slot]);
+            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            const uint2 rs = st.rng[slot];
+            rng = Rng{rs.x, rs.y};
+            it = st.isect[slot];
+            o = xyz(ro), d = xyz(rd);
+            hit_t = ro.w;
+            tag = __float_as_uint(rd.w);
 
-        int object_id = __ldg(sc.obj_idxs + (tag & TAG_INDEX));
-        object_id = object_id >= 0 ? object_id : -object_id - 1;
-        const ObjectPOD ob = sc.objects[object_id];
-        const int material_id = ob.bsdf_emitter >> 16;
-        const int emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
-        const Material &mat = sc.mats[material_id];
+            int object_id = __ldg(sc.obj_idxs + (tag & TAG_INDEX));
+            object_id = object_id >= 0 ? object_id : -object_id - 1;
+            ob = sc.objects[object_id];
+            material_id = ob.bsdf_emitter >> 16;
+            emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
 
-        float direct_pdf = 1;
-        // ---- pick an emitter (tracing_func.cuh:210-225)
-        int num = sc.num_emitters;
-        num -= emitter_id > 0 && num > 1;
-        uint32_t emit_id = (rng.next_u32() % uint32_t(num)) + 1;
-        emit_id += emit_id >= uint32_t(emitter_id) && emitter_id > 0;
-        direct_pdf = 1.f / float(num);
-        emit_id = emit_id * uint32_t(emitter_id == 0 || num > 1);
-        const EmitterPOD &em = sc.emitters[emit_id];
-        // ---- pick a primitive on it (object.cuh:45-49, wavefront_pt.cu:254-259)
-        const ObjectPOD eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
-        direct_pdf *= eo.inv_area;
-        int emit_prim = int(rng.next_u32() % uint32_t(eo.prim_num)) + eo.prim_offset;
-        emit_prim = __ldg(sc.emitter_prims + emit_prim);
+            // ---- pick an emitter (tracing_func.cuh:210-225)
+            int num = sc.num_emitters;
+            num -= emitter_id > 0 && num > 1;
+            emit_id = (rng.next_u32() % uint32_t(num)) + 1;
+            emit_id += emit_id >= uint32_t(emitter_id) && emitter_id > 0;
+            direct_pdf = 1.f / float(num);
+            emit_id = emit_id * uint32_t(emitter_id == 0 || num > 1);
+            const EmitterPOD &em = sc.emitters[emit_id];
+            // ---- pick a primitive on it (object.cuh:45-49, wavefront_pt.cu:254-259)
+            const ObjectPOD eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
+            direct_pdf *= eo.inv_area;
+            int emit_prim = int(rng.next_u32() % uint32_t(eo.prim_num)) + eo.prim_offset;
+            emit_prim = __ldg(sc.emitter_prims + emit_prim);
 
-        const V3 hit_pos = advance(o, d, hit_t);
-        o = hit_pos;
-        V4 direct_comp = mk4(0, 0, 0, 1);
-        V3 sd = emitter_sample(sc, em, hit_pos, xyz(it), direct_comp, direct_pdf, rng.next2d(), emit_prim) - hit_pos;
-        float emit_len_mis = length(sd);
-        sd *= __frcp_rn(emit_len_mis);
-        // ---- NEE shadow ray + MIS (wavefront_pt.cu:273-289)
-        if (emit_id != 0) {
-            ++local_shadow;
-            if (unoccluded<ORDERED>(sc, s_cached, hit_pos, sd, emit_len_mis - kEps)) {
+            hit_pos = advance(o, d, hit_t);
+            o = hit_pos;
+            sd = emitter_sample(sc, em, hit_pos, xyz(it), direct_comp, direct_pdf, rng.next2d(), emit_prim) - hit_pos;
+            emit_len_mis = length(sd);
+            sd *= __frcp_rn(emit_len_mis);
+        }
+        // ---- part 2 (whole warp): NEE shadow ray (wavefront_pt.cu:273-275)
+        const bool need_shadow = valid && emit_id != 0;
+        local_shadow += need_shadow;
+        const bool visible = unoccluded<MODE>(sc, s_cached, hit_pos, sd, emit_len_mis - kEps, need_shadow);
+        // ---- part 3 (per lane): MIS, emission, BSDF sample, write back
+        if (valid) {
+            const Material &mat = sc.mats[material_id];
+            const EmitterPOD &em = sc.emitters[emit_id];
+            if (need_shadow && visible) { // wavefront_pt.cu:276-289
                 emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
                 rdc += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
                        (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
             }
+            // ---- emission with MIS against light sampling (wavefront_pt.cu:291-302, object.cuh:51-56)
+            float pdf = st.pdf[slot],
+                  emission_weight = pdf / (pdf + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, hit_t) *
+                                                     (emitter_id > 0) * secondary_bounce * ((tag & TAG_DELTA) == 0));
+            const V4 L = (thp * emitter_eval(sc.emitters[emitter_id], d, it, true)) * emission_weight + rdc;
+            st.L[slot] = to_f4(L);
+
+            // ---- sample the next direction (wavefront_pt.cu:304-312)
+            int lobe = LOBE_NONE;
+            d = bsdf_sample(sc, mat, d, it, thp, pdf, rng, lobe);
+            tag &= ~TAG_DELTA;
+            tag |= uint32_t((lobe & LOBE_SPECULAR) > 0) << 30;
+
+            st.thp[slot] = to_f4(thp);
+            st.rng[slot] = make_uint2(rng.d0, rng.d1);
+            st.ray_o[slot] = make_float4(o.x, o.y, o.z, hit_t);
+            st.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
+            st.pdf[slot] = pdf;
         }
-        // ---- emission with MIS against light sampling (wavefront_pt.cu:291-302, object.cuh:51-56)
-        float pdf = st.pdf[slot],
-              emission_weight = pdf / (pdf + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, hit_t) *
-                                                 (emitter_id > 0) * secondary_bounce * ((tag & TAG_DELTA) == 0));
-        const V4 L = (thp * emitter_eval(sc.emitters[emitter_id], d, it, true)) * emission_weight + rdc;
-        st.L[slot] = to_f4(L);
-
-        // ---- sample the next direction (wavefront_pt.cu:304-312)
-        int lobe = LOBE_NONE;
-        d = bsdf_sample(sc, mat, d, it, thp, pdf, rng, lobe);
-        tag &= ~TAG_DELTA;
-        tag |= uint32_t((lobe & LOBE_SPECULAR) > 0) << 30;
-
-        st.thp[slot] = to_f4(thp);
-        st.rng[slot] = make_uint2(rng.d0, rng.d1);
-        st.ray_o[slot] = make_float4(o.x, o.y, o.z, hit_t);
-        st.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
-        st.pdf[slot] = pdf;
     }
     // per-warp ray statistics (Mrays/s accounting)
     for (int off = 16; off > 0; off >>= 1)
@@ -241,7 +257,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
 // k_trace — reference: fused_closesthit_shader (wavefront_pt.cu:141-207) + the sort/lower_bound
 // compaction of wf_path_tracer.cu:197-202
 // ------------------------------------------------------------------------------------------------
-template <bool ORDERED>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
                                                   const int *__restrict__ q_count, int *work, uint32_t *q_next,
                                                   int *q_next_count, int bounce) {
@@ -252,13 +268,17 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
     for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
         const int i = chunk * 32 + lane;
         bool alive = false;
-        uint32_t slot = 0;
-        if (i < count) {
+        uint32_t slot = 0, tag = 0;
+        const bool valid = i < count;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        if (valid) {
             slot = queue[i];
             const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
-            const V3 o = xyz(ro), d = xyz(rd);
-            uint32_t tag = __float_as_uint(rd.w) & 0xd0000000u; // reset(): clear hit flag and hit index
-            const Hit h = closest_hit<ORDERED>(sc, s_cached, o, d);
+            o = xyz(ro), d = xyz(rd);
+            tag = __float_as_uint(rd.w) & 0xd0000000u; // reset(): clear hit flag and hit index
+        }
+        const Hit h = closest_hit<MODE>(sc, s_cached, o, d, valid); // all 32 lanes call
+        if (valid) {
             V4 thp = from_f4(st.thp[slot]);
             if (h.prim >= 0) {
                 tag |= TAG_HIT | TAG_ACTIVE | uint32_t(h.prim);
@@ -649,6 +669,8 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     CUDA_OK(cudaMemsetAsync(d_out_, 0, P * sizeof(float4), stream_));
     m.stats.alloc(4);
     CUDA_OK(cudaMemsetAsync(m.stats.p, 0, 4 * sizeof(unsigned long long), stream_));
+    if (const char *e = getenv("CPTB200_BLOCKS_PER_SM"))
+        blocks_per_sm_ = std::max(1, atoi(e));
     // default number of samples in flight: ~8M paths, at least 1, at most 64
     set_samples_in_flight(int(std::min<size_t>(64, std::max<size_t>(1, (size_t(8) << 20) / P))));
     CUDA_OK(cudaStreamSynchronize(stream_));
@@ -711,9 +733,6 @@ void Renderer::ensure_capacity(int samples) {
     m.capacity_samples = std::max(samples, m.capacity_samples);
 }
 
-template <bool ORDERED>
-static void launch_pipeline(Renderer::Impl *, cudaStream_t); // (declared for symmetry; real work below)
-
 void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write_output, bool use_variance) {
     Impl &m = *impl_;
     CUDA_OK(cudaSetDevice(device_));
@@ -725,8 +744,19 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     int *work = m.counters.p + (D + 2);    // one per launch
     CUDA_OK(cudaMemsetAsync(m.counters.p, 0, m.counters.n * sizeof(int), stream_));
     const size_t smem = size_t(m.dev.num_cache) * sizeof(uint4);
-    const int grid = num_sms_ * 8;
-    const bool ordered = traversal_ == TRAVERSAL_ORDERED;
+    const int grid = num_sms_ * blocks_per_sm_;
+    const int mode = traversal_;
+#define LAUNCH_MODE(kernel, ...)                                                                                       \
+    do {                                                                                                               \
+        if (mode == 0)                                                                                                 \
+            kernel<0><<<grid, kBlock, smem, stream_>>>(__VA_ARGS__);                                                   \
+        else if (mode == 1)                                                                                            \
+            kernel<1><<<grid, kBlock, smem, stream_>>>(__VA_ARGS__);                                                   \
+        else if (mode == 2)                                                                                            \
+            kernel<2><<<grid, kBlock, smem, stream_>>>(__VA_ARGS__);                                                   \
+        else                                                                                                           \
+            kernel<3><<<grid, kBlock, smem, stream_>>>(__VA_ARGS__);                                                   \
+    } while (0)
     CUDA_OK(cudaEventRecord(m.ev0, stream_));
     int wk = 0;
     size_t kev_used = 0;
@@ -747,27 +777,21 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         }
     };
     mark(0, 0);
-    if (ordered)
-        k_raygen<true><<<grid, kBlock, smem, stream_>>>(m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk++);
-    else
-        k_raygen<false><<<grid, kBlock, smem, stream_>>>(m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk++);
+    LAUNCH_MODE(k_raygen, m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
+    ++wk;
     unsigned long long *shadow_counter = m.stats.p + 1;
     int launches = 1, traced = 0, shaded = 0;
     for (int b = 0; b < D; b++) {
         uint32_t *q_cur = m.queue[b & 1].p, *q_nxt = m.queue[(b + 1) & 1].p;
         mark(1, b);
-        if (ordered)
-            k_shade<true><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, shadow_counter, b > 0);
-        else
-            k_shade<false><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, shadow_counter, b > 0);
+        LAUNCH_MODE(k_shade, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0);
+        ++wk;
         ++launches, ++shaded;
         if (b + 1 >= D)
             break;
         mark(2, b);
-        if (ordered)
-            k_trace<true><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, q_nxt, q_counts + b + 1, b);
-        else
-            k_trace<false><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk++, q_nxt, q_counts + b + 1, b);
+        LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b);
+        ++wk;
         ++launches, ++traced;
     }
     mark(3, 0);
@@ -929,7 +953,7 @@ std::string Renderer::info() const {
     std::ostringstream os;
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
-       << " cached), traversal=" << (traversal_ == TRAVERSAL_ORDERED ? "ordered" : "dfs")
+       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-ww" : "ordered-vote")))
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations
        << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();

@@ -85,7 +85,7 @@ class Renderer {
     void ensure_capacity(int samples);
 
     int device_ = 0, w_ = 0, h_ = 0, seed_offset_ = 0, accum_cnt_ = 0, max_depth_ = 0;
-    int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148;
+    int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148, blocks_per_sm_ = 12;
     bool variance_on_ = false, kernel_timing_ = false;
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);

