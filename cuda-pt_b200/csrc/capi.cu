@@ -246,6 +246,10 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
             if (value < 0 || value > 3)
                 throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (while-while) or 3 (warp vote)");
             r->impl->set_traversal(int(value));
+        } else if (k == "rules") {
+            if (value != 0 && value != 1)
+                throw std::runtime_error("rules must be 0 (wavefront) or 1 (megakernel pt)");
+            r->impl->set_rules(int(value));
         } else if (k == "kernel_timing") {
             r->impl->set_kernel_timing(value != 0);
         } else if (k == "max_depth") {
@@ -265,6 +269,8 @@ int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key) {
         return r->impl->samples_in_flight();
     if (k == "max_depth")
         return r->impl->max_depth();
+    if (k == "rules")
+        return r->impl->rules();
     return -1;
 }
 

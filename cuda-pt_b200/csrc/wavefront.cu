@@ -52,10 +52,17 @@ struct PathState {
     float4 *isect; // n.xyz, half2 uv
     uint2 *rng;
     float *pdf;
+    uint32_t *lobes; // megakernel-rules mode: diffuse | specular << 8 | transmit << 16 bounce counters
 };
 
 struct BatchParams {
     int W, H, P, S, first_accum, seed_offset;
+    int rules; // 0: wavefront termination rules, 1: megakernel ("pt") rules
+};
+
+// termination parameters of the megakernel rules (MaxDepthParams, src/core/max_depth.h:26-42)
+struct PtRules {
+    int enabled, bounce, max_diffuse, max_specular, max_transmit;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -131,6 +138,8 @@ __global__ void __launch_bounds__(kBlock)
             st.thp[slot] = make_float4(1, 1, 1, 1);
             st.pdf[slot] = 1.f;
             st.rng[slot] = make_uint2(rng.d0, rng.d1);
+            if (bp.rules)
+                st.lobes[slot] = 0u;
         }
         const Hit h = closest_hit<MODE>(sc, s_cached, o, d, inside); // all 32 lanes call (warp-synchronous modes)
         if (inside) {
@@ -140,6 +149,8 @@ __global__ void __launch_bounds__(kBlock)
                 tag = TAG_ACTIVE | TAG_HIT | uint32_t(h.prim);
                 st.isect[slot] = make_interaction(sc, h.prim, h.u, h.v);
                 hit_any = true;
+            } else if (bp.rules) {
+                L += mk4(1, 1, 1, 1) * null_or_env(sc, d); // megakernel_pt.cu:181-184: radiance(0,0,0,1) += throughput * Le
             } else {
                 L = null_or_env(sc, d);
             }
@@ -157,7 +168,7 @@ __global__ void __launch_bounds__(kBlock)
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
                                                   const int *__restrict__ q_count, int *work,
-                                                  unsigned long long *shadow_counter, int secondary_bounce) {
+                                                  unsigned long long *shadow_counter, int secondary_bounce, PtRules pt) {
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
     const int lane = threadIdx.x & 31;
@@ -221,23 +232,57 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
         if (valid) {
             const Material &mat = sc.mats[material_id];
             const EmitterPOD &em = sc.emitters[emit_id];
-            if (need_shadow && visible) { // wavefront_pt.cu:276-289
-                emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
-                rdc += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
-                       (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+            float pdf = st.pdf[slot];
+            // emission MIS weight against light sampling (wavefront_pt.cu:291-298 == megakernel_pt.cu:96-103, object.cuh:51-56)
+            const float emission_weight =
+                pdf / (pdf + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, hit_t) * (emitter_id > 0) *
+                                 secondary_bounce * ((tag & TAG_DELTA) == 0));
+            V4 L;
+            if (!pt.enabled) {
+                if (need_shadow && visible) { // wavefront_pt.cu:276-289
+                    emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
+                    rdc += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
+                           (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+                }
+                // (2) account for emission, and accumulate to payload buffer (wavefront_pt.cu:299-302)
+                L = (thp * emitter_eval(sc.emitters[emitter_id], d, it, true)) * emission_weight + rdc;
+            } else {
+                // megakernel order (megakernel_pt.cu:105-152): emission first, then the NEE term, then the NaN scrub
+                L = rdc;
+                L += (thp * emitter_eval(sc.emitters[emitter_id], d, it, true)) * emission_weight;
+                if (need_shadow && visible) {
+                    emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
+                    L += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
+                         (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+                }
             }
-            // ---- emission with MIS against light sampling (wavefront_pt.cu:291-302, object.cuh:51-56)
-            float pdf = st.pdf[slot],
-                  emission_weight = pdf / (pdf + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, hit_t) *
-                                                     (emitter_id > 0) * secondary_bounce * ((tag & TAG_DELTA) == 0));
-            const V4 L = (thp * emitter_eval(sc.emitters[emitter_id], d, it, true)) * emission_weight + rdc;
-            st.L[slot] = to_f4(L);
 
             // ---- sample the next direction (wavefront_pt.cu:304-312)
             int lobe = LOBE_NONE;
             d = bsdf_sample(sc, mat, d, it, thp, pdf, rng, lobe);
             tag &= ~TAG_DELTA;
             tag |= uint32_t((lobe & LOBE_SPECULAR) > 0) << 30;
+            if (pt.enabled) { // megakernel_pt.cu:159-180
+                if (bad_rgb(L))
+                    L = splat4(0);
+                uint32_t c = st.lobes[slot];
+                c += uint32_t((lobe & LOBE_DIFFUSE) > 0) + (uint32_t((lobe & LOBE_SPECULAR) > 0) << 8) +
+                     (uint32_t((lobe & LOBE_TRANSMIT) > 0) << 16);
+                st.lobes[slot] = c;
+                bool go_on = !(int(c & 0xFF) >= pt.max_diffuse || int((c >> 8) & 0xFF) >= pt.max_specular ||
+                               int((c >> 16) & 0xFF) >= pt.max_transmit);
+                const float max_value = max3(thp);
+                go_on = go_on && !(max_value < kThpEps);
+                if (go_on && pt.bounce >= 1 && max_value < kRRThreshold) {
+                    if (rng.next1d() > max_value)
+                        go_on = false;
+                    else
+                        thp *= float(1. / max_value);
+                }
+                if (!go_on)
+                    tag &= ~TAG_ACTIVE;
+            }
+            st.L[slot] = to_f4(L);
 
             st.thp[slot] = to_f4(thp);
             st.rng[slot] = make_uint2(rng.d0, rng.d1);
@@ -260,7 +305,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
                                                   const int *__restrict__ q_count, int *work, uint32_t *q_next,
-                                                  int *q_next_count, int bounce) {
+                                                  int *q_next_count, int bounce, int pt_rules) {
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
     const int lane = threadIdx.x & 31;
@@ -269,13 +314,14 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
         const int i = chunk * 32 + lane;
         bool alive = false;
         uint32_t slot = 0, tag = 0;
-        const bool valid = i < count;
+        bool valid = i < count;
         V3 o{0, 0, 0}, d{0, 0, 1};
         if (valid) {
             slot = queue[i];
             const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
             o = xyz(ro), d = xyz(rd);
             tag = __float_as_uint(rd.w) & 0xd0000000u; // reset(): clear hit flag and hit index
+            valid = (tag & TAG_ACTIVE) != 0;           // megakernel rules: k_shade may have ended the path
         }
         const Hit h = closest_hit<MODE>(sc, s_cached, o, d, valid); // all 32 lanes call
         if (valid) {
@@ -285,7 +331,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
                 st.isect[slot] = make_interaction(sc, h.prim, h.u, h.v);
                 alive = true;
                 const float max_value = max3(thp);
-                if (bounce >= kRRBounce && max_value < kRRThreshold) {
+                if (!pt_rules && bounce >= kRRBounce && max_value < kRRThreshold) {
                     const uint2 rs = st.rng[slot];
                     Rng rng{rs.x, rs.y};
                     const bool survive = rng.next1d() < max_value && max_value > kThpEps;
@@ -316,20 +362,23 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_splat(const float4 *__restrict__ Lbuf, float4 *__restrict__ image,
                                                float4 *__restrict__ out, float *__restrict__ var, int P, int S,
-                                               int first_accum, int write_output, int gamma) {
+                                               int first_accum, int write_output, int gamma, int scrub) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         V4 acc = from_f4(image[p]);
         float variance = var ? var[p] : 0.f;
         for (int s = 0; s < S; s++) {
             V4 L = from_f4(Lbuf[size_t(s) * P + p]);
-            L = bad_rgb(L) ? mk4(0, 0, 0, 1) : L;
+            L = (scrub && bad_rgb(L)) ? mk4(0, 0, 0, 1) : L; // wavefront_pt.cu:487 (the megakernel scrubs per bounce instead)
             if (var) {
                 const int accum_cnt = first_accum + s;
-                float cur_val = (L.x + L.y + L.z) * 0.33333333f, old_mean = (acc.x + acc.y + acc.z) * 0.33333333f,
-                      new_mean = old_mean + cur_val, rcp_cnt = 1.f / float(accum_cnt);
-                old_mean = accum_cnt > 1 ? old_mean / float(accum_cnt - 1) : 0;
-                new_mean *= rcp_cnt;
-                variance = (float(accum_cnt - 1) * variance + (cur_val - old_mean) * (cur_val - new_mean)) * rcp_cnt;
+                // rounding points pinned to the reference kernel's SASS: only `cur - new_sum * rcp` and
+                // `(n-1) * var + prod` are fused there
+                const float cur_val = __fmul_rn(__fadd_rn(__fadd_rn(L.x, L.y), L.z), 0.33333333f);
+                float old_mean = __fmul_rn(__fadd_rn(__fadd_rn(acc.x, acc.y), acc.z), 0.33333333f);
+                const float new_sum = __fadd_rn(cur_val, old_mean), rcp_cnt = 1.f / float(accum_cnt);
+                old_mean = accum_cnt > 1 ? __fdividef(old_mean, float(accum_cnt - 1)) : 0.f;
+                const float d_new = fmaf(new_sum, -rcp_cnt, cur_val), d_old = __fsub_rn(cur_val, old_mean);
+                variance = __fmul_rn(fmaf(float(accum_cnt - 1), variance, __fmul_rn(d_old, d_new)), rcp_cnt);
             }
             acc += L;
         }
@@ -444,6 +493,8 @@ struct Renderer::Impl {
     DevBuf<float4> ray_o, ray_d, thp, L, isect;
     DevBuf<uint2> rng;
     DevBuf<float> pdf;
+    DevBuf<uint32_t> lobes;
+    int caps[3] = {16, 16, 16};
     DevBuf<uint32_t> queue[2];
     DevBuf<int> counters;                 // [0..D] queue sizes, [D+1 ..] work counters
     DevBuf<unsigned long long> stats;     // closest, shadow, shaded
@@ -510,11 +561,16 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     w_ = scene.width();
     h_ = scene.height();
     max_depth_ = scene.config[CPTS_CFG_MAX_DEPTH];
+    // renderer type of the XML (scene.cu:975-1000): 0 / 8 = megakernel PT -> its termination rules, 1 = wavefront
+    rules_ = (scene.config[CPTS_CFG_RENDERER] == 0 || scene.config[CPTS_CFG_RENDERER] == 8) ? 1 : 0;
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&impl_->ev0));
     CUDA_OK(cudaEventCreate(&impl_->ev1));
 
     Impl &m = *impl_;
+    m.caps[0] = scene.config[CPTS_CFG_MAX_DIFFUSE];
+    m.caps[1] = scene.config[CPTS_CFG_MAX_SPECULAR];
+    m.caps[2] = scene.config[CPTS_CFG_MAX_TRANSMIT];
     // ---- geometry / BVH
     {
         std::vector<float4> tmp(scene.nodes.size());
@@ -727,6 +783,7 @@ void Renderer::ensure_capacity(int samples) {
     m.isect.alloc(slots);
     m.rng.alloc(slots);
     m.pdf.alloc(slots);
+    m.lobes.alloc(slots);
     m.queue[0].alloc(slots);
     m.queue[1].alloc(slots);
     m.counters.alloc(size_t(3 * (max_depth_ + 2) + 4)); // D+2 queue sizes, then one work counter per launch (<= 2D+1)
@@ -738,8 +795,8 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     CUDA_OK(cudaSetDevice(device_));
     ensure_capacity(samples);
     const int P = w_ * h_, D = max_depth_;
-    PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p};
-    BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_};
+    PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p, m.lobes.p};
+    BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_, rules_};
     int *q_counts = m.counters.p;          // D + 1 entries
     int *work = m.counters.p + (D + 2);    // one per launch
     CUDA_OK(cudaMemsetAsync(m.counters.p, 0, m.counters.n * sizeof(int), stream_));
@@ -784,19 +841,20 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     for (int b = 0; b < D; b++) {
         uint32_t *q_cur = m.queue[b & 1].p, *q_nxt = m.queue[(b + 1) & 1].p;
         mark(1, b);
-        LAUNCH_MODE(k_shade, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0);
+        const PtRules pt{rules_, b, m.caps[0], m.caps[1], m.caps[2]};
+        LAUNCH_MODE(k_shade, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt);
         ++wk;
         ++launches, ++shaded;
         if (b + 1 >= D)
             break;
         mark(2, b);
-        LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b);
+        LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         ++wk;
         ++launches, ++traced;
     }
     mark(3, 0);
     k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples,
-                                               first_accum, write_output ? 1 : 0, gamma ? 1 : 0);
+                                               first_accum, write_output ? 1 : 0, gamma ? 1 : 0, rules_ == 0 ? 1 : 0);
     mark(-1, 0);
     k_fold_stats<<<1, 32, 0, stream_>>>(q_counts, traced, shaded, m.stats.p);
     launches += 2;
@@ -955,7 +1013,7 @@ std::string Renderer::info() const {
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
        << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-ww" : "ordered-vote")))
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations
-       << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
+       << ", rules " << (rules_ ? "megakernel-pt" : "wavefront") << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();
 }
 

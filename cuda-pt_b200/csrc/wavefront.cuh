@@ -66,6 +66,8 @@ class Renderer {
     void enable_variance(bool on);
     void set_accum_count(int c) { accum_cnt_ = c; }
     void set_kernel_timing(bool on) { kernel_timing_ = on; }
+    void set_rules(int r) { rules_ = r; }
+    int rules() const { return rules_; }
     KernelTimes kernel_times() const { return ktimes_; }
 
     int width() const { return w_; }
@@ -85,7 +87,7 @@ class Renderer {
     void ensure_capacity(int samples);
 
     int device_ = 0, w_ = 0, h_ = 0, seed_offset_ = 0, accum_cnt_ = 0, max_depth_ = 0;
-    int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148, blocks_per_sm_ = 12;
+    int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
     bool variance_on_ = false, kernel_timing_ = false;
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);

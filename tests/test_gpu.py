@@ -64,6 +64,21 @@ def test_all_materials_bit_exact_vs_reference(traversal):
     assert np.array_equal(out[16][1].view(np.uint32), var_ref.view(np.uint32))
 
 
+def test_megakernel_rules_bit_exact_vs_reference_pt():
+    """`renderer type="pt"` scenes: the megakernel's termination rules (lobe caps, throughput cut-off, Russian
+    roulette from bounce 1 with an exactly rounded 1/max, per-bounce NaN scrub, emission-before-NEE accumulation)
+    served by the wavefront kernels; golden = PathTracer<SingleTileScheduler>::render_raw x 64."""
+    r = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), 0, 0)
+    assert r.get_option("rules") == 0
+    r.set_option("rules", 1)
+    out = r.render_to_host(64, False)
+    ref = load_frame("cbox_pt_256_pt_f0064.bin")
+    assert rel_l2(out, ref) <= 1e-4
+    frac = bit_exact_fraction(out, ref)
+    assert frac == 1.0, frac
+    r.close()
+
+
 def test_batch_equals_per_sample_and_is_deterministic():
     scene = os.path.join(GOLDEN, "cbox_mats_256.cpts")
     imgs = []
