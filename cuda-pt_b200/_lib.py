@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcpt_b200.so")
-SOURCES = ["wavefront.cu", "capi.cu", "scene_host.cpp", "scene_xml.cpp"]
+SOURCES = ["wavefront.cu", "capi.cu", "scene_host.cpp", "scene_xml.cpp", "image_io.cpp"]
 NVCC_FLAGS = [
     "-O3", "--use_fast_math", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + ["-I" + os.path.join(REPO_ROOT, "include"), "-I" + CSRC]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH, "-lz"]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,0 +1,19 @@
+// 8-bit image input for the XML scene loader (PNG only); see image_io.cpp
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace cptb {
+
+struct Image8 {
+    int width = 0, height = 0, channels = 0; // channels as stored in the file (1 grey, 2 grey+a, 3 rgb, 4 rgba)
+    std::vector<uint8_t> data;
+};
+
+Image8 decode_png(const std::string &path); // throws std::runtime_error
+// 8-bit channel conversion with the rules of the decoder the reference links (stb_image's convert_format)
+std::vector<uint8_t> convert_channels(const Image8 &img, int want_channels);
+std::vector<uint8_t> load_image8(const std::string &path, int want_channels, int &width, int &height);
+
+} // namespace cptb

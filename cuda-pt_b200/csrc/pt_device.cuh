@@ -627,18 +627,17 @@ PT_DEV V3 bsdf_sample(const DevScene &sc, const Material &m, V3 in, float4 it, V
 }
 
 // ======================= emitters (reference: src/core/emitter.cuh:32-359, src/impl/emitter.cu:26-73) =======================
-struct Quat {
-    float x, y, z, w;
-};
-PT_DEV Quat qmul(Quat a, Quat q) {
-    return Quat{a.w * q.x + a.x * q.w + a.y * q.z - a.z * q.y, a.w * q.y - a.x * q.z + a.y * q.w + a.z * q.x,
-                a.w * q.z + a.x * q.y - a.y * q.x + a.z * q.w, a.w * q.w - a.x * q.x - a.y * q.y - a.z * q.z};
-}
-PT_DEV V3 qrotate(float4 r, V3 v) {
-    Quat q{r.x, r.y, r.z, r.w}, vq{v.x, v.y, v.z, 0.0f};
-    Quat qv = qmul(q, vq);
-    Quat out = qmul(qv, Quat{-q.x, -q.y, -q.z, q.w});
-    return V3{out.x, out.y, out.z};
+// q * (v,0) * conj(q) (quaternion.cuh:54-84).  The rounding points are pinned to the reference's SASS for
+// EnvMapEmitter::eval_le / ::sample: every component is a left-to-right fma chain whose first product pair
+// is fma(a, b, +-(c * d)); the zero terms of the pure-vector operand are kept (they only matter for -0).
+PT_DEV V3 qrotate(float4 q, V3 v) {
+    const float X = fmaf(-v.y, q.z, fmaf(v.z, q.y, fmaf(v.x, q.w, __fmul_rn(0.f, q.x))));
+    const float Y = fmaf(v.x, q.z, fmaf(0.f, q.y, fmaf(v.y, q.w, -__fmul_rn(v.z, q.x))));
+    const float Z = fmaf(0.f, q.z, fmaf(-v.x, q.y, fmaf(v.z, q.w, __fmul_rn(v.y, q.x))));
+    const float W = fmaf(-v.z, q.z, fmaf(-v.y, q.y, fmaf(0.f, q.w, -__fmul_rn(v.x, q.x))));
+    return V3{fmaf(q.y, Z, fmaf(q.z, -Y, fmaf(q.w, X, -__fmul_rn(q.x, W)))),
+              fmaf(q.x, -Z, fmaf(q.w, Y, fmaf(q.z, X, -__fmul_rn(q.y, W)))),
+              fmaf(q.w, Z, fmaf(q.x, Y, fmaf(-q.y, X, -__fmul_rn(q.z, W))))};
 }
 PT_DEV V4 envmap_lookup(const EmitterPOD &e, V3 dir) {
     V3 d = qrotate(e.rot, dir);

@@ -7,8 +7,10 @@
 // integrated build; this one exists so the library, its tests and the
 // benchmark are self-contained.
 //
+// Image textures and environment maps are decoded from PNG files (image_io.cpp).
 // Not supported (clear errors, never silent): sphere shapes (reference default build is
-// TRIANGLE_ONLY), image textures / environment maps (no image decoder is linked here), media.
+// TRIANGLE_ONLY), JPEG / HDR images, participating media.
+#include "image_io.h"
 #include "scene_host.h"
 
 #include <algorithm>
@@ -564,6 +566,58 @@ int linearize(const Builder &b, int id, int depth, int cache_levels, std::vector
     return sub + 1;
 }
 
+// ---- image textures (src/impl/textures.cu:53-81,92-131,169-203) ----
+struct TexInfo {
+    std::string diff, spec, glos, rough1, rough2, normal;
+    bool rough_ior = false;
+};
+
+// float4 texels = byte / 255 * scale + offset; normal maps use scale 2, offset -1
+int add_texture4(HostScene &out, const std::string &path, bool normal_map) {
+    HostTexture t;
+    const std::vector<uint8_t> px = load_image8(path, 4, t.width, t.height);
+    const float offset = normal_map ? -1.f : 0.f, scale = normal_map ? 2.f : 1.f;
+    t.channels = 4;
+    t.texels.resize(px.size());
+    for (size_t i = 0; i < px.size(); i++)
+        t.texels[i] = (static_cast<float>(px[i]) / 255.0f) * scale + offset;
+    out.textures.push_back(std::move(t));
+    return int(out.textures.size()) - 1;
+}
+
+float roughness_to_alpha_host(float roughness) { // cuda_utils.cuh:115-120 (host instantiation: libm logf)
+    roughness = std::fmax(roughness, 1e-3f);
+    const float x = std::log(roughness);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+// two single-channel maps packed as float2.  Upstream reads the second map one byte ahead (`data2[i + 1]`,
+// textures.cu:122); that is reproduced, with the out-of-range read of the very last texel clamped
+int add_texture2(HostScene &out, const std::string &path1, const std::string &path2, bool is_ior) {
+    HostTexture t;
+    const std::vector<uint8_t> a = load_image8(path1, 1, t.width, t.height);
+    std::vector<uint8_t> b;
+    if (path2.length() > 1) {
+        int w2 = 0, h2 = 0;
+        b = load_image8(path2, 1, w2, h2);
+        if (w2 != t.width || h2 != t.height)
+            throw std::runtime_error("scene: composed roughness images differ in size");
+    }
+    const float offset = is_ior ? 1.f : 0.f, scale = is_ior ? 1.5f : 1.f;
+    t.channels = 2;
+    t.texels.resize(a.size() * 2);
+    for (size_t i = 0; i < a.size(); i++) {
+        float v1 = static_cast<float>(a[i]) / 255.0f;
+        float v2 = b.empty() ? v1 : static_cast<float>(b[std::min(i + 1, b.size() - 1)]) / 255.0f;
+        v1 = v1 * scale + offset;
+        v2 = v2 * scale + offset;
+        t.texels[2 * i] = is_ior ? roughness_to_alpha_host(v1) : v1;
+        t.texels[2 * i + 1] = is_ior ? roughness_to_alpha_host(v2) : v2;
+    }
+    out.textures.push_back(std::move(t));
+    return int(out.textures.size()) - 1;
+}
+
 } // namespace
 
 void load_xml(const std::string &path, HostScene &out) {
@@ -615,10 +669,29 @@ void load_xml(const std::string &path, HostScene &out) {
         get_bool(*film, {"gamma_correction"}, gamma);
     }
 
-    // ---- textures are only checked for use (no decoder here)
-    std::map<std::string, bool> texture_ids;
-    for (auto t : root.children("texture"))
-        texture_ids[t->attr_or("id", "")] = true;
+    // ---- texture declarations (scene.cu:662-700): id -> image paths
+    std::map<std::string, TexInfo> tex_map;
+    for (auto t : root.children("texture")) {
+        TexInfo info;
+        for (auto c : t->children("string")) {
+            const std::string n = c->attr_or("name", ""), v = folder + c->attr_or("value", "");
+            if (n == "diffuse" || n == "emission")
+                info.diff = v;
+            else if (n == "specular")
+                info.spec = v;
+            else if (n == "glossy" || n == "sigma_a")
+                info.glos = v;
+            else if (n == "rough1" || n == "roughness_1" || n == "ior")
+                info.rough1 = v, info.rough_ior = n == "ior";
+            else if (n == "rough2" || n == "roughness_2")
+                info.rough2 = v, info.rough_ior = false;
+            else if (n == "normal")
+                info.normal = v;
+            else
+                throw std::runtime_error("scene: unsupported texture type '" + n + "'");
+        }
+        tex_map.emplace(t->attr_or("id", ""), info); // first declaration of an id wins (unordered_map::emplace)
+    }
     if (!root.children("medium").empty())
         throw std::runtime_error("scene: participating media are outside the wavefront surface path");
 
@@ -638,10 +711,23 @@ void load_xml(const std::string &path, HostScene &out) {
             if (dst)
                 memcpy(dst, col, sizeof(col));
         }
-        if (auto r = b->first("ref"))
-            if (r->attr_or("type", "") == "texture")
-                throw std::runtime_error("scene: BSDF '" + id + "' references an image texture; image textures are "
-                                         "not supported by this loader");
+        if (auto r = b->first("ref")) // only the first <ref> child is inspected upstream (scene.cu:193-236)
+            if (r->attr_or("type", "") == "texture") {
+                auto it = tex_map.find(r->attr_or("id", ""));
+                if (it == tex_map.end())
+                    throw std::runtime_error("scene: BSDF '" + id + "' references an unknown texture");
+                const TexInfo &ti = it->second;
+                if (!ti.diff.empty())
+                    rec.tex[0] = add_texture4(out, ti.diff, false);
+                if (!ti.spec.empty())
+                    rec.tex[1] = add_texture4(out, ti.spec, false);
+                if (!ti.glos.empty())
+                    rec.tex[2] = add_texture4(out, ti.glos, false);
+                if (!ti.normal.empty())
+                    rec.tex[3] = add_texture4(out, ti.normal, true);
+                if (!ti.rough1.empty())
+                    rec.tex[4] = add_texture2(out, ti.rough1, ti.rough2, ti.rough_ior);
+            }
         if (type == "lambertian") {
             rec.type = CPTS_BSDF_LAMBERTIAN, rec.flags = 0x01 | 0x10;
         } else if (type == "specular") {
@@ -790,10 +876,15 @@ void load_xml(const std::string &path, HostScene &out) {
             for (int k = 0; k < 3; k++)
                 rec.Le[k] = emission[k] * scaler[k];
             rec.Le[3] = 1.f * scaler[0];
-            if (auto r = e->first("ref"))
-                if (r->attr_or("type", "") == "texture")
-                    throw std::runtime_error("scene: emitter '" + id + "' uses an image texture / environment map; "
-                                             "image textures are not supported by this loader");
+            if (auto r = e->first("ref")) // scene.cu:395-417
+                if (r->attr_or("type", "") == "texture") {
+                    auto it = tex_map.find(r->attr_or("id", ""));
+                    if (it == tex_map.end())
+                        throw std::runtime_error("scene: emitter '" + id + "' references an unknown texture");
+                    if (it->second.diff.empty())
+                        throw std::runtime_error("scene: the texture of emitter '" + id + "' has no 'emission' image");
+                    rec.tex = add_texture4(out, it->second.diff, false);
+                }
             auto bound = emitter_obj.find(id);
             if (type == "point") {
                 rec.type = CPTS_EMIT_POINT;
@@ -818,8 +909,17 @@ void load_xml(const std::string &path, HostScene &out) {
                             rec.cos_val = std::cos(float(atof(f->attr_or("value", "0").c_str())) * kDeg2Rad);
                     }
                 }
-            } else if (type == "envmap") {
-                throw std::runtime_error("scene: environment maps need an image texture, which this loader does not decode");
+            } else if (type == "envmap") { // scene.cu:460-478
+                rec.type = CPTS_EMIT_ENVMAP;
+                envmap_id = int(out.emitters.size());
+                float scale = 1.f, azimuth = 0.f, zenith = 0.f;
+                get_float(*e, {"scaler"}, scale);
+                get_float(*e, {"azimuth"}, azimuth);
+                get_float(*e, {"zenith"}, zenith);
+                rec.Le[0] = rec.Le[1] = rec.Le[2] = 0.f, rec.Le[3] = 1.f; // Emitter(Vec4(0, 1), -1, false), emitter.cuh:320
+                rec.scale = scale, rec.azimuth = azimuth * kDeg2Rad, rec.zenith = zenith * kDeg2Rad;
+                if (rec.tex < 0)
+                    throw std::runtime_error("scene: the texture for the environment map is empty");
             } else {
                 throw std::runtime_error("scene: unknown emitter type '" + type + "'");
             }

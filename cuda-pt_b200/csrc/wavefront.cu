@@ -413,6 +413,18 @@ __global__ void k_fold_stats(const int *__restrict__ q_counts, int traced_bounce
 // derived material / emitter parameters are computed on the device with the same math functions the
 // reference uses inside its device-side constructors (virtual_funcs.cu:85-98, bsdf_plastic.cu:25-36,
 // fresnel.cuh:62-75, cuda_utils.cuh:115-120, emitter.cuh:349-353)
+// Hamilton product with the rounding points of the reference's create_envmap_source kernel (quaternion.cuh:54-60):
+// fma(a, b, +-(c * d)) for the first two terms of a component, then one fma per remaining term
+struct Quat {
+    float x, y, z, w;
+};
+__device__ Quat qmul(Quat a, Quat q) {
+    return Quat{fmaf(-a.z, q.y, fmaf(a.y, q.z, fmaf(a.w, q.x, __fmul_rn(a.x, q.w)))),
+                fmaf(a.z, q.x, fmaf(a.y, q.w, fmaf(a.w, q.y, -__fmul_rn(a.x, q.z)))),
+                fmaf(a.z, q.w, fmaf(-a.y, q.x, fmaf(a.w, q.z, __fmul_rn(a.x, q.y)))),
+                fmaf(-a.z, q.z, fmaf(-a.y, q.y, fmaf(a.w, q.w, -__fmul_rn(a.x, q.x))))};
+}
+
 __device__ float roughness_to_alpha_dev(float roughness) {
     roughness = fmaxf(roughness, 1e-3f);
     float x = logf(roughness);

@@ -147,6 +147,27 @@ int lobe_flags_for(int type) {
     }
 }
 
+// reads the texels of one of the reference's pitched 2-D textures (src/impl/textures.cu:134-165) back to the
+// host through the resource descriptor of the texture object; returns the index in `descs`
+int grab_texture(cudaTextureObject_t obj, std::vector<CptsTexDesc> &descs, std::vector<float> &data) {
+    cudaResourceDesc rd{};
+    CUDA_CHECK_RETURN(cudaGetTextureObjectResourceDesc(&rd, obj));
+    if (rd.resType != cudaResourceTypePitch2D) {
+        fprintf(stderr, "unexpected texture resource type %d\n", int(rd.resType));
+        exit(3);
+    }
+    const int ch = (rd.res.pitch2D.desc.y ? 1 : 0) + (rd.res.pitch2D.desc.z ? 1 : 0) + (rd.res.pitch2D.desc.w ? 1 : 0) + 1;
+    CptsTexDesc d{};
+    d.width = int(rd.res.pitch2D.width), d.height = int(rd.res.pitch2D.height), d.channels = ch;
+    d.offset = data.size();
+    const size_t row = size_t(d.width) * ch * sizeof(float);
+    data.resize(data.size() + size_t(d.width) * d.height * ch);
+    CUDA_CHECK_RETURN(cudaMemcpy2D(data.data() + d.offset, row, rd.res.pitch2D.devPtr, rd.res.pitch2D.pitchInBytes, row,
+                                   d.height, cudaMemcpyDeviceToHost));
+    descs.push_back(d);
+    return int(descs.size()) - 1;
+}
+
 void dump_scene(const Scene &scene, const std::string &xml_path, const std::string &out_path) {
     Writer w(out_path);
 
@@ -202,6 +223,18 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
     doc.LoadFile(xml_path.c_str());
     const tinyxml2::XMLElement *root = doc.FirstChildElement("scene");
 
+    // texture object tables of the reference: 5 x num_bsdfs, diffuse | specular | glossy | normal | roughness
+    // (src/core/textures.cuh:129-139,152-166)
+    std::vector<CptsTexDesc> tex_descs;
+    std::vector<float> tex_data;
+    std::vector<cudaTextureObject_t> tex_table(size_t(scene.num_bsdfs) * 5, 0);
+    if (scene.num_bsdfs > 0)
+        CUDA_CHECK_RETURN(cudaMemcpy(tex_table.data(), scene.textures.diff_tex,
+                                     tex_table.size() * sizeof(cudaTextureObject_t), cudaMemcpyDeviceToHost));
+    size_t num_bsdf_tex4 = 0;
+    for (size_t i = 0; i < size_t(scene.num_bsdfs) * 4; i++)
+        num_bsdf_tex4 += tex_table[i] != 0;
+
     std::vector<CptsBsdf> bsdfs(scene.num_bsdfs);
     const tinyxml2::XMLElement *be = root->FirstChildElement("brdf");
     for (int i = 0; i < scene.num_bsdfs; i++, be = be->NextSiblingElement("brdf")) {
@@ -209,8 +242,10 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
         CptsBsdf b{};
         b.type = info.type;
         b.flags = lobe_flags_for(info.type);
-        for (int k = 0; k < 5; k++)
-            b.tex[k] = -1;
+        for (int k = 0; k < 5; k++) {
+            const cudaTextureObject_t t = tex_table[size_t(k) * scene.num_bsdfs + i];
+            b.tex[k] = t ? grab_texture(t, tex_descs, tex_data) : -1;
+        }
         for (int k = 0; k < 4; k++) {
             b.k_d[k] = info.bsdf.k_d[k];
             b.k_s[k] = info.bsdf.k_s[k];
@@ -250,6 +285,7 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
     ems[0].obj_ref = -1;
     ems[0].tex = -1;
     ems[0].Le[3] = 1.f; // Emitter(Vec4(0,0,0)) => w = 1
+    size_t next_emitter_tex = num_bsdf_tex4; // host_tex_4d = [BSDF float4 textures..., emitter textures...] (scene.cu:204-232,406-409)
     const tinyxml2::XMLElement *ee = root->FirstChildElement("emitter");
     for (int i = 1; i <= scene.num_emitters; i++, ee = ee->NextSiblingElement("emitter")) {
         CptsEmitter e{};
@@ -264,6 +300,14 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
         for (int k = 0; k < 3; k++)
             e.Le[k] = emission[k] * scaler[k];
         e.Le[3] = 1.f * scaler[0];
+        if (const tinyxml2::XMLElement *r = ee->FirstChildElement("ref")) // only the first <ref> is looked at (scene.cu:395-397)
+            if (r->Attribute("type") && !strcmp(r->Attribute("type"), "texture")) {
+                if (next_emitter_tex >= scene.host_tex_4d.size()) {
+                    fprintf(stderr, "emitter texture bookkeeping mismatch\n");
+                    exit(3);
+                }
+                e.tex = grab_texture(scene.host_tex_4d[next_emitter_tex++].object(), tex_descs, tex_data);
+            }
         for (size_t o = 0; o < scene.objects.size(); o++)
             if (scene.objects[o].emitter_id == i)
                 e.obj_ref = int(o); // last bound shape wins, as in the loader's map
@@ -308,6 +352,11 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
         ems[i] = e;
     }
     w.section("emitters", ems.data(), sizeof(CptsEmitter), ems.size());
+
+    if (!tex_descs.empty()) {
+        w.section("tex_desc", tex_descs.data(), sizeof(CptsTexDesc), tex_descs.size());
+        w.section("tex_data", tex_data.data(), 4, tex_data.size());
+    }
 
     bool has_dispersion = false;
     for (const auto &b : bsdfs)

@@ -81,7 +81,7 @@ def test_scene_errors(tmp_path):
         cpt.Scene(str(x))
     x.write_text('<scene version="1.2"><sensor><film/></sensor><brdf type="lambertian" id="a">'
                  '<ref type="texture" id="t"/></brdf></scene>')
-    with pytest.raises(cpt.CptError, match="texture"):
+    with pytest.raises(cpt.CptError, match="unknown texture"):
         cpt.Scene(str(x))
     x.write_text('<scene version="1.2"><sensor></scene>')
     with pytest.raises(cpt.CptError, match="xml"):
@@ -92,6 +92,78 @@ def test_scene_errors(tmp_path):
     t.write_bytes(data[: len(data) // 2])
     with pytest.raises(cpt.CptError):
         cpt.Scene(str(t))
+
+
+def test_png_decoder_and_texture_conversion_match_an_independent_decoder(tmp_path):
+    """The loader's own PNG reader (grey / RGB / RGBA / palette / 16-bit) against PIL, plus the texel conversion rules
+    of src/impl/textures.cu:53-131 (byte/255, normal maps *2-1, luma for grey requests, 16->8 bit = high byte,
+    the `data2[i + 1]` read of the second roughness map, roughness_to_alpha for ior maps)."""
+    from PIL import Image
+    sc = cpt.Scene(os.path.join(SCENES, "texroom_wfpt_256.xml"))
+    out = tmp_path / "texroom.cpts"
+    sc.save(str(out))
+    d = read_cpts(str(out))
+    td = np.frombuffer(d["tex_desc"].tobytes(), dtype=np.dtype([("w", "<i4"), ("h", "<i4"), ("c", "<i4"), ("p", "<i4"), ("off", "<u8")]))
+    data = d["tex_data"].ravel()
+    tex_dir = os.path.join(ROOT, "scenes", "assets", "tex")
+
+    def get(i):
+        t = td[i]
+        o, n = int(t["off"]), int(t["w"]) * int(t["h"]) * int(t["c"])
+        return data[o:o + n].reshape(int(t["h"]), int(t["w"]), int(t["c"]))
+
+    def rgba(name, normal=False):
+        im = Image.open(os.path.join(tex_dir, name))
+        a = np.asarray(im.convert("RGB") if im.mode == "P" else im)
+        if a.shape[2] == 3:
+            a = np.concatenate([a, np.full(a.shape[:2] + (1,), 255, np.uint8)], -1)
+        a = a.astype(np.float32) / np.float32(255)
+        return a * np.float32(2) + np.float32(-1) if normal else a
+
+    def grey(name):
+        a = np.asarray(Image.open(os.path.join(tex_dir, name)))
+        if a.dtype != np.uint8:
+            return (a.astype(np.uint32) >> 8).astype(np.uint8)
+        if a.ndim == 3:
+            a = a.astype(np.int32)
+            return ((a[..., 0] * 77 + a[..., 1] * 150 + 29 * a[..., 2]) >> 8).astype(np.uint8)
+        return a
+
+    # texture order = BSDF order x (diffuse, specular, glossy, normal, roughness), then emitters
+    expect = [rgba("albedo.png"), rgba("normal.png", True), rgba("albedo_warm.png"), rgba("specular.png"), rgba("glossy.png"),
+              rgba("glossy.png"), rgba("normal.png", True)]
+    for i, e in enumerate(expect):
+        assert np.array_equal(get(i), e), i
+    rough = get(7)
+    assert rough.shape[2] == 2
+    assert np.array_equal(rough[..., 0], grey("rough_x.png").astype(np.float32) / np.float32(255))
+    b = grey("rough_y.png").ravel()
+    shifted = np.concatenate([b[1:], b[-1:]]).reshape(rough.shape[:2]).astype(np.float32) / np.float32(255)
+    assert np.array_equal(rough[..., 1], shifted)
+    ior = get(12)
+    v = grey("ior16.png").astype(np.float32) / np.float32(255) * np.float32(1.5) + np.float32(1)
+    x = np.log(np.maximum(v, np.float32(1e-3))).astype(np.float32)
+    alpha = (np.float32(1.62142) + np.float32(0.819955) * x + np.float32(0.1734) * x * x + np.float32(0.0171201) * x * x * x +
+             np.float32(0.000640711) * x * x * x * x)
+    assert np.abs(ior[..., 0] - alpha).max() < 1e-6
+    assert np.array_equal(get(len(td) - 1), rgba("envmap.png")) and np.array_equal(get(len(td) - 2), rgba("emission.png"))
+    bs = np.frombuffer(d["bsdfs"].tobytes(), dtype=np.int32).reshape(len(d["bsdfs"]), -1)
+    assert bs[0, -10:-5].tolist() == [0, -1, -1, 1, -1]  # floor: diffuse + normal
+    assert sc.config["envmap_id"] == 3
+
+
+def test_image_errors(tmp_path):
+    x = tmp_path / "t.xml"
+    notpng = tmp_path / "a.jpg"
+    notpng.write_bytes(b"\xff\xd8\xff\xe0 not really a jpeg")
+    x.write_text('<scene version="1.2"><sensor><film/></sensor><brdf type="lambertian" id="a">'
+                 '<ref type="texture" id="t"/></brdf><texture id="t"><string name="diffuse" value="a.jpg"/></texture></scene>')
+    with pytest.raises(cpt.CptError, match="PNG"):
+        cpt.Scene(str(x))
+    x.write_text('<scene version="1.2"><sensor><film/></sensor><brdf type="lambertian" id="a">'
+                 '<ref type="texture" id="t"/></brdf><texture id="t"><string name="diffuse" value="none.png"/></texture></scene>')
+    with pytest.raises(cpt.CptError, match="cannot open"):
+        cpt.Scene(str(x))
 
 
 @needs_meshes
