@@ -250,6 +250,8 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
             if (value != 0 && value != 1)
                 throw std::runtime_error("rules must be 0 (wavefront) or 1 (megakernel pt)");
             r->impl->set_rules(int(value));
+        } else if (k == "split_shadow") {
+            r->impl->set_split_shadow(value != 0);
         } else if (k == "kernel_timing") {
             r->impl->set_kernel_timing(value != 0);
         } else if (k == "max_depth") {
@@ -271,6 +273,8 @@ int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key) {
         return r->impl->max_depth();
     if (k == "rules")
         return r->impl->rules();
+    if (k == "split_shadow")
+        return r->impl->split_shadow() ? 1 : 0;
     return -1;
 }
 
@@ -289,16 +293,16 @@ int cpt_b200_stats(cpt_b200_renderer *r, uint64_t *stats8) {
     });
 }
 
-int cpt_b200_kernel_times(cpt_b200_renderer *r, double *ms4, uint64_t *launches4, uint64_t *units4) {
+int cpt_b200_kernel_times(cpt_b200_renderer *r, double *ms5, uint64_t *launches5, uint64_t *units5) {
     REQUIRE(r);
-    REQUIRE(ms4);
+    REQUIRE(ms5);
     const cptb::KernelTimes t = r->impl->kernel_times();
-    for (int i = 0; i < 4; i++) {
-        ms4[i] = t.ms[i];
-        if (launches4)
-            launches4[i] = t.launches[i];
-        if (units4)
-            units4[i] = t.units[i];
+    for (int i = 0; i < 5; i++) {
+        ms5[i] = t.ms[i];
+        if (launches5)
+            launches5[i] = t.launches[i];
+        if (units5)
+            units5[i] = t.units[i];
     }
     return 0;
 }

@@ -38,6 +38,7 @@ enum : int { TEX_DIFF = 0, TEX_SPEC, TEX_GLOS, TEX_NORMAL, TEX_ROUGH };
 
 // ray tag bits (reference: core/ray.cuh:37-97)
 constexpr uint32_t TAG_ACTIVE = 0x10000000u, TAG_HIT = 0x20000000u, TAG_DELTA = 0x40000000u, TAG_INDEX = 0x0fffffffu;
+constexpr uint32_t TAG_NEE_VISIBLE = 0x80000000u; // ours (split pipeline): k_shadow -> k_shade hand-over, never visible outside a bounce
 
 // ---- device scene tables ----
 struct Material { // 160 B

@@ -163,14 +163,102 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 // ------------------------------------------------------------------------------------------------
+// NEE set-up shared by k_shade and k_shadow: object -> (material, emitter), emitter + primitive pick, emitter
+// sample, shadow ray (wavefront_pt.cu:237-272).  Consumes 1 + 1 + 2 draws of the path's sampler.
+// ------------------------------------------------------------------------------------------------
+struct NeeSetup {
+    uint32_t emit_id;
+    int material_id, emitter_id;
+    ObjectPOD ob;
+    V3 hit_pos, sd;    // shadow ray origin / unit direction
+    float len;         // distance to the sampled point
+    float direct_pdf;
+    V4 direct_comp;    // sampled emitter radiance
+};
+__device__ __forceinline__ void nee_setup(const DevScene &sc, V3 o, V3 d, float hit_t, uint32_t tag, float4 it, Rng &rng,
+                                          NeeSetup &ns) {
+    int object_id = __ldg(sc.obj_idxs + (tag & TAG_INDEX));
+    object_id = object_id >= 0 ? object_id : -object_id - 1;
+    ns.ob = sc.objects[object_id];
+    ns.material_id = ns.ob.bsdf_emitter >> 16;
+    ns.emitter_id = ((ns.ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+
+    // ---- pick an emitter (tracing_func.cuh:210-225)
+    int num = sc.num_emitters;
+    num -= ns.emitter_id > 0 && num > 1;
+    uint32_t emit_id = (rng.next_u32() % uint32_t(num)) + 1;
+    emit_id += emit_id >= uint32_t(ns.emitter_id) && ns.emitter_id > 0;
+    ns.direct_pdf = 1.f / float(num);
+    emit_id = emit_id * uint32_t(ns.emitter_id == 0 || num > 1);
+    ns.emit_id = emit_id;
+    const EmitterPOD &em = sc.emitters[emit_id];
+    // ---- pick a primitive on it (object.cuh:45-49, wavefront_pt.cu:254-259)
+    const ObjectPOD eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
+    ns.direct_pdf *= eo.inv_area;
+    int emit_prim = int(rng.next_u32() % uint32_t(eo.prim_num)) + eo.prim_offset;
+    emit_prim = __ldg(sc.emitter_prims + emit_prim);
+
+    ns.hit_pos = advance(o, d, hit_t);
+    ns.direct_comp = mk4(0, 0, 0, 1);
+    ns.sd = emitter_sample(sc, em, ns.hit_pos, xyz(it), ns.direct_comp, ns.direct_pdf, rng.next2d(), emit_prim) - ns.hit_pos;
+    ns.len = length(ns.sd);
+    ns.sd *= __frcp_rn(ns.len);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shadow — the NEE visibility ray of fused_ray_bounce_shader (wavefront_pt.cu:273-275) as its own
+// low-register traversal kernel: re-derives the shadow ray from the path's sampler state (which it does not
+// advance) and leaves the answer in bit 31 of the ray tag for k_shade<SPLIT>
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_shadow(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
+                                                   const int *__restrict__ q_count, int *work,
+                                                   unsigned long long *shadow_counter) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    unsigned int local_shadow = 0;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        const bool valid = i < count;
+        uint32_t slot = 0, tag = 0;
+        bool need_shadow = false;
+        V3 so{0, 0, 0}, sd{0, 0, 1};
+        float range = 0;
+        if (valid) {
+            slot = queue[i];
+            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            const uint2 rs = st.rng[slot];
+            Rng rng{rs.x, rs.y};
+            tag = __float_as_uint(rd.w);
+            NeeSetup ns;
+            nee_setup(sc, xyz(ro), xyz(rd), ro.w, tag, st.isect[slot], rng, ns);
+            need_shadow = ns.emit_id != 0;
+            so = ns.hit_pos, sd = ns.sd, range = ns.len - kEps;
+        }
+        local_shadow += need_shadow;
+        const bool visible = unoccluded<MODE>(sc, s_cached, so, sd, range, need_shadow);
+        if (valid)
+            st.ray_d[slot].w = __uint_as_float(visible && need_shadow ? (tag | TAG_NEE_VISIBLE) : (tag & ~TAG_NEE_VISIBLE));
+    }
+    for (int off = 16; off > 0; off >>= 1)
+        local_shadow += __shfl_down_sync(0xffffffffu, local_shadow, off);
+    if (lane == 0 && local_shadow)
+        atomicAdd(shadow_counter, (unsigned long long)local_shadow);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_shade — reference: fused_ray_bounce_shader (wavefront_pt.cu:213-314)
+// MODE >= 0: the shadow ray is traced here; MODE == -1 (split pipeline): k_shadow already traced it
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
                                                   const int *__restrict__ q_count, int *work,
                                                   unsigned long long *shadow_counter, int secondary_bounce, PtRules pt) {
     extern __shared__ uint4 s_cached[];
-    stage_cached_nodes(sc, s_cached);
+    if constexpr (MODE >= 0)
+        stage_cached_nodes(sc, s_cached);
     const int lane = threadIdx.x & 31;
     const int count = *q_count;
     unsigned int local_shadow = 0;
@@ -197,37 +285,22 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
             o = xyz(ro), d = xyz(rd);
             hit_t = ro.w;
             tag = __float_as_uint(rd.w);
-
-            int object_id = __ldg(sc.obj_idxs + (tag & TAG_INDEX));
-            object_id = object_id >= 0 ? object_id : -object_id - 1;
-            ob = sc.objects[object_id];
-            material_id = ob.bsdf_emitter >> 16;
-            emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
-
-            // ---- pick an emitter (tracing_func.cuh:210-225)
-            int num = sc.num_emitters;
-            num -= emitter_id > 0 && num > 1;
-            emit_id = (rng.next_u32() % uint32_t(num)) + 1;
-            emit_id += emit_id >= uint32_t(emitter_id) && emitter_id > 0;
-            direct_pdf = 1.f / float(num);
-            emit_id = emit_id * uint32_t(emitter_id == 0 || num > 1);
-            const EmitterPOD &em = sc.emitters[emit_id];
-            // ---- pick a primitive on it (object.cuh:45-49, wavefront_pt.cu:254-259)
-            const ObjectPOD eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
-            direct_pdf *= eo.inv_area;
-            int emit_prim = int(rng.next_u32() % uint32_t(eo.prim_num)) + eo.prim_offset;
-            emit_prim = __ldg(sc.emitter_prims + emit_prim);
-
-            hit_pos = advance(o, d, hit_t);
+            NeeSetup ns;
+            nee_setup(sc, o, d, hit_t, tag, it, rng, ns);
+            emit_id = ns.emit_id, material_id = ns.material_id, emitter_id = ns.emitter_id, ob = ns.ob;
+            hit_pos = ns.hit_pos, sd = ns.sd, emit_len_mis = ns.len, direct_pdf = ns.direct_pdf, direct_comp = ns.direct_comp;
             o = hit_pos;
-            sd = emitter_sample(sc, em, hit_pos, xyz(it), direct_comp, direct_pdf, rng.next2d(), emit_prim) - hit_pos;
-            emit_len_mis = length(sd);
-            sd *= __frcp_rn(emit_len_mis);
         }
         // ---- part 2 (whole warp): NEE shadow ray (wavefront_pt.cu:273-275)
         const bool need_shadow = valid && emit_id != 0;
-        local_shadow += need_shadow;
-        const bool visible = unoccluded<MODE>(sc, s_cached, hit_pos, sd, emit_len_mis - kEps, need_shadow);
+        bool visible;
+        if constexpr (MODE >= 0) {
+            local_shadow += need_shadow;
+            visible = unoccluded<MODE>(sc, s_cached, hit_pos, sd, emit_len_mis - kEps, need_shadow);
+        } else {
+            visible = (tag & TAG_NEE_VISIBLE) != 0;
+            tag &= ~TAG_NEE_VISIBLE;
+        }
         // ---- part 3 (per lane): MIS, emission, BSDF sample, write back
         if (valid) {
             const Material &mat = sc.mats[material_id];
@@ -320,7 +393,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
             slot = queue[i];
             const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
             o = xyz(ro), d = xyz(rd);
-            tag = __float_as_uint(rd.w) & 0xd0000000u; // reset(): clear hit flag and hit index
+            tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index (and the split pipeline's NEE bit)
             valid = (tag & TAG_ACTIVE) != 0;           // megakernel rules: k_shade may have ended the path
         }
         const Hit h = closest_hit<MODE>(sc, s_cached, o, d, valid); // all 32 lanes call
@@ -784,7 +857,7 @@ void Renderer::enable_variance(bool on) {
 
 void Renderer::ensure_capacity(int samples) {
     Impl &m = *impl_;
-    if (samples <= m.capacity_samples && int(m.counters.n) >= 3 * (max_depth_ + 2) + 4)
+    if (samples <= m.capacity_samples && int(m.counters.n) >= 4 * (max_depth_ + 2) + 4)
         return;
     CUDA_OK(cudaStreamSynchronize(stream_));
     const size_t slots = size_t(w_) * h_ * size_t(std::max(samples, m.capacity_samples));
@@ -798,7 +871,7 @@ void Renderer::ensure_capacity(int samples) {
     m.lobes.alloc(slots);
     m.queue[0].alloc(slots);
     m.queue[1].alloc(slots);
-    m.counters.alloc(size_t(3 * (max_depth_ + 2) + 4)); // D+2 queue sizes, then one work counter per launch (<= 2D+1)
+    m.counters.alloc(size_t(4 * (max_depth_ + 2) + 4)); // D+2 queue sizes, then one work counter per launch (<= 3D+1)
     m.capacity_samples = std::max(samples, m.capacity_samples);
 }
 
@@ -852,9 +925,17 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     int launches = 1, traced = 0, shaded = 0;
     for (int b = 0; b < D; b++) {
         uint32_t *q_cur = m.queue[b & 1].p, *q_nxt = m.queue[(b + 1) & 1].p;
-        mark(1, b);
         const PtRules pt{rules_, b, m.caps[0], m.caps[1], m.caps[2]};
-        LAUNCH_MODE(k_shade, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt);
+        if (split_shadow_) {
+            mark(4, b);
+            LAUNCH_MODE(k_shadow, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter);
+            ++wk, ++launches;
+            mark(1, b);
+            k_shade<-1><<<grid, kBlock, 0, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt);
+        } else {
+            mark(1, b);
+            LAUNCH_MODE(k_shade, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt);
+        }
         ++wk;
         ++launches, ++shaded;
         if (b + 1 >= D)

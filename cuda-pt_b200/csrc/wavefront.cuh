@@ -28,9 +28,9 @@ struct RenderStats {
 
 // per-kernel device time (CUDA events around every launch, only when "kernel_timing" is enabled)
 struct KernelTimes {
-    double ms[4] = {0, 0, 0, 0};         // raygen, shade, trace, splat
-    uint64_t launches[4] = {0, 0, 0, 0};
-    uint64_t units[4] = {0, 0, 0, 0};    // pixel-samples, shaded segments, traced segments, pixel-samples
+    double ms[5] = {0, 0, 0, 0, 0};         // raygen, shade, trace, splat, shadow (split pipeline only)
+    uint64_t launches[5] = {0, 0, 0, 0, 0};
+    uint64_t units[5] = {0, 0, 0, 0, 0};    // pixel-samples, shaded segments, traced segments, pixel-samples, shaded segments
 };
 
 class Renderer {
@@ -67,6 +67,8 @@ class Renderer {
     void set_accum_count(int c) { accum_cnt_ = c; }
     void set_kernel_timing(bool on) { kernel_timing_ = on; }
     void set_rules(int r) { rules_ = r; }
+    void set_split_shadow(bool on) { split_shadow_ = on; }
+    bool split_shadow() const { return split_shadow_; }
     int rules() const { return rules_; }
     KernelTimes kernel_times() const { return ktimes_; }
 
@@ -88,7 +90,7 @@ class Renderer {
 
     int device_ = 0, w_ = 0, h_ = 0, seed_offset_ = 0, accum_cnt_ = 0, max_depth_ = 0;
     int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
-    bool variance_on_ = false, kernel_timing_ = false;
+    bool variance_on_ = false, kernel_timing_ = false, split_shadow_ = true;
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);
     cudaStream_t stream_ = nullptr;

@@ -170,10 +170,10 @@ class WavefrontRenderer:
 
     def kernel_times(self):
         """Per-kernel device time (needs set_option("kernel_timing", 1)): {name: (ms, launches, units)}."""
-        ms, ln, un = (C.c_double * 4)(), (C.c_uint64 * 4)(), (C.c_uint64 * 4)()
+        ms, ln, un = (C.c_double * 5)(), (C.c_uint64 * 5)(), (C.c_uint64 * 5)()
         check(lib().cpt_b200_kernel_times(self._h, ms, ln, un))
         return {k: {"ms": float(ms[i]), "launches": int(ln[i]), "units": int(un[i])}
-                for i, k in enumerate(["raygen", "shade", "trace", "splat"])}
+                for i, k in enumerate(["raygen", "shade", "trace", "splat", "shadow"])}
 
     def info(self):
         buf = C.create_string_buffer(1024)

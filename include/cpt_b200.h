@@ -92,17 +92,18 @@ int cpt_b200_height(const cpt_b200_renderer *r);
  * megakernel_pt.cu:159-180 - default taken from the scene's <renderer type>), "samples_in_flight" (>=1),
  * "traversal" (0 ordered pair-node, 1 reference DFS order, 2/3 experimental loop shapes),
  * "max_depth" (MaxDepthParams::max_depth, src/core/max_depth.h:26-42), "kernel_timing" (0/1: CUDA events
- * around every launch, read back with cpt_b200_kernel_times) */
+ * around every launch, read back with cpt_b200_kernel_times), "split_shadow" (1, default: the NEE visibility
+ * ray runs in its own traversal kernel before the shading kernel; 0: traced inside the shading kernel) */
 int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value);
 int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key);
 
 /* stats[8]: pixel-samples, closest-hit rays after the primary one, shadow rays, shaded segments,
  * kernel launches, device microseconds, 0, 0 (cumulative since creation) */
 int cpt_b200_stats(cpt_b200_renderer *r, uint64_t *stats8);
-/* cumulative per-kernel device time when "kernel_timing" is on; index 0 raygen+primary hit, 1 shade
- * (NEE + BSDF), 2 trace (closest hit + RR + compaction), 3 splat.  units = pixel-samples (0,3) or path
- * segments (1,2) those launches processed. */
-int cpt_b200_kernel_times(cpt_b200_renderer *r, double *ms4, uint64_t *launches4, uint64_t *units4);
+/* cumulative per-kernel device time when "kernel_timing" is on; 5 entries: 0 raygen+primary hit, 1 shade
+ * (NEE + BSDF), 2 trace (closest hit + RR + compaction), 3 splat, 4 shadow (NEE visibility kernel of the
+ * split pipeline).  units = pixel-samples (0,3) or path segments (1,2,4) those launches processed. */
+int cpt_b200_kernel_times(cpt_b200_renderer *r, double *ms5, uint64_t *launches5, uint64_t *units5);
 /* PythonRenderer::info (python_render.cuh) — copies a one-line description */
 int cpt_b200_info(const cpt_b200_renderer *r, char *buf, int buf_len);
 /* the CUDA stream all work of this handle is issued on (as a cudaStream_t value) */

@@ -45,7 +45,7 @@ def test_cornell_c0_bit_exact_vs_reference(traversal):
         assert bit_exact_fraction(out[n][0], ref) == 1.0, n  # RGB and alpha
     var_ref = np.fromfile(os.path.join(GOLDEN, "cbox_wfpt_256_wfpt_var_f0064.bin"), dtype=np.float32).reshape(256, 256, 1)
     assert np.array_equal(out[64][1].view(np.uint32), var_ref.view(np.uint32))
-    assert st["launches"] == 64 * (1 + 5 + 4 + 2)
+    assert st["launches"] == 64 * (1 + 5 + 5 + 4 + 2)  # raygen, 5 x (shadow + shade), 4 x trace, splat + stats fold
 
 
 def test_seed_offset_bit_exact_vs_reference():
@@ -89,6 +89,24 @@ def test_xml_loader_textures_statistically_equal_reference():
     rel = np.abs(bo - br).sum(-1) / np.maximum(br.sum(-1), 1e-3)
     assert np.median(rel) < 0.02 and np.quantile(rel, 0.9) < 0.08, (np.median(rel), np.quantile(rel, 0.9))
     assert abs(ours.mean() / ref.mean() - 1) < 0.01
+
+
+@pytest.mark.parametrize("scene,frame", [("cbox_mats_256.cpts", "cbox_mats_256_wfpt_f0016.bin"), ("texroom_256.cpts", None)])
+def test_fused_and_split_shadow_pipelines_agree(scene, frame):
+    """The NEE visibility ray traced inside the shading kernel ("split_shadow" 0) or by its own kernel (1, default)."""
+    outs = []
+    for split in (0, 1):
+        r = cpt.WavefrontRenderer(os.path.join(GOLDEN, scene), 0, 0)
+        r.set_option("split_shadow", split)
+        assert r.get_option("split_shadow") == split
+        r.render_batch(16, False)
+        outs.append(r.download_output())
+        st = r.stats()
+        assert st["launches"] == 1 + 8 * (2 if split else 1) + 7 + 2
+        r.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    if frame:
+        assert bit_exact_fraction(outs[1], load_frame(frame)) == 1.0
 
 
 def test_megakernel_rules_bit_exact_vs_reference_pt():
@@ -242,17 +260,22 @@ def test_full_size_properties():
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_DUMP) and have_vader()), reason="reference harness / vader mesh not on this box")
-def test_live_reference_vader_bit_exact(tmp_path):
-    """The unmodified reference renders vader (SBVH, thin lens, 2 lights, 16 bounces) right now on this GPU; our
-    kernels render from the scene it dumped.  Also checks the committed frame."""
+@pytest.mark.parametrize("xml", ["vader_wfpt_256.xml", "vader_tex_wfpt_256.xml"])
+def test_live_reference_vader_bit_exact(tmp_path, xml):
+    """The unmodified reference renders vader (SBVH, thin lens, 2 lights, 16 bounces; second case: plus 2K glossy /
+    roughness / normal / albedo textures and an environment map) right now on this GPU; our kernels render from
+    the scene it dumped.  Also checks the committed frame."""
+    if "tex" in xml and not os.path.exists(os.path.join(ROOT, "scenes", "assets", "tex2k", "envmap.png")):
+        pytest.skip("2K placeholder textures not generated (python tools/make_assets.py --size 2048)")
     prefix = str(tmp_path / "vader")
-    subprocess.run([REF_DUMP, "render", os.path.join(SCENES, "vader_wfpt_256.xml"), prefix, "wfpt", "0", "2,8"],
+    subprocess.run([REF_DUMP, "render", os.path.join(SCENES, xml), prefix, "wfpt", "0", "2,8"],
                    check=True, capture_output=True, cwd=ROOT)
     r = cpt.WavefrontRenderer(prefix + ".cpts", 0, 0)
     for n in (2, 8):
         r.render_batch(n - r.counter(), False)
         ref = np.fromfile(f"{prefix}_wfpt_f{n:04d}.bin", dtype=np.float32).reshape(256, 256, 4)
         assert bit_exact_fraction(r.download_output(), ref) == 1.0, n
-    gold = load_frame("vader_256_wfpt_f0008.bin")
-    assert rel_l2(r.download_output(), gold) <= 1e-4  # the SBVH build is threaded: allow a different primitive order
+    if "tex" not in xml:
+        gold = load_frame("vader_256_wfpt_f0008.bin")
+        assert rel_l2(r.download_output(), gold) <= 1e-4  # the SBVH build is threaded: allow a different primitive order
     r.close()

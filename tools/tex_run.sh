@@ -1,17 +1,19 @@
-set -x
-mkdir -p gpurun_out/ref2 gpurun_out/xmlcmp
-R=oracle/_ref/ref_dump
-X=scenes/xml
-$R render $X/texroom_wfpt_256.xml gpurun_out/ref2/texroom_256 wfpt 0 1,2,16,64 > gpurun_out/ref2/texroom.log 2>&1
-tail -5 gpurun_out/ref2/texroom.log
-ls -la gpurun_out/ref2
-python tools/parity_check.py gpurun_out/ref2 2>&1 | tail -20
-# our XML loader + PNG decoder against the reference frames
-python - <<'PY'
-import numpy as np, cuda_pt_b200 as cpt
-r = cpt.WavefrontRenderer("scenes/xml/texroom_wfpt_256.xml", 0, 0)
-for n in range(64): r.render_raw(False)
-out = r.download_output()
-ref = np.fromfile("gpurun_out/ref2/texroom_256_wfpt_f0064.bin", dtype=np.float32).reshape(256,256,4)
-print("xml-loader vs reference f64: rel_l2 =", np.linalg.norm(out[...,:3].astype(np.float64)-ref[...,:3])/np.linalg.norm(ref[...,:3].astype(np.float64)), "mean", out[...,:3].mean(), ref[...,:3].mean())
+python -m pytest tests -m gpu -q -x 2>&1 | tail -15
+python tools/quick_bench.py scenes/xml/vader_wfpt_1080p.xml 32 0 16
+CPTB200_X=1 python - <<'PY'
+import os, sys, time
+sys.path.insert(0, os.getcwd())
+import cuda_pt_b200 as cpt
+xml="scenes/xml/vader_wfpt_1080p.xml"; spp=32
+for split in (0,1,0,1):
+    r = cpt.WavefrontRenderer(xml, 0, 0)
+    r.set_option("samples_in_flight", 16); r.set_option("kernel_timing", 1); r.set_option("split_shadow", split)
+    r.render_batch(32, False)
+    s0 = r.stats(); k0 = r.kernel_times()
+    r.render_batch(spp, False); r.sync()
+    s1 = r.stats(); k1 = r.kernel_times()
+    dev = (s1["device_us"] - s0["device_us"]) / 1e6
+    kt = {k: round((k1[k]["ms"] - k0[k]["ms"]) / spp, 3) for k in k1}
+    print(f"split={split}: {dev/spp*1e3:.3f} ms/spp, {(s1['rays']-s0['rays'])/dev/1e6:.1f} Mrays/s {kt}", flush=True)
+    r.close()
 PY
