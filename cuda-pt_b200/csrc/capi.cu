@@ -251,7 +251,11 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
                 throw std::runtime_error("rules must be 0 (wavefront) or 1 (megakernel pt)");
             r->impl->set_rules(int(value));
         } else if (k == "split_shadow") {
-            r->impl->set_split_shadow(value != 0);
+            r->impl->set_pipeline(value != 0 ? 1 : 0);
+        } else if (k == "pipeline") {
+            if (value < 0 || value > 3)
+                throw std::runtime_error("pipeline must be 0 (fused), 1 (split shadow kernel), 2 (dynamic-fetch traversal kernels) or 3 (deferred NEE)");
+            r->impl->set_pipeline(int(value));
         } else if (k == "kernel_timing") {
             r->impl->set_kernel_timing(value != 0);
         } else if (k == "max_depth") {
@@ -274,7 +278,9 @@ int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key) {
     if (k == "rules")
         return r->impl->rules();
     if (k == "split_shadow")
-        return r->impl->split_shadow() ? 1 : 0;
+        return r->impl->pipeline() != 0 ? 1 : 0;
+    if (k == "pipeline")
+        return r->impl->pipeline();
     return -1;
 }
 
@@ -289,7 +295,8 @@ int cpt_b200_stats(cpt_b200_renderer *r, uint64_t *stats8) {
         stats8[3] = s.shaded;
         stats8[4] = s.launches;
         stats8[5] = uint64_t(s.device_ms * 1000.0);
-        stats8[6] = stats8[7] = 0;
+        stats8[6] = s.shadow_traced;
+        stats8[7] = 0;
     });
 }
 

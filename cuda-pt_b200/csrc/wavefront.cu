@@ -249,13 +249,176 @@ __global__ void __launch_bounds__(kBlock) k_shadow(DevScene sc, PathState st, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dynamic-fetch pipeline ("pipeline" 2).  Traversal is the whole cost of this path and a warp that walks 32
+// rays to completion idles most of its lanes on the longest ray, so traversal runs in two pure kernels
+// (k_anyhit, k_intersect) whose warps keep their lanes full: whenever kRefill lanes are idle they pull the
+// next rays of the queue.  Everything that is not traversal moves into coherent companion kernels:
+//   k_shadow_gen  NEE set-up -> shadow ray {o, range}{d, start} + queue of rays that need a traversal
+//   k_anyhit      any-hit traversal, sets TAG_NEE_VISIBLE
+//   k_shade<-1>   shading (reads the bit)
+//   k_intersect   closest-hit traversal -> hit record {t, u, v, prim}
+//   k_resolve     interaction, miss/envmap, Russian roulette, compaction (the epilogue of k_trace)
+// Same boxes, same slab / triangle arithmetic, same tie rule as the ordered traversal of traverse.cuh.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRefill = 8;  // refill a warp when at least this many lanes are idle
+constexpr int kGrab = 128;  // rays a warp reserves per global atomic
+constexpr int kSteps = 4;   // traversal steps between refill checks
+
+struct RayBufs {
+    float4 *sh_o; // shadow ray origin, w = range
+    float4 *sh_d; // shadow ray direction, w = bits(start DFS index of the cached phase)
+    float4 *hit;  // closest hit {t, u, v, bits(prim)}
+};
+
+__global__ void __launch_bounds__(kBlock) k_shadow_gen(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue,
+                                                       const int *__restrict__ q_count, int *work, uint32_t *sq,
+                                                       int *sq_count, unsigned long long *shadow_counter) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    unsigned int local_shadow = 0;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        uint32_t slot = 0;
+        bool traverse = false;
+        if (i < count) {
+            slot = queue[i];
+            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            const uint2 rs = st.rng[slot];
+            Rng rng{rs.x, rs.y};
+            uint32_t tag = __float_as_uint(rd.w) & ~TAG_NEE_VISIBLE;
+            NeeSetup ns;
+            nee_setup(sc, xyz(ro), xyz(rd), ro.w, tag, st.isect[slot], rng, ns);
+            if (ns.emit_id != 0) {
+                ++local_shadow;
+                const float range = ns.len - kEps;
+                const V3 inv_d = rcp3(ns.sd), o_div = ns.hit_pos * inv_d;
+                const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, range, sc.num_nodes);
+                if (start >= sc.num_nodes) {
+                    tag |= TAG_NEE_VISIBLE; // no cached frontier node on the way: unoccluded (tracing_func.cuh:49)
+                } else {
+                    traverse = true;
+                    rb.sh_o[slot] = make_float4(ns.hit_pos.x, ns.hit_pos.y, ns.hit_pos.z, range);
+                    rb.sh_d[slot] = make_float4(ns.sd.x, ns.sd.y, ns.sd.z, __int_as_float(start));
+                }
+            }
+            st.ray_d[slot].w = __uint_as_float(tag);
+        }
+        warp_push(sq, sq_count, traverse, slot, lane);
+    }
+    for (int off = 16; off > 0; off >>= 1)
+        local_shadow += __shfl_down_sync(0xffffffffu, local_shadow, off);
+    if (lane == 0 && local_shadow)
+        atomicAdd(shadow_counter, (unsigned long long)local_shadow);
+}
+
+// warp-level work distribution for the dynamic-fetch kernels: the warp owns [next, end) of the queue and
+// reserves kGrab more entries with one atomic when it runs dry.  Returns how many entries the idle lanes may
+// take now (0 when the queue is exhausted) and advances `next`; `first` = index of the first one.
+__device__ __forceinline__ int warp_take(int *work, int count, int lane, int n_idle, int &next, int &end, bool &more, int &first) {
+    if (next >= end) {
+        int b = 0;
+        if (lane == 0)
+            b = atomicAdd(work, kGrab);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        next = b;
+        end = min(b + kGrab, count);
+        if (b >= count) {
+            more = false;
+            return 0;
+        }
+    }
+    const int take = min(n_idle, end - next);
+    first = next;
+    next += take;
+    return take;
+}
+
+__global__ void __launch_bounds__(kBlock) k_anyhit(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ sq,
+                                                   const int *__restrict__ sq_count, int *work) {
+    const int lane = threadIdx.x & 31;
+    const int count = *sq_count;
+    int stack_ref[kStackSize];
+    int sp = 0, cur = kTraversalDone, start = 0;
+    uint32_t slot = 0;
+    V3 o{0, 0, 0}, d{0, 0, 1}, inv_d{0, 0, 0}, o_div{0, 0, 0};
+    float range = 0;
+    bool active = false, more = true;
+    int next = 0, end = 0;
+    while (true) {
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        const int n_idle = 32 - __popc(act);
+        if (more && n_idle >= kRefill) {
+            int first = 0;
+            const int take = warp_take(work, count, lane, n_idle, next, end, more, first);
+            const int rank = __popc(~act & ((1u << lane) - 1u));
+            if (!active && rank < take) {
+                slot = sq[first + rank];
+                const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
+                o = xyz(a), d = xyz(b), range = a.w, start = __float_as_int(b.w);
+                inv_d = rcp3(d), o_div = o * inv_d;
+                cur = sc.wroot, sp = 0, active = true;
+            }
+        } else if (act == 0)
+            break;
+#pragma unroll 1
+        for (int k = 0; k < kSteps; k++) {
+            if (active) {
+                bool occluded = false;
+                if (cur >= 0) {
+                    const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
+                                 b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+                    float t0, t1;
+                    const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < range &&
+                                    __float_as_int(a1.w) > start;
+                    const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < range &&
+                                    __float_as_int(b1.w) > start;
+                    const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+                    if (h0 && h1) {
+                        stack_ref[sp++] = r1;
+                        cur = r0;
+                    } else if (h0 || h1) {
+                        cur = h0 ? r0 : r1;
+                    } else {
+                        cur = sp > 0 ? stack_ref[--sp] : kTraversalDone;
+                    }
+                } else {
+                    const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+                    for (int idx = base; idx < base + cnt; idx++) {
+                        float u, v;
+                        if (hit_triangle(sc.tris, idx, o, d, u, v, range) > kEps) {
+                            occluded = true;
+                            break;
+                        }
+                    }
+                    cur = sp > 0 ? stack_ref[--sp] : kTraversalDone;
+                }
+                if (occluded || cur == kTraversalDone) {
+                    if (!occluded) {
+                        float *tagp = &st.ray_d[slot].w;
+                        *tagp = __uint_as_float(__float_as_uint(*tagp) | TAG_NEE_VISIBLE);
+                    }
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_shade — reference: fused_ray_bounce_shader (wavefront_pt.cu:213-314)
-// MODE >= 0: the shadow ray is traced here; MODE == -1 (split pipeline): k_shadow already traced it
+// MODE >= 0: the shadow ray is traced here; MODE == -1 (split pipeline): k_shadow already traced it;
+// MODE == -2 (deferred-NEE pipeline): nothing is traced yet - the radiance is written for the occluded case,
+// the value for the unoccluded case goes to rb.hit together with the shadow ray, and only paths for which the
+// two differ (in any bit) are queued for k_shadow_apply.  NEE samples that cannot change the pixel (emitter
+// facing away, BSDF value zero, delta lobes) therefore never cost a traversal, and the result stays exact.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
                                                   const int *__restrict__ q_count, int *work,
-                                                  unsigned long long *shadow_counter, int secondary_bounce, PtRules pt) {
+                                                  unsigned long long *shadow_counter, int secondary_bounce, PtRules pt,
+                                                  RayBufs rb, uint32_t *sq, int *sq_count) {
     extern __shared__ uint4 s_cached[];
     if constexpr (MODE >= 0)
         stage_cached_nodes(sc, s_cached);
@@ -293,14 +456,18 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
         }
         // ---- part 2 (whole warp): NEE shadow ray (wavefront_pt.cu:273-275)
         const bool need_shadow = valid && emit_id != 0;
-        bool visible;
+        bool visible, queue_shadow = false;
         if constexpr (MODE >= 0) {
             local_shadow += need_shadow;
             visible = unoccluded<MODE>(sc, s_cached, hit_pos, sd, emit_len_mis - kEps, need_shadow);
-        } else {
+        } else if constexpr (MODE == -1) {
             visible = (tag & TAG_NEE_VISIBLE) != 0;
             tag &= ~TAG_NEE_VISIBLE;
+        } else {
+            local_shadow += need_shadow;
+            visible = true; // evaluate the unoccluded candidate; k_shadow_apply decides
         }
+        const float shadow_range = emit_len_mis - kEps;
         // ---- part 3 (per lane): MIS, emission, BSDF sample, write back
         if (valid) {
             const Material &mat = sc.mats[material_id];
@@ -310,23 +477,28 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
             const float emission_weight =
                 pdf / (pdf + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, hit_t) * (emitter_id > 0) *
                                  secondary_bounce * ((tag & TAG_DELTA) == 0));
-            V4 L;
+            // L: radiance if the shadow ray is blocked, Lv: if it is not (or was not needed)
+            V4 L, Lv;
+            const V4 emis = thp * emitter_eval(sc.emitters[emitter_id], d, it, true);
             if (!pt.enabled) {
+                V4 rdc_v = rdc;
                 if (need_shadow && visible) { // wavefront_pt.cu:276-289
                     emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
-                    rdc += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
-                           (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+                    rdc_v += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
+                             (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
                 }
                 // (2) account for emission, and accumulate to payload buffer (wavefront_pt.cu:299-302)
-                L = (thp * emitter_eval(sc.emitters[emitter_id], d, it, true)) * emission_weight + rdc;
+                Lv = emis * emission_weight + rdc_v;
+                L = emis * emission_weight + rdc;
             } else {
                 // megakernel order (megakernel_pt.cu:105-152): emission first, then the NEE term, then the NaN scrub
                 L = rdc;
-                L += (thp * emitter_eval(sc.emitters[emitter_id], d, it, true)) * emission_weight;
+                L += emis * emission_weight;
+                Lv = L;
                 if (need_shadow && visible) {
                     emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
-                    L += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
-                         (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+                    Lv += thp * direct_comp * bsdf_eval(sc, mat, it, sd, d) *
+                          (float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
                 }
             }
 
@@ -338,6 +510,8 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
             if (pt.enabled) { // megakernel_pt.cu:159-180
                 if (bad_rgb(L))
                     L = splat4(0);
+                if (bad_rgb(Lv))
+                    Lv = splat4(0);
                 uint32_t c = st.lobes[slot];
                 c += uint32_t((lobe & LOBE_DIFFUSE) > 0) + (uint32_t((lobe & LOBE_SPECULAR) > 0) << 8) +
                      (uint32_t((lobe & LOBE_TRANSMIT) > 0) << 16);
@@ -355,7 +529,19 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
                 if (!go_on)
                     tag &= ~TAG_ACTIVE;
             }
-            st.L[slot] = to_f4(L);
+            if constexpr (MODE == -2) {
+                const float4 a = to_f4(L), b = to_f4(Lv);
+                queue_shadow = need_shadow && (__float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y) ||
+                                               __float_as_uint(a.z) != __float_as_uint(b.z) || __float_as_uint(a.w) != __float_as_uint(b.w));
+                if (queue_shadow) {
+                    rb.sh_o[slot] = make_float4(hit_pos.x, hit_pos.y, hit_pos.z, shadow_range);
+                    rb.sh_d[slot] = make_float4(sd.x, sd.y, sd.z, 0.f);
+                    rb.hit[slot] = b;
+                }
+                st.L[slot] = a;
+            } else {
+                st.L[slot] = to_f4(Lv);
+            }
 
             st.thp[slot] = to_f4(thp);
             st.rng[slot] = make_uint2(rng.d0, rng.d1);
@@ -363,12 +549,189 @@ __global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, con
             st.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
             st.pdf[slot] = pdf;
         }
+        if constexpr (MODE == -2)
+            warp_push(sq, sq_count, queue_shadow, slot, lane);
     }
     // per-warp ray statistics (Mrays/s accounting)
     for (int off = 16; off > 0; off >>= 1)
         local_shadow += __shfl_down_sync(0xffffffffu, local_shadow, off);
     if (lane == 0 && local_shadow)
         atomicAdd(shadow_counter, (unsigned long long)local_shadow);
+}
+
+// deferred-NEE pipeline: trace the queued shadow rays; an unoccluded ray swaps in the radiance k_shade<-2> prepared
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_shadow_apply(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ sq,
+                                                         const int *__restrict__ sq_count, int *work) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *sq_count;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        const bool valid = i < count;
+        uint32_t slot = 0;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        float range = 0;
+        if (valid) {
+            slot = sq[i];
+            const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
+            o = xyz(a), d = xyz(b), range = a.w;
+        }
+        const bool visible = unoccluded<MODE>(sc, s_cached, o, d, range, valid);
+        if (valid && visible)
+            st.L[slot] = rb.hit[slot];
+    }
+}
+
+// what happens to a path once its extension ray is traced (wavefront_pt.cu:160-206): interaction at a hit +
+// Russian roulette, environment / null emitter on a miss.  Returns whether the path goes on to the next bounce.
+__device__ __forceinline__ bool resolve_hit(const DevScene &sc, PathState &st, uint32_t slot, uint32_t tag, V3 d, float hit_t,
+                                            float hit_u, float hit_v, int prim, int bounce, int pt_rules) {
+    bool alive = false;
+    V4 thp = from_f4(st.thp[slot]);
+    if (prim >= 0) {
+        tag |= TAG_HIT | TAG_ACTIVE | uint32_t(prim);
+        st.isect[slot] = make_interaction(sc, prim, hit_u, hit_v);
+        alive = true;
+        const float max_value = max3(thp);
+        if (!pt_rules && bounce >= kRRBounce && max_value < kRRThreshold) {
+            const uint2 rs = st.rng[slot];
+            Rng rng{rs.x, rs.y};
+            const bool survive = rng.next1d() < max_value && max_value > kThpEps;
+            alive = survive;
+            if (!survive)
+                tag &= ~TAG_ACTIVE;
+            thp *= survive ? 1.f / max_value : 0.f;
+            st.thp[slot] = to_f4(thp);
+            st.rng[slot] = make_uint2(rng.d0, rng.d1);
+        }
+    } else {
+        V4 L = from_f4(st.L[slot]);
+        L += thp * null_or_env(sc, d);
+        st.L[slot] = to_f4(L);
+        tag &= ~TAG_ACTIVE;
+    }
+    st.ray_o[slot].w = hit_t;
+    st.ray_d[slot].w = __uint_as_float(tag);
+    return alive;
+}
+
+// closest-hit traversal with dynamic ray fetch (see the pipeline note above k_shadow_gen)
+__global__ void __launch_bounds__(kBlock) k_intersect(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue,
+                                                      const int *__restrict__ q_count, int *work) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int sp = 0, cur = kTraversalDone, start = 0;
+    uint32_t slot = 0;
+    V3 o{0, 0, 0}, d{0, 0, 1}, inv_d{0, 0, 0}, o_div{0, 0, 0};
+    float ht = kMaxDist, hu = 0, hv = 0;
+    int hprim = -1;
+    bool active = false, more = true;
+    int next = 0, end = 0;
+    const float inf = __int_as_float(0x7f800000);
+    while (true) {
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        const int n_idle = 32 - __popc(act);
+        if (more && n_idle >= kRefill) {
+            int first = 0;
+            const int take = warp_take(work, count, lane, n_idle, next, end, more, first);
+            const int rank = __popc(~act & ((1u << lane) - 1u));
+            if (!active && rank < take) {
+                slot = queue[first + rank];
+                const float4 a = st.ray_o[slot], b = st.ray_d[slot];
+                if (__float_as_uint(b.w) & TAG_ACTIVE) { // megakernel rules: k_shade may have ended the path
+                    o = xyz(a), d = xyz(b);
+                    inv_d = rcp3(d), o_div = o * inv_d;
+                    start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+                    ht = kMaxDist, hu = hv = 0.f, hprim = -1;
+                    cur = sc.wroot, sp = 0, active = true;
+                }
+            }
+        } else if (act == 0)
+            break;
+#pragma unroll 1
+        for (int k = 0; k < kSteps; k++) {
+            if (active) {
+                bool pop = false;
+                if (cur >= 0) {
+                    const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
+                                 b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+                    float t0, t1;
+                    const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < ht &&
+                                    __float_as_int(a1.w) > start;
+                    const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < ht &&
+                                    __float_as_int(b1.w) > start;
+                    const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+                    if (h0 && h1) {
+                        const bool swap = t1 < t0;
+                        stack_ref[sp] = swap ? r0 : r1;
+                        stack_t[sp] = swap ? t0 : t1;
+                        ++sp;
+                        cur = swap ? r1 : r0;
+                    } else if (h0 || h1) {
+                        cur = h0 ? r0 : r1;
+                    } else {
+                        pop = true;
+                    }
+                } else {
+                    const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+                    for (int idx = base; idx < base + cnt; idx++) {
+                        float u, v;
+                        const float dist = hit_triangle(sc.tris, idx, o, d, u, v, inf);
+                        // equal distances: the reference keeps the first hit in DFS order == the smaller primitive index
+                        const bool better = dist > kEps && (dist < ht || (dist == ht && idx < hprim));
+                        ht = better ? dist : ht;
+                        hu = better ? u : hu;
+                        hv = better ? v : hv;
+                        hprim = better ? idx : hprim;
+                    }
+                    pop = true;
+                }
+                if (pop) {
+                    cur = kTraversalDone;
+                    while (sp > 0) {
+                        --sp;
+                        if (stack_t[sp] < ht) {
+                            cur = stack_ref[sp];
+                            break;
+                        }
+                    }
+                    if (cur == kTraversalDone) {
+                        rb.hit[slot] = make_float4(ht, hu, hv, __int_as_float(hprim));
+                        active = false;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// the per-path epilogue of k_trace for the dynamic-fetch pipeline: reads k_intersect's hit records in queue order
+__global__ void __launch_bounds__(kBlock) k_resolve(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue,
+                                                    const int *__restrict__ q_count, int *work, uint32_t *q_next,
+                                                    int *q_next_count, int bounce, int pt_rules) {
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        bool alive = false;
+        uint32_t slot = 0;
+        if (i < count) {
+            slot = queue[i];
+            const float4 rd = st.ray_d[slot];
+            const uint32_t tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index
+            if (tag & TAG_ACTIVE) {
+                const float4 h = rb.hit[slot];
+                alive = resolve_hit(sc, st, slot, tag, xyz(rd), h.x, h.y, h.z, __float_as_int(h.w), bounce, pt_rules);
+            }
+        }
+        warp_push(q_next, q_next_count, alive, slot, lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -397,33 +760,8 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
             valid = (tag & TAG_ACTIVE) != 0;           // megakernel rules: k_shade may have ended the path
         }
         const Hit h = closest_hit<MODE>(sc, s_cached, o, d, valid); // all 32 lanes call
-        if (valid) {
-            V4 thp = from_f4(st.thp[slot]);
-            if (h.prim >= 0) {
-                tag |= TAG_HIT | TAG_ACTIVE | uint32_t(h.prim);
-                st.isect[slot] = make_interaction(sc, h.prim, h.u, h.v);
-                alive = true;
-                const float max_value = max3(thp);
-                if (!pt_rules && bounce >= kRRBounce && max_value < kRRThreshold) {
-                    const uint2 rs = st.rng[slot];
-                    Rng rng{rs.x, rs.y};
-                    const bool survive = rng.next1d() < max_value && max_value > kThpEps;
-                    alive = survive;
-                    if (!survive)
-                        tag &= ~TAG_ACTIVE;
-                    thp *= survive ? 1.f / max_value : 0.f;
-                    st.thp[slot] = to_f4(thp);
-                    st.rng[slot] = make_uint2(rng.d0, rng.d1);
-                }
-            } else {
-                V4 L = from_f4(st.L[slot]);
-                L += thp * null_or_env(sc, d);
-                st.L[slot] = to_f4(L);
-                tag &= ~TAG_ACTIVE;
-            }
-            st.ray_o[slot].w = h.t;
-            st.ray_d[slot].w = __uint_as_float(tag);
-        }
+        if (valid)
+            alive = resolve_hit(sc, st, slot, tag, d, h.t, h.u, h.v, h.prim, bounce, pt_rules);
         warp_push(q_next, q_next_count, alive, slot, lane);
     }
 }
@@ -471,8 +809,12 @@ __global__ void __launch_bounds__(256) k_splat(const float4 *__restrict__ Lbuf, 
 
 // folds the per-bounce queue sizes of a finished batch into the cumulative ray statistics
 __global__ void k_fold_stats(const int *__restrict__ q_counts, int traced_bounces, int shaded_bounces,
-                             unsigned long long *stats) {
+                             unsigned long long *stats, const int *__restrict__ sq_counts, int shadow_queues) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long queued = 0;
+        for (int b = 0; b < shadow_queues; b++)
+            queued += (unsigned long long)sq_counts[b];
+        stats[3] += queued;
         unsigned long long closest = 0, shaded = 0;
         for (int b = 0; b < shaded_bounces; b++)
             shaded += (unsigned long long)q_counts[b];
@@ -580,7 +922,8 @@ struct Renderer::Impl {
     DevBuf<float> pdf;
     DevBuf<uint32_t> lobes;
     int caps[3] = {16, 16, 16};
-    DevBuf<uint32_t> queue[2];
+    DevBuf<uint32_t> queue[2], shadow_queue;
+    DevBuf<float4> sh_o, sh_d, hit; // dynamic-fetch pipeline: shadow rays and hit records
     DevBuf<int> counters;                 // [0..D] queue sizes, [D+1 ..] work counters
     DevBuf<unsigned long long> stats;     // closest, shadow, shaded
     std::vector<cudaTextureObject_t> tex_objs;
@@ -857,7 +1200,7 @@ void Renderer::enable_variance(bool on) {
 
 void Renderer::ensure_capacity(int samples) {
     Impl &m = *impl_;
-    if (samples <= m.capacity_samples && int(m.counters.n) >= 4 * (max_depth_ + 2) + 4)
+    if (samples <= m.capacity_samples && int(m.counters.n) >= 8 * (max_depth_ + 2) + 8 && (pipeline_ < 2 || m.hit.n > 0))
         return;
     CUDA_OK(cudaStreamSynchronize(stream_));
     const size_t slots = size_t(w_) * h_ * size_t(std::max(samples, m.capacity_samples));
@@ -871,7 +1214,13 @@ void Renderer::ensure_capacity(int samples) {
     m.lobes.alloc(slots);
     m.queue[0].alloc(slots);
     m.queue[1].alloc(slots);
-    m.counters.alloc(size_t(4 * (max_depth_ + 2) + 4)); // D+2 queue sizes, then one work counter per launch (<= 3D+1)
+    if (pipeline_ >= 2) {
+        m.shadow_queue.alloc(slots);
+        m.sh_o.alloc(slots);
+        m.sh_d.alloc(slots);
+        m.hit.alloc(slots);
+    }
+    m.counters.alloc(size_t(8 * (max_depth_ + 2) + 8)); // D+2 queue sizes, D+2 shadow-queue sizes, then one work counter per launch (<= 5D+1)
     m.capacity_samples = std::max(samples, m.capacity_samples);
 }
 
@@ -883,11 +1232,14 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p, m.lobes.p};
     BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_, rules_};
     int *q_counts = m.counters.p;          // D + 1 entries
-    int *work = m.counters.p + (D + 2);    // one per launch
+    int *sq_counts = m.counters.p + (D + 2); // D + 1 entries (dynamic-fetch pipeline)
+    int *work = m.counters.p + 2 * (D + 2);  // one per launch
+    RayBufs rb{m.sh_o.p, m.sh_d.p, m.hit.p};
     CUDA_OK(cudaMemsetAsync(m.counters.p, 0, m.counters.n * sizeof(int), stream_));
     const size_t smem = size_t(m.dev.num_cache) * sizeof(uint4);
     const int grid = num_sms_ * blocks_per_sm_;
     const int mode = traversal_;
+    const int pipeline_ = (this->pipeline_ == 2 && traversal_ != 0) ? 1 : this->pipeline_; // dynamic fetch exists for the ordered traversal only
 #define LAUNCH_MODE(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (mode == 0)                                                                                                 \
@@ -926,22 +1278,46 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     for (int b = 0; b < D; b++) {
         uint32_t *q_cur = m.queue[b & 1].p, *q_nxt = m.queue[(b + 1) & 1].p;
         const PtRules pt{rules_, b, m.caps[0], m.caps[1], m.caps[2]};
-        if (split_shadow_) {
+        if (pipeline_ == 3) {
+            mark(1, b);
+            k_shade<-2><<<grid, kBlock, 0, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt, rb,
+                                                      m.shadow_queue.p, sq_counts + b);
+            ++wk, ++launches;
+            mark(4, b);
+            LAUNCH_MODE(k_shadow_apply, m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+        } else if (pipeline_ == 2) {
+            mark(4, b);
+            k_shadow_gen<<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, m.shadow_queue.p,
+                                                          sq_counts + b, shadow_counter);
+            ++wk, ++launches;
+            mark(4, b);
+            k_anyhit<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+            ++wk, ++launches;
+            mark(1, b);
+            k_shade<-1><<<grid, kBlock, 0, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt, rb, nullptr, nullptr);
+        } else if (pipeline_ == 1) {
             mark(4, b);
             LAUNCH_MODE(k_shadow, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter);
             ++wk, ++launches;
             mark(1, b);
-            k_shade<-1><<<grid, kBlock, 0, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt);
+            k_shade<-1><<<grid, kBlock, 0, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt, rb, nullptr, nullptr);
         } else {
             mark(1, b);
-            LAUNCH_MODE(k_shade, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt);
+            LAUNCH_MODE(k_shade, m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt, rb, nullptr, nullptr);
         }
         ++wk;
         ++launches, ++shaded;
         if (b + 1 >= D)
             break;
         mark(2, b);
-        LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+        if (pipeline_ == 2) {
+            k_intersect<<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk);
+            ++wk, ++launches;
+            mark(2, b);
+            k_resolve<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+        } else {
+            LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+        }
         ++wk;
         ++launches, ++traced;
     }
@@ -949,7 +1325,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples,
                                                first_accum, write_output ? 1 : 0, gamma ? 1 : 0, rules_ == 0 ? 1 : 0);
     mark(-1, 0);
-    k_fold_stats<<<1, 32, 0, stream_>>>(q_counts, traced, shaded, m.stats.p);
+    k_fold_stats<<<1, 32, 0, stream_>>>(q_counts, traced, shaded, m.stats.p, sq_counts, pipeline_ >= 2 ? shaded : 0);
     launches += 2;
     CUDA_OK(cudaEventRecord(m.ev1, stream_));
     CUDA_OK(cudaGetLastError());
@@ -1097,6 +1473,7 @@ RenderStats Renderer::stats() {
     s.closest_rays = h[0];
     s.shadow_rays = h[1];
     s.shaded = h[2];
+    s.shadow_traced = pipeline_ >= 2 ? h[3] : h[1];
     return s;
 }
 
@@ -1106,7 +1483,7 @@ std::string Renderer::info() const {
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
        << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-ww" : "ordered-vote")))
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations
-       << ", rules " << (rules_ ? "megakernel-pt" : "wavefront") << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
+       << ", pipeline " << pipeline_ << ", rules " << (rules_ ? "megakernel-pt" : "wavefront") << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();
 }
 

@@ -20,7 +20,8 @@ enum Traversal : int { TRAVERSAL_ORDERED = 0, TRAVERSAL_DFS = 1 };
 struct RenderStats {
     uint64_t samples = 0;      // pixel-samples (primary rays)
     uint64_t closest_rays = 0; // extension (closest-hit) traversals after the primary one
-    uint64_t shadow_rays = 0;  // NEE any-hit traversals
+    uint64_t shadow_rays = 0;  // NEE shadow rays of the algorithm (one per shaded segment whose sampled emitter is not the null emitter)
+    uint64_t shadow_traced = 0; // of those, how many needed a BVH traversal (pipelines 2/3 skip rays that cannot matter)
     uint64_t shaded = 0;       // path segments shaded
     uint64_t launches = 0;     // kernels launched
     double device_ms = 0;      // device time spent in render batches (CUDA events)
@@ -67,8 +68,10 @@ class Renderer {
     void set_accum_count(int c) { accum_cnt_ = c; }
     void set_kernel_timing(bool on) { kernel_timing_ = on; }
     void set_rules(int r) { rules_ = r; }
-    void set_split_shadow(bool on) { split_shadow_ = on; }
-    bool split_shadow() const { return split_shadow_; }
+    // 0: NEE ray traced inside the shading kernel; 1: own shadow kernel; 2: dynamic-fetch traversal kernels;
+    // 3: deferred NEE (shade first, trace only the shadow rays that can change the radiance)
+    void set_pipeline(int p) { pipeline_ = p; }
+    int pipeline() const { return pipeline_; }
     int rules() const { return rules_; }
     KernelTimes kernel_times() const { return ktimes_; }
 
@@ -90,7 +93,8 @@ class Renderer {
 
     int device_ = 0, w_ = 0, h_ = 0, seed_offset_ = 0, accum_cnt_ = 0, max_depth_ = 0;
     int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
-    bool variance_on_ = false, kernel_timing_ = false, split_shadow_ = true;
+    bool variance_on_ = false, kernel_timing_ = false;
+    int pipeline_ = 3;
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);
     cudaStream_t stream_ = nullptr;

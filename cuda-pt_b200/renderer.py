@@ -163,7 +163,7 @@ class WavefrontRenderer:
     def stats(self):
         arr = (C.c_uint64 * 8)()
         check(lib().cpt_b200_stats(self._h, arr))
-        keys = ["samples", "closest_rays", "shadow_rays", "shaded", "launches", "device_us"]
+        keys = ["samples", "closest_rays", "shadow_rays", "shaded", "launches", "device_us", "shadow_traced"]
         d = {k: int(arr[i]) for i, k in enumerate(keys)}
         d["rays"] = d["samples"] + d["closest_rays"] + d["shadow_rays"]
         return d

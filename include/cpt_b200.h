@@ -92,13 +92,16 @@ int cpt_b200_height(const cpt_b200_renderer *r);
  * megakernel_pt.cu:159-180 - default taken from the scene's <renderer type>), "samples_in_flight" (>=1),
  * "traversal" (0 ordered pair-node, 1 reference DFS order, 2/3 experimental loop shapes),
  * "max_depth" (MaxDepthParams::max_depth, src/core/max_depth.h:26-42), "kernel_timing" (0/1: CUDA events
- * around every launch, read back with cpt_b200_kernel_times), "split_shadow" (1, default: the NEE visibility
- * ray runs in its own traversal kernel before the shading kernel; 0: traced inside the shading kernel) */
+ * around every launch, read back with cpt_b200_kernel_times), "pipeline" (0: the NEE visibility ray is traced
+ * inside the shading kernel; 1: in its own traversal kernel before shading; 2: dynamic-fetch traversal
+ * kernels; 3: deferred NEE - shade first, then trace only the shadow rays that can change the radiance),
+ * "split_shadow" (legacy alias: 0 -> pipeline 0, 1 -> pipeline 1) */
 int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value);
 int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key);
 
-/* stats[8]: pixel-samples, closest-hit rays after the primary one, shadow rays, shaded segments,
- * kernel launches, device microseconds, 0, 0 (cumulative since creation) */
+/* stats[8]: pixel-samples, closest-hit rays after the primary one, shadow rays (one per shaded segment whose
+ * sampled emitter is not the null emitter, wavefront_pt.cu:273), shaded segments, kernel launches, device
+ * microseconds, shadow rays that needed a BVH traversal (<= shadow rays), 0 (cumulative since creation) */
 int cpt_b200_stats(cpt_b200_renderer *r, uint64_t *stats8);
 /* cumulative per-kernel device time when "kernel_timing" is on; 5 entries: 0 raygen+primary hit, 1 shade
  * (NEE + BSDF), 2 trace (closest hit + RR + compaction), 3 splat, 4 shadow (NEE visibility kernel of the
