@@ -34,7 +34,13 @@ BYTES_PER_UNIT = {"raygen": 100, "shade": 172, "trace": 140, "splat": 64}
 METRIC = "Mrays/s (primary + closest-hit + shadow traversals), wavefront PT, 1920x1080"
 
 
+WORKLOADS = {"c1": "vader_wfpt_1080p.xml",       # BASELINE config 1 (default): vader geometry, no image assets
+             "c2": "vader_tex_wfpt_1080p.xml"}    # texture-heavy stand-in: + 2K glossy/roughness/normal/albedo maps + envmap
+
+
 def pick_scene(arg):
+    if arg in WORKLOADS:
+        return os.path.join(ROOT, "scenes", "xml", WORKLOADS[arg]), WORKLOADS[arg]
     if arg:
         return arg, os.path.basename(arg)
     vader = os.path.join(ROOT, "scenes", "xml", "vader_wfpt_1080p.xml")
@@ -176,8 +182,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default=None)
-    ap.add_argument("--spp-per-step", type=int, default=8)
-    ap.add_argument("--traversal", type=int, default=0)
+    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--traversal", type=int, default=2)
+    ap.add_argument("--pipeline", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     scene, workload = pick_scene(args.scene)
@@ -208,6 +215,7 @@ def main():
     r = cpt.WavefrontRenderer(sc, local_rank, 0)
     r.set_option("samples_in_flight", S)
     r.set_option("traversal", args.traversal)
+    r.set_option("pipeline", args.pipeline)
     r.set_option("kernel_timing", 1)
     # weak scaling: every rank renders its own K*S sample numbers of the same seed stream
     r.set_counter(rank * (K + Wm) * S * 2)
@@ -294,6 +302,9 @@ def main():
         dms = kt1[k]["ms"] - kt0[k]["ms"]
         units = kt1[k]["units"] - kt0[k]["units"]
         n = kt1[k]["launches"] - kt0[k]["launches"]
+        if k == "shade":  # SURVEY 8d's "shade" unit (NEE + BSDF, 172 B/seg) covers our shading kernel + shadow kernel(s)
+            dms += kt1["shadow"]["ms"] - kt0["shadow"]["ms"]
+            n += kt1["shadow"]["launches"] - kt0["shadow"]["launches"]
         if n == 0 or dms <= 0:
             continue
         bpu = BYTES_PER_UNIT[k]
@@ -303,6 +314,11 @@ def main():
         stages[k] = {"ms_per_step": dms / K, "launches_per_step": n / K, "units_per_step": units / K,
                      "bytes_per_unit": bpu, "achieved_gbs": gbs, "frac": gbs / peak,
                      "avg_launch_ms": dms / n, "share_of_step": dms / max(total_kernel_ms, 1e-9)}
+    sh_ms = kt1["shadow"]["ms"] - kt0["shadow"]["ms"]
+    sh_traced = st1["shadow_traced"] - st0["shadow_traced"]
+    if sh_ms > 0:
+        stages["shade"]["of_which_shadow_kernels_ms_per_step"] = sh_ms / K
+        stages["shade"]["shadow_rays_traced_per_step"] = sh_traced / K
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic = None
@@ -311,7 +327,7 @@ def main():
             traffic = json.load(open(prof)).get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": {"raygen": "k_raygen", "shade": "k_shade", "trace": "k_trace", "splat": "k_splat"}[dom],
+    roofline = {"bound": "hbm", "kernel": {"raygen": "k_raygen", "shade": "k_shade+k_shadow_apply", "trace": "k_trace", "splat": "k_splat"}[dom],
                 "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
                 "traffic": traffic, "peak_source": peak_src,
                 "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; BVH/triangle reads are L2-served "
@@ -325,12 +341,19 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "vader geometry bundled with the reference (textures/envmap not shipped upstream, removed); fixed seeds",
+           "data": ("vader geometry bundled with the reference + seeded placeholder 2K textures and environment map (tools/make_assets.py); fixed seeds"
+                    if "tex" in workload else
+                    "vader geometry bundled with the reference (textures/envmap not shipped upstream, removed); fixed seeds"),
            "config": {"workload": workload, "width": W, "height": H, "spp_per_step": S, "max_depth": cfg["max_depth"],
                       "triangles": cfg["num_prims"], "parallelism": f"sample-split x{world}, 1 NCCL all-reduce of the fp32 accumulator per step" if world > 1 else "1 GPU",
                       "l2_note": f"path-state pool {S * W * H * 92 / 1e6:.0f} MB per step >> 126 MB L2 (no flush needed)",
-                      "traversal": "ordered pair-node" if args.traversal == 0 else "reference DFS order"},
+                      "traversal": {0: "ordered pair-node", 1: "reference DFS order", 2: "ordered pair-node, 256-bit node loads", 3: "ordered, warp-vote"}[args.traversal],
+                      "pipeline": {0: "fused", 1: "split shadow kernel", 2: "dynamic-fetch traversal", 3: "deferred NEE"}[args.pipeline],
+                      "ray_accounting": "rays = primary + closest-hit + NEE shadow rays of the algorithm (SURVEY.md 8d, one shadow ray per shaded "
+                                        "segment whose sampled emitter is not the null emitter); shadow rays that provably cannot change the "
+                                        "radiance are not traversed (shadow_traced_frac)"},
            "msamples_per_s": samples / (ms * 1e-3) / 1e6, "rays_per_sample": rays / samples,
+           "shadow_traced_frac": (st1["shadow_traced"] - st0["shadow_traced"]) / max(1, st1["shadow_rays"] - st0["shadow_rays"]),
            "gpu_launches": int((st1["launches"] - st0["launches"])), "wall_s": t_wall,
            "clocks": clk, "e2e": e2e, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline}
     print(json.dumps(out))

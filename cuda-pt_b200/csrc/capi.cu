@@ -244,7 +244,7 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
             r->impl->set_samples_in_flight(int(value));
         else if (k == "traversal") {
             if (value < 0 || value > 3)
-                throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (while-while) or 3 (warp vote)");
+                throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads) or 3 (warp vote)");
             r->impl->set_traversal(int(value));
         } else if (k == "rules") {
             if (value != 0 && value != 1)

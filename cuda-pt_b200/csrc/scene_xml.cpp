@@ -426,7 +426,7 @@ struct Builder {
     int max_leaf = 16;
     int max_depth = 0;
     static constexpr int kBins = 16;
-    static constexpr float kTraverse = 0.2f;
+    float kTraverse = 0.2f; // SAH cost of one inner-node visit relative to one triangle test
 
     int build(int base, int count, int depth) {
         const int id = int(nodes.size());
@@ -978,6 +978,8 @@ void load_xml(const std::string &path, HostScene &out) {
     const size_t P0 = V[0].size();
     Builder bld;
     bld.max_leaf = max_node_num;
+    if (const char *e = getenv("CPTB200_SAH_TRAVERSE")) // builder tuning knob (experiments)
+        bld.kTraverse = float(atof(e));
     bld.refs.resize(P0);
     {
         // primitive -> object word (bvh.cu:85-92; no media, triangles only)

@@ -128,117 +128,26 @@ constexpr int kLeafBaseMask = (1 << kLeafCountShift) - 1;
 
 constexpr int kTraversalDone = 0x7fffffff; // "cur" value meaning: stack exhausted
 
-PT_DEV Hit closest_hit_ww(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
-    Hit h{kMaxDist, 0.f, 0.f, -1, 0};
-    const V3 inv_d = rcp3(d), o_div = o * inv_d;
-    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
-    int stack_ref[kStackSize];
-    float stack_t[kStackSize];
-    int sp = 0;
-    int cur = sc.wroot;
-    const float inf = __int_as_float(0x7f800000);
-    // "while-while": all lanes of a warp descend inner nodes together until each holds a leaf (or is done),
-    // then all test triangles together; keeps the two code paths from alternating lane by lane
-    while (cur != kTraversalDone) {
-        while (cur >= 0 && cur != kTraversalDone) {
-            const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
-                         b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
-            float t0, t1;
-            const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < h.t &&
-                            __float_as_int(a1.w) > start;
-            const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < h.t &&
-                            __float_as_int(b1.w) > start;
-            const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
-            if (h0 && h1) {
-                const bool swap = t1 < t0;
-                stack_ref[sp] = swap ? r0 : r1;
-                stack_t[sp] = swap ? t0 : t1;
-                ++sp;
-                cur = swap ? r1 : r0;
-            } else if (h0 || h1) {
-                cur = h0 ? r0 : r1;
-            } else {
-                cur = kTraversalDone;
-                while (sp > 0) {
-                    --sp;
-                    if (stack_t[sp] < h.t) {
-                        cur = stack_ref[sp];
-                        break;
-                    }
-                }
-            }
-        }
-        if (cur == kTraversalDone)
-            break;
-        {
-            const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
-            for (int idx = base; idx < base + cnt; idx++) {
-                float u, v;
-                const float dist = hit_triangle(sc.tris, idx, o, d, u, v, inf);
-                // equal distances: the reference keeps the first hit in DFS order == the smaller primitive index
-                const bool valid = dist > kEps && (dist < h.t || (dist == h.t && idx < h.prim));
-                h.t = valid ? dist : h.t;
-                h.u = valid ? u : h.u;
-                h.v = valid ? v : h.v;
-                h.prim = valid ? idx : h.prim;
-            }
-        }
-        cur = kTraversalDone;
-        while (sp > 0) {
-            --sp;
-            if (stack_t[sp] < h.t) {
-                cur = stack_ref[sp];
-                break;
-            }
-        }
+// one pair node = 64 B.  WIDE: two 256-bit loads (LDG.E.256, sm_100) instead of four 128-bit ones - half the
+// load instructions and L1 line visits per node for the same bytes
+template <bool WIDE>
+PT_DEV void load_pair_node(const float4 *__restrict__ wnodes, int cur, float4 &a0, float4 &a1, float4 &b0, float4 &b1) {
+    if constexpr (WIDE) {
+        const float4 *p = wnodes + 4 * cur;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w), "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w)
+                     : "l"(p));
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w), "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w)
+                     : "l"(p + 2));
+    } else {
+        a0 = __ldg(wnodes + 4 * cur), a1 = __ldg(wnodes + 4 * cur + 1), b0 = __ldg(wnodes + 4 * cur + 2),
+        b1 = __ldg(wnodes + 4 * cur + 3);
     }
-    if (h.prim >= 0)
-        h.obj_word = __ldg(sc.obj_idxs + h.prim);
-    return h;
-}
-
-PT_DEV bool unoccluded_ww(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist) {
-    const V3 inv_d = rcp3(d), o_div = o * inv_d;
-    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, max_dist, sc.num_nodes);
-    if (start >= sc.num_nodes)
-        return true;
-    int stack_ref[kStackSize];
-    int sp = 0;
-    int cur = sc.wroot;
-    while (cur != kTraversalDone) {
-        while (cur >= 0 && cur != kTraversalDone) {
-            const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
-                         b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
-            float t0, t1;
-            const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < max_dist &&
-                            __float_as_int(a1.w) > start;
-            const bool h1 = slab_test(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < max_dist &&
-                            __float_as_int(b1.w) > start;
-            const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
-            if (h0 && h1) {
-                stack_ref[sp++] = r1;
-                cur = r0;
-            } else if (h0 || h1) {
-                cur = h0 ? r0 : r1;
-            } else {
-                cur = sp > 0 ? stack_ref[--sp] : kTraversalDone;
-            }
-        }
-        if (cur == kTraversalDone)
-            break;
-        const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
-        for (int idx = base; idx < base + cnt; idx++) {
-            float u, v;
-            const float dist = hit_triangle(sc.tris, idx, o, d, u, v, max_dist);
-            if (dist > kEps)
-                return false;
-        }
-        cur = sp > 0 ? stack_ref[--sp] : kTraversalDone;
-    }
-    return true;
 }
 
 // variant with one inner-or-leaf step per loop iteration (lanes alternate freely between the two paths)
+template <bool WIDE>
 PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
     Hit h{kMaxDist, 0.f, 0.f, -1, 0};
     const V3 inv_d = rcp3(d), o_div = o * inv_d;
@@ -250,8 +159,8 @@ PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, 
     const float inf = __int_as_float(0x7f800000);
     while (true) {
         if (cur >= 0) {
-            const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
-                         b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+            float4 a0, a1, b0, b1;
+            load_pair_node<WIDE>(sc.wnodes, cur, a0, a1, b0, b1);
             float t0, t1;
             const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < h.t &&
                             __float_as_int(a1.w) > start;
@@ -300,6 +209,7 @@ PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, 
     return h;
 }
 
+template <bool WIDE>
 PT_DEV bool unoccluded_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist) {
     const V3 inv_d = rcp3(d), o_div = o * inv_d;
     const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, max_dist, sc.num_nodes);
@@ -310,8 +220,8 @@ PT_DEV bool unoccluded_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, 
     int cur = sc.wroot;
     while (true) {
         if (cur >= 0) {
-            const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
-                         b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+            float4 a0, a1, b0, b1;
+            load_pair_node<WIDE>(sc.wnodes, cur, a0, a1, b0, b1);
             float t0, t1;
             const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < max_dist &&
                             __float_as_int(a1.w) > start;
@@ -486,7 +396,8 @@ PT_DEV bool unoccluded_vote(const DevScene &sc, const uint4 *s_cached, V3 o, V3 
     return clear;
 }
 
-// MODE: 0 ordered (step per iteration), 1 reference DFS order, 2 ordered "while-while", 3 ordered warp-vote scheduler.
+// MODE: 0 ordered (per-thread stack in local memory), 1 reference DFS order, 2 ordered with 256-bit node loads,
+// 3 ordered warp-vote scheduler.
 // `active` = this lane carries a ray; MODE 3 is warp-synchronous and must be called by all 32 lanes.
 template <int MODE> PT_DEV Hit closest_hit(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, bool active = true) {
     if constexpr (MODE == 3)
@@ -495,11 +406,11 @@ template <int MODE> PT_DEV Hit closest_hit(const DevScene &sc, const uint4 *s_ca
     if (!active)
         return miss;
     if constexpr (MODE == 0)
-        return closest_hit_ordered(sc, s_cached, o, d);
+        return closest_hit_ordered<false>(sc, s_cached, o, d);
     else if constexpr (MODE == 1)
         return closest_hit_dfs(sc, s_cached, o, d);
     else
-        return closest_hit_ww(sc, s_cached, o, d);
+        return closest_hit_ordered<true>(sc, s_cached, o, d);
 }
 template <int MODE> PT_DEV bool unoccluded(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist, bool active = true) {
     if constexpr (MODE == 3)
@@ -507,11 +418,11 @@ template <int MODE> PT_DEV bool unoccluded(const DevScene &sc, const uint4 *s_ca
     if (!active)
         return true;
     if constexpr (MODE == 0)
-        return unoccluded_ordered(sc, s_cached, o, d, max_dist);
+        return unoccluded_ordered<false>(sc, s_cached, o, d, max_dist);
     else if constexpr (MODE == 1)
         return unoccluded_dfs(sc, s_cached, o, d, max_dist);
     else
-        return unoccluded_ww(sc, s_cached, o, d, max_dist);
+        return unoccluded_ordered<true>(sc, s_cached, o, d, max_dist);
 }
 
 } // namespace cptb

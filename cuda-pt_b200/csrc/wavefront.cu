@@ -260,9 +260,9 @@ __global__ void __launch_bounds__(kBlock) k_shadow(DevScene sc, PathState st, co
 //   k_resolve     interaction, miss/envmap, Russian roulette, compaction (the epilogue of k_trace)
 // Same boxes, same slab / triangle arithmetic, same tie rule as the ordered traversal of traverse.cuh.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRefill = 8;  // refill a warp when at least this many lanes are idle
 constexpr int kGrab = 128;  // rays a warp reserves per global atomic
-constexpr int kSteps = 4;   // traversal steps between refill checks
+// kRefill (refill a warp when at least this many lanes are idle) and kSteps (traversal steps between refill
+// checks) are launch parameters: env CPTB200_DYN_REFILL (default 8) / CPTB200_DYN_STEPS (default 4)
 
 struct RayBufs {
     float4 *sh_o; // shadow ray origin, w = range
@@ -335,8 +335,9 @@ __device__ __forceinline__ int warp_take(int *work, int count, int lane, int n_i
     return take;
 }
 
-__global__ void __launch_bounds__(kBlock) k_anyhit(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ sq,
-                                                   const int *__restrict__ sq_count, int *work) {
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_anyhit(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ sq,
+                                                         const int *__restrict__ sq_count, int *work, int kRefill, int kSteps) {
     const int lane = threadIdx.x & 31;
     const int count = *sq_count;
     int stack_ref[kStackSize];
@@ -618,8 +619,9 @@ __device__ __forceinline__ bool resolve_hit(const DevScene &sc, PathState &st, u
 }
 
 // closest-hit traversal with dynamic ray fetch (see the pipeline note above k_shadow_gen)
-__global__ void __launch_bounds__(kBlock) k_intersect(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue,
-                                                      const int *__restrict__ q_count, int *work) {
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_intersect(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue,
+                                                            const int *__restrict__ q_count, int *work, int kRefill, int kSteps) {
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
     const int lane = threadIdx.x & 31;
@@ -1155,6 +1157,12 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     CUDA_OK(cudaMemsetAsync(m.stats.p, 0, 4 * sizeof(unsigned long long), stream_));
     if (const char *e = getenv("CPTB200_BLOCKS_PER_SM"))
         blocks_per_sm_ = std::max(1, atoi(e));
+    if (const char *e = getenv("CPTB200_DYN_REFILL"))
+        dyn_refill_ = std::min(32, std::max(1, atoi(e)));
+    if (const char *e = getenv("CPTB200_DYN_STEPS"))
+        dyn_steps_ = std::max(1, atoi(e));
+    if (const char *e = getenv("CPTB200_DYN_MINB"))
+        dyn_minb_ = atoi(e);
     // default number of samples in flight: ~8M paths, at least 1, at most 64
     set_samples_in_flight(int(std::min<size_t>(64, std::max<size_t>(1, (size_t(8) << 20) / P))));
     CUDA_OK(cudaStreamSynchronize(stream_));
@@ -1291,7 +1299,10 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
                                                           sq_counts + b, shadow_counter);
             ++wk, ++launches;
             mark(4, b);
-            k_anyhit<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+            if (dyn_minb_ >= 12)
+                k_anyhit<12><<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
+            else
+                k_anyhit<8><<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
             ++wk, ++launches;
             mark(1, b);
             k_shade<-1><<<grid, kBlock, 0, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt, rb, nullptr, nullptr);
@@ -1311,7 +1322,10 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             break;
         mark(2, b);
         if (pipeline_ == 2) {
-            k_intersect<<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk);
+            if (dyn_minb_ >= 12)
+                k_intersect<12><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, dyn_refill_, dyn_steps_);
+            else
+                k_intersect<8><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, dyn_refill_, dyn_steps_);
             ++wk, ++launches;
             mark(2, b);
             k_resolve<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
@@ -1481,7 +1495,7 @@ std::string Renderer::info() const {
     std::ostringstream os;
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
-       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-ww" : "ordered-vote")))
+       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : "ordered-vote")))
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations
        << ", pipeline " << pipeline_ << ", rules " << (rules_ ? "megakernel-pt" : "wavefront") << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();

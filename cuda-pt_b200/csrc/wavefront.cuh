@@ -92,9 +92,10 @@ class Renderer {
     void ensure_capacity(int samples);
 
     int device_ = 0, w_ = 0, h_ = 0, seed_offset_ = 0, accum_cnt_ = 0, max_depth_ = 0;
-    int s_max_ = 1, traversal_ = TRAVERSAL_ORDERED, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
+    int s_max_ = 1, traversal_ = 2 /* ordered pair-node traversal with 256-bit node loads */, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
     bool variance_on_ = false, kernel_timing_ = false;
     int pipeline_ = 3;
+    int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);
     cudaStream_t stream_ = nullptr;

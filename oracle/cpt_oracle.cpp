@@ -16,7 +16,10 @@
  *   frames             src/core/so3.cuh:201-252
  *   BSDFs              src/bsdf/{lambert,specular,translucent,plastic,ggx_conductor,dispersion,forward}.cuh,
  *                      src/impl/bsdf_{ggx,plastic,dispersion}.cu, src/bsdf/fresnel.cuh:28-140
- *   emitters           src/core/emitter.cuh:32-303 (point, area, area-spot; no environment maps here)
+ *   emitters           src/core/emitter.cuh:32-359, src/impl/emitter.cu:26-73 (point, area, area-spot, environment map)
+ *   image textures     src/core/textures.cuh:79-117 (lookups), texture-object set-up src/impl/textures.cu:134-165;
+ *                      texels are the ones the reference decoded (scene dump); bilinear filter restated with the
+ *                      8-bit fractional weights of the texture unit
  *   per-bounce logic   src/pt_impl/wavefront_pt.cu:71-314 (raygen, shade, closest-hit + RR), :476-503 (splat),
  *                      host loop src/pt_impl/wf_path_tracer.cu:175-230, emitter pick tracing_func.cuh:210-225
  *
@@ -150,6 +153,9 @@ struct Scene {
     std::vector<CptsEmitter> emitters;
     std::vector<float> tris; // 12 floats per primitive
     std::vector<float> cie, d65;
+    std::vector<CptsTexDesc> tex_desc; // image textures as the reference decoded them (float texels)
+    std::vector<float> tex_data;
+    float env_rot[4] = {0, 0, 0, 1};   // environment-map rotation quaternion (emitter.cuh:349-353)
     // derived material parameters (device constructors of the reference)
     std::vector<float> alpha_x, alpha_y, eta, diff_f;
     int num_nodes() const { return int(nodes.size() / 8); }
@@ -221,6 +227,10 @@ Scene *load_scene(const char *path) {
             read_vec(fp, s, sc->bsdfs);
         else if (name == "emitters")
             read_vec(fp, s, sc->emitters);
+        else if (name == "tex_desc")
+            read_vec(fp, s, sc->tex_desc);
+        else if (name == "tex_data")
+            read_vec(fp, s, sc->tex_data);
         else if (name == "cie_xyz")
             read_vec(fp, s, sc->cie);
         else if (name == "d65_spd")
@@ -261,8 +271,15 @@ Scene *load_scene(const char *path) {
         }
     }
     for (const auto &e : sc->emitters)
-        if (e.type == CPTS_EMIT_ENVMAP)
-            throw std::string("oracle: environment maps are not restated");
+        if (e.type == CPTS_EMIT_ENVMAP) { // rot = angleAxis(azimuth, z) * angleAxis(zenith, x)  (quaternion.cuh:45-60)
+            const float sy = std::sin(e.azimuth * 0.5f), cy = std::cos(e.azimuth * 0.5f), sp = std::sin(e.zenith * 0.5f),
+                        cp = std::cos(e.zenith * 0.5f);
+            const float a[4] = {0, 0, sy, cy}, q[4] = {sp, 0, 0, cp};
+            sc->env_rot[0] = a[3] * q[0] + a[0] * q[3] + a[1] * q[2] - a[2] * q[1];
+            sc->env_rot[1] = a[3] * q[1] - a[0] * q[2] + a[1] * q[3] + a[2] * q[0];
+            sc->env_rot[2] = a[3] * q[2] + a[0] * q[1] - a[1] * q[0] + a[2] * q[3];
+            sc->env_rot[3] = a[3] * q[3] - a[0] * q[0] - a[1] * q[1] - a[2] * q[2];
+        }
     return sc;
 }
 
@@ -372,6 +389,35 @@ Isect interaction(const Scene &sc, int prim, float u, float v) { // primitives.c
     return it;
 }
 
+// ---- image textures: what tex2D<floatN> returns for the reference's texture objects (textures.cu:134-165:
+// normalised coordinates, wrap addressing, bilinear filter with 8-bit fractional weights) ---------------------
+void tex2d(const Scene &sc, int index, float u, float v, float out[4]) {
+    const CptsTexDesc &t = sc.tex_desc[index];
+    const float *base = sc.tex_data.data() + t.offset;
+    const int W = t.width, H = t.height, C = t.channels;
+    const float x = (u - std::floor(u)) * W - 0.5f, y = (v - std::floor(v)) * H - 0.5f;
+    const float fx = std::floor(x), fy = std::floor(y);
+    const float a = std::floor((x - fx) * 256.f + 0.5f) / 256.f, b = std::floor((y - fy) * 256.f + 0.5f) / 256.f;
+    const int x0 = ((int(fx) % W) + W) % W, x1 = (x0 + 1) % W, y0 = ((int(fy) % H) + H) % H, y1 = (y0 + 1) % H;
+    for (int c = 0; c < 4; c++) {
+        if (c >= C) {
+            out[c] = 0.f;
+            continue;
+        }
+        const float t00 = base[(size_t(y0) * W + x0) * C + c], t10 = base[(size_t(y0) * W + x1) * C + c],
+                    t01 = base[(size_t(y1) * W + x0) * C + c], t11 = base[(size_t(y1) * W + x1) * C + c];
+        out[c] = (1 - a) * (1 - b) * t00 + a * (1 - b) * t10 + (1 - a) * b * t01 + a * b * t11;
+    }
+}
+// PackedHalf2::lerp of a primitive's vertex uvs (vec2_half.cuh:182-186): every product and sum rounded to half
+void lerp_uv(const Scene &sc, int prim, float u, float v, float &tu, float &tv) {
+    const float hw = hround(1.f - u - v), hu = hround(u), hv = hround(v);
+    for (int c = 0; c < 2; c++) {
+        const float a = hround(sc.uv[0][2 * prim + c]), b = hround(sc.uv[1][2 * prim + c]), cc = hround(sc.uv[2][2 * prim + c]);
+        (c == 0 ? tu : tv) = hround(hround(hround(a * hw) + hround(b * hu)) + hround(cc * hv));
+    }
+}
+
 // ---- frames (so3.cuh:201-252) -----------------------------------------------------------------------
 struct M3 {
     V3 r[3];
@@ -394,12 +440,13 @@ inline V3 rot_t(const M3 &m, V3 v) {
             m.r[0].z * v.x + m.r[1].z * v.y + m.r[2].z * v.z};
 }
 inline V3 to_world(V3 n, V3 local) { return rot(frame(n, true), local); }
-// without normal maps eval_normal() reduces to R_w2l^T (0,0,1) (textures.cuh:79-90)
-inline V3 shading_normal(V3 n, M3 *R = nullptr) {
+// eval_normal / eval_normal_reused (textures.cuh:79-103): R_w2l^T applied to the (normalised) normal-map texel,
+// (0,0,1) without a normal map
+inline V3 shading_normal(V3 n, M3 *R = nullptr, V3 pn = V3{0, 0, 1}) {
     const M3 m = frame(n, false);
     if (R)
         *R = m;
-    return rot_t(m, V3{0, 0, 1});
+    return rot_t(m, pn);
 }
 
 // ---- sampling warps (sampling.cuh:27-67) --------------------------------------------------------------
@@ -536,22 +583,47 @@ bool dispersion_wl(const CptsBsdf &m, V3 in, V3 out, V3 n, float &wl) { // dispe
 
 // ---- BSDF interface ---------------------------------------------------------------------------------------
 struct Mat {
-    const CptsBsdf *b;
+    const CptsBsdf *b; // colours already replaced by this hit's texture lookups
     float ax, ay, eta, diff_f;
+    V3 pn{0, 0, 1};    // tangent-space normal of the normal map at this hit
 };
+// per-hit material: textures.cuh:79-117 lookups folded into a local copy of the BSDF record
+Mat resolve_material(const Scene &sc, int mat_id, float u, float v, CptsBsdf &local) {
+    local = sc.bsdfs[mat_id];
+    Mat m{&local, sc.alpha_x[mat_id], sc.alpha_y[mat_id], sc.eta[mat_id], sc.diff_f[mat_id]};
+    float t[4];
+    float *dst[3] = {local.k_d, local.k_s, local.k_g};
+    for (int k = 0; k < 3; k++)
+        if (local.tex[k] >= 0 && !(k == 0 && (local.type == CPTS_BSDF_TRANSLUCENT || local.type == CPTS_BSDF_DISPERSION))) {
+            tex2d(sc, local.tex[k], u, v, t);
+            memcpy(dst[k], t, sizeof(t));
+        }
+    if (local.tex[3] >= 0) {
+        tex2d(sc, local.tex[3], u, v, t);
+        m.pn = normalize(V3{t[0], t[1], t[2]});
+    }
+    if (local.tex[4] >= 0) { // eval_rough: GGX alpha pair, or the ior of a det-refraction BSDF (translucent.cuh:106)
+        tex2d(sc, local.tex[4], u, v, t);
+        if (local.type == CPTS_BSDF_GGX_CONDUCTOR)
+            m.ax = t[0], m.ay = t[1];
+        else if (local.type == CPTS_BSDF_TRANSLUCENT)
+            local.k_d[0] = t[0];
+    }
+    return m;
+}
 float bsdf_pdf(const Scene &sc, const Mat &m, V3 nrm, V3 out, V3 in) {
     const CptsBsdf &b = *m.b;
     switch (b.type) {
-    case CPTS_BSDF_LAMBERTIAN: return std::max(dot(shading_normal(nrm), out), 0.f) * INV_PI;
+    case CPTS_BSDF_LAMBERTIAN: return std::max(dot(shading_normal(nrm, nullptr, m.pn), out), 0.f) * INV_PI;
     case CPTS_BSDF_PLASTIC: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         const float dwo = std::fabs(dot(out, n)), dwi = std::fabs(dot(in, n)), Fi = fresnel_simple(m.eta, dwi),
                     sp = Fi / (Fi + b.extras[1] * (1.f - Fi));
         const V3 rd = in - n * (2.f * dot(in, n));
         return dot(rd, out) < 1.f - THP_EPS ? INV_PI * dwo * (1.f - sp) : sp;
     }
     case CPTS_BSDF_PLASTIC_FORWARD: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         const float dwi = dot(in, n), Fi = fresnel_simple(m.eta, -dwi), sp = Fi / (Fi + b.extras[1] * (1.f - Fi));
         const V3 rd = in - n * (2.f * dwi);
         float p = 0;
@@ -561,13 +633,13 @@ float bsdf_pdf(const Scene &sc, const Mat &m, V3 nrm, V3 out, V3 in) {
     }
     case CPTS_BSDF_GGX_CONDUCTOR: {
         M3 R;
-        shading_normal(nrm, &R);
+        shading_normal(nrm, &R, m.pn);
         const V3 li = -rot(R, in), lo = rot(R, out), wh = normalize(lo + li);
         const float pv = ggx_D(wh, m.ax, m.ay) * ggx_G1(li, m.ax, m.ay) * (std::fabs(dot(li, wh)) / std::fabs(li.z));
         return ((li.z > 0) ^ (lo.z > 0)) ? 0 : pv * (1.f / (4.f * dot(wh, li)));
     }
     case CPTS_BSDF_DISPERSION: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         float p = 0;
         if (((dot(n, in) > 0) ^ (dot(n, out) > 0)) == false) {
             float wl = 0;
@@ -586,17 +658,17 @@ V4 bsdf_eval(const Scene &sc, const Mat &m, V3 nrm, V3 out, V3 in) {
     const V4 kd = v4(b.k_d), ks = v4(b.k_s), kg = v4(b.k_g);
     switch (b.type) {
     case CPTS_BSDF_LAMBERTIAN: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         const float ct = dot(n, out), di = dot(n, in);
         return kd * std::max(0.f, ct) * INV_PI * float((di > 0) ^ (ct > 0));
     }
     case CPTS_BSDF_SPECULAR: {
-        const V3 n = shading_normal(nrm), rd = normalize(in + n * (-2.f * dot(in, n)));
+        const V3 n = shading_normal(nrm, nullptr, m.pn), rd = normalize(in + n * (-2.f * dot(in, n)));
         return ks * float(dot(out, rd) > 0.99999f);
     }
-    case CPTS_BSDF_TRANSLUCENT: return dielectric_eval(shading_normal(nrm), out, in, ks, b.k_d[0]);
+    case CPTS_BSDF_TRANSLUCENT: return dielectric_eval(shading_normal(nrm, nullptr, m.pn), out, in, ks, b.k_d[0]);
     case CPTS_BSDF_PLASTIC: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         const float rwo = dot(out, n), rwi = dot(in, n), dwo = std::fabs(rwo), dwi = std::fabs(rwi),
                     Fi = fresnel_simple(m.eta, dwi), Fo = fresnel_simple(m.eta, dwo);
         const V3 rd = in - n * (2.f * rwi);
@@ -607,7 +679,7 @@ V4 bsdf_eval(const Scene &sc, const Mat &m, V3 nrm, V3 out, V3 in) {
         return (b.extras[3] > 0 || ((rwo > 0) ^ (rwi > 0))) ? brdf : v4(0, 1);
     }
     case CPTS_BSDF_PLASTIC_FORWARD: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         const float dwi = dot(in, n), Fi = fresnel_simple(m.eta, std::fabs(dwi));
         const V3 rd = in - n * (2.f * dwi);
         V4 brdf = dot(in, out) < 1.f - THP_EPS
@@ -618,7 +690,7 @@ V4 bsdf_eval(const Scene &sc, const Mat &m, V3 nrm, V3 out, V3 in) {
     }
     case CPTS_BSDF_GGX_CONDUCTOR: {
         M3 R;
-        const V3 n = shading_normal(nrm, &R), li = -rot(R, in), lo = rot(R, out);
+        const V3 n = shading_normal(nrm, &R, m.pn), li = -rot(R, in), lo = rot(R, out);
         V3 wh = normalize(lo + li);
         if (!(wh.z > 0))
             wh = -wh;
@@ -629,7 +701,7 @@ V4 bsdf_eval(const Scene &sc, const Mat &m, V3 nrm, V3 out, V3 in) {
         return kg * g * std::max(0.f, dot(out, n));
     }
     case CPTS_BSDF_DISPERSION: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         float wl = 0;
         const bool valid = dispersion_wl(b, in, out, n, wl);
         const float eta = valid ? b.extras[0] + b.extras[1] / (wl * wl) : b.extras[0];
@@ -646,21 +718,21 @@ V3 bsdf_sample(const Scene &sc, const Mat &m, V3 in, V3 nrm, V4 &thp, float &pdf
     switch (b.type) {
     case CPTS_BSDF_LAMBERTIAN: {
         const float ux = rng.f(), uy = rng.f();
-        const V3 local = cos_hemisphere(ux, uy, pdf), n = shading_normal(nrm), out = to_world(n, local);
+        const V3 local = cos_hemisphere(ux, uy, pdf), n = shading_normal(nrm, nullptr, m.pn), out = to_world(n, local);
         thp = thp * kd * float((dot(n, in) > 0) ^ (dot(n, out) > 0));
         lobe = b.flags;
         return out;
     }
     case CPTS_BSDF_SPECULAR: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         pdf = 1.f;
         lobe = b.flags;
         thp = thp * ks;
         return in - n * (2.f * dot(in, n));
     }
-    case CPTS_BSDF_TRANSLUCENT: return dielectric_sample(in, shading_normal(nrm), ks, b.k_d[0], thp, rng, pdf, lobe);
+    case CPTS_BSDF_TRANSLUCENT: return dielectric_sample(in, shading_normal(nrm, nullptr, m.pn), ks, b.k_d[0], thp, rng, pdf, lobe);
     case CPTS_BSDF_PLASTIC: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         const float rdi = dot(n, in), di = std::fabs(rdi), Fi = fresnel_simple(m.eta, di), sp = Fi / (Fi + b.extras[1] * (1.f - Fi));
         V3 out;
         if (rng.f() < sp) {
@@ -685,7 +757,7 @@ V3 bsdf_sample(const Scene &sc, const Mat &m, V3 in, V3 nrm, V4 &thp, float &pdf
         return out;
     }
     case CPTS_BSDF_PLASTIC_FORWARD: {
-        const V3 n = shading_normal(nrm);
+        const V3 n = shading_normal(nrm, nullptr, m.pn);
         const float di = dot(n, in), Fi = fresnel_simple(m.eta, std::fabs(di)), sp = Fi / (Fi + b.extras[1] * (1.f - Fi));
         if (rng.f() < sp) {
             pdf = sp;
@@ -701,7 +773,7 @@ V3 bsdf_sample(const Scene &sc, const Mat &m, V3 in, V3 nrm, V4 &thp, float &pdf
     }
     case CPTS_BSDF_GGX_CONDUCTOR: {
         M3 R;
-        const V3 n = shading_normal(nrm, &R), li = -rot(R, in);
+        const V3 n = shading_normal(nrm, &R, m.pn), li = -rot(R, in);
         const float ux = rng.f(), uy = rng.f();
         const V3 wh = ggx_sample_wh(li, m.ax, m.ay, ux, uy);
         const float D = ggx_D(wh, m.ax, m.ay), dim = dot(li, wh);
@@ -717,7 +789,7 @@ V3 bsdf_sample(const Scene &sc, const Mat &m, V3 in, V3 nrm, V4 &thp, float &pdf
     }
     case CPTS_BSDF_DISPERSION: {
         const float wl = rng.f() * 471.f + 360.f, eta = b.extras[0] + b.extras[1] / (wl * wl);
-        const V3 r = dielectric_sample(in, shading_normal(nrm), ks, eta, thp, rng, pdf, lobe);
+        const V3 r = dielectric_sample(in, shading_normal(nrm, nullptr, m.pn), ks, eta, thp, rng, pdf, lobe);
         thp = thp * wavelength_rgb(sc, wl);
         pdf *= 1.f / 471.f;
         return r;
@@ -730,14 +802,44 @@ V3 bsdf_sample(const Scene &sc, const Mat &m, V3 in, V3 nrm, V4 &thp, float &pdf
 }
 
 // ---- emitters (emitter.cuh) ---------------------------------------------------------------------------------
-V4 emitter_eval(const CptsEmitter &e, V3 inci, V3 n) {
+V4 envmap_lookup(const Scene &sc, const CptsEmitter &e, V3 dir) { // emitter.cu:36-46,67-73
+    const float *q = sc.env_rot;
+    auto mul = [](const float a[4], const float b[4], float o[4]) {
+        o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+        o[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+        o[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+        o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    };
+    const float vq[4] = {dir.x, dir.y, dir.z, 0.f}, conj[4] = {-q[0], -q[1], -q[2], q[3]};
+    float qv[4], r[4];
+    mul(q, vq, qv);
+    mul(qv, conj, r);
+    const float ty = std::acos(std::min(std::max(r[2], -1.f), 1.f)) * INV_PI, px = (std::atan2(r[1], r[0]) + PI) * INV_PI * 0.5f;
+    float t[4];
+    tex2d(sc, e.tex, px, ty, t);
+    return V4{t[0], t[1], t[2], t[3]} * e.scale;
+}
+V4 emitter_le(const Scene &sc, const CptsEmitter &e, float tu, float tv) { // AreaSource::scaled_Le (emitter.cuh:154-156)
+    if (e.tex < 0)
+        return v4(e.Le);
+    float t[4];
+    tex2d(sc, e.tex, tu, tv, t);
+    return V4{t[0], t[1], t[2], t[3]} * e.Le[3];
+}
+V4 emitter_eval(const Scene &sc, const CptsEmitter &e, V3 inci, V3 n, float tu, float tv) {
     if (e.type == CPTS_EMIT_AREA)
-        return dot(inci, n) < 0 ? v4(e.Le) : V4{0, 0, 0, 1};
+        return dot(inci, n) < 0 ? emitter_le(sc, e, tu, tv) : V4{0, 0, 0, 1};
     if (e.type == CPTS_EMIT_AREA_SPOT)
-        return dot(inci, n) < -e.cos_val ? v4(e.Le) : V4{0, 0, 0, 1};
+        return dot(inci, n) < -e.cos_val ? emitter_le(sc, e, tu, tv) : V4{0, 0, 0, 1};
+    if (e.type == CPTS_EMIT_ENVMAP)
+        return envmap_lookup(sc, e, inci);
     return {0, 0, 0, 1};
 }
-V3 emitter_sample(const Scene &sc, const CptsEmitter &e, V3 hit, V4 &le, float &pdf, float ux, float uy, int prim) {
+V4 null_or_env(const Scene &sc, V3 dir) { // c_emitter[envmap_id]->eval_le(&ray.d)
+    const int id = sc.cfg[CPTS_CFG_ENVMAP_ID];
+    return id > 0 ? envmap_lookup(sc, sc.emitters[id], dir) : V4{0, 0, 0, 1};
+}
+V3 emitter_sample(const Scene &sc, const CptsEmitter &e, V3 hit, V3 hit_n, V4 &le, float &pdf, float ux, float uy, int prim) {
     if (e.type == CPTS_EMIT_POINT) {
         const V3 p{e.pos[0], e.pos[1], e.pos[2]};
         le = v4(e.Le) * std::min(1.f / std::max(len2(p - hit), 1e-5f), 1.f);
@@ -755,8 +857,16 @@ V3 emitter_sample(const Scene &sc, const CptsEmitter &e, V3 hit, V4 &le, float &
         th = normalize(th);
         const float c = dot(n, th);
         pdf *= float(c > 0) / c;
-        le = v4(e.Le) * float(e.type == CPTS_EMIT_AREA ? c > 0 : c > e.cos_val);
+        float tu = 0, tv = 0;
+        if (e.tex >= 0)
+            lerp_uv(sc, prim, ux, uy, tu, tv);
+        le = emitter_le(sc, e, tu, tv) * float(e.type == CPTS_EMIT_AREA ? c > 0 : c > e.cos_val);
         return p;
+    }
+    if (e.type == CPTS_EMIT_ENVMAP) { // emitter.cu:26-46; surface hits always have a unit normal
+        const V3 dir = to_world(hit_n, cos_hemisphere(ux, uy, pdf));
+        le = envmap_lookup(sc, e, dir);
+        return hit + dir * 5e3f;
     }
     pdf = 1;
     le = v4(0.f);
@@ -795,7 +905,7 @@ V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int m
     bool delta = false;
     Hit h = closest_hit(sc, o, d);
     if (h.prim < 0)
-        return L; // null emitter: (0,0,0,1)
+        return null_or_env(sc, d); // null emitter: (0,0,0,1)
     Isect it = interaction(sc, h.prim, h.u, h.v);
     const int num_emitters = int(sc.emitters.size()) - 1;
     for (int bounce = 0; bounce < max_depth; bounce++) {
@@ -805,7 +915,8 @@ V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int m
         obj_id = obj_id >= 0 ? obj_id : -obj_id - 1;
         const CptsObject &ob = sc.objects[obj_id];
         const int mat_id = ob.bsdf_emitter >> 16, emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
-        const Mat m{&sc.bsdfs[mat_id], sc.alpha_x[mat_id], sc.alpha_y[mat_id], sc.eta[mat_id], sc.diff_f[mat_id]};
+        CptsBsdf local_bsdf;
+        const Mat m = resolve_material(sc, mat_id, it.u, it.v, local_bsdf);
         int num = num_emitters;
         num -= emitter_id > 0 && num > 1;
         uint32_t eid = rng.u32() % uint32_t(num) + 1;
@@ -821,7 +932,7 @@ V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int m
         o = hit_pos;
         V4 direct{0, 0, 0, 1};
         const float ux = rng.f(), uy = rng.f();
-        V3 sd = emitter_sample(sc, em, hit_pos, direct, direct_pdf, ux, uy, eprim) - hit_pos;
+        V3 sd = emitter_sample(sc, em, hit_pos, it.n, direct, direct_pdf, ux, uy, eprim) - hit_pos;
         const float dist = std::sqrt(len2(sd));
         sd = sd * (1.f / dist);
         V4 rdc = L;
@@ -832,9 +943,9 @@ V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int m
                 rdc = rdc + thp * direct * bsdf_eval(sc, m, it.n, sd, d) * (mis > EPS ? 1.f / mis : 0.f);
             }
         }
-        const float sa = ob.inv_area * h.t * h.t / std::max(std::fabs(dot(d, shading_normal(it.n))), 1e-4f);
+        const float sa = ob.inv_area * h.t * h.t / std::max(std::fabs(dot(d, shading_normal(it.n, nullptr, m.pn))), 1e-4f);
         const float w = pdf / (pdf + sa * float(emitter_id > 0) * float(bounce > 0) * float(!delta));
-        L = (thp * emitter_eval(sc.emitters[emitter_id], d, it.n)) * w + rdc;
+        L = (thp * emitter_eval(sc, sc.emitters[emitter_id], d, it.n, it.u, it.v)) * w + rdc;
         int lobe = 0;
         d = bsdf_sample(sc, m, d, it.n, thp, pdf, rng, lobe);
         delta = (lobe & LOBE_SPECULAR) != 0;
@@ -844,7 +955,7 @@ V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int m
         cnt.closest++;
         h = closest_hit(sc, o, d);
         if (h.prim < 0) {
-            L = L + thp * V4{0, 0, 0, 1};
+            L = L + thp * null_or_env(sc, d);
             break;
         }
         it = interaction(sc, h.prim, h.u, h.v);

@@ -125,6 +125,23 @@ def test_oracle_pinned_to_reference_all_materials():
     assert abs(mean[calm][:, :3].mean() - ref[calm][:, :3].mean()) < 0.02 * ref[calm][:, :3].mean()
 
 
+def test_oracle_pinned_to_reference_textures_and_envmap():
+    """Image textures in every slot + a rotated environment map (texels from the reference's own scene dump).  The
+    texture unit's fixed-point filter weights and fast-math differ on a CPU, and ior / roughness / normal maps turn
+    such differences into different paths, so the pin is on robust statistics here as well."""
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "texroom_256.cpts"))
+    s, st = sc.render(64)
+    ref = load_frame("texroom_256_wfpt_f0064.bin")
+    mean = s / 64
+    d = np.abs(mean[..., :3] - ref[..., :3]).max(-1)
+    assert np.median(d) < 1e-4
+    assert (d < 1e-2 * np.maximum(ref[..., :3].max(-1), 1e-2)).mean() > 0.8
+    assert abs(mean[..., :3].mean() / ref[..., :3].mean() - 1) < 5e-3
+    assert rel_l2(mean, ref) < 2e-2
+    one, _ = sc.render(1)
+    assert (np.abs(one[..., :3] - load_frame("texroom_256_wfpt_f0001.bin")[..., :3]).max(-1) < 1e-3).mean() > 0.85
+
+
 def test_oracle_rows_subset_matches_full():
     sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
     full, _ = sc.render(2)
