@@ -910,7 +910,8 @@ template <typename T> struct DevBuf {
 };
 
 struct Renderer::Impl {
-    DevBuf<float4> nodes, tris, norms, wnodes;
+    DevBuf<float4> nodes, norms, arena; // arena = [pair nodes | triangles]
+    size_t arena_nodes = 0, l2_window_bytes = 0;
     DevBuf<uint4> cache_nodes, uvs;
     DevBuf<int> obj_idxs, emitter_prims;
     DevBuf<ObjectPOD> objects;
@@ -1018,14 +1019,18 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         memcpy(n4.data(), norms.data(), n4.size() * sizeof(float4));
         std::vector<uint4> u4(uvs.size());
         memcpy(u4.data(), uvs.data(), u4.size() * sizeof(uint4));
-        m.tris.upload(t4);
         m.norms.upload(n4);
         m.uvs.upload(u4);
         PairLayout pl;
         build_pair_layout(scene, pl);
         std::vector<float4> w4(pl.wnodes.size());
         memcpy(w4.data(), pl.wnodes.data(), w4.size() * sizeof(float4));
-        m.wnodes.upload(w4);
+        // traversal arena: pair nodes and triangles in one allocation, so that one L2 access-policy window can pin both
+        // (the 4-5 GB path-state pool streams through L2 every bounce and would otherwise keep evicting them)
+        m.arena.alloc(w4.size() + t4.size());
+        CUDA_OK(cudaMemcpy(m.arena.p, w4.data(), w4.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(m.arena.p + w4.size(), t4.data(), t4.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        m.arena_nodes = w4.size();
         m.pair_depth = pl.max_depth;
         m.nesting_violations = pl.nesting_violations;
         m.dev.wroot = pl.root;
@@ -1107,14 +1112,35 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     m.dev.nodes = m.nodes.p;
     m.dev.cache_nodes = m.cache_nodes.p;
     m.dev.obj_idxs = m.obj_idxs.p;
-    m.dev.tris = m.tris.p;
+    m.dev.tris = m.arena.p + m.arena_nodes;
     m.dev.norms = m.norms.p;
     m.dev.uvs = m.uvs.p;
     m.dev.objects = m.objects.p;
     m.dev.emitter_prims = m.emitter_prims.p;
     m.dev.mats = m.mats.p;
     m.dev.emitters = m.emitters.p;
-    m.dev.wnodes = m.wnodes.p;
+    m.dev.wnodes = m.arena.p;
+    // L2 residency for the traversal arena (env CPTB200_L2_PERSIST=0 turns it off)
+    {
+        const char *e = getenv("CPTB200_L2_PERSIST");
+        const size_t bytes = m.arena.n * sizeof(float4);
+        if ((!e || atoi(e) != 0) && bytes > 0 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            const size_t want = std::min<size_t>(bytes, size_t(prop.persistingL2CacheMaxSize));
+            size_t have = 0;
+            cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+            if (have < want)
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = m.arena.p;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, size_t(prop.accessPolicyMaxWindowSize));
+            attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(want) / double(attr.accessPolicyWindow.num_bytes)));
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(stream_, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess)
+                m.l2_window_bytes = attr.accessPolicyWindow.num_bytes;
+            cudaGetLastError();
+        }
+    }
     m.dev.num_nodes = scene.num_nodes();
     m.dev.num_cache = int(scene.cache_nodes.size());
     m.dev.num_prims = scene.num_prims();
@@ -1497,7 +1523,7 @@ std::string Renderer::info() const {
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
        << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : "ordered-vote")))
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations
-       << ", pipeline " << pipeline_ << ", rules " << (rules_ ? "megakernel-pt" : "wavefront") << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
+       << ", L2 window " << (impl_->l2_window_bytes >> 20) << " MB, pipeline " << pipeline_ << ", rules " << (rules_ ? "megakernel-pt" : "wavefront") << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();
 }
 
