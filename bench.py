@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--traversal", type=int, default=2)
     ap.add_argument("--pipeline", type=int, default=3)
+    ap.add_argument("--split", default="samples", choices=["samples", "tiles"],
+                    help="multi-GPU partition: samples (weak scaling, default) or tiles = bands of rows (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     scene, workload = pick_scene(args.scene)
@@ -217,8 +219,15 @@ def main():
     r.set_option("traversal", args.traversal)
     r.set_option("pipeline", args.pipeline)
     r.set_option("kernel_timing", 1)
-    # weak scaling: every rank renders its own K*S sample numbers of the same seed stream
-    r.set_counter(rank * (K + Wm) * S * 2)
+    if args.split == "tiles" and world > 1:
+        # strong scaling: the frame is cut into bands of rows, every rank traces all S samples of its band
+        from cuda_pt_b200.distributed import row_range
+        lo, hi = row_range(H, world, rank)
+        r.set_option("row_end", hi)
+        r.set_option("row_begin", lo)
+    else:
+        # weak scaling: every rank renders its own K*S sample numbers of the same seed stream
+        r.set_counter(rank * (K + Wm) * S * 2)
     ext = torch.cuda.ExternalStream(r.stream(), device=dev)
     acc = cpt.device_tensor(r.accumulator_ptr(), (H, W, 4), local_rank, r)
 
@@ -340,12 +349,13 @@ def main():
         cpu_baseline = cpu_oracle_rate(tmp, W, H)
 
     out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
-           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (args.split == "tiles" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
            "data": ("vader geometry bundled with the reference + seeded placeholder 2K textures and environment map (tools/make_assets.py); fixed seeds"
                     if "tex" in workload else
                     "vader geometry bundled with the reference (textures/envmap not shipped upstream, removed); fixed seeds"),
            "config": {"workload": workload, "width": W, "height": H, "spp_per_step": S, "max_depth": cfg["max_depth"],
-                      "triangles": cfg["num_prims"], "parallelism": f"sample-split x{world}, 1 NCCL all-reduce of the fp32 accumulator per step" if world > 1 else "1 GPU",
+                      "triangles": cfg["num_prims"], "parallelism": (f"{'row-band tile' if args.split == 'tiles' else 'sample'}-split x{world}, 1 NCCL all-reduce of the fp32 accumulator per step"
+                                      if world > 1 else "1 GPU"),
                       "l2_note": f"path-state pool {S * W * H * 92 / 1e6:.0f} MB per step >> 126 MB L2 (no flush needed)",
                       "traversal": {0: "ordered pair-node", 1: "reference DFS order", 2: "ordered pair-node, 256-bit node loads", 3: "ordered, warp-vote"}[args.traversal],
                       "pipeline": {0: "fused", 1: "split shadow kernel", 2: "dynamic-fetch traversal", 3: "deferred NEE"}[args.pipeline],

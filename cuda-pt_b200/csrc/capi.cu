@@ -256,6 +256,14 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
             if (value < 0 || value > 3)
                 throw std::runtime_error("pipeline must be 0 (fused), 1 (split shadow kernel), 2 (dynamic-fetch traversal kernels) or 3 (deferred NEE)");
             r->impl->set_pipeline(int(value));
+        } else if (k == "row_begin" || k == "row_end") {
+            const int h = r->impl->height();
+            if (value < 0 || value > h)
+                throw std::runtime_error("row_begin / row_end must lie in [0, height]");
+            if (k == "row_begin")
+                r->impl->set_rows(int(value), r->impl->row_end());
+            else
+                r->impl->set_rows(r->impl->row_begin(), int(value));
         } else if (k == "kernel_timing") {
             r->impl->set_kernel_timing(value != 0);
         } else if (k == "max_depth") {
@@ -281,6 +289,10 @@ int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key) {
         return r->impl->pipeline() != 0 ? 1 : 0;
     if (k == "pipeline")
         return r->impl->pipeline();
+    if (k == "row_begin")
+        return r->impl->row_begin();
+    if (k == "row_end")
+        return r->impl->row_end();
     return -1;
 }
 

@@ -57,6 +57,7 @@ struct PathState {
 
 struct BatchParams {
     int W, H, P, S, first_accum, seed_offset;
+    int row0, row1; // rows [row0,row1) of the frame are rendered (tile split across GPUs); pixel indices stay global
     int rules; // 0: wavefront termination rules, 1: megakernel ("pt") rules
 };
 
@@ -119,13 +120,14 @@ __global__ void __launch_bounds__(kBlock)
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
     const int lane = threadIdx.x & 31;
-    const int tiles_x = (bp.W + 7) >> 3, tiles_y = (bp.H + 3) >> 2, tiles = tiles_x * tiles_y;
+    const int ty0 = bp.row0 >> 2;
+    const int tiles_x = (bp.W + 7) >> 3, tiles_y = ((bp.row1 + 3) >> 2) - ty0, tiles = tiles_x * tiles_y;
     const int total = tiles * bp.S;
     for (int task = warp_next_chunk(work, lane); task < total; task = warp_next_chunk(work, lane)) {
         const int s = task / tiles, tile = task - s * tiles;
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int px = (tx << 3) + (lane & 7), py = (ty << 2) + (lane >> 3);
-        const bool inside = px < bp.W && py < bp.H;
+        const int px = (tx << 3) + (lane & 7), py = ((ty + ty0) << 2) + (lane >> 3);
+        const bool inside = px < bp.W && py >= bp.row0 && py < bp.row1;
         bool hit_any = false;
         uint32_t slot = 0;
         V3 o{0, 0, 0}, d{0, 0, 1};
@@ -775,8 +777,9 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_splat(const float4 *__restrict__ Lbuf, float4 *__restrict__ image,
                                                float4 *__restrict__ out, float *__restrict__ var, int P, int S,
-                                               int first_accum, int write_output, int gamma, int scrub) {
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+                                               int first_accum, int write_output, int gamma, int scrub, int p_begin,
+                                               int p_end) {
+    for (int p = p_begin + blockIdx.x * blockDim.x + threadIdx.x; p < p_end; p += gridDim.x * blockDim.x) {
         V4 acc = from_f4(image[p]);
         float variance = var ? var[p] : 0.f;
         for (int s = 0; s < S; s++) {
@@ -1261,10 +1264,12 @@ void Renderer::ensure_capacity(int samples) {
 void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write_output, bool use_variance) {
     Impl &m = *impl_;
     CUDA_OK(cudaSetDevice(device_));
+    if (row_begin() >= row_end())
+        throw std::runtime_error("cpt_b200: empty row range (row_begin >= row_end)");
     ensure_capacity(samples);
     const int P = w_ * h_, D = max_depth_;
     PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p, m.lobes.p};
-    BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_, rules_};
+    BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_, row0_, row1_ > 0 ? std::min(row1_, h_) : h_, rules_};
     int *q_counts = m.counters.p;          // D + 1 entries
     int *sq_counts = m.counters.p + (D + 2); // D + 1 entries (dynamic-fetch pipeline)
     int *work = m.counters.p + 2 * (D + 2);  // one per launch
@@ -1363,13 +1368,14 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     }
     mark(3, 0);
     k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples,
-                                               first_accum, write_output ? 1 : 0, gamma ? 1 : 0, rules_ == 0 ? 1 : 0);
+                                               first_accum, write_output ? 1 : 0, gamma ? 1 : 0, rules_ == 0 ? 1 : 0, row0_ * w_,
+                                               (row1_ > 0 ? std::min(row1_, h_) : h_) * w_);
     mark(-1, 0);
     k_fold_stats<<<1, 32, 0, stream_>>>(q_counts, traced, shaded, m.stats.p, sq_counts, pipeline_ >= 2 ? shaded : 0);
     launches += 2;
     CUDA_OK(cudaEventRecord(m.ev1, stream_));
     CUDA_OK(cudaGetLastError());
-    host_stats_.samples += uint64_t(P) * samples;
+    host_stats_.samples += uint64_t(w_) * uint64_t(row_end() - row_begin()) * samples;
     host_stats_.launches += launches;
 }
 

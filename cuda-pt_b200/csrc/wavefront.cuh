@@ -68,6 +68,10 @@ class Renderer {
     void set_accum_count(int c) { accum_cnt_ = c; }
     void set_kernel_timing(bool on) { kernel_timing_ = on; }
     void set_rules(int r) { rules_ = r; }
+    // tile split: only rows [row0,row1) of the frame are rendered and accumulated (row1 <= 0: to the bottom)
+    void set_rows(int row0, int row1) { row0_ = row0, row1_ = row1; }
+    int row_begin() const { return row0_; }
+    int row_end() const { return row1_ > 0 ? (row1_ < h_ ? row1_ : h_) : h_; }
     // 0: NEE ray traced inside the shading kernel; 1: own shadow kernel; 2: dynamic-fetch traversal kernels;
     // 3: deferred NEE (shade first, trace only the shadow rays that can change the radiance)
     void set_pipeline(int p) { pipeline_ = p; }
@@ -94,7 +98,7 @@ class Renderer {
     int device_ = 0, w_ = 0, h_ = 0, seed_offset_ = 0, accum_cnt_ = 0, max_depth_ = 0;
     int s_max_ = 1, traversal_ = 2 /* ordered pair-node traversal with 256-bit node loads */, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
     bool variance_on_ = false, kernel_timing_ = false;
-    int pipeline_ = 3;
+    int pipeline_ = 3, row0_ = 0, row1_ = 0;
     int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);

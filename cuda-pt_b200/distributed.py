@@ -27,6 +27,18 @@ def sample_range(total_spp, world, rank):
     return base, count
 
 
+def row_range(height, world, rank, align=4):
+    """Tile split (SURVEY.md 8e "tile partitioning"): contiguous bands of rows, multiples of `align` rows (the ray
+    generation kernel works on 8x4-pixel tiles), balanced to within one band unit.  Returns (row_begin, row_end)."""
+    if world < 1 or not (0 <= rank < world) or height <= 0:
+        raise ValueError("bad row split")
+    units = (int(height) + align - 1) // align
+    q, r = divmod(units, int(world))
+    lo = rank * q + min(rank, r)
+    hi = lo + q + (1 if rank < r else 0)
+    return min(lo * align, height), min(hi * align, height)
+
+
 def reference_seed_offset(rank, base_offset=0):
     """ddp_render.py:141-143 — `local_rank * 4201 + <random base>` (the base is passed in, not drawn here)."""
     return int(rank) * 4201 + int(base_offset)
@@ -52,15 +64,27 @@ def reduce_rendered_image(image, spp, group=None):
     return acc / n, int(n.item())
 
 
-def render_distributed(renderer, total_spp, gamma=False, group=None):
+def render_distributed(renderer, total_spp, gamma=False, group=None, split="samples"):
     """Render `total_spp` samples split over the ranks of `group` and return the reduced mean image
     (torch tensor [H, W, 4] on the renderer's device, identical on every rank).
 
+    split="samples": every rank renders the full frame for its share of the sample numbers (perfectly balanced; equals
+    the 1-GPU image up to fp32 summation order).  split="tiles": every rank renders all samples of its band of rows
+    (disjoint pixels, so the zero-filled SUM reproduces the 1-GPU image bit for bit; load follows the image content).
     `renderer` is a cuda_pt_b200.WavefrontRenderer freshly created or reset (counter 0)."""
     from .renderer import device_tensor
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    base, count = sample_range(total_spp, world, rank)
+    if split == "tiles":
+        lo, hi = row_range(renderer.height, world, rank)
+        base, count = 0, int(total_spp) if hi > lo else 0
+        if hi > lo:
+            renderer.set_option("row_end", hi)
+            renderer.set_option("row_begin", lo)
+    elif split == "samples":
+        base, count = sample_range(total_spp, world, rank)
+    else:
+        raise ValueError("split must be 'samples' or 'tiles'")
     renderer.set_counter(base)  # this rank's sample numbers are base+1 .. base+count
     if count > 0:
         renderer.render_batch(count, False)

@@ -95,7 +95,9 @@ int cpt_b200_height(const cpt_b200_renderer *r);
  * around every launch, read back with cpt_b200_kernel_times), "pipeline" (0: the NEE visibility ray is traced
  * inside the shading kernel; 1: in its own traversal kernel before shading; 2: dynamic-fetch traversal
  * kernels; 3: deferred NEE - shade first, then trace only the shadow rays that can change the radiance),
- * "split_shadow" (legacy alias: 0 -> pipeline 0, 1 -> pipeline 1) */
+ * "split_shadow" (legacy alias: 0 -> pipeline 0, 1 -> pipeline 1), "row_begin" / "row_end" (tile split across GPUs:
+ * only rows [row_begin,row_end) are traced and accumulated, pixel indices and therefore sample streams stay those of
+ * the full frame; set row_end first when moving the window down) */
 int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value);
 int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key);
 

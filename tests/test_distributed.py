@@ -29,6 +29,45 @@ def test_sample_range_partitions_exactly():
     assert cd.reference_seed_offset(3, 10) == 3 * 4201 + 10
 
 
+def test_row_range_partitions_exactly():
+    for height in (4, 256, 1080, 1081, 30):
+        for world in (1, 2, 3, 8):
+            rows = []
+            for r in range(world):
+                lo, hi = cd.row_range(height, world, r)
+                assert lo % 4 == 0 and lo <= hi <= height
+                rows += list(range(lo, hi))
+            assert rows == list(range(height))
+            sizes = [cd.row_range(height, world, r)[1] - cd.row_range(height, world, r)[0] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 4 + 3
+    with pytest.raises(ValueError):
+        cd.row_range(100, 2, 2)
+
+
+def _tile_worker(rank, world, port, total_spp, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import oracle
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    lo, hi = cd.row_range(64, world, rank)            # split the band [96,160) of the frame into per-rank tiles
+    s = np.zeros((256, 256, 4), np.float32)
+    sc.render(total_spp, rows=(96 + lo, 96 + hi), sum_image=s)
+    t = torch.from_numpy(s.copy())
+    cd.reduce_sum_(t)                                  # zero-filled SUM of disjoint tiles
+    if rank == 0:
+        np.save(os.path.join(out_dir, "tiles.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_tile_split_is_bit_identical_to_single_process(tmp_path):
+    import oracle
+    mp.spawn(_tile_worker, args=(2, 29519, 3, str(tmp_path)), nprocs=2, join=True)
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    one, _ = sc.render(3, rows=(96, 160))
+    assert np.array_equal(np.load(tmp_path / "tiles.npy"), one)  # disjoint pixels: x + 0 == x exactly
+
+
 def _worker(rank, world, port, total_spp, out_dir):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
     import oracle

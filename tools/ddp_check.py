@@ -8,12 +8,16 @@ rank, lr = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 scene = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref", "cbox_wfpt_256.cpts")
-r = cpt.WavefrontRenderer(scene, lr, 0)
-mean = cd.render_distributed(r, 64)
-if rank == 0:
-    ref = np.fromfile(scene.replace(".cpts", "_wfpt_f0064.bin"), dtype=np.float32).reshape(256, 256, 4)
-    m = mean.cpu().numpy()
-    rel = np.linalg.norm((m - ref)[..., :3]) / np.linalg.norm(ref[..., :3])
-    print(f"[ddp_check] world={dist.get_world_size()} rel_l2 vs reference 64-spp frame = {rel:.3e}, max abs = {np.abs(m-ref)[...,:3].max():.3e}")
-    assert rel < 1e-6
+ref = np.fromfile(scene.replace(".cpts", "_wfpt_f0064.bin"), dtype=np.float32).reshape(256, 256, 4)
+for split in ("samples", "tiles"):
+    r = cpt.WavefrontRenderer(scene, lr, 0)
+    mean = cd.render_distributed(r, 64, split=split)
+    if rank == 0:
+        m = mean.cpu().numpy()
+        rel = np.linalg.norm((m - ref)[..., :3]) / np.linalg.norm(ref[..., :3])
+        exact = float((m[..., :3] == ref[..., :3]).all(-1).mean())
+        print(f"[ddp_check] world={dist.get_world_size()} split={split}: rel_l2 vs reference 64-spp frame = {rel:.3e}, "
+              f"max abs = {np.abs(m-ref)[...,:3].max():.3e}, bit-identical pixels = {exact*100:.2f}%")
+        assert rel < 1e-6
+    r.close()
 dist.destroy_process_group()
