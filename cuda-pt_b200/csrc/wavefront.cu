@@ -1278,7 +1278,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     const size_t smem = size_t(m.dev.num_cache) * sizeof(uint4);
     const int grid = num_sms_ * blocks_per_sm_;
     const int mode = traversal_;
-    const int pipeline_ = (this->pipeline_ == 2 && traversal_ != 0) ? 1 : this->pipeline_; // dynamic fetch exists for the ordered traversal only
+    const int pipeline_ = (this->pipeline_ == 2 && (traversal_ == 1 || traversal_ == 3)) ? 1 : this->pipeline_; // dynamic fetch exists for the ordered traversal only
 #define LAUNCH_MODE(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (mode == 0)                                                                                                 \

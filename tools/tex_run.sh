@@ -1,18 +1,6 @@
-python -m pytest tests -m gpu -q -x -k "pipelines or pt_rules or megakernel" 2>&1 | tail -15
-python - <<'PY'
-import os, sys, time
-sys.path.insert(0, os.getcwd())
-import cuda_pt_b200 as cpt
-xml="scenes/xml/vader_wfpt_1080p.xml"; spp=32
-for pipe in (1,3,1,3):
-    r = cpt.WavefrontRenderer(xml, 0, 0)
-    r.set_option("samples_in_flight", 16); r.set_option("kernel_timing", 1); r.set_option("pipeline", pipe)
-    r.render_batch(32, False)
-    s0 = r.stats(); k0 = r.kernel_times()
-    r.render_batch(spp, False); r.sync()
-    s1 = r.stats(); k1 = r.kernel_times()
-    dev = (s1["device_us"] - s0["device_us"]) / 1e6
-    kt = {k: round((k1[k]["ms"] - k0[k]["ms"]) / spp, 3) for k in k1}
-    print(f"pipeline={pipe}: traced {(s1["shadow_traced"]-s0["shadow_traced"])/max(1,(s1["shadow_rays"]-s0["shadow_rays"])):.3f} of shadow rays; {dev/spp*1e3:.3f} ms/spp, {(s1['rays']-s0['rays'])/dev/1e6:.1f} Mrays/s {kt}", flush=True)
-    r.close()
-PY
+python -m pytest tests -m gpu -q -x -k "row_range or pipelines" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/ddp_check.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM" | tail -5
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 8 --warmup 3 2>&1 | tail -1 > gpurun_out/r01b/bench_ours_n2.json; python -c "
+import json; d=json.loads(open('gpurun_out/r01b/bench_ours_n2.json').read()); print('N=2 samples:', d['value'], d['ms_per_step'], d['e2e']['value'], d['scaling'], d['config']['parallelism'])"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 2 --steps 8 --warmup 3 --split tiles 2>&1 | tail -1 > gpurun_out/r01b/bench_ours_n2_tiles.json; python -c "
+import json; d=json.loads(open('gpurun_out/r01b/bench_ours_n2_tiles.json').read()); print('N=2 tiles:', d['value'], d['ms_per_step'], d['e2e']['value'], d['scaling'], d['config']['parallelism'])"
