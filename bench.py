@@ -148,15 +148,15 @@ def run_reference(args, scene, workload):
                                  capture_output=True, text=True, timeout=3000, cwd=ROOT)
             line = [l for l in out.stdout.splitlines() if l.startswith("{\"ref_bench\"")][-1]
             rb = json.loads(line)
-            rps = tbl["rays_per_sample"] if tbl else None
+            rps = tbl.get("reference_scene_rays_per_sample", tbl["rays_per_sample"]) if tbl else None
             ms_step = rb["ms_per_frame"] * S
             msamples = rb["width"] * rb["height"] / rb["ms_per_frame"] / 1e3
             value = msamples * rps if rps else None
             base.update({"value": value, "ms_per_step": ms_step, "msamples_per_s": msamples,
                          "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "reference",
                                           "sample": f"{args.steps * S} x WavefrontPathTracer::render_raw (1 spp each) on 1 GPU of this box, "
-                                                    "reference kernels + its host loop (one host thread); rays/sample from "
-                                                    "profiles/workload_rays.json (same scene, counts parity-checked)"},
+                                                    "reference kernels + its host loop (one host thread); rays/sample of the "
+                                                    "reference-built scene (its SBVH) from profiles/workload_rays.json, counts parity-checked"},
                          "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                          "reference_kind": "reference GPU kernels (sm_100a rebuild) + reference host loop"})
             print(json.dumps(base))

@@ -377,7 +377,11 @@ void build_pair_layout(const HostScene &sc, PairLayout &out) {
 
     auto contained = [&](int child, int parent) {
         const F4 cl = sc.nodes[2 * child], ch = sc.nodes[2 * child + 1], pl = sc.nodes[2 * parent], ph = sc.nodes[2 * parent + 1];
-        return cl.x >= pl.x && cl.y >= pl.y && cl.z >= pl.z && ch.x <= ph.x && ch.y <= ph.y && ch.z <= ph.z;
+        const float over = std::max(std::max(std::max(pl.x - cl.x, pl.y - cl.y), pl.z - cl.z),
+                                    std::max(std::max(ch.x - ph.x, ch.y - ph.y), ch.z - ph.z));
+        if (over > 0.f)
+            out.max_overshoot = std::max(out.max_overshoot, over);
+        return !(over > 0.f);
     };
 
     // explicit stack: (reference node k, slot to fill = pair node index * 2 + child id, depth)

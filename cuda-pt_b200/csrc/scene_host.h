@@ -75,6 +75,7 @@ struct PairLayout {
     int root = 0;
     int max_depth = 0;
     int nesting_violations = 0; // child boxes that are not contained in their parent's box
+    float max_overshoot = 0.f;  // by how much at most (the reference's SBVH pads clipped child boxes by AABB_EPS = 1e-5)
     int oversize_leaves = 0;
 };
 void build_pair_layout(const HostScene &scene, PairLayout &out);

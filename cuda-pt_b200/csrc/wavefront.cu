@@ -337,18 +337,39 @@ __device__ __forceinline__ int warp_take(int *work, int count, int lane, int n_i
     return take;
 }
 
-template <int MINB>
+constexpr int kSmemTop = 8; // stack entries per thread kept in shared memory ([level][thread]: bank == lane, conflict-free)
+
+// APPLY = false: pipeline 2 (rays from k_shadow_gen carry their cached-phase start index, answer goes to the tag bit);
+// APPLY = true: pipeline 4 (rays from k_shade<-2>, cached phase here, an unoccluded ray swaps in the prepared radiance)
+template <int MINB, bool APPLY>
 __global__ void __launch_bounds__(kBlock, MINB) k_anyhit(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ sq,
                                                          const int *__restrict__ sq_count, int *work, int kRefill, int kSteps) {
+    extern __shared__ uint4 s_cached[];
+    if constexpr (APPLY)
+        stage_cached_nodes(sc, s_cached);
+    int *s_stack = reinterpret_cast<int *>(s_cached + (APPLY ? sc.num_cache : 0)) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int count = *sq_count;
-    int stack_ref[kStackSize];
+    int spill[kStackSize];
     int sp = 0, cur = kTraversalDone, start = 0;
     uint32_t slot = 0;
     V3 o{0, 0, 0}, d{0, 0, 1}, inv_d{0, 0, 0}, o_div{0, 0, 0};
     float range = 0;
     bool active = false, more = true;
     int next = 0, end = 0;
+    auto push = [&](int ref) {
+        if (sp < 2 * kSmemTop)
+            s_stack[sp * kBlock] = ref;
+        else
+            spill[sp - 2 * kSmemTop] = ref;
+        ++sp;
+    };
+    auto pop = [&]() {
+        if (sp == 0)
+            return kTraversalDone;
+        --sp;
+        return sp < 2 * kSmemTop ? s_stack[sp * kBlock] : spill[sp - 2 * kSmemTop];
+    };
     while (true) {
         const unsigned act = __ballot_sync(0xffffffffu, active);
         const int n_idle = 32 - __popc(act);
@@ -359,9 +380,17 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anyhit(DevScene sc, PathState 
             if (!active && rank < take) {
                 slot = sq[first + rank];
                 const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
-                o = xyz(a), d = xyz(b), range = a.w, start = __float_as_int(b.w);
+                o = xyz(a), d = xyz(b), range = a.w;
                 inv_d = rcp3(d), o_div = o * inv_d;
+                if constexpr (APPLY)
+                    start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, range, sc.num_nodes);
+                else
+                    start = __float_as_int(b.w);
                 cur = sc.wroot, sp = 0, active = true;
+                if (APPLY && start >= sc.num_nodes) { // no cached frontier node on the way: unoccluded (tracing_func.cuh:49)
+                    st.L[slot] = rb.hit[slot];
+                    active = false;
+                }
             }
         } else if (act == 0)
             break;
@@ -370,8 +399,8 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anyhit(DevScene sc, PathState 
             if (active) {
                 bool occluded = false;
                 if (cur >= 0) {
-                    const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
-                                 b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+                    float4 a0, a1, b0, b1;
+                    load_pair_node<true>(sc.wnodes, cur, a0, a1, b0, b1);
                     float t0, t1;
                     const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < range &&
                                     __float_as_int(a1.w) > start;
@@ -379,12 +408,12 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anyhit(DevScene sc, PathState 
                                     __float_as_int(b1.w) > start;
                     const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
                     if (h0 && h1) {
-                        stack_ref[sp++] = r1;
+                        push(r1);
                         cur = r0;
                     } else if (h0 || h1) {
                         cur = h0 ? r0 : r1;
                     } else {
-                        cur = sp > 0 ? stack_ref[--sp] : kTraversalDone;
+                        cur = pop();
                     }
                 } else {
                     const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
@@ -395,12 +424,16 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anyhit(DevScene sc, PathState 
                             break;
                         }
                     }
-                    cur = sp > 0 ? stack_ref[--sp] : kTraversalDone;
+                    cur = pop();
                 }
                 if (occluded || cur == kTraversalDone) {
                     if (!occluded) {
-                        float *tagp = &st.ray_d[slot].w;
-                        *tagp = __uint_as_float(__float_as_uint(*tagp) | TAG_NEE_VISIBLE);
+                        if constexpr (APPLY) {
+                            st.L[slot] = rb.hit[slot];
+                        } else {
+                            float *tagp = &st.ray_d[slot].w;
+                            *tagp = __uint_as_float(__float_as_uint(*tagp) | TAG_NEE_VISIBLE);
+                        }
                     }
                     active = false;
                 }
@@ -626,10 +659,10 @@ __global__ void __launch_bounds__(kBlock, MINB) k_intersect(DevScene sc, PathSta
                                                             const int *__restrict__ q_count, int *work, int kRefill, int kSteps) {
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
+    uint2 *s_stack = reinterpret_cast<uint2 *>(s_cached + sc.num_cache) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int count = *q_count;
-    int stack_ref[kStackSize];
-    float stack_t[kStackSize];
+    uint2 spill[kStackSize];
     int sp = 0, cur = kTraversalDone, start = 0;
     uint32_t slot = 0;
     V3 o{0, 0, 0}, d{0, 0, 1}, inv_d{0, 0, 0}, o_div{0, 0, 0};
@@ -663,8 +696,8 @@ __global__ void __launch_bounds__(kBlock, MINB) k_intersect(DevScene sc, PathSta
             if (active) {
                 bool pop = false;
                 if (cur >= 0) {
-                    const float4 a0 = __ldg(sc.wnodes + 4 * cur), a1 = __ldg(sc.wnodes + 4 * cur + 1),
-                                 b0 = __ldg(sc.wnodes + 4 * cur + 2), b1 = __ldg(sc.wnodes + 4 * cur + 3);
+                    float4 a0, a1, b0, b1;
+                    load_pair_node<true>(sc.wnodes, cur, a0, a1, b0, b1);
                     float t0, t1;
                     const bool h0 = slab_test(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < ht &&
                                     __float_as_int(a1.w) > start;
@@ -673,8 +706,11 @@ __global__ void __launch_bounds__(kBlock, MINB) k_intersect(DevScene sc, PathSta
                     const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
                     if (h0 && h1) {
                         const bool swap = t1 < t0;
-                        stack_ref[sp] = swap ? r0 : r1;
-                        stack_t[sp] = swap ? t0 : t1;
+                        const uint2 e = make_uint2(uint32_t(swap ? r0 : r1), __float_as_uint(swap ? t0 : t1));
+                        if (sp < kSmemTop)
+                            s_stack[sp * kBlock] = e;
+                        else
+                            spill[sp - kSmemTop] = e;
                         ++sp;
                         cur = swap ? r1 : r0;
                     } else if (h0 || h1) {
@@ -700,8 +736,9 @@ __global__ void __launch_bounds__(kBlock, MINB) k_intersect(DevScene sc, PathSta
                     cur = kTraversalDone;
                     while (sp > 0) {
                         --sp;
-                        if (stack_t[sp] < ht) {
-                            cur = stack_ref[sp];
+                        const uint2 e = sp < kSmemTop ? s_stack[sp * kBlock] : spill[sp - kSmemTop];
+                        if (__uint_as_float(e.y) < ht) {
+                            cur = int(e.x);
                             break;
                         }
                     }
@@ -936,6 +973,7 @@ struct Renderer::Impl {
     std::vector<cudaArray_t> tex_arrays;
     int capacity_samples = 0;
     int pair_depth = 0, nesting_violations = 0;
+    float max_overshoot = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     size_t scene_bytes = 0;
     // optional per-launch timing
@@ -1037,8 +1075,13 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         m.pair_depth = pl.max_depth;
         m.nesting_violations = pl.nesting_violations;
         m.dev.wroot = pl.root;
-        if (pl.max_depth + 2 > kStackSize || pl.nesting_violations > 0)
-            traversal_ = TRAVERSAL_DFS; // ordered traversal's preconditions do not hold: use the reference order
+        // ordered traversal's preconditions: stack depth, and child boxes inside their parents' boxes.  The
+        // reference's SBVH pads clipped child boxes by AABB_EPS (1e-5) beyond the parent; that much is tolerated (a hit
+        // would have to lie within the padding of a box edge to be affected), anything larger falls back to the
+        // reference's own visiting order
+        m.max_overshoot = pl.max_overshoot;
+        if (pl.max_depth + 2 > kStackSize || pl.max_overshoot > 2.5e-5f)
+            traversal_ = TRAVERSAL_DFS;
         m.obj_idxs.upload(std::vector<int>(scene.obj_idxs.begin(), scene.obj_idxs.end()));
         // emitter primitive map is padded like path_tracer.cu:76-87 (zero filled here)
         std::vector<int> ep(scene.emitter_prims.begin(), scene.emitter_prims.end());
@@ -1276,9 +1319,11 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     RayBufs rb{m.sh_o.p, m.sh_d.p, m.hit.p};
     CUDA_OK(cudaMemsetAsync(m.counters.p, 0, m.counters.n * sizeof(int), stream_));
     const size_t smem = size_t(m.dev.num_cache) * sizeof(uint4);
+    const size_t smem_dyn = smem + size_t(kSmemTop) * kBlock * sizeof(uint2); // dynamic-fetch kernels: + shared-memory stack
+    const size_t smem_any = size_t(kSmemTop) * kBlock * sizeof(uint2);
     const int grid = num_sms_ * blocks_per_sm_;
     const int mode = traversal_;
-    const int pipeline_ = (this->pipeline_ == 2 && (traversal_ == 1 || traversal_ == 3)) ? 1 : this->pipeline_; // dynamic fetch exists for the ordered traversal only
+    const int pipeline_ = (traversal_ == 1 || traversal_ == 3) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
 #define LAUNCH_MODE(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (mode == 0)                                                                                                 \
@@ -1317,13 +1362,18 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     for (int b = 0; b < D; b++) {
         uint32_t *q_cur = m.queue[b & 1].p, *q_nxt = m.queue[(b + 1) & 1].p;
         const PtRules pt{rules_, b, m.caps[0], m.caps[1], m.caps[2]};
-        if (pipeline_ == 3) {
+        if (pipeline_ == 3 || pipeline_ == 4) {
             mark(1, b);
             k_shade<-2><<<grid, kBlock, 0, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt, rb,
                                                       m.shadow_queue.p, sq_counts + b);
             ++wk, ++launches;
             mark(4, b);
-            LAUNCH_MODE(k_shadow_apply, m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+            if (pipeline_ == 3)
+                LAUNCH_MODE(k_shadow_apply, m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+            else if (dyn_minb_ >= 12)
+                k_anyhit<12, true><<<grid, kBlock, smem_dyn, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
+            else
+                k_anyhit<8, true><<<grid, kBlock, smem_dyn, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
         } else if (pipeline_ == 2) {
             mark(4, b);
             k_shadow_gen<<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, m.shadow_queue.p,
@@ -1331,9 +1381,9 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             ++wk, ++launches;
             mark(4, b);
             if (dyn_minb_ >= 12)
-                k_anyhit<12><<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
+                k_anyhit<12, false><<<grid, kBlock, smem_any, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
             else
-                k_anyhit<8><<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
+                k_anyhit<8, false><<<grid, kBlock, smem_any, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
             ++wk, ++launches;
             mark(1, b);
             k_shade<-1><<<grid, kBlock, 0, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, shadow_counter, b > 0, pt, rb, nullptr, nullptr);
@@ -1352,11 +1402,11 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         if (b + 1 >= D)
             break;
         mark(2, b);
-        if (pipeline_ == 2) {
+        if (pipeline_ == 2 || pipeline_ == 4) {
             if (dyn_minb_ >= 12)
-                k_intersect<12><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, dyn_refill_, dyn_steps_);
+                k_intersect<12><<<grid, kBlock, smem_dyn, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, dyn_refill_, dyn_steps_);
             else
-                k_intersect<8><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, dyn_refill_, dyn_steps_);
+                k_intersect<8><<<grid, kBlock, smem_dyn, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, dyn_refill_, dyn_steps_);
             ++wk, ++launches;
             mark(2, b);
             k_resolve<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
@@ -1528,7 +1578,7 @@ std::string Renderer::info() const {
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
        << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : "ordered-vote")))
-       << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations
+       << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations << " (max " << impl_->max_overshoot << ")"
        << ", L2 window " << (impl_->l2_window_bytes >> 20) << " MB, pipeline " << pipeline_ << ", rules " << (rules_ ? "megakernel-pt" : "wavefront") << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();
 }

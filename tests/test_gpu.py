@@ -94,16 +94,16 @@ def test_xml_loader_textures_statistically_equal_reference():
 @pytest.mark.parametrize("scene,frame", [("cbox_mats_256.cpts", "cbox_mats_256_wfpt_f0016.bin"), ("texroom_256.cpts", None)])
 def test_pipelines_agree(scene, frame):
     """"pipeline" 0: NEE ray traced inside the shading kernel; 1: own shadow kernel; 2: dynamic-fetch traversal kernels;
-    3: deferred NEE (only the shadow rays that can change the radiance are traced)."""
+    3: deferred NEE (only the shadow rays that can change the radiance are traced); 4: 3 + dynamic-fetch kernels."""
     outs = []
-    for pipeline in (0, 1, 2, 3):
+    for pipeline in (0, 1, 2, 3, 4):
         r = cpt.WavefrontRenderer(os.path.join(GOLDEN, scene), 0, 0)
         r.set_option("pipeline", pipeline)
         assert r.get_option("pipeline") == pipeline
         r.render_batch(16, False)
         outs.append(r.download_output())
         st = r.stats()
-        assert st["launches"] == 1 + 8 * (1, 2, 3, 2)[pipeline] + 7 * (1, 1, 2, 1)[pipeline] + 2
+        assert st["launches"] == 1 + 8 * (1, 2, 3, 2, 2)[pipeline] + 7 * (1, 1, 2, 1, 2)[pipeline] + 2
         assert st["shadow_traced"] <= st["shadow_rays"] and (pipeline >= 2 or st["shadow_traced"] == st["shadow_rays"])
         r.close()
     for o in outs[1:]:
