@@ -193,6 +193,24 @@ def test_render_offline_matches_reference_render_semantics():
     r.close(); r2.close()
 
 
+def test_pt_front_end_writes_the_png_of_render_offline(tmp_path):
+    """apps/pt.c -> render.png: same bytes as cpt_b200_render_offline through Python (TracerBase::render semantics)."""
+    from PIL import Image
+    import __graft_entry__ as g
+    g._build_pt_app()
+    scene = os.path.join(SCENES, "cbox_pt_256.xml") if have_meshes() else os.path.join(GOLDEN, "cbox_wfpt_256.cpts")
+    out = tmp_path / "render.png"
+    res = subprocess.run([os.path.join(ROOT, "cuda-pt_b200", "pt"), scene, str(out)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert "Image saved" in res.stdout
+    png = np.asarray(Image.open(out))
+    cfg = cpt.Scene(scene).config
+    r = cpt.WavefrontRenderer(scene, 0, 0)
+    ref = r.render_offline(cfg["spp"], bool(cfg["gamma"]))
+    r.close()
+    assert png.shape == ref.shape and np.array_equal(png, ref)
+
+
 def test_python_renderer_surface():
     import torch
     pr = cpt.PythonRenderer(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), 0, 0)

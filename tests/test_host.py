@@ -94,6 +94,24 @@ def test_scene_errors(tmp_path):
         cpt.Scene(str(t))
 
 
+def test_pt_front_end_in_plain_c_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """apps/pt.c (the reference's `pt <xml>` over the C ABI) compiles with gcc alone; on a box without a GPU it must
+    exit non-zero with the library's message instead of falling back to anything."""
+    import subprocess
+    import torch
+    import __graft_entry__ as g
+    g._build_pt_app()
+    exe = os.path.join(ROOT, "cuda-pt_b200", "pt")
+    assert os.path.exists(exe)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 1 and "Usage" in res.stderr
+    res = subprocess.run([exe, str(tmp_path / "nope.xml")], capture_output=True, text=True)
+    assert res.returncode == 2 and "cannot open" in res.stderr
+    if not torch.cuda.is_available():
+        res = subprocess.run([exe, os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), str(tmp_path / "o.png")], capture_output=True, text=True)
+        assert res.returncode == 3 and "no CPU fallback" in res.stderr and not (tmp_path / "o.png").exists()
+
+
 def test_png_decoder_and_texture_conversion_match_an_independent_decoder(tmp_path):
     """The loader's own PNG reader (grey / RGB / RGBA / palette / 16-bit) against PIL, plus the texel conversion rules
     of src/impl/textures.cu:53-131 (byte/255, normal maps *2-1, luma for grey requests, 16->8 bit = high byte,
