@@ -13,6 +13,8 @@
 #include "image_io.h"
 #include "scene_host.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -566,6 +568,40 @@ int linearize(const Builder &b, int id, int depth, int cache_levels, std::vector
     return sub + 1;
 }
 
+// ---- spectral tables for the dispersion BSDF (ColorSpaceXYZ::init, src/impl/xyz.cu:808-830): CIE 1931 2-degree
+// observer 360-830 nm and D65 300-830 nm at 1 nm.  The numbers ship as data/spectral_tables.bin next to the library
+// (read back at run time from the reference's own device textures by the golden-vector harness, tests/golden/README.md);
+// CPTB200_DATA overrides the directory.
+void load_spectral_tables(HostScene &out) {
+    std::string dir;
+    if (const char *e = getenv("CPTB200_DATA"))
+        dir = e;
+    else {
+        Dl_info info{};
+        if (dladdr(reinterpret_cast<const void *>(&load_spectral_tables), &info) && info.dli_fname) {
+            dir = info.dli_fname;
+            const size_t slash = dir.find_last_of('/');
+            dir = (slash == std::string::npos ? std::string(".") : dir.substr(0, slash)) + "/data";
+        }
+    }
+    const std::string path = dir + "/spectral_tables.bin";
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp)
+        throw std::runtime_error("scene: dispersion BSDF needs the spectral tables, cannot open '" + path + "'");
+    char magic[8];
+    int32_t n[2] = {0, 0};
+    bool ok = fread(magic, 1, 8, fp) == 8 && memcmp(magic, "CPTSPEC1", 8) == 0 && fread(n, 4, 2, fp) == 2 && n[0] == 471 && n[1] == 531;
+    if (ok) {
+        out.cie_xyz.resize(size_t(n[0]));
+        out.d65_spd.resize(size_t(n[1]));
+        ok = fread(out.cie_xyz.data(), sizeof(F4), out.cie_xyz.size(), fp) == out.cie_xyz.size() &&
+             fread(out.d65_spd.data(), sizeof(float), out.d65_spd.size(), fp) == out.d65_spd.size();
+    }
+    fclose(fp);
+    if (!ok)
+        throw std::runtime_error("scene: malformed spectral table file '" + path + "'");
+}
+
 // ---- image textures (src/impl/textures.cu:53-81,92-131,169-203) ----
 struct TexInfo {
     std::string diff, spec, glos, rough1, rough2, normal;
@@ -1049,6 +1085,11 @@ void load_xml(const std::string &path, HostScene &out) {
     cfg[CPTS_CFG_NUM_PRIMS] = int(P0), cfg[CPTS_CFG_NUM_NODES] = out.num_nodes();
     cfg[CPTS_CFG_NUM_CACHE] = int(out.cache_nodes.size()), cfg[CPTS_CFG_CACHE_LEVEL] = cache_level;
     cfg[CPTS_CFG_MAX_NODE_NUM] = max_node_num, cfg[CPTS_CFG_USE_SBVH] = 0;
+    for (const auto &b : out.bsdfs)
+        if (b.type == CPTS_BSDF_DISPERSION && out.cie_xyz.empty()) {
+            load_spectral_tables(out);
+            break;
+        }
     validate_scene(out);
 }
 
