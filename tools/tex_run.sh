@@ -1,26 +1,16 @@
-python -m pytest tests -m gpu -q -x -k "live_reference" 2>&1 | tail -3
-for w in vader_wfpt_1080p vader_tex_wfpt_1080p; do
-oracle/_ref/ref_dump dump scenes/xml/$w.xml /tmp/$w.cpts > /dev/null 2>&1
-python - $w <<'PY'
-import os, sys
-sys.path.insert(0, os.getcwd())
+python - <<'PY'
+import os, sys, numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, "tests")
 import cuda_pt_b200 as cpt
-w = sys.argv[1]
-for trav in (2, 1):
-    r = cpt.WavefrontRenderer(f"/tmp/{w}.cpts", 0, 0)
-    r.set_option("samples_in_flight", 16); r.set_option("kernel_timing", 1); r.set_option("traversal", trav)
+ref = np.fromfile("tests/golden/ref/cbox_mats_256_wfpt_f0016.bin", dtype=np.float32).reshape(256,256,4)[..., :3].astype(np.float64)
+for scene in ("scenes/xml/cbox_mats_wfpt_256.xml", "tests/golden/ref/cbox_mats_256.cpts"):
+    r = cpt.WavefrontRenderer(scene, 0, 0)
     r.render_batch(16, False)
-    s0 = r.stats(); k0 = r.kernel_times()
-    r.render_batch(32, False); r.sync()
-    s1 = r.stats(); k1 = r.kernel_times()
-    dev = (s1["device_us"] - s0["device_us"]) / 1e6
-    kt = {k: round((k1[k]["ms"] - k0[k]["ms"]) / 32, 3) for k in k1}
-    print(f"{w} (reference-loaded scene) trav={trav}: {dev/32*1e3:.3f} ms/spp {kt} rays/sample {(s1['rays']-s0['rays'])/(s1['samples']-s0['samples']):.4f} | {r.info()[90:200]}", flush=True)
-    if trav == 2: a = r.download_output()
-    else:
-        b = r.download_output()
-        import numpy as np
-        print("   ordered vs dfs on the SBVH scene, 48 spp: bit-identical px", float((a==b).all(-1).mean()), "rel_l2", float(np.linalg.norm(a[...,:3]-b[...,:3])/np.linalg.norm(b[...,:3])))
-    r.close()
+    o = r.download_output()[..., :3].astype(np.float64); r.close()
+    a, b = np.minimum(o, 4.0), np.minimum(ref, 4.0)
+    bo, br = a.reshape(16,16,16,16,3).mean((1,3)), b.reshape(16,16,16,16,3).mean((1,3))
+    rel = np.abs(bo-br).sum(-1)/np.maximum(br.sum(-1),1e-2)
+    np.set_printoptions(linewidth=200, precision=2, suppress=True)
+    print(scene, "median", np.median(rel), "p90", np.quantile(rel,0.9), "mean ratio", a.mean()/b.mean())
+    print(rel)
 PY
-done
