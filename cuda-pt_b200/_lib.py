@@ -10,7 +10,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libcpt_b200.so")
+LIB_PATH = os.environ.get("CPTB200_LIB", os.path.join(PKG_DIR, "libcpt_b200.so"))  # override: A/B builds of the kernels
 SOURCES = ["wavefront.cu", "capi.cu", "scene_host.cpp", "scene_xml.cpp", "image_io.cpp"]
 NVCC_FLAGS = [
     "-O3", "--use_fast_math", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I" + os.path.join(REPO_ROOT, "include"), "-I" + CSRC]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CPTB200_NVCC_EXTRA", "").split() + ["-I" + os.path.join(REPO_ROOT, "include"), "-I" + CSRC]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH, "-lz", "-ldl"]
     if verbose:
         print(" ".join(cmd))

@@ -43,6 +43,9 @@ namespace cptb {
     } while (0)
 
 constexpr int kBlock = 128;
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 6 // register budget of the traversal-free shading kernels: 6 CTAs/SM -> <= 85 registers
+#endif
 
 struct PathState {
     float4 *ray_o; // o.xyz, hit_t
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anyhit(DevScene sc, PathState 
 // facing away, BSDF value zero, delta lobes) therefore never cost a traversal, and the result stays exact.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_shade(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
+__global__ void __launch_bounds__(kBlock, (MODE < 0 ? SHADE_MIN_BLOCKS : 1)) k_shade(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
                                                   const int *__restrict__ q_count, int *work,
                                                   unsigned long long *shadow_counter, int secondary_bounce, PtRules pt,
                                                   RayBufs rb, uint32_t *sq, int *sq_count) {
