@@ -247,8 +247,8 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
                 throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads) or 3 (warp vote)");
             r->impl->set_traversal(int(value));
         } else if (k == "rules") {
-            if (value != 0 && value != 1)
-                throw std::runtime_error("rules must be 0 (wavefront) or 1 (megakernel pt)");
+            if (value < 0 || value > 2)
+                throw std::runtime_error("rules must be 0 (wavefront), 1 (megakernel pt) or 2 (volumetric pt)");
             r->impl->set_rules(int(value));
         } else if (k == "split_shadow") {
             r->impl->set_pipeline(value != 0 ? 1 : 0);

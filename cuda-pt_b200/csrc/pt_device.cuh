@@ -30,7 +30,8 @@ enum : int {
     LOBE_SPECULAR = 0x02,
     LOBE_GLOSSY = 0x04,
     LOBE_REFLECT = 0x10,
-    LOBE_TRANSMIT = 0x20
+    LOBE_TRANSMIT = 0x20,
+    LOBE_VOLUME = 0x40 // SCAT_VOLUME (enums.cuh:48): scattering inside a medium
 };
 enum : int { MAT_LAMBERT = 0, MAT_SPECULAR, MAT_TRANSLUCENT, MAT_PLASTIC, MAT_PLASTIC_FWD, MAT_GGX, MAT_DISPERSION, MAT_FORWARD };
 enum : int { EM_NULL = 0, EM_POINT, EM_AREA, EM_AREA_SPOT, EM_ENVMAP };
@@ -86,6 +87,8 @@ struct DevScene {
     // re-laid-out ordered-traversal structure built at renderer construction
     const float4 *wnodes;      // 4 float4 per inner node (see bvh_relayout.cpp)
     int num_nodes, num_cache, num_prims, num_emitters, envmap_id, wroot;
+    const struct MediumPOD *media; // [0] = vacuum (volumetric path only)
+    int num_media, cam_vol;
     cudaTextureObject_t cie, d65; // spectral tables for the dispersion BSDF
 };
 
@@ -185,9 +188,13 @@ PT_DEV float hit_triangle(const float4 *__restrict__ tris, int index, V3 o, V3 d
 
 // shading normal + half-precision uv at a hit (reference: primitives.cuh:109-123, aos.cuh:305-319,
 // vec2_half.cuh:182-186).  Returns {n.xyz, bits(half2 uv)}.
-PT_DEV float4 make_interaction(const DevScene &sc, int index, float u, float v) {
+// NormalArray::eval (aos.cuh:305-319): interpolated, normalised vertex normal
+PT_DEV V3 interp_normal(const DevScene &sc, int index, float u, float v) {
     const float4 a = __ldg(sc.norms + 3 * index), b = __ldg(sc.norms + 3 * index + 1), c = __ldg(sc.norms + 3 * index + 2);
-    V3 n = normalized(lerp3(xyz(a), 1.f - u - v, xyz(b), u, xyz(c), v));
+    return normalized(lerp3(xyz(a), 1.f - u - v, xyz(b), u, xyz(c), v));
+}
+PT_DEV float4 make_interaction(const DevScene &sc, int index, float u, float v) {
+    V3 n = interp_normal(sc, index, u, v);
     const uint4 pk = __ldg(sc.uvs + index);
     const __half2 h1 = *reinterpret_cast<const __half2 *>(&pk.x), h2 = *reinterpret_cast<const __half2 *>(&pk.y),
                   h3 = *reinterpret_cast<const __half2 *>(&pk.z);

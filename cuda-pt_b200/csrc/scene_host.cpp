@@ -154,6 +154,8 @@ void load_cpts(const std::string &path, HostScene &out) {
             read_into(fp, s, out.cie_xyz, "cie_xyz");
         else if (name == "d65_spd")
             read_into(fp, s, out.d65_spd, "d65_spd");
+        else if (name == "media")
+            read_into(fp, s, out.media, "media");
         else if (name == "tex_desc")
             read_into(fp, s, tex_desc, "tex_desc");
         else if (name == "tex_data")
@@ -202,6 +204,8 @@ void save_cpts(const HostScene &sc, const std::string &path) {
         w.put("cie_xyz", sc.cie_xyz.data(), 16, sc.cie_xyz.size());
         w.put("d65_spd", sc.d65_spd.data(), 4, sc.d65_spd.size());
     }
+    if (!sc.media.empty())
+        w.put("media", sc.media.data(), sizeof(CptsMedium), sc.media.size());
     if (!sc.textures.empty()) {
         std::vector<CptsTexDesc> desc;
         std::vector<float> data;
@@ -253,6 +257,20 @@ void validate_scene(const HostScene &sc) {
             fail("sphere primitives are not supported (reference default build is TRIANGLE_ONLY, defines.cuh:26)");
         if (size_t(w & 0x000fffff) >= sc.objects.size())
             fail("primitive references an unknown object");
+        const int medium = (w >> 20) & 0xff; // bits 20-27: medium bound by the object, bit 30: cullable (scene.cu:903-932)
+        if (medium != 0 && size_t(medium) >= sc.media.size())
+            fail("primitive references an unknown medium");
+    }
+    if (sc.media.size() > 256)
+        fail("at most 255 media (8-bit medium index)");
+    if (sc.config[CPTS_CFG_CAM_VOL] < 0 || (sc.config[CPTS_CFG_CAM_VOL] > 0 && size_t(sc.config[CPTS_CFG_CAM_VOL]) >= sc.media.size()))
+        fail("camera medium index out of range");
+    for (size_t i = 1; i < sc.media.size(); i++) {
+        if (sc.media[i].type != CPTS_MEDIUM_HOMOGENEOUS)
+            fail("grid (NanoVDB) media are not supported: only homogeneous media");
+        if (sc.media[i].phase_type != CPTS_PHASE_ISOTROPIC && sc.media[i].phase_type != CPTS_PHASE_HG &&
+            sc.media[i].phase_type != CPTS_PHASE_DUO_HG)
+            fail("unsupported phase function (isotropic, hg and hg-duo are)");
     }
     for (const auto &o : sc.objects) {
         const int bsdf = o.bsdf_emitter >> 16;

@@ -44,6 +44,7 @@ struct HostScene {
     std::vector<CptsBsdf> bsdfs;
     std::vector<CptsEmitter> emitters; // [0] = null emitter
     std::vector<HostTexture> textures;
+    std::vector<CptsMedium> media; // [0] = vacuum; empty when the scene has no participating media
     std::vector<F4> cie_xyz;    // 471 samples, 360..830 nm (only present when a dispersion BSDF needs it)
     std::vector<float> d65_spd; // 531 samples, 300..830 nm
 

@@ -9,7 +9,7 @@
 //
 // Image textures and environment maps are decoded from PNG files (image_io.cpp).
 // Not supported (clear errors, never silent): sphere shapes (reference default build is
-// TRIANGLE_ONLY), JPEG / HDR images, participating media.
+// TRIANGLE_ONLY), JPEG / HDR images, grid (NanoVDB) media.
 #include "image_io.h"
 #include "scene_host.h"
 
@@ -674,7 +674,7 @@ void load_xml(const std::string &path, HostScene &out) {
     const XNode *rdr = root.first("renderer"), *acc = root.first("accelerator"), *sensor = root.first("sensor");
     if (!sensor)
         throw std::runtime_error("scene: <sensor> missing");
-    int spp = 256, max_depth = 8, max_diffuse = 4, max_specular = 2, max_transmit = 8;
+    int spp = 256, max_depth = 8, max_diffuse = 4, max_specular = 2, max_transmit = 8, max_volume = 3;
     bool have_depth = false;
     int rdr_type = 0;
     if (rdr) {
@@ -685,6 +685,7 @@ void load_xml(const std::string &path, HostScene &out) {
         get_int(*rdr, {"max_diffuse"}, max_diffuse);
         get_int(*rdr, {"max_specular"}, max_specular);
         get_int(*rdr, {"max_transmit"}, max_transmit);
+        get_int(*rdr, {"max_volume"}, max_volume);
     }
     if (!have_depth) // MaxDepthParams default constructor (max_depth.h:35-41)
         max_depth = std::max(std::max(8, 8), std::max(4, 2));
@@ -728,8 +729,76 @@ void load_xml(const std::string &path, HostScene &out) {
         }
         tex_map.emplace(t->attr_or("id", ""), info); // first declaration of an id wins (unordered_map::emplace)
     }
-    if (!root.children("medium").empty())
-        throw std::runtime_error("scene: participating media are outside the wavefront surface path");
+    // ---- phase functions and media (scene.cu:702-900): index 0 of each table is the dummy / vacuum entry
+    std::map<std::string, int> phase_ids, medium_ids;
+    std::vector<std::pair<int, std::array<float, 4>>> phases(1, {CPTS_PHASE_ISOTROPIC, {0, 0, 0, 0}});
+    for (auto ph : root.children("phase")) {
+        std::string type = ph->attr_or("type", "hg");
+        if (type.empty())
+            type = "hg";
+        std::pair<int, std::array<float, 4>> rec{CPTS_PHASE_ISOTROPIC, {0, 0, 0, 0}}; // Vec4() = (0,0,0,0)
+        if (type == "hg") {
+            float g = 0.2f;
+            if (auto f = ph->first("float")) // only the first <float> child is inspected upstream
+                if (f->attr_or("name", "") == "g")
+                    g = float(atof(f->attr_or("value", "0.2").c_str()));
+            rec.first = CPTS_PHASE_HG, rec.second[0] = g;
+        } else if (type == "hg-duo") {
+            float g1 = 0.2f, g2 = 0.8f, w = 0.5f;
+            if (auto f = ph->first("float")) { // upstream advances with NextSiblingElement("string"): one <float> only
+                const std::string n = f->attr_or("name", "");
+                const float v = float(atof(f->attr_or("value", "0").c_str()));
+                if (n == "g1")
+                    g1 = v;
+                else if (n == "g2")
+                    g2 = v;
+                else if (n == "weight")
+                    w = v;
+            }
+            rec.first = CPTS_PHASE_DUO_HG, rec.second = {g1, g2, w, 1.f}; // Vec4(g1, g2, weight): w = 1
+        } else if (type == "rayleigh") {
+            throw std::runtime_error("scene: the Rayleigh phase function is not supported (isotropic, hg, hg-duo are)");
+        } // "isotropic", "sggx" and unknown types fall back to isotropic upstream
+        phase_ids[ph->attr_or("id", "")] = int(phases.size());
+        phases.push_back(rec);
+    }
+    {
+        int idx = 1;
+        for (auto md : root.children("medium")) {
+            const std::string id = md->attr_or("id", ""), type = md->attr_or("type", "homogeneous");
+            if (type != "homogeneous")
+                throw std::runtime_error("scene: medium '" + id + "' is a grid (NanoVDB) volume; only homogeneous media are supported");
+            int phase_id = 0;
+            if (auto r = md->first("ref"))
+                if (r->attr_or("type", "") == "phase") {
+                    auto it = phase_ids.find(r->attr_or("id", ""));
+                    if (it != phase_ids.end())
+                        phase_id = it->second;
+                }
+            if (phase_id == 0)
+                throw std::runtime_error("scene: volume '" + id + "' has no valid phase function");
+            float scale = 1.f;
+            get_float(*md, {"scale", "scaler"}, scale);
+            float sa[4] = {0, 0, 0, 1}, ss[4] = {1, 1, 1, 1};
+            for (auto c : md->children("rgb")) {
+                const std::string n = c->attr_or("name", "");
+                if (n == "sigma_a")
+                    parse_color(c->attr_or("value", "0"), sa);
+                else if (n == "sigma_s")
+                    parse_color(c->attr_or("value", "1"), ss);
+            }
+            if (out.media.empty())
+                out.media.push_back(CptsMedium{}); // vacuum
+            CptsMedium rec{};
+            rec.type = CPTS_MEDIUM_HOMOGENEOUS, rec.phase_type = phases[phase_id].first;
+            for (int k = 0; k < 4; k++) {
+                rec.sigma_a[k] = sa[k] * scale, rec.sigma_s[k] = ss[k] * scale; // create_homogeneous_volume (vol_homo.cu:26-32)
+                rec.phase[k] = phases[phase_id].second[k];
+            }
+            out.media.push_back(rec);
+            medium_ids[id] = idx++;
+        }
+    }
 
     // ---- BSDFs (scene.cu:184-359)
     std::map<std::string, int> bsdf_ids;
@@ -843,6 +912,7 @@ void load_xml(const std::string &path, HostScene &out) {
     std::array<std::vector<F3>, 3> V, N;
     std::array<std::vector<F2>, 3> UV;
     std::map<std::string, int> emitter_obj;
+    std::vector<int> obj_medium;
     for (auto sh : root.children("shape")) {
         const std::string type = sh->attr_or("type", "obj");
         if (type != "obj")
@@ -869,6 +939,20 @@ void load_xml(const std::string &path, HostScene &out) {
         }
         if (bsdf < 0)
             throw std::runtime_error("scene: object with no BSDF");
+        // medium bound by this shape + "cullable" flag (parseObjectMediumRef, scene.cu:903-932)
+        int medium_word = 0;
+        for (auto r : sh->children("ref"))
+            if (r->attr_or("type", "") == "medium") {
+                auto it = medium_ids.find(r->attr_or("id", ""));
+                if (it != medium_ids.end())
+                    medium_word = it->second & 0xff;
+            }
+        if (medium_word) {
+            if (auto fb = sh->first("bool")) // only the first <bool> child is inspected upstream
+                if (fb->attr_or("name", "") == "cullable" && fb->attr_or("value", "false") == "true")
+                    medium_word += 1 << 10;
+        }
+        obj_medium.push_back(medium_word);
         ObjMesh mesh;
         load_obj(filename, mesh);
         Obj o{bsdf, emitter, int(V[0].size()), int(mesh.v[0].size()), 0.f};
@@ -1048,7 +1132,7 @@ void load_xml(const std::string &path, HostScene &out) {
         }
         for (size_t i = 0; i < P0; i++) {
             const int src = bld.refs[i].prim, o = prim_obj[src];
-            out.obj_idxs[i] = o & 0x000fffff;
+            out.obj_idxs[i] = (o & 0x000fffff) | (obj_medium[o] << 20); // bits 20-27 medium, bit 30 cullable (bvh.cu:85-97)
             for (int k = 0; k < 3; k++) {
                 out.verts[k][i] = V[k][src];
                 out.norms[k][i] = N[k][src];
@@ -1085,6 +1169,8 @@ void load_xml(const std::string &path, HostScene &out) {
     cfg[CPTS_CFG_NUM_PRIMS] = int(P0), cfg[CPTS_CFG_NUM_NODES] = out.num_nodes();
     cfg[CPTS_CFG_NUM_CACHE] = int(out.cache_nodes.size()), cfg[CPTS_CFG_CACHE_LEVEL] = cache_level;
     cfg[CPTS_CFG_MAX_NODE_NUM] = max_node_num, cfg[CPTS_CFG_USE_SBVH] = 0;
+    cfg[CPTS_CFG_MAX_VOLUME] = max_volume, cfg[CPTS_CFG_NUM_MEDIA] = out.media.empty() ? 0 : int(out.media.size()) - 1;
+    cfg[CPTS_CFG_CAM_VOL] = 0; // Scene::cam_vol_id is never set by the loader (scene.cu:939)
     for (const auto &b : out.bsdfs)
         if (b.type == CPTS_BSDF_DISPERSION && out.cie_xyz.empty()) {
             load_spectral_tables(out);

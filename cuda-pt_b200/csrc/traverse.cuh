@@ -88,10 +88,10 @@ struct Hit {
 // ---------------------------------------------------------------------------------------------
 // strict mode: reference DFS
 // ---------------------------------------------------------------------------------------------
-PT_DEV Hit closest_hit_dfs(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
-    Hit h{kMaxDist, 0.f, 0.f, -1, 0};
+PT_DEV Hit closest_hit_dfs(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float t_max = kMaxDist) {
+    Hit h{t_max, 0.f, 0.f, -1, 0};
     const V3 inv_d = rcp3(d), o_div = o * inv_d;
-    int node_idx = cached_entry(s_cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+    int node_idx = cached_entry(s_cached, sc.num_cache, inv_d, o_div, t_max, 0);
     float t_near = 0;
     while (node_idx < sc.num_nodes) {
         const float4 lo = __ldg(sc.nodes + 2 * node_idx), hi = __ldg(sc.nodes + 2 * node_idx + 1);
@@ -169,10 +169,10 @@ PT_DEV void load_pair_node(const float4 *__restrict__ wnodes, int cur, float4 &a
 
 // variant with one inner-or-leaf step per loop iteration (lanes alternate freely between the two paths)
 template <bool WIDE, bool FINITE>
-PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d) {
-    Hit h{kMaxDist, 0.f, 0.f, -1, 0};
+PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float t_max = kMaxDist) {
+    Hit h{t_max, 0.f, 0.f, -1, 0};
     const V3 inv_d = rcp3(d), o_div = o * inv_d;
-    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, t_max, 0);
     int stack_ref[kStackSize];
     float stack_t[kStackSize];
     int sp = 0;
@@ -438,6 +438,15 @@ template <int MODE> PT_DEV Hit closest_hit(const DevScene &sc, const uint4 *s_ca
             return closest_hit_ordered<true, true>(sc, s_cached, o, d);
         return closest_hit_ordered<true, false>(sc, s_cached, o, d);
     }
+}
+// closest hit closer than `t_max` (the volumetric path's transmittance march, megakernel_vpt.cu:104-160); per-lane call
+template <int MODE> PT_DEV Hit closest_hit_bounded(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float t_max) {
+    if constexpr (MODE == 1)
+        return closest_hit_dfs(sc, s_cached, o, d, t_max);
+    else if constexpr (MODE == 0)
+        return closest_hit_ordered<false, false>(sc, s_cached, o, d, t_max);
+    else
+        return closest_hit_ordered<true, false>(sc, s_cached, o, d, t_max);
 }
 template <int MODE> PT_DEV bool unoccluded(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float max_dist, bool active = true) {
     if constexpr (MODE == 3)

@@ -1,0 +1,152 @@
+// volume.cuh — participating media for the volumetric path: homogeneous media with isotropic,
+// Henyey-Greenstein and two-lobe HG phase functions, and the 3-deep nested-volume stack.
+//
+// Reference: src/volume/homogeneous.cuh:28-88 (distance sampling, transmittance), src/core/medium.cuh:72-112 (Medium
+// base = vacuum: surface event, transmittance 1), src/volume/henyey_greenstein.cuh:28-108 (phase functions),
+// src/pt_impl/megakernel_vpt.cu:59-94 (BankStack).  POD tables instead of device-side virtual objects.
+#pragma once
+#include "pt_device.cuh"
+
+namespace cptb {
+
+struct MediumPOD { // 80 B
+    int type, phase_type; // type < 0: vacuum (media[0])
+    int pad0, pad1;
+    float4 sigma_a, sigma_s, sigma_t;
+    float4 phase; // hg: g ; duo-hg: g1, g2, weight
+};
+
+struct MediumSample {
+    V4 local_thp;
+    float dist;
+    uint32_t flag; // 1: medium (scattering) event, 0: surface event
+};
+
+enum : int { PHASE_NULL = 0, PHASE_ISOTROPIC = 1, PHASE_HG = 2, PHASE_DUO_HG = 3 };
+
+// ---- nested volumes: one 4-byte bank, x = depth, y/z/w = medium ids (megakernel_vpt.cu:59-94) ----
+struct BankStack {
+    uint32_t bits; // byte 0 = x (depth), bytes 1..3 = y, z, w
+    PT_DEV static BankStack make(int val) {
+        BankStack s{0u};
+        if (val > 0)
+            s.bits = 1u | (uint32_t(uint8_t(val)) << 8);
+        return s;
+    }
+    PT_DEV int depth() const { return int(bits & 0xffu); }
+    PT_DEV int top() const {
+        const int d = depth();
+        return d > 0 ? int((bits >> (8 * d)) & 0xffu) : 0;
+    }
+    PT_DEV void push(int val) {
+        const int d = depth();
+        const uint32_t v = uint32_t(val) & 0xffu;
+        if (d < 3 && v != 0xffu) {
+            const int nd = d + 1;
+            bits = (bits & ~(0xffu << (8 * nd)) & ~0xffu) | (v << (8 * nd)) | uint32_t(nd);
+        }
+    }
+    PT_DEV int pop() {
+        int res = 0;
+        const int d = depth();
+        if (d > 0) {
+            res = int((bits >> (8 * d)) & 0xffu);
+            bits = (bits & ~0xffu) | uint32_t(d - 1);
+        }
+        return res;
+    }
+};
+
+// ---- distance sampling (homogeneous.cuh:45-82; vacuum: medium.cuh:84-87, no sampler draws) ----
+PT_DEV MediumSample medium_sample(const MediumPOD &m, float hit_t, Rng &rng) {
+    MediumSample msp;
+    if (m.type < 0) {
+        msp.local_thp = splat4(1.f);
+        msp.dist = hit_t;
+        msp.flag = 0;
+        return msp;
+    }
+    const int channel = int(rng.next_u32() % 3u);
+    const float st_c = channel == 0 ? m.sigma_t.x : (channel == 1 ? m.sigma_t.y : m.sigma_t.z);
+    msp.dist = -logf(1.f - rng.next1d()) / st_c;
+    const bool is_medium = msp.dist < hit_t;
+    msp.dist = fminf(msp.dist, hit_t);
+    const float exp_y_x = expf(-(m.sigma_t.y - m.sigma_t.x) * msp.dist), exp_z_x = expf(-(m.sigma_t.z - m.sigma_t.x) * msp.dist),
+                exp_z_y = expf(-(m.sigma_t.z - m.sigma_t.y) * msp.dist), exp_x_y = __frcp_rn(exp_y_x), exp_x_z = __frcp_rn(exp_z_x),
+                exp_y_z = __frcp_rn(exp_z_y);
+    msp.local_thp = is_medium ? mk4(3.f / (m.sigma_t.x + m.sigma_t.y * exp_y_x + m.sigma_t.z * exp_z_x),
+                                    3.f / (m.sigma_t.x * exp_x_y + m.sigma_t.y + m.sigma_t.z * exp_z_y),
+                                    3.f / (m.sigma_t.x * exp_x_z + m.sigma_t.y * exp_y_z + m.sigma_t.z)) *
+                                    from_f4(m.sigma_s)
+                              : mk4(3.f / (1.f + exp_y_x + exp_z_x), 3.f / (exp_x_y + 1.f + exp_z_y), 3.f / (exp_x_z + exp_y_z + 1.f));
+    msp.flag = uint32_t(is_medium);
+    return msp;
+}
+
+// transmittance over `dist` (homogeneous.cuh:84-87; vacuum: 1)
+PT_DEV V4 medium_transmittance(const MediumPOD &m, float dist) {
+    if (m.type < 0)
+        return splat4(1.f);
+    return mk4(expf(-m.sigma_t.x * dist), expf(-m.sigma_t.y * dist), expf(-m.sigma_t.z * dist), 1.f);
+}
+
+// ---- phase functions (henyey_greenstein.cuh) ----
+// g^2 is a stored member of the reference's phase objects (rounded once in the constructor): keep it a rounded
+// product here, or `1 + g*g` contracts into one fma
+PT_DEV float sq_rn(float g) { return __fmul_rn(g, g); }
+PT_DEV float hg_phase(float cos_theta, float g, float g2) {
+    const float denom = 1.f + g2 - 2.f * g * cos_theta;
+    return kInvPi * 0.25f * (1.f - g2) / denom * rsqrtf(denom);
+}
+PT_DEV V3 hg_sample(Rng &rng, float g, float g2) {
+    const V2 uv = rng.next2d();
+    const float sqr_term = (1.f - g2) / (1.f + g - 2.f * g * uv.x);
+    const float cos_theta = (1.f + g2 - sqr_term * sqr_term) / (2.f * g);
+    const float sin_theta = sqrtf(fmaxf(0, 1 - cos_theta * cos_theta));
+    float sin_phi = 0, cos_phi = 0;
+    sincospif(2.f * uv.y, &sin_phi, &cos_phi);
+    return V3{cos_phi * sin_theta, sin_phi * sin_theta, cos_theta};
+}
+PT_DEV float phase_eval(const MediumPOD &m, V3 indir, V3 outdir) {
+    switch (m.phase_type) {
+    case PHASE_ISOTROPIC: return kInvPi * 0.25f;
+    case PHASE_HG: return hg_phase(dot(indir, outdir), m.phase.x, sq_rn(m.phase.x));
+    case PHASE_DUO_HG: {
+        const float c = dot(indir, outdir);
+        // ph1 * w + ph2 * (1 - w): the reference's SASS fuses the first product, rounds the second
+        return fmaf(hg_phase(c, m.phase.x, sq_rn(m.phase.x)), m.phase.z, __fmul_rn(hg_phase(c, m.phase.y, sq_rn(m.phase.y)), 1.f - m.phase.z));
+    }
+    default: return 0.f; // PhaseFunction base (phase.cuh): vacuum never scatters
+    }
+}
+// Medium::scatter (medium.cuh:95-101): samples the phase function, scales the throughput by its weight, returns the
+// new world-space direction; `pdf` receives the weight
+PT_DEV V3 medium_scatter(const MediumPOD &m, V3 raydir, V4 &throughput, Rng &rng, float &pdf) {
+    V3 local{0, 0, 1};
+    float weight = 1.f;
+    switch (m.phase_type) {
+    case PHASE_ISOTROPIC: {
+        float dummy = 0;
+        local = sample_sphere_uniform(rng.next2d(), dummy);
+        break;
+    }
+    case PHASE_HG: local = hg_sample(rng, m.phase.x, sq_rn(m.phase.x)); break;
+    case PHASE_DUO_HG: { // MixedHGPhaseFunction::sample: both lobes are sampled, one is kept
+        const float g1 = m.phase.x, g2 = m.phase.y, w = m.phase.z;
+        const V3 dir1 = hg_sample(rng, g1, sq_rn(g1)), dir2 = hg_sample(rng, g2, sq_rn(g2));
+        const float pdf1 = hg_phase(dot(V3{0, 0, 1}, dir1), g1, sq_rn(g1)), pdf2 = hg_phase(dot(V3{0, 0, 1}, dir2), g2, sq_rn(g2));
+        const bool use_first = rng.next1d() < w;
+        float mis_w = use_first ? pdf1 : pdf2;
+        mis_w /= fmaf(w, pdf1, __fmul_rn(1.f - w, pdf2));
+        local = use_first ? dir1 : dir2;
+        weight = mis_w;
+        break;
+    }
+    default: break;
+    }
+    throughput *= weight;
+    pdf = weight;
+    return to_world(raydir, local);
+}
+
+} // namespace cptb

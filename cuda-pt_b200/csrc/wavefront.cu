@@ -19,6 +19,7 @@
 //   * S samples are in flight at once (180 GB HBM3e) so late bounces still fill 148 SMs;
 //   * near-child-first traversal over a re-laid-out copy of the SAME tree (traverse.cuh).
 #include "traverse.cuh"
+#include "volume.cuh"
 #include "wavefront.cuh"
 
 #include <algorithm>
@@ -61,7 +62,8 @@ struct PathState {
 struct BatchParams {
     int W, H, P, S, first_accum, seed_offset;
     int row0, row1; // rows [row0,row1) of the frame are rendered (tile split across GPUs); pixel indices stay global
-    int rules; // 0: wavefront termination rules, 1: megakernel ("pt") rules
+    int rules; // 0: wavefront termination rules, 1: megakernel ("pt") rules, 2: volumetric ("vpt")
+    int max_depth, max_diffuse, max_specular, max_transmit, max_volume; // MaxDepthParams (volumetric kernel)
 };
 
 // termination parameters of the megakernel rules (MaxDepthParams, src/core/max_depth.h:26-42)
@@ -182,8 +184,7 @@ struct NeeSetup {
 };
 __device__ __forceinline__ void nee_setup(const DevScene &sc, V3 o, V3 d, float hit_t, uint32_t tag, float4 it, Rng &rng,
                                           NeeSetup &ns) {
-    int object_id = __ldg(sc.obj_idxs + (tag & TAG_INDEX));
-    object_id = object_id >= 0 ? object_id : -object_id - 1;
+    const int object_id = __ldg(sc.obj_idxs + (tag & TAG_INDEX)) & 0x000fffff; // extract_object_info (tracing_func.cuh:38-41)
     ns.ob = sc.objects[object_id];
     ns.material_id = ns.ob.bsdf_emitter >> 16;
     ns.emitter_id = ((ns.ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
@@ -811,6 +812,190 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_vpt — volumetric path tracer: the reference's render_vpt_kernel (src/pt_impl/megakernel_vpt.cu:203-456) and its
+// transmittance march occlusion_transmittance_estimate (:104-201) on this library's traversal, BSDF, emitter and
+// medium code.  One path per thread, whole path inside the kernel (the reference's structure; wavefront-ising the
+// medium events is the follow-up), S samples in flight, radiance to the path pool's L for k_splat.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ V4 nee_transmittance(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, BankStack nested, float max_dist,
+                                unsigned int &segments) {
+    float total_dist = 0;
+    V4 Tr = splat4(1.f);
+    while (total_dist < max_dist) {
+        const float min_dist0 = max_dist - total_dist;
+        const Hit h = closest_hit_bounded<MODE>(sc, s_cached, o, d, min_dist0);
+        ++segments;
+        const float min_dist = h.prim >= 0 ? h.t : min_dist0;
+        const int info = h.prim >= 0 ? h.obj_word : int(0xffffffffu); // INVALID_OBJ
+        const bool is_alpha = (info & 0x40000000) == 0x40000000;
+        int active_medium = (info >> 20) & 0xff;
+        if (active_medium == 0 || !is_alpha) { // opaque surface in the way
+            Tr = splat4(0.f);
+            break;
+        }
+        const bool is_in_medium = h.prim >= 0 && dot(interp_normal(sc, max(h.prim, 0), h.u, h.v), d) > 0;
+        if (is_in_medium) {
+            active_medium = nested.pop();
+        } else {
+            const int old_active = nested.top();
+            nested.push(active_medium);
+            active_medium = old_active;
+        }
+        Tr *= medium_transmittance(sc.media[active_medium], min_dist);
+        total_dist += min_dist;
+        o = advance(o, d, min_dist);
+    }
+    return Tr;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_vpt(DevScene sc, CameraPOD cam, PathState st, BatchParams bp, int *work,
+                                                 unsigned long long *stats) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int ty0 = bp.row0 >> 2;
+    const int tiles_x = (bp.W + 7) >> 3, tiles_y = ((bp.row1 + 3) >> 2) - ty0, tiles = tiles_x * tiles_y;
+    const int total = tiles * bp.S;
+    unsigned int n_closest = 0, n_shadow = 0, n_shaded = 0, n_segments = 0;
+    for (int task = warp_next_chunk(work, lane); task < total; task = warp_next_chunk(work, lane)) {
+        const int s = task / tiles, tile = task - s * tiles;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int px = (tx << 3) + (lane & 7), py = ((ty + ty0) << 2) + (lane >> 3);
+        if (!(px < bp.W && py >= bp.row0 && py < bp.row1))
+            continue;
+        const int gidx = px + py * bp.W;
+        const uint32_t slot = uint32_t(s) * uint32_t(bp.P) + uint32_t(gidx);
+        Rng rng;
+        rng.seed(gidx, bp.seed_offset + (bp.first_accum + s) * kSeedScaler);
+        BankStack nested = BankStack::make(sc.cam_vol);
+        V3 o, d;
+        camera_ray(cam, px, py, rng, o, d);
+        int diff_b = 0, spec_b = 0, trans_b = 0, volm_b = 0;
+        V4 throughput = mk4(1, 1, 1), radiance = mk4(0, 0, 0);
+        float emission_weight = 1.f;
+        bool delta = false;
+        for (int b = 0; b < bp.max_depth; b++) {
+            // ---- step 1: closest hit
+            const Hit h = closest_hit<MODE>(sc, s_cached, o, d, true);
+            if (b > 0)
+                ++n_closest;
+            if (h.prim < 0) { // definitely not inside a volume
+                radiance += throughput * null_or_env(sc, d);
+                break;
+            }
+            const int obj_info = h.obj_word;
+            const int hit_med_idx = (obj_info >> 20) & 0xff, object_id = obj_info & 0x000fffff;
+            const ObjectPOD ob = sc.objects[object_id];
+            const int material_id = ob.bsdf_emitter >> 16, emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+            const bool hit_emitter = emitter_id > 0;
+            // ---- medium event or surface event
+            const MediumPOD &medium = sc.media[nested.top()];
+            const MediumSample md = medium_sample(medium, h.t, rng);
+            throughput *= md.local_thp;
+            const bool alpha_mask = (obj_info & 0x40000000) == 0x40000000;
+            if (alpha_mask && md.flag == 0) {
+                // reached a cullable medium boundary: step through it, no NEE, the bounce counter still advances
+                o = advance(o, d, md.dist);
+                const float4 it = make_interaction(sc, h.prim, h.u, h.v);
+                const bool same_hemisphere = dot(d, xyz(it)) > 0;
+                if (same_hemisphere) // leaving the medium
+                    nested.pop();
+                else
+                    nested.push(hit_med_idx);
+                continue;
+            }
+            ++n_shaded;
+            V4 direct_comp = splat4(0, 1), nee_tr = splat4(0, 1);
+            // ---- sample an emitter (the hit emitter is excluded only for surface events)
+            float direct_pdf = 1;
+            const int no_sample = md.flag > 0 ? 0 : emitter_id;
+            int num = sc.num_emitters;
+            num -= no_sample > 0 && num > 1;
+            uint32_t emit_id = (rng.next_u32() % uint32_t(num)) + 1;
+            emit_id += emit_id >= uint32_t(no_sample) && no_sample > 0;
+            direct_pdf = 1.f / float(num);
+            emit_id = emit_id * uint32_t(no_sample == 0 || num > 1);
+            const EmitterPOD &em = sc.emitters[emit_id];
+            const ObjectPOD eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
+            direct_pdf *= eo.inv_area;
+            int emit_prim = int(rng.next_u32() % uint32_t(eo.prim_num)) + eo.prim_offset;
+            emit_prim = __ldg(sc.emitter_prims + emit_prim);
+            const V3 so = advance(o, d, md.dist);
+            V3 sd = emitter_sample(sc, em, so, V3{0, 0, 1}, direct_comp, direct_pdf, rng.next2d(), emit_prim) - so;
+            float emit_len_mis = length(sd);
+            sd *= __frcp_rn(emit_len_mis);
+            if (emit_id != 0) {
+                ++n_shadow;
+                nee_tr = nee_transmittance<MODE>(sc, s_cached, so, sd, nested, emit_len_mis - kEps, n_segments);
+            }
+            int lobe = LOBE_NONE;
+            V4 nee_thp;
+            if (md.flag > 0) { // medium event
+                radiance += throughput * splat4(0, 1); // Medium::query_emission: homogeneous media do not emit
+                const float phase_pdf = phase_eval(medium, sd, d);
+                nee_thp = splat4(phase_pdf, 1.f);
+                emit_len_mis = direct_pdf + phase_pdf;
+                lobe = LOBE_VOLUME;
+                d = medium_scatter(medium, d, throughput, rng, emission_weight);
+                delta = false;
+            } else {
+                const float4 it = make_interaction(sc, h.prim, h.u, h.v);
+                const Material &mat = sc.mats[material_id];
+                emission_weight = emission_weight / (emission_weight + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, h.t) *
+                                                                           hit_emitter * (b > 0) * (!delta));
+                radiance += throughput * emitter_eval(sc.emitters[emitter_id], d, it, true) * emission_weight;
+                emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
+                nee_thp = bsdf_eval(sc, mat, it, sd, d);
+                const bool same_hemisphere = dot(d, xyz(it)) > 0;
+                d = bsdf_sample(sc, mat, d, it, throughput, emission_weight, rng, lobe);
+                delta = (lobe & LOBE_SPECULAR) > 0;
+                // crossing the interface of a bounded medium: incident and scattered direction on opposite sides
+                if (((dot(xyz(it), d) > 0) ^ same_hemisphere) == false) {
+                    if (same_hemisphere)
+                        nested.pop();
+                    else
+                        nested.push(hit_med_idx);
+                }
+            }
+            radiance += nee_tr * throughput * direct_comp *
+                        (nee_thp * float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+            o = so;
+            if (bad_rgb(radiance))
+                radiance = splat4(0);
+            diff_b += (lobe & LOBE_DIFFUSE) > 0;
+            spec_b += (lobe & LOBE_SPECULAR) > 0;
+            trans_b += (lobe & LOBE_TRANSMIT) > 0;
+            volm_b += (lobe & LOBE_VOLUME) > 0;
+            if (diff_b >= bp.max_diffuse || spec_b >= bp.max_specular || trans_b >= bp.max_transmit || volm_b >= bp.max_volume)
+                break;
+            const float max_value = max3(throughput);
+            if (max_value < kThpEps)
+                break;
+            if (b >= kRRBounce && max_value < kRRThreshold) {
+                if (rng.next1d() > max_value)
+                    break;
+                throughput *= float(1. / max_value);
+            }
+        }
+        st.L[slot] = to_f4(radiance);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        n_closest += __shfl_down_sync(0xffffffffu, n_closest, off);
+        n_shadow += __shfl_down_sync(0xffffffffu, n_shadow, off);
+        n_shaded += __shfl_down_sync(0xffffffffu, n_shaded, off);
+        n_segments += __shfl_down_sync(0xffffffffu, n_segments, off);
+    }
+    if (lane == 0) {
+        atomicAdd(stats + 0, (unsigned long long)n_closest);
+        atomicAdd(stats + 1, (unsigned long long)n_shadow);
+        atomicAdd(stats + 2, (unsigned long long)n_shaded);
+        atomicAdd(stats + 3, (unsigned long long)n_segments);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_splat — reference: radiance_splat (wavefront_pt.cu:476-503), estimate_variance
 // (tracing_func.cuh:194-208), Vec4::gamma_corr (vec4.cuh:213-217)
 // samples of a batch are added in sample order, so the fp32 sum is the one the reference produces
@@ -959,6 +1144,8 @@ struct Renderer::Impl {
     DevBuf<int> obj_idxs, emitter_prims;
     DevBuf<ObjectPOD> objects;
     DevBuf<Material> mats;
+    DevBuf<MediumPOD> media;
+    int max_volume = 0;
     DevBuf<EmitterPOD> emitters;
     DevScene dev{};
     CameraPOD cam{};
@@ -1037,7 +1224,7 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     h_ = scene.height();
     max_depth_ = scene.config[CPTS_CFG_MAX_DEPTH];
     // renderer type of the XML (scene.cu:975-1000): 0 / 8 = megakernel PT -> its termination rules, 1 = wavefront
-    rules_ = (scene.config[CPTS_CFG_RENDERER] == 0 || scene.config[CPTS_CFG_RENDERER] == 8) ? 1 : 0;
+    rules_ = (scene.config[CPTS_CFG_RENDERER] == 0 || scene.config[CPTS_CFG_RENDERER] == 8) ? 1 : (scene.config[CPTS_CFG_RENDERER] == 6 ? 2 : 0);
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&impl_->ev0));
     CUDA_OK(cudaEventCreate(&impl_->ev1));
@@ -1190,6 +1377,28 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
             cudaGetLastError();
         }
     }
+    {
+        std::vector<MediumPOD> med(std::max<size_t>(scene.media.size(), 1));
+        for (size_t i = 0; i < med.size(); i++) {
+            MediumPOD mp{};
+            mp.type = -1; // vacuum
+            if (i > 0 && i < scene.media.size()) {
+                const CptsMedium &c = scene.media[i];
+                mp.type = c.type, mp.phase_type = c.phase_type;
+                mp.sigma_a = make_float4(c.sigma_a[0], c.sigma_a[1], c.sigma_a[2], c.sigma_a[3]);
+                mp.sigma_s = make_float4(c.sigma_s[0], c.sigma_s[1], c.sigma_s[2], c.sigma_s[3]);
+                mp.sigma_t = make_float4(c.sigma_a[0] + c.sigma_s[0], c.sigma_a[1] + c.sigma_s[1], c.sigma_a[2] + c.sigma_s[2],
+                                         c.sigma_a[3] + c.sigma_s[3]); // HomogeneousMedium ctor (homogeneous.cuh:37-42)
+                mp.phase = make_float4(c.phase[0], c.phase[1], c.phase[2], c.phase[3]);
+            }
+            med[i] = mp;
+        }
+        m.media.upload(med);
+        m.dev.media = m.media.p;
+        m.dev.num_media = int(med.size()) - 1;
+        m.dev.cam_vol = scene.config[CPTS_CFG_CAM_VOL];
+        m.max_volume = scene.config[CPTS_CFG_MAX_VOLUME];
+    }
     m.dev.num_nodes = scene.num_nodes();
     m.dev.num_cache = int(scene.cache_nodes.size());
     m.dev.num_prims = scene.num_prims();
@@ -1315,7 +1524,8 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     ensure_capacity(samples);
     const int P = w_ * h_, D = max_depth_;
     PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p, m.lobes.p};
-    BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_, row0_, row1_ > 0 ? std::min(row1_, h_) : h_, rules_};
+    BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_, row0_, row1_ > 0 ? std::min(row1_, h_) : h_, rules_,
+                   max_depth_, m.caps[0], m.caps[1], m.caps[2], m.max_volume > 0 ? m.max_volume : max_depth_};
     int *q_counts = m.counters.p;          // D + 1 entries
     int *sq_counts = m.counters.p + (D + 2); // D + 1 entries (dynamic-fetch pipeline)
     int *work = m.counters.p + 2 * (D + 2);  // one per launch
@@ -1357,6 +1567,19 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             m.kev_bounce.push_back(bounce);
         }
     };
+    if (rules_ == 2) { // volumetric path: one kernel per batch + the splat
+        mark(0, 0);
+        LAUNCH_MODE(k_vpt, m.dev, m.cam, st, bp, work, m.stats.p);
+        mark(3, 0);
+        k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples, first_accum,
+                                                   write_output ? 1 : 0, gamma ? 1 : 0, 0, row0_ * w_, row_end() * w_);
+        mark(-1, 0);
+        CUDA_OK(cudaEventRecord(m.ev1, stream_));
+        CUDA_OK(cudaGetLastError());
+        host_stats_.samples += uint64_t(w_) * uint64_t(row_end() - row_begin()) * samples;
+        host_stats_.launches += 2;
+        return;
+    }
     mark(0, 0);
     LAUNCH_MODE(k_raygen, m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
     ++wk;
@@ -1572,7 +1795,7 @@ RenderStats Renderer::stats() {
     s.closest_rays = h[0];
     s.shadow_rays = h[1];
     s.shaded = h[2];
-    s.shadow_traced = pipeline_ >= 2 ? h[3] : h[1];
+    s.shadow_traced = rules_ == 2 ? h[1] : (pipeline_ >= 2 ? h[3] : h[1]);
     return s;
 }
 
@@ -1582,7 +1805,7 @@ std::string Renderer::info() const {
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
        << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : "ordered-vote")))
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations << " (max " << impl_->max_overshoot << ")"
-       << ", L2 window " << (impl_->l2_window_bytes >> 20) << " MB, pipeline " << pipeline_ << ", rules " << (rules_ ? "megakernel-pt" : "wavefront") << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
+       << ", L2 window " << (impl_->l2_window_bytes >> 20) << " MB, pipeline " << pipeline_ << ", rules " << (rules_ == 2 ? "volumetric-pt" : (rules_ ? "megakernel-pt" : "wavefront")) << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();
 }
 

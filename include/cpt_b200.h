@@ -89,7 +89,8 @@ int cpt_b200_width(const cpt_b200_renderer *r);
 int cpt_b200_height(const cpt_b200_renderer *r);
 
 /* options: "rules" (0 wavefront termination rules, wavefront_pt.cu:186-195; 1 megakernel "pt" rules,
- * megakernel_pt.cu:159-180 - default taken from the scene's <renderer type>), "samples_in_flight" (>=1),
+ * megakernel_pt.cu:159-180; 2 volumetric path tracer with participating media, megakernel_vpt.cu:203-456 - default
+ * taken from the scene's <renderer type>), "samples_in_flight" (>=1),
  * "traversal" (0 ordered pair-node, 1 reference DFS order, 2/3 experimental loop shapes),
  * "max_depth" (MaxDepthParams::max_depth, src/core/max_depth.h:26-42), "kernel_timing" (0/1: CUDA events
  * around every launch, read back with cpt_b200_kernel_times), "pipeline" (0: the NEE visibility ray is traced

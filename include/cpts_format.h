@@ -62,6 +62,9 @@ enum {
     CPTS_CFG_CACHE_LEVEL = 16,
     CPTS_CFG_MAX_NODE_NUM = 17,
     CPTS_CFG_USE_SBVH = 18,
+    CPTS_CFG_MAX_VOLUME = 19, /* MaxDepthParams::max_volume (volumetric path only) */
+    CPTS_CFG_NUM_MEDIA = 20,  /* real media; the "media" section holds num+1 (index 0 = vacuum) */
+    CPTS_CFG_CAM_VOL = 21,    /* medium the camera sits in (Scene::cam_vol_id) */
     CPTS_CFG_COUNT = 32
 };
 
@@ -137,6 +140,20 @@ typedef struct CptsObject {
     int32_t prim_num;
     float inv_area;
 } CptsObject;
+
+/* "media" section, 64 B per entry (optional; volumetric path).  Entry 0 is the vacuum.  The per-primitive object word
+ * ("obj_idxs") carries the medium an object bounds in bits 20-27 and the "cullable" (alpha) flag in bit 30
+ * (src/impl/scene.cu:903-932). */
+enum { CPTS_MEDIUM_HOMOGENEOUS = 0, CPTS_MEDIUM_GRID = 1 };
+enum { CPTS_PHASE_NULL = 0, CPTS_PHASE_ISOTROPIC = 1, CPTS_PHASE_HG = 2, CPTS_PHASE_DUO_HG = 3, CPTS_PHASE_RAYLEIGH = 4, CPTS_PHASE_SGGX = 5 };
+typedef struct CptsMedium {
+    int32_t type;       /* CPTS_MEDIUM_* */
+    int32_t phase_type; /* CPTS_PHASE_* */
+    float sigma_a[4];   /* already multiplied by the density scale (vol_homo.cu:26-32) */
+    float sigma_s[4];
+    float phase[4];     /* hg: g; duo-hg: g1, g2, weight */
+    int32_t pad[2];
+} CptsMedium;
 
 /* "tex_desc" section: one per texture; texels live in "tex_data" (float) at `offset` floats. */
 typedef struct CptsTexDesc {

@@ -38,6 +38,7 @@
 #define private public
 #include "renderer/wf_path_tracer.cuh"
 #undef private
+#include "renderer/volume_pt.cuh"
 
 #include "cpts_format.h"
 
@@ -191,6 +192,9 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
     cfg[CPTS_CFG_CACHE_LEVEL] = scene.config.bvh.cache_level;
     cfg[CPTS_CFG_MAX_NODE_NUM] = scene.config.bvh.max_node_num;
     cfg[CPTS_CFG_USE_SBVH] = scene.config.bvh.use_sbvh;
+    cfg[CPTS_CFG_MAX_VOLUME] = scene.config.md.max_volume;
+    cfg[CPTS_CFG_NUM_MEDIA] = scene.num_medium;
+    cfg[CPTS_CFG_CAM_VOL] = scene.cam_vol_id;
     w.section("config", cfg, 4, CPTS_CFG_COUNT);
 
     static_assert(sizeof(DeviceCamera) == CPTS_CAM_COUNT * sizeof(float), "camera POD size");
@@ -353,6 +357,23 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
     }
     w.section("emitters", ems.data(), sizeof(CptsEmitter), ems.size());
 
+    if (scene.num_medium > 0) { // host-side records of the media (scene.cu:775-900); entry 0 = vacuum
+        std::vector<CptsMedium> media(size_t(scene.num_medium) + 1);
+        memset(media.data(), 0, media.size() * sizeof(CptsMedium));
+        for (int i = 1; i <= scene.num_medium && size_t(i) < scene.medium_infos.size(); i++) {
+            const MediumInfo &mi = scene.medium_infos[i];
+            CptsMedium m{};
+            m.type = int(mi.mtype);
+            m.phase_type = int(mi.ptype);
+            for (int k = 0; k < 4; k++) {
+                m.sigma_a[k] = mi.med_param.sigma_a[k] * (mi.mtype == MediumType::Homogeneous ? mi.med_param.scale : 1.f);
+                m.sigma_s[k] = mi.med_param.sigma_s[k] * (mi.mtype == MediumType::Homogeneous ? mi.med_param.scale : 1.f);
+                m.phase[k] = mi.med_param.phase[k];
+            }
+            media[i] = m;
+        }
+        w.section("media", media.data(), sizeof(CptsMedium), media.size());
+    }
     if (!tex_descs.empty()) {
         w.section("tex_desc", tex_descs.data(), sizeof(CptsTexDesc), tex_descs.size());
         w.section("tex_data", tex_data.data(), 4, tex_data.size());
@@ -386,6 +407,8 @@ std::unique_ptr<TracerBase> make_renderer(const Scene &scene, const std::string 
     std::unique_ptr<TracerBase> r;
     if (mode == "wfpt")
         r = std::make_unique<WavefrontPathTracer>(scene);
+    else if (mode == "vpt")
+        r = std::make_unique<VolumePathTracer>(scene);
     else
         r = std::make_unique<PathTracer<SingleTileScheduler>>(scene, false);
     return r;

@@ -1,4 +1,4 @@
-for v in "" _mb8 _mb5 "" _mb8; do
-  if [ -n "$v" ]; then export CPTB200_LIB=$PWD/cuda-pt_b200/libcpt_b200$v.so; else unset CPTB200_LIB; fi
-  echo "variant '$v'"; python tools/quick_bench.py scenes/xml/vader_wfpt_1080p.xml 32 2 16
-done
+mkdir -p gpurun_out/ref4
+oracle/_ref/ref_dump render scenes/xml/medium_cbox_vpt_256.xml gpurun_out/ref4/medium_cbox_256 vpt 0 1,2,16,64 > gpurun_out/ref4/log.txt 2>&1
+tail -5 gpurun_out/ref4/log.txt; ls -la gpurun_out/ref4
+oracle/_ref/ref_dump bench scenes/xml/medium_cbox_vpt_256.xml vpt 4 32 2>/dev/null | grep ref_bench
