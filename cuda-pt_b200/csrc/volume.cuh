@@ -66,8 +66,12 @@ PT_DEV MediumSample medium_sample(const MediumPOD &m, float hit_t, Rng &rng) {
         msp.flag = 0;
         return msp;
     }
-    const int channel = int(rng.next_u32() % 3u);
-    const float st_c = channel == 0 ? m.sigma_t.x : (channel == 1 ? m.sigma_t.y : m.sigma_t.z);
+    // TinySampler::discrete1D returns a signed int (sampler.cuh:49-58), so `% 3` yields -2..2 and `sigma_t[channel]`
+    // reads the members laid out before sigma_t for negative draws: [-1] = sigma_s.w, [-2] = sigma_s.z
+    // (homogeneous.cuh:31-34,48-49).  Reproduced: it changes the sampled distance by sigma_a / sigma_t.
+    const int channel = int(rng.next_u32()) % 3;
+    const float st_c = channel == 0 ? m.sigma_t.x
+                                    : (channel == 1 ? m.sigma_t.y : (channel == 2 ? m.sigma_t.z : (channel == -1 ? m.sigma_s.w : m.sigma_s.z)));
     msp.dist = -logf(1.f - rng.next1d()) / st_c;
     const bool is_medium = msp.dist < hit_t;
     msp.dist = fminf(msp.dist, hit_t);

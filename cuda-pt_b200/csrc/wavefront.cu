@@ -945,7 +945,11 @@ __global__ void __launch_bounds__(kBlock) k_vpt(DevScene sc, CameraPOD cam, Path
                 const Material &mat = sc.mats[material_id];
                 emission_weight = emission_weight / (emission_weight + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, h.t) *
                                                                            hit_emitter * (b > 0) * (!delta));
-                radiance += throughput * emitter_eval(sc.emitters[emitter_id], d, it, true) * emission_weight;
+                { // (throughput * Le) * w + radiance with the last product fused, as in the reference's SASS
+                    const V4 tl = throughput * emitter_eval(sc.emitters[emitter_id], d, it, true);
+                    radiance = V4{fmaf(tl.x, emission_weight, radiance.x), fmaf(tl.y, emission_weight, radiance.y),
+                                  fmaf(tl.z, emission_weight, radiance.z), fmaf(tl.w, emission_weight, radiance.w)};
+                }
                 emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
                 nee_thp = bsdf_eval(sc, mat, it, sd, d);
                 const bool same_hemisphere = dot(d, xyz(it)) > 0;

@@ -11,4 +11,5 @@ $R render $X/cbox_pt_256.xml gpurun_out/ref/cbox_pt_256 pt 0 1,64 > gpurun_out/r
 $R render $X/cbox_mats_wfpt_256.xml gpurun_out/ref/cbox_mats_256 wfpt 0 1,2,16,64 > gpurun_out/ref/cbox_mats.log 2>&1
 $R render $X/vader_wfpt_256.xml gpurun_out/ref/vader_256 wfpt 0 1,8 > gpurun_out/ref/vader_256.log 2>&1
 $R render $X/texroom_wfpt_256.xml gpurun_out/ref/texroom_256 wfpt 0 1,64 > gpurun_out/ref/texroom.log 2>&1
+$R render $X/medium_cbox_vpt_256.xml gpurun_out/ref/medium_cbox_256 vpt 0 1,64 > gpurun_out/ref/medium.log 2>&1
 ls -la gpurun_out/ref | head -60

@@ -16,7 +16,7 @@
  *   dump   <xml> <out.cpts>
  *          load the XML with the reference loader and write the flat scene
  *          (include/cpts_format.h) that our renderer and the CPU oracle read.
- *   render <xml> <out_prefix> <mode: wfpt|pt> <seed_offset> <frame,frame,...>
+ *   render <xml> <out_prefix> <mode: wfpt|pt|vpt> <seed_offset> <frame,frame,...>
  *          run render_raw() and save the float RGBA output buffer after the
  *          listed (1-based) frame counts as <out_prefix>_fNNNN.bin, and the
  *          scene as <out_prefix>.cpts (same in-process Scene => same BVH /

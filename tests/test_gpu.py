@@ -150,6 +150,52 @@ def test_xml_loader_all_materials_incl_dispersion_statistically_equal_reference(
     assert abs(ours.mean() / ref.mean() - 1) < 0.05
 
 
+@pytest.mark.parametrize("traversal", [1, 2])
+def test_volumetric_path_bit_exact_vs_reference_vpt(traversal):
+    """Participating media: homogeneous media with HG / isotropic / two-lobe HG phase functions, nested
+    volume stack, transmittance march through cullable boundaries - against the reference's megakernel VPT frames
+    (RGB, alpha and variance).  Includes the reference's signed `discrete1D() % 3` channel pick."""
+    r = cpt.WavefrontRenderer(os.path.join(GOLDEN, "medium_cbox_256.cpts"), 0, 0)
+    assert r.get_option("rules") == 2 and "volumetric" in r.info()
+    r.set_option("traversal", traversal)
+    r.enable_variance(True)
+    r.render_raw(False)
+    assert bit_exact_fraction(r.download_output(), load_frame("medium_cbox_256_vpt_f0001.bin")) == 1.0
+    for _ in range(63):
+        r.render_raw(False)
+    ref = load_frame("medium_cbox_256_vpt_f0064.bin")
+    out = r.download_output()
+    assert rel_l2(out, ref) <= 1e-4
+    assert bit_exact_fraction(out, ref) == 1.0
+    var_ref = np.fromfile(os.path.join(GOLDEN, "medium_cbox_256_vpt_var_f0064.bin"), dtype=np.float32).reshape(256, 256, 1)
+    assert np.array_equal(r.download_variance().view(np.uint32), var_ref.view(np.uint32))
+    st = r.stats()
+    assert st["launches"] == 64 * 2 and st["shadow_rays"] > 0 and st["closest_rays"] > 0
+    # several samples in flight give the same sum as one sample per launch
+    q = cpt.WavefrontRenderer(os.path.join(GOLDEN, "medium_cbox_256.cpts"), 0, 0)
+    q.set_option("traversal", traversal)
+    q.render_batch(64, False)
+    assert np.array_equal(q.download_output().view(np.uint32), out.view(np.uint32))
+    q.close()
+    r.close()
+
+
+@pytest.mark.skipif(not have_meshes(), reason="cornell meshes not on this box")
+def test_xml_loader_media_scene_statistically_equal_reference():
+    """Our XML loader on the medium scene (media / phase / cullable parsing): a different BVH gives different light
+    sample streams, so block statistics against the reference's 64-spp frame."""
+    r = cpt.WavefrontRenderer(os.path.join(SCENES, "medium_cbox_vpt_256.xml"), 0, 0)
+    assert r.get_option("rules") == 2
+    r.render_batch(64, False)
+    ours = np.minimum(r.download_output()[..., :3].astype(np.float64), 4.0)
+    r.close()
+    ref = np.minimum(load_frame("medium_cbox_256_vpt_f0064.bin")[..., :3].astype(np.float64), 4.0)
+    bo, br = ours.reshape(16, 16, 16, 16, 3).mean((1, 3)), ref.reshape(16, 16, 16, 16, 3).mean((1, 3))
+    rel = np.abs(bo - br).sum(-1) / np.maximum(br.sum(-1), 1e-2)
+    assert np.median(rel) < 0.05, np.median(rel)
+    assert abs(ours.mean() / ref.mean() - 1) < 0.02
+
+
 def test_megakernel_rules_bit_exact_vs_reference_pt():
     """`renderer type="pt"` scenes: the megakernel's termination rules (lobe caps, throughput cut-off, Russian
     roulette from bounce 1 with an exactly rounded 1/max, per-bounce NaN scrub, emission-before-NEE accumulation)

@@ -170,6 +170,28 @@ def test_png_decoder_and_texture_conversion_match_an_independent_decoder(tmp_pat
     assert sc.config["envmap_id"] == 3
 
 
+@needs_meshes
+def test_xml_loader_media_match_the_reference_dump(tmp_path):
+    """<phase>/<medium> parsing, the medium + cullable bits of the per-primitive object word and the volumetric limits,
+    against the scene the reference's loader produced for the same XML."""
+    sc = cpt.Scene(os.path.join(SCENES, "medium_cbox_vpt_256.xml"))
+    out = tmp_path / "m.cpts"
+    sc.save(str(out))
+    a, b = read_cpts(str(out)), read_cpts(os.path.join(GOLDEN, "medium_cbox_256.cpts"))
+    assert np.array_equal(a["media"], b["media"])
+    for k in (3, 4, 5, 6, 8, 9, 10, 12, 13, 19, 20, 21):  # depth limits, renderer, counts, max_volume, num_media, cam_vol
+        assert a["config"][k] == b["config"][k], k
+    assert sorted(np.unique(a["obj_idxs"] >> 20).tolist()) == sorted(np.unique(b["obj_idxs"] >> 20).tolist()) == [0, 1025, 1026, 1027]
+    # per object: same medium word
+    med = lambda d: {int(w & 0xfffff): int(w >> 20) for w in d["obj_idxs"]}
+    assert med(a) == med(b)
+    x = tmp_path / "g.xml"
+    x.write_text('<scene version="1.2"><sensor><film/></sensor><phase type="isotropic" id="p"/>'
+                 '<medium type="grid" id="m"><ref type="phase" id="p"/></medium></scene>')
+    with pytest.raises(cpt.CptError, match="grid"):
+        cpt.Scene(str(x))
+
+
 def test_image_errors(tmp_path):
     x = tmp_path / "t.xml"
     notpng = tmp_path / "a.jpg"
