@@ -35,7 +35,8 @@ METRIC = "Mrays/s (primary + closest-hit + shadow traversals), wavefront PT, 192
 
 
 WORKLOADS = {"c1": "vader_wfpt_1080p.xml",       # BASELINE config 1 (default): vader geometry, no image assets
-             "c2": "vader_tex_wfpt_1080p.xml"}    # texture-heavy stand-in: + 2K glossy/roughness/normal/albedo maps + envmap
+             "c2": "vader_tex_wfpt_1080p.xml",    # texture-heavy stand-in: + 2K glossy/roughness/normal/albedo maps + envmap
+             "vpt": "medium_cbox_vpt_1080p.xml"}  # participating media (homogeneous), volumetric path tracer
 
 
 def pick_scene(arg):
@@ -144,7 +145,8 @@ def run_reference(args, scene, workload):
     tbl = rays_table().get(workload)
     if scene.endswith(".xml") and os.path.exists(ref_dump):
         try:
-            out = subprocess.run([ref_dump, "bench", scene, "wfpt", str(args.warmup * S), str(args.steps * S)],
+            mode = "vpt" if "vpt" in workload else "wfpt"
+            out = subprocess.run([ref_dump, "bench", scene, mode, str(args.warmup * S), str(args.steps * S)],
                                  capture_output=True, text=True, timeout=3000, cwd=ROOT)
             line = [l for l in out.stdout.splitlines() if l.startswith("{\"ref_bench\"")][-1]
             rb = json.loads(line)
@@ -336,7 +338,7 @@ def main():
             traffic = json.load(open(prof)).get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": {"raygen": "k_raygen", "shade": "k_shade+k_shadow_apply", "trace": "k_trace", "splat": "k_splat"}[dom],
+    roofline = {"bound": "hbm", "kernel": "k_vpt" if "vpt" in workload else {"raygen": "k_raygen", "shade": "k_shade+k_shadow_apply", "trace": "k_trace", "splat": "k_splat"}[dom],
                 "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
                 "traffic": traffic, "peak_source": peak_src,
                 "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; BVH/triangle reads are L2-served "
@@ -350,7 +352,9 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (args.split == "tiles" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
-           "data": ("vader geometry bundled with the reference + seeded placeholder 2K textures and environment map (tools/make_assets.py); fixed seeds"
+           "data": ("cornell box geometry bundled with the reference + three homogeneous media (the reference's medium-cbox scene); fixed seeds"
+                    if "vpt" in workload else
+                    "vader geometry bundled with the reference + seeded placeholder 2K textures and environment map (tools/make_assets.py); fixed seeds"
                     if "tex" in workload else
                     "vader geometry bundled with the reference (textures/envmap not shipped upstream, removed); fixed seeds"),
            "config": {"workload": workload, "width": W, "height": H, "spp_per_step": S, "max_depth": cfg["max_depth"],

@@ -44,6 +44,9 @@ namespace cptb {
     } while (0)
 
 constexpr int kBlock = 128;
+#ifndef VPT_MIN_BLOCKS
+#define VPT_MIN_BLOCKS 8 // register budget of the volumetric megakernel: 8 CTAs/SM (64 registers) measured best of 1/4/6/8
+#endif
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 6 // register budget of the traversal-free shading kernels: 6 CTAs/SM -> <= 85 registers
 #endif
@@ -850,7 +853,7 @@ __device__ V4 nee_transmittance(const DevScene &sc, const uint4 *s_cached, V3 o,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_vpt(DevScene sc, CameraPOD cam, PathState st, BatchParams bp, int *work,
+__global__ void __launch_bounds__(kBlock, VPT_MIN_BLOCKS) k_vpt(DevScene sc, CameraPOD cam, PathState st, BatchParams bp, int *work,
                                                  unsigned long long *stats) {
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
