@@ -22,6 +22,9 @@
  *                      8-bit fractional weights of the texture unit
  *   per-bounce logic   src/pt_impl/wavefront_pt.cu:71-314 (raygen, shade, closest-hit + RR), :476-503 (splat),
  *                      host loop src/pt_impl/wf_path_tracer.cu:175-230, emitter pick tracing_func.cuh:210-225
+ *   megakernel rules   src/pt_impl/megakernel_pt.cu:59-186 ("pt": lobe caps, throughput cut-off, RR from bounce 1)
+ *   participating media src/pt_impl/megakernel_vpt.cu:59-456, src/volume/homogeneous.cuh:45-88,
+ *                      src/volume/henyey_greenstein.cuh:28-108, src/core/medium.cuh:72-112 (homogeneous media only)
  *
  * It is a TOLERANCE oracle: the reference runs on the GPU with --use_fast_math (approximate
  * rcp/sqrt/div, flush-to-zero), which cannot be reproduced bit-for-bit on a CPU.
@@ -71,7 +74,7 @@ inline V4 expxyz(V4 a) { return {std::exp(a.x), std::exp(a.y), std::exp(a.z), 1.
 constexpr float EPS = 1e-3f, THP_EPS = 1e-4f, MAX_DIST = 1e7f, PI = 3.1415926535897f, INV_PI = 1.f / PI;
 constexpr int SEED_SCALER = 11467, RR_BOUNCE = 2;
 constexpr float RR_THRESHOLD = 0.1f;
-enum { LOBE_DIFFUSE = 1, LOBE_SPECULAR = 2, LOBE_GLOSSY = 4, LOBE_REFLECT = 0x10, LOBE_TRANSMIT = 0x20 };
+enum { LOBE_DIFFUSE = 1, LOBE_SPECULAR = 2, LOBE_GLOSSY = 4, LOBE_REFLECT = 0x10, LOBE_TRANSMIT = 0x20, LOBE_VOLUME = 0x40 };
 
 // ---- half helpers -------------------------------------------------------------------------------
 float half_to_float(uint16_t h) {
@@ -153,6 +156,7 @@ struct Scene {
     std::vector<CptsEmitter> emitters;
     std::vector<float> tris; // 12 floats per primitive
     std::vector<float> cie, d65;
+    std::vector<CptsMedium> media;     // [0] = vacuum (volumetric path)
     std::vector<CptsTexDesc> tex_desc; // image textures as the reference decoded them (float texels)
     std::vector<float> tex_data;
     float env_rot[4] = {0, 0, 0, 1};   // environment-map rotation quaternion (emitter.cuh:349-353)
@@ -227,6 +231,8 @@ Scene *load_scene(const char *path) {
             read_vec(fp, s, sc->bsdfs);
         else if (name == "emitters")
             read_vec(fp, s, sc->emitters);
+        else if (name == "media")
+            read_vec(fp, s, sc->media);
         else if (name == "tex_desc")
             read_vec(fp, s, sc->tex_desc);
         else if (name == "tex_data")
@@ -326,10 +332,10 @@ struct Hit {
     float t, u, v;
     int prim;
 };
-Hit closest_hit(const Scene &sc, V3 o, V3 d) { // tracing_func.cuh:117-181
-    Hit h{MAX_DIST, 0, 0, -1};
+Hit closest_hit(const Scene &sc, V3 o, V3 d, float t_max = MAX_DIST) { // tracing_func.cuh:117-181
+    Hit h{t_max, 0, 0, -1};
     const V3 inv_d{1.f / d.x, 1.f / d.y, 1.f / d.z}, o_div = o * inv_d;
-    int node = cached_entry(sc, inv_d, o_div, MAX_DIST, 0);
+    int node = cached_entry(sc, inv_d, o_div, t_max, 0);
     const int N = sc.num_nodes();
     while (node < N) {
         const float *nd = &sc.nodes[8 * node];
@@ -873,21 +879,14 @@ V3 emitter_sample(const Scene &sc, const CptsEmitter &e, V3 hit, V3 hit_n, V4 &l
     return {0, 0, 0};
 }
 
-// ---- one path (wavefront_pt.cu:71-314; loop structure of wf_path_tracer.cu:175-230) ----------------------------
-struct Counts {
-    uint64_t closest = 0, shadow = 0, shaded = 0;
-};
-V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int max_depth, Counts &cnt) {
-    const int W = sc.cfg[CPTS_CFG_WIDTH];
-    Rng rng;
-    rng.seed(px + py * W, int(uint32_t(seed_offset) + uint32_t(accum) * uint32_t(SEED_SCALER)));
+void camera_ray(const Scene &sc, int px, int py, Rng &rng, V3 &o, V3 &d) {
     // camera (camera_model.cuh:58-87)
     const float *c = sc.cam;
     const float xp = rng.f() + float(px), yp = rng.f() + float(py);
     const float nx = (xp - c[CPTS_CAM_HW]) * c[CPTS_CAM_INV_FOCAL] * c[CPTS_CAM_SIGN_X], ny = (c[CPTS_CAM_HH] - yp) * c[CPTS_CAM_INV_FOCAL];
     const M3 R{{{c[0], c[1], c[2]}, {c[3], c[4], c[5]}, {c[6], c[7], c[8]}}};
     const V3 T{c[9], c[10], c[11]};
-    V3 o, d = normalize(rot(R, V3{nx, ny, 1.f}));
+    d = normalize(rot(R, V3{nx, ny, 1.f}));
     if (c[CPTS_CAM_FOCAL_DIST] == 0) {
         o = T + V3{c[1], c[4], c[7]} * ny + V3{c[0], c[3], c[6]} * nx;
         d = normalize(rot(R, V3{0, 0, 1}));
@@ -899,6 +898,19 @@ V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int m
         d = normalize(focus - o);
     } else
         o = T;
+
+}
+
+// ---- one path (wavefront_pt.cu:71-314; loop structure of wf_path_tracer.cu:175-230) ----------------------------
+struct Counts {
+    uint64_t closest = 0, shadow = 0, shaded = 0;
+};
+V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int max_depth, Counts &cnt) {
+    const int W = sc.cfg[CPTS_CFG_WIDTH];
+    Rng rng;
+    rng.seed(px + py * W, int(uint32_t(seed_offset) + uint32_t(accum) * uint32_t(SEED_SCALER)));
+    V3 o, d;
+    camera_ray(sc, px, py, rng, o, d);
 
     V4 thp{1, 1, 1, 1}, L{0, 0, 0, 1};
     float pdf = 1.f;
@@ -970,6 +982,250 @@ V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int m
     return L;
 }
 
+// ---- participating media (src/volume/homogeneous.cuh:45-88, src/core/medium.cuh:72-112, src/volume/henyey_greenstein.cuh,
+// nested-volume stack of megakernel_vpt.cu:59-94) ------------------------------------------------------------------
+struct MediumSampleO {
+    V4 local_thp;
+    float dist;
+    int flag;
+};
+MediumSampleO medium_sample(const CptsMedium *m, float hit_t, Rng &rng) { // m == nullptr: vacuum
+    if (!m)
+        return {v4(1.f), hit_t, 0};
+    const float st[3] = {m->sigma_a[0] + m->sigma_s[0], m->sigma_a[1] + m->sigma_s[1], m->sigma_a[2] + m->sigma_s[2]};
+    // signed `discrete1D() % 3`: negative draws index the members in front of sigma_t
+    const int channel = int(rng.u32()) % 3;
+    const float st_c = channel >= 0 ? st[channel] : (channel == -1 ? m->sigma_s[3] : m->sigma_s[2]);
+    float dist = -std::log(1.f - rng.f()) / st_c;
+    const bool is_medium = dist < hit_t;
+    dist = std::min(dist, hit_t);
+    const float eyx = std::exp(-(st[1] - st[0]) * dist), ezx = std::exp(-(st[2] - st[0]) * dist), ezy = std::exp(-(st[2] - st[1]) * dist);
+    const float exy = 1.f / eyx, exz = 1.f / ezx, eyz = 1.f / ezy;
+    MediumSampleO out;
+    out.local_thp = is_medium ? V4{3.f / (st[0] + st[1] * eyx + st[2] * ezx), 3.f / (st[0] * exy + st[1] + st[2] * ezy),
+                                   3.f / (st[0] * exz + st[1] * eyz + st[2]), 1.f} * v4(m->sigma_s)
+                              : V4{3.f / (1.f + eyx + ezx), 3.f / (exy + 1.f + ezy), 3.f / (exz + eyz + 1.f), 1.f};
+    out.dist = dist, out.flag = int(is_medium);
+    return out;
+}
+V4 medium_transmittance(const CptsMedium *m, float dist) {
+    if (!m)
+        return v4(1.f);
+    return {std::exp(-(m->sigma_a[0] + m->sigma_s[0]) * dist), std::exp(-(m->sigma_a[1] + m->sigma_s[1]) * dist),
+            std::exp(-(m->sigma_a[2] + m->sigma_s[2]) * dist), 1.f};
+}
+float hg_phase(float c, float g) {
+    const float g2 = g * g, denom = 1.f + g2 - 2.f * g * c;
+    return INV_PI * 0.25f * (1.f - g2) / denom / std::sqrt(denom);
+}
+V3 hg_sample(Rng &rng, float g) {
+    const float ux = rng.f(), uy = rng.f(), g2 = g * g;
+    const float sq = (1.f - g2) / (1.f + g - 2.f * g * ux), ct = (1.f + g2 - sq * sq) / (2.f * g), st = std::sqrt(std::max(0.f, 1.f - ct * ct));
+    return {std::cos(2.f * uy * PI) * st, std::sin(2.f * uy * PI) * st, ct};
+}
+float phase_eval(const CptsMedium &m, V3 a, V3 b) {
+    const float c = dot(a, b);
+    switch (m.phase_type) {
+    case CPTS_PHASE_ISOTROPIC: return INV_PI * 0.25f;
+    case CPTS_PHASE_HG: return hg_phase(c, m.phase[0]);
+    case CPTS_PHASE_DUO_HG: return hg_phase(c, m.phase[0]) * m.phase[2] + hg_phase(c, m.phase[1]) * (1.f - m.phase[2]);
+    default: return 0.f;
+    }
+}
+V3 medium_scatter(const CptsMedium &m, V3 raydir, V4 &thp, Rng &rng, float &pdf) {
+    V3 local{0, 0, 1};
+    float weight = 1.f;
+    if (m.phase_type == CPTS_PHASE_ISOTROPIC) {
+        const float ux = rng.f(), uy = rng.f(), ct = 2.f * ux - 1.f, st = std::sqrt(1.f - ct * ct);
+        local = {std::cos(2.f * uy * PI) * st, std::sin(2.f * uy * PI) * st, ct};
+    } else if (m.phase_type == CPTS_PHASE_HG) {
+        local = hg_sample(rng, m.phase[0]);
+    } else if (m.phase_type == CPTS_PHASE_DUO_HG) {
+        const V3 d1 = hg_sample(rng, m.phase[0]), d2 = hg_sample(rng, m.phase[1]);
+        const float p1 = hg_phase(d1.z, m.phase[0]), p2 = hg_phase(d2.z, m.phase[1]), w = m.phase[2];
+        const bool first = rng.f() < w;
+        weight = (first ? p1 : p2) / (w * p1 + (1.f - w) * p2);
+        local = first ? d1 : d2;
+    }
+    thp = thp * weight;
+    pdf = weight;
+    return to_world(raydir, local);
+}
+struct BankStackO {
+    int depth = 0, v[3] = {0, 0, 0};
+    int top() const { return depth > 0 ? v[depth - 1] : 0; }
+    void push(int x) {
+        if (depth < 3 && (x & 0xff) != 0xff)
+            v[depth++] = x & 0xff;
+    }
+    int pop() { return depth > 0 ? v[--depth] : 0; }
+};
+const CptsMedium *medium_of(const Scene &sc, int idx) { return (idx > 0 && size_t(idx) < sc.media.size()) ? &sc.media[idx] : nullptr; }
+V3 interp_normal(const Scene &sc, int prim, float u, float v) {
+    auto at = [&](int k) { return V3{sc.n[k][3 * prim], sc.n[k][3 * prim + 1], sc.n[k][3 * prim + 2]}; };
+    return normalize(at(0) * (1.f - u - v) + at(1) * u + at(2) * v);
+}
+// occlusion_transmittance_estimate (megakernel_vpt.cu:104-201)
+V4 nee_transmittance(const Scene &sc, V3 o, V3 d, BankStackO nested, float max_dist) {
+    float total = 0;
+    V4 Tr = v4(1.f);
+    while (total < max_dist) {
+        const float bound = max_dist - total;
+        const Hit h = closest_hit(sc, o, d, bound);
+        const float seg = h.prim >= 0 ? h.t : bound;
+        const int info = h.prim >= 0 ? sc.obj_idxs[h.prim] : -1;
+        int active = (info >> 20) & 0xff;
+        if (active == 0 || (info & 0x40000000) == 0)
+            return v4(0.f);
+        if (h.prim >= 0 && dot(interp_normal(sc, h.prim, h.u, h.v), d) > 0) {
+            active = nested.pop();
+        } else {
+            const int old = nested.top();
+            nested.push(active);
+            active = old;
+        }
+        Tr = Tr * medium_transmittance(medium_of(sc, active), seg);
+        total += seg;
+        o = o + d * seg;
+    }
+    return Tr;
+}
+
+// ---- one path under the megakernel rules: rules 1 = megakernel_pt.cu:59-186, rules 2 = megakernel_vpt.cu:203-456 -------------
+V4 trace_path_megakernel(const Scene &sc, int px, int py, int accum, int seed_offset, int max_depth, int rules, Counts &cnt) {
+    const int W = sc.cfg[CPTS_CFG_WIDTH];
+    Rng rng;
+    rng.seed(px + py * W, int(uint32_t(seed_offset) + uint32_t(accum) * uint32_t(SEED_SCALER)));
+    V3 o, d;
+    camera_ray(sc, px, py, rng, o, d);
+    const int max_diffuse = sc.cfg[CPTS_CFG_MAX_DIFFUSE], max_specular = sc.cfg[CPTS_CFG_MAX_SPECULAR], max_transmit = sc.cfg[CPTS_CFG_MAX_TRANSMIT];
+    const int max_volume = sc.cfg[CPTS_CFG_MAX_VOLUME] > 0 ? sc.cfg[CPTS_CFG_MAX_VOLUME] : max_depth;
+    const int rr_bounce = rules == 2 ? 2 : 1; // megakernel_vpt.cu:28 / megakernel_pt.cu:27
+    const int num_emitters = int(sc.emitters.size()) - 1;
+    BankStackO nested;
+    if (rules == 2 && sc.cfg[CPTS_CFG_CAM_VOL] > 0)
+        nested.push(sc.cfg[CPTS_CFG_CAM_VOL]);
+    V4 thp{1, 1, 1, 1}, radiance{0, 0, 0, 1};
+    float ew = 1.f;
+    bool delta = false;
+    int diff_b = 0, spec_b = 0, trans_b = 0, volm_b = 0;
+    for (int b = 0; b < max_depth; b++) {
+        const Hit h = closest_hit(sc, o, d);
+        if (b > 0)
+            cnt.closest++;
+        if (h.prim < 0) {
+            radiance = radiance + thp * null_or_env(sc, d);
+            break;
+        }
+        const int info = sc.obj_idxs[h.prim], object_id = info & 0xfffff, hit_med = (info >> 20) & 0xff;
+        const CptsObject &ob = sc.objects[object_id];
+        const int mat_id = ob.bsdf_emitter >> 16, emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+        const CptsMedium *medium = rules == 2 ? medium_of(sc, nested.top()) : nullptr;
+        MediumSampleO md{v4(1.f), h.t, 0};
+        if (rules == 2) {
+            md = medium_sample(medium, h.t, rng);
+            thp = thp * md.local_thp;
+            if ((info & 0x40000000) && md.flag == 0) { // cullable boundary: step through, no shading
+                o = o + d * md.dist;
+                if (dot(d, interaction(sc, h.prim, h.u, h.v).n) > 0)
+                    nested.pop();
+                else
+                    nested.push(hit_med);
+                continue;
+            }
+        }
+        cnt.shaded++;
+        const Isect it = interaction(sc, h.prim, h.u, h.v);
+        CptsBsdf local_bsdf;
+        const Mat m = resolve_material(sc, mat_id, it.u, it.v, local_bsdf);
+        const V3 so = o + d * md.dist;
+        if (rules == 1) { // emission before the emitter is sampled (megakernel_pt.cu:96-110)
+            const float sa = ob.inv_area * h.t * h.t / std::max(std::fabs(dot(d, shading_normal(it.n, nullptr, m.pn))), 1e-4f);
+            ew = ew / (ew + sa * float(emitter_id > 0) * float(b > 0) * float(!delta));
+            radiance = radiance + (thp * emitter_eval(sc, sc.emitters[emitter_id], d, it.n, it.u, it.v)) * ew;
+        }
+        const int no_sample = (rules == 2 && md.flag > 0) ? 0 : emitter_id;
+        int num = num_emitters;
+        num -= no_sample > 0 && num > 1;
+        uint32_t eid = rng.u32() % uint32_t(num) + 1;
+        eid += eid >= uint32_t(no_sample) && no_sample > 0;
+        float direct_pdf = 1.f / float(num);
+        eid *= uint32_t(no_sample == 0 || num > 1);
+        const CptsEmitter &em = sc.emitters[eid];
+        const CptsObject &eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
+        direct_pdf *= eo.inv_area;
+        const uint32_t pick = rng.u32() % uint32_t(eo.prim_num) + uint32_t(eo.prim_offset);
+        const int eprim = pick < sc.emitter_prims.size() ? sc.emitter_prims[pick] : 0;
+        V4 direct{0, 0, 0, 1};
+        const float ux = rng.f(), uy = rng.f();
+        V3 sd = emitter_sample(sc, em, so, rules == 2 ? V3{0, 0, 1} : it.n, direct, direct_pdf, ux, uy, eprim) - so;
+        const float dist = std::sqrt(len2(sd));
+        sd = sd * (1.f / dist);
+        int lobe = 0;
+        if (rules == 1) {
+            if (eid != 0) {
+                cnt.shadow++;
+                if (unoccluded(sc, so, sd, dist - EPS)) {
+                    const float mis = direct_pdf + bsdf_pdf(sc, m, it.n, sd, d) * float(em.is_sphere != 0);
+                    radiance = radiance + thp * direct * bsdf_eval(sc, m, it.n, sd, d) * (mis > EPS ? 1.f / mis : 0.f);
+                }
+            }
+            o = so;
+            d = bsdf_sample(sc, m, d, it.n, thp, ew, rng, lobe);
+            delta = (lobe & LOBE_SPECULAR) != 0;
+        } else {
+            V4 nee_tr{0, 0, 0, 1}, nee_thp;
+            if (eid != 0) {
+                cnt.shadow++;
+                nee_tr = nee_transmittance(sc, so, sd, nested, dist - EPS);
+            }
+            float mis;
+            if (md.flag > 0) { // medium event
+                radiance = radiance + thp * V4{0, 0, 0, 1};
+                const float pp = phase_eval(*medium, sd, d);
+                nee_thp = v4(pp, 1.f);
+                mis = direct_pdf + pp;
+                lobe = LOBE_VOLUME;
+                d = medium_scatter(*medium, d, thp, rng, ew);
+                delta = false;
+            } else {
+                const float sa = ob.inv_area * h.t * h.t / std::max(std::fabs(dot(d, shading_normal(it.n, nullptr, m.pn))), 1e-4f);
+                ew = ew / (ew + sa * float(emitter_id > 0) * float(b > 0) * float(!delta));
+                radiance = radiance + (thp * emitter_eval(sc, sc.emitters[emitter_id], d, it.n, it.u, it.v)) * ew;
+                mis = direct_pdf + bsdf_pdf(sc, m, it.n, sd, d) * float(em.is_sphere != 0);
+                nee_thp = bsdf_eval(sc, m, it.n, sd, d);
+                const bool same = dot(d, it.n) > 0;
+                d = bsdf_sample(sc, m, d, it.n, thp, ew, rng, lobe);
+                delta = (lobe & LOBE_SPECULAR) != 0;
+                if (((dot(it.n, d) > 0) != same) == false) {
+                    if (same)
+                        nested.pop();
+                    else
+                        nested.push(hit_med);
+                }
+            }
+            radiance = radiance + nee_tr * thp * direct * (nee_thp * (mis > EPS ? 1.f / mis : 0.f));
+            o = so;
+        }
+        if (std::isnan(radiance.x) || std::isnan(radiance.y) || std::isnan(radiance.z) || std::isinf(radiance.x) || std::isinf(radiance.y) ||
+            std::isinf(radiance.z))
+            radiance = v4(0.f);
+        diff_b += (lobe & LOBE_DIFFUSE) != 0, spec_b += (lobe & LOBE_SPECULAR) != 0, trans_b += (lobe & LOBE_TRANSMIT) != 0,
+            volm_b += (lobe & LOBE_VOLUME) != 0;
+        if (diff_b >= max_diffuse || spec_b >= max_specular || trans_b >= max_transmit || (rules == 2 && volm_b >= max_volume))
+            break;
+        const float mx = std::max(thp.x, std::max(thp.y, thp.z));
+        if (mx < THP_EPS)
+            break;
+        if (b >= rr_bounce && mx < RR_THRESHOLD) {
+            if (rng.f() > mx)
+                break;
+            thp = thp * float(1. / mx);
+        }
+    }
+    return radiance;
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------
@@ -1011,6 +1267,36 @@ int oracle_render(void *hs, int first_accum, int spp, int seed_offset, int max_d
                 V4 L = trace_path(sc, x, y, first_accum + s, seed_offset, max_depth, cnt);
                 if (std::isnan(L.x) || std::isnan(L.y) || std::isnan(L.z) || std::isinf(L.x) || std::isinf(L.y) || std::isinf(L.z))
                     L = V4{0, 0, 0, 1};
+                dst[0] += L.x, dst[1] += L.y, dst[2] += L.z, dst[3] += L.w;
+            }
+        }
+        c0 += cnt.closest, c1 += cnt.shadow, c2 += cnt.shaded;
+    }
+    if (stats3)
+        stats3[0] = c0, stats3[1] = c1, stats3[2] = c2;
+    return 0;
+}
+
+/* Same, under the termination rules of the reference's megakernels: rules 1 = "pt" (megakernel_pt.cu), rules 2 = "vpt" with
+ * participating media (megakernel_vpt.cu).  No NaN scrub at the splat (these kernels scrub per bounce). */
+int oracle_render_megakernel(void *hs, int rules, int first_accum, int spp, int seed_offset, int max_depth, int row0, int row1,
+                             float *sum_rgba, uint64_t *stats3) {
+    Scene &sc = *static_cast<Scene *>(hs);
+    const int W = sc.cfg[CPTS_CFG_WIDTH], H = sc.cfg[CPTS_CFG_HEIGHT];
+    if (rules != 1 && rules != 2)
+        return 1;
+    if (max_depth <= 0)
+        max_depth = sc.cfg[CPTS_CFG_MAX_DEPTH];
+    if (row1 <= 0 || row1 > H)
+        row1 = H;
+    uint64_t c0 = 0, c1 = 0, c2 = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c0, c1, c2)
+    for (int y = row0; y < row1; y++) {
+        Counts cnt;
+        for (int x = 0; x < W; x++) {
+            float *dst = sum_rgba + 4 * (size_t(y) * W + x);
+            for (int s = 0; s < spp; s++) {
+                const V4 L = trace_path_megakernel(sc, x, y, first_accum + s, seed_offset, max_depth, rules, cnt);
                 dst[0] += L.x, dst[1] += L.y, dst[2] += L.z, dst[3] += L.w;
             }
         }

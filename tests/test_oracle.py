@@ -142,6 +142,39 @@ def test_oracle_pinned_to_reference_textures_and_envmap():
     assert (np.abs(one[..., :3] - load_frame("texroom_256_wfpt_f0001.bin")[..., :3]).max(-1) < 1e-3).mean() > 0.85
 
 
+def test_oracle_megakernel_pt_rules_pinned_to_reference():
+    """`rules=1`: the megakernel's termination rules (lobe caps, throughput cut-off, RR from bounce 1, per-bounce NaN
+    scrub, emission before NEE; megakernel_pt.cu:59-186) against the reference's `pt` frame of the same scene."""
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
+    s, st = sc.render(64, rules=1)
+    ref = load_frame("cbox_pt_256_pt_f0064.bin")
+    mean = s / 64
+    assert rel_l2(mean, ref) < 1e-3
+    d = np.abs(mean[..., :3] - ref[..., :3]).max(-1)
+    assert np.median(d) < 1e-6
+    assert (d < 1e-3 * np.maximum(ref[..., :3].max(-1), 1e-3)).mean() > 0.99
+
+
+def test_oracle_volumetric_rules_pinned_to_reference():
+    """`rules=2`: participating media (distance sampling incl. the signed channel pick, transmittance march, nested
+    volumes, HG / isotropic / two-lobe HG phase functions; megakernel_vpt.cu:59-456) against the reference's VPT frames."""
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "medium_cbox_256.cpts"))
+    one, st1 = sc.render(1, rules=2)
+    ref1 = load_frame("medium_cbox_256_vpt_f0001.bin")
+    d1 = np.abs(one[..., :3] - ref1[..., :3]).max(-1)
+    assert (d1 < 1e-3 * np.maximum(ref1[..., :3].max(-1), 1e-3)).mean() > 0.98   # same paths in > 98 % of the pixels
+    s, st = sc.render(64, rules=2)
+    ref = load_frame("medium_cbox_256_vpt_f0064.bin")
+    mean = s / 64
+    d = np.abs(mean[..., :3] - ref[..., :3]).max(-1)
+    assert np.median(d) < 1e-5
+    assert abs(mean[..., :3].mean() / ref[..., :3].mean() - 1) < 1e-3
+    assert rel_l2(mean, ref) < 1e-2
+    assert 10.0 < st["rays"] / st["samples"] < 10.7
+    with pytest.raises(ValueError):
+        sc.render(1, rules=3)
+
+
 def test_oracle_rows_subset_matches_full():
     sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
     full, _ = sc.render(2)

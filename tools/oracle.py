@@ -30,6 +30,7 @@ def lib():
         L.oracle_last_error.restype = C.c_char_p
         L.oracle_config.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_render_megakernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_rng.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.oracle_float_to_half.restype = C.c_uint16
         L.oracle_float_to_half.argtypes = [C.c_float]
@@ -51,14 +52,21 @@ class OracleScene:
         lib().oracle_config(self._h, cfg)
         self.width, self.height, self.spp, self.max_depth = cfg[0], cfg[1], cfg[2], cfg[3]
 
-    def render(self, spp, seed_offset=0, first_accum=1, max_depth=0, rows=None, sum_image=None):
-        """Returns (sum image H x W x 4 float32, stats dict).  Mean = sum / spp."""
+    def render(self, spp, seed_offset=0, first_accum=1, max_depth=0, rows=None, sum_image=None, rules=0):
+        """Returns (sum image H x W x 4 float32, stats dict).  Mean = sum / spp.
+        rules: 0 wavefront termination rules, 1 megakernel "pt", 2 volumetric "vpt" (participating media)."""
         if sum_image is None:
             sum_image = np.zeros((self.height, self.width, 4), dtype=np.float32)
         stats = (C.c_uint64 * 3)()
         r0, r1 = rows if rows else (0, 0)
-        lib().oracle_render(self._h, first_accum, spp, seed_offset, max_depth, r0, r1,
-                            C.c_void_p(sum_image.ctypes.data), stats)
+        if rules:
+            rc = lib().oracle_render_megakernel(self._h, rules, first_accum, spp, seed_offset, max_depth, r0, r1,
+                                                C.c_void_p(sum_image.ctypes.data), stats)
+            if rc:
+                raise ValueError("oracle: rules must be 0, 1 or 2")
+        else:
+            lib().oracle_render(self._h, first_accum, spp, seed_offset, max_depth, r0, r1,
+                                C.c_void_p(sum_image.ctypes.data), stats)
         nrows = (r1 - r0) if rows else self.height
         samples = nrows * self.width * spp
         return sum_image, {"samples": samples, "closest_rays": int(stats[0]), "shadow_rays": int(stats[1]),
