@@ -110,19 +110,19 @@ def rays_table():
     return json.load(open(p)) if os.path.exists(p) else {}
 
 
-def cpu_oracle_rate(scene_cpts, width, height, budget_s=12.0):
+def cpu_oracle_rate(scene_cpts, width, height, budget_s=12.0, rules=0):
     """Mrays/s of the CPU oracle (OpenMP, all host cores) on a bounded sample: 1 sample of a centred row band."""
     import oracle
     sc = oracle.OracleScene(scene_cpts)
     mid = height // 2
     t0 = time.perf_counter()
-    _, st = sc.render(1, rows=(mid - 4, mid + 4))
+    _, st = sc.render(1, rows=(mid - 4, mid + 4), rules=rules)
     dt = max(time.perf_counter() - t0, 1e-3)
     rows = int(min(height, max(16, 8 * budget_s / dt)))
     rows -= rows % 2
     r0 = max(0, mid - rows // 2)
     t0 = time.perf_counter()
-    _, st = sc.render(1, rows=(r0, r0 + rows))
+    _, st = sc.render(1, rows=(r0, r0 + rows), rules=rules)
     dt = time.perf_counter() - t0
     return {"value": st["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"1 spp x rows [{r0},{r0 + rows}) of {width}x{height} ({st['samples']} paths, {st['rays']} rays, {dt:.1f} s), "
@@ -140,8 +140,10 @@ def run_reference(args, scene, workload):
     ref_dump = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
     base = {"metric": METRIC, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "impl": "reference",
-            "data": "vader geometry bundled with the reference; textures/envmap not shipped upstream, removed",
-            "config": {"workload": workload, "width": 1920, "height": 1080, "spp_per_step": S, "max_depth": 16}}
+            "data": ("cornell box geometry bundled with the reference + three homogeneous media" if "vpt" in workload else
+                     "vader geometry bundled with the reference; textures/envmap not shipped upstream, removed" if "tex" not in workload else
+                     "vader geometry + seeded placeholder 2K textures and environment map (tools/make_assets.py)"),
+            "config": {"workload": workload, "width": 1920, "height": 1080, "spp_per_step": S}}
     tbl = rays_table().get(workload)
     if scene.endswith(".xml") and os.path.exists(ref_dump):
         try:
@@ -171,7 +173,7 @@ def run_reference(args, scene, workload):
         sc.set_film(1920, 1080)
     tmp = os.path.join(tempfile.gettempdir(), "bench_scene_ref.cpts")
     sc.save(tmp)
-    cb = cpu_oracle_rate(tmp, 1920, 1080, budget_s=20.0)
+    cb = cpu_oracle_rate(tmp, 1920, 1080, budget_s=20.0, rules={6: 2, 0: 1, 8: 1}.get(sc.config["renderer"], 0))
     base.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
                  "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(base))
@@ -348,7 +350,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         tmp = os.path.join(tempfile.gettempdir(), "bench_scene.cpts")
         sc.save(tmp)
-        cpu_baseline = cpu_oracle_rate(tmp, W, H)
+        cpu_baseline = cpu_oracle_rate(tmp, W, H, rules=int(r.get_option("rules")))
 
     out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (args.split == "tiles" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",

@@ -923,8 +923,7 @@ V4 trace_path(const Scene &sc, int px, int py, int accum, int seed_offset, int m
     for (int bounce = 0; bounce < max_depth; bounce++) {
         // ---- shade (fused_ray_bounce_shader)
         cnt.shaded++;
-        int obj_id = sc.obj_idxs[h.prim];
-        obj_id = obj_id >= 0 ? obj_id : -obj_id - 1;
+        const int obj_id = sc.obj_idxs[h.prim] & 0x000fffff; // extract_object_info (tracing_func.cuh:38-41)
         const CptsObject &ob = sc.objects[obj_id];
         const int mat_id = ob.bsdf_emitter >> 16, emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
         CptsBsdf local_bsdf;
