@@ -138,7 +138,7 @@ def run_reference(args, scene, workload):
         return
     S = args.spp_per_step
     ref_dump = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
-    base = {"metric": METRIC, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    base = {"metric": METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "impl": "reference",
             "data": ("cornell box geometry bundled with the reference + three homogeneous media" if "vpt" in workload else
                      "vader geometry bundled with the reference; textures/envmap not shipped upstream, removed" if "tex" not in workload else
@@ -158,7 +158,7 @@ def run_reference(args, scene, workload):
             value = msamples * rps if rps else None
             base.update({"value": value, "ms_per_step": ms_step, "msamples_per_s": msamples,
                          "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "reference",
-                                          "sample": f"{args.steps * S} x WavefrontPathTracer::render_raw (1 spp each) on 1 GPU of this box, "
+                                          "sample": f"{args.steps * S} x {'VolumePathTracer' if mode == 'vpt' else 'WavefrontPathTracer'}::render_raw (1 spp each) on 1 GPU of this box, "
                                                     "reference kernels + its host loop (one host thread); rays/sample of the "
                                                     "reference-built scene (its SBVH) from profiles/workload_rays.json, counts parity-checked"},
                          "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -332,6 +332,12 @@ def main():
     if sh_ms > 0:
         stages["shade"]["of_which_shadow_kernels_ms_per_step"] = sh_ms / K
         stages["shade"]["shadow_rays_traced_per_step"] = sh_traced / K
+    if "vpt" in workload and "raygen" in stages:  # rules=2: the whole path runs in k_vpt, timed in the raygen slot;
+        stages["vpt"] = stages.pop("raygen")       # per path it reads the camera sample and writes 16 B of radiance,
+        v = stages["vpt"]                          # everything else stays in registers
+        v["bytes_per_unit"] = 16
+        v["achieved_gbs"] = v["units_per_step"] * 16 / (v["ms_per_step"] * 1e-3) / 1e9
+        v["frac"] = v["achieved_gbs"] / peak
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic = None
@@ -340,7 +346,7 @@ def main():
             traffic = json.load(open(prof)).get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_vpt" if "vpt" in workload else {"raygen": "k_raygen", "shade": "k_shade+k_shadow_apply", "trace": "k_trace", "splat": "k_splat"}[dom],
+    roofline = {"bound": "hbm", "kernel": {"vpt": "k_vpt", "raygen": "k_raygen", "shade": "k_shade+k_shadow_apply", "trace": "k_trace", "splat": "k_splat"}[dom],
                 "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
                 "traffic": traffic, "peak_source": peak_src,
                 "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; BVH/triangle reads are L2-served "
@@ -352,7 +358,7 @@ def main():
         sc.save(tmp)
         cpu_baseline = cpu_oracle_rate(tmp, W, H, rules=int(r.get_option("rules")))
 
-    out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
+    out = {"metric": METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (args.split == "tiles" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
            "data": ("cornell box geometry bundled with the reference + three homogeneous media (the reference's medium-cbox scene); fixed seeds"
                     if "vpt" in workload else
