@@ -89,6 +89,8 @@ struct DevScene {
     int num_nodes, num_cache, num_prims, num_emitters, envmap_id, wroot;
     const struct MediumPOD *media; // [0] = vacuum (volumetric path only)
     int num_media, cam_vol;
+    const struct GridPOD *grids;     // grid media (volume.cuh)
+    cudaTextureObject_t blackbody;   // emission colour table of grid media
     cudaTextureObject_t cie, d65; // spectral tables for the dispersion BSDF
 };
 

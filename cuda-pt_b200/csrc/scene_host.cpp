@@ -156,6 +156,14 @@ void load_cpts(const std::string &path, HostScene &out) {
             read_into(fp, s, out.d65_spd, "d65_spd");
         else if (name == "media")
             read_into(fp, s, out.media, "media");
+        else if (name == "grids")
+            read_into(fp, s, out.grids, "grids");
+        else if (name == "grid_bricks")
+            read_into(fp, s, out.grid_bricks, "grid_bricks");
+        else if (name == "grid_data")
+            read_into(fp, s, out.grid_data, "grid_data");
+        else if (name == "blackbody")
+            read_into(fp, s, out.blackbody, "blackbody");
         else if (name == "tex_desc")
             read_into(fp, s, tex_desc, "tex_desc");
         else if (name == "tex_data")
@@ -206,6 +214,12 @@ void save_cpts(const HostScene &sc, const std::string &path) {
     }
     if (!sc.media.empty())
         w.put("media", sc.media.data(), sizeof(CptsMedium), sc.media.size());
+    if (!sc.grids.empty()) {
+        w.put("grids", sc.grids.data(), sizeof(CptsGrid), sc.grids.size());
+        w.put("grid_bricks", sc.grid_bricks.data(), 4, sc.grid_bricks.size());
+        w.put("grid_data", sc.grid_data.data(), 4, sc.grid_data.size());
+        w.put("blackbody", sc.blackbody.data(), 16, sc.blackbody.size());
+    }
     if (!sc.textures.empty()) {
         std::vector<CptsTexDesc> desc;
         std::vector<float> data;
@@ -266,12 +280,40 @@ void validate_scene(const HostScene &sc) {
     if (sc.config[CPTS_CFG_CAM_VOL] < 0 || (sc.config[CPTS_CFG_CAM_VOL] > 0 && size_t(sc.config[CPTS_CFG_CAM_VOL]) >= sc.media.size()))
         fail("camera medium index out of range");
     for (size_t i = 1; i < sc.media.size(); i++) {
-        if (sc.media[i].type != CPTS_MEDIUM_HOMOGENEOUS)
-            fail("grid (NanoVDB) media are not supported: only homogeneous media");
+        if (sc.media[i].type == CPTS_MEDIUM_GRID) {
+            if (sc.media[i].grid < 0 || size_t(sc.media[i].grid) >= sc.grids.size() || sc.grids[sc.media[i].grid].medium != int(i))
+                fail("grid medium without a matching entry in the 'grids' section");
+        } else if (sc.media[i].type != CPTS_MEDIUM_HOMOGENEOUS)
+            fail("unknown medium type");
         if (sc.media[i].phase_type != CPTS_PHASE_ISOTROPIC && sc.media[i].phase_type != CPTS_PHASE_HG &&
             sc.media[i].phase_type != CPTS_PHASE_DUO_HG)
             fail("unsupported phase function (isotropic, hg and hg-duo are)");
     }
+    for (const auto &g : sc.grids) { // every brick table and every brick pool must lie inside its section
+        if (g.ch[CPTS_GRID_DENSITY].ncomp != 1)
+            fail("grid medium without a density channel");
+        if (!(g.majorant > 0.f) || !(g.scale > 0.f))
+            fail("grid medium with a non-positive majorant or density scale");
+        for (int c = 0; c < 3; c++) {
+            const CptsGridChannel &ch = g.ch[c];
+            if (ch.ncomp == 0)
+                continue;
+            if (ch.ncomp != (c == CPTS_GRID_ALBEDO ? 3 : 1))
+                fail("grid channel with an unexpected component count");
+            if (ch.nb[0] <= 0 || ch.nb[1] <= 0 || ch.nb[2] <= 0 || ch.nb[0] > 4096 || ch.nb[1] > 4096 || ch.nb[2] > 4096)
+                fail("grid channel with an invalid brick count");
+            const uint64_t nbricks = uint64_t(ch.nb[0]) * ch.nb[1] * ch.nb[2];
+            if (ch.brick_offset + nbricks > sc.grid_bricks.size())
+                fail("grid brick table outside 'grid_bricks'");
+            for (uint64_t b = 0; b < nbricks; b++) {
+                const int32_t id = sc.grid_bricks[ch.brick_offset + b];
+                if (id < -1 || (id >= 0 && ch.data_offset + (uint64_t(id) + 1) * 512 * ch.ncomp > sc.grid_data.size()))
+                    fail("grid brick outside 'grid_data'");
+            }
+        }
+    }
+    if (!sc.grids.empty() && sc.blackbody.empty())
+        fail("grid media need the 'blackbody' emission table (the reference loads it for every scene, vol_grid.cu:304-326)");
     for (const auto &o : sc.objects) {
         const int bsdf = o.bsdf_emitter >> 16;
         int em = o.bsdf_emitter & 0xFFFF;

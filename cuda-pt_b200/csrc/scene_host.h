@@ -45,6 +45,11 @@ struct HostScene {
     std::vector<CptsEmitter> emitters; // [0] = null emitter
     std::vector<HostTexture> textures;
     std::vector<CptsMedium> media; // [0] = vacuum; empty when the scene has no participating media
+    // grid media (cpts_format.h "grids"): brick tables + brick pools of every channel, and the emission colour table
+    std::vector<CptsGrid> grids;
+    std::vector<int32_t> grid_bricks;
+    std::vector<float> grid_data;
+    std::vector<F4> blackbody;
     std::vector<F4> cie_xyz;    // 471 samples, 360..830 nm (only present when a dispersion BSDF needs it)
     std::vector<float> d65_spd; // 531 samples, 300..830 nm
 

@@ -10,8 +10,8 @@
 namespace cptb {
 
 struct MediumPOD { // 80 B
-    int type, phase_type; // type < 0: vacuum (media[0])
-    int pad0, pad1;
+    int type, phase_type; // type < 0: vacuum (media[0]); 0: homogeneous; 1: grid
+    int grid, pad1;       // grid media: index into DevScene::grids
     float4 sigma_a, sigma_s, sigma_t;
     float4 phase; // hg: g ; duo-hg: g1, g2, weight
 };
@@ -21,6 +21,24 @@ struct MediumSample {
     float dist;
     uint32_t flag; // 1: medium (scattering) event, 0: surface event
 };
+
+// ---- grid media: brick grids in place of the reference's NanoVDB trees (include/cpts_format.h "grids") ----
+// One lookup = one brick-table read + one voxel read (two dependent loads), where the reference's accessor walks
+// root -> upper -> lower -> leaf for every jittered sample.
+struct GridChannelPOD {
+    float inv_mat[9], vec[3];
+    int bmin[3], nb[3];
+    float bg[3];
+    int ncomp;
+    const int *bricks;
+    const float *data;
+};
+struct GridPOD {
+    float scale, temp_scale, em_scale, majorant;
+    float aabb_min[3], aabb_max[3];
+    GridChannelPOD ch[3]; // density, albedo, temperature
+};
+enum : int { MEDIUM_HOMOGENEOUS = 0, MEDIUM_GRID = 1 };
 
 enum : int { PHASE_NULL = 0, PHASE_ISOTROPIC = 1, PHASE_HG = 2, PHASE_DUO_HG = 3 };
 
@@ -92,6 +110,110 @@ PT_DEV V4 medium_transmittance(const MediumPOD &m, float dist) {
     if (m.type < 0)
         return splat4(1.f);
     return mk4(expf(-m.sigma_t.x * dist), expf(-m.sigma_t.y * dist), expf(-m.sigma_t.z * dist), 1.f);
+}
+
+// ---- grid media (src/volume/grid.cuh:51-92, src/impl/vol_grid.cu:97-211) ----
+// nearest-voxel address of a jittered world position: index = inv_mat * (pos - vec) (NanoVDB math::matMult: two fmaf
+// and one rounded product per row), + offset, roundf.  Returns the float offset into the channel's pool or -1.
+PT_DEV long long grid_voxel(const GridChannelPOD &c, V3 pos, float offset) {
+    const float x = pos.x - c.vec[0], y = pos.y - c.vec[1], z = pos.z - c.vec[2];
+    const float fi = __fadd_rn(fmaf(x, c.inv_mat[0], fmaf(y, c.inv_mat[1], __fmul_rn(z, c.inv_mat[2]))), offset);
+    const float fj = __fadd_rn(fmaf(x, c.inv_mat[3], fmaf(y, c.inv_mat[4], __fmul_rn(z, c.inv_mat[5]))), offset);
+    const float fk = __fadd_rn(fmaf(x, c.inv_mat[6], fmaf(y, c.inv_mat[7], __fmul_rn(z, c.inv_mat[8]))), offset);
+    const int i = int(roundf(fi)) - c.bmin[0], j = int(roundf(fj)) - c.bmin[1], k = int(roundf(fk)) - c.bmin[2];
+    if (unsigned(i) >= unsigned(c.nb[0] << 3) || unsigned(j) >= unsigned(c.nb[1] << 3) || unsigned(k) >= unsigned(c.nb[2] << 3))
+        return -1;
+    const int b = __ldg(c.bricks + ((i >> 3) * c.nb[1] + (j >> 3)) * c.nb[2] + (k >> 3));
+    if (b < 0)
+        return -1;
+    return ((long long)b * 512 + (((i & 7) << 6) | ((j & 7) << 3) | (k & 7))) * c.ncomp;
+}
+PT_DEV float grid_scalar(const GridChannelPOD &c, V3 pos, float offset) {
+    const long long a = grid_voxel(c, pos, offset);
+    return a < 0 ? c.bg[0] : __ldg(c.data + a);
+}
+PT_DEV V4 grid_albedo(const GridPOD &g, const MediumPOD &m, V3 pos, float offset) {
+    const GridChannelPOD &c = g.ch[1];
+    if (c.ncomp == 0) // constant albedo
+        return mk4(m.sigma_a.x, m.sigma_a.y, m.sigma_a.z);
+    const long long a = grid_voxel(c, pos, offset);
+    return a < 0 ? mk4(c.bg[0], c.bg[1], c.bg[2]) : mk4(__ldg(c.data + a), __ldg(c.data + a + 1), __ldg(c.data + a + 2));
+}
+// AABB::intersect(ray, t_near, t_far) (src/core/aabb.cuh:78-85)
+PT_DEV bool grid_span(const GridPOD &g, V3 o, V3 d, float &t_near, float &t_far) {
+    const float ix = __frcp_rn(d.x), iy = __frcp_rn(d.y), iz = __frcp_rn(d.z);
+    const float ox = __fmul_rn(o.x, ix), oy = __fmul_rn(o.y, iy), oz = __fmul_rn(o.z, iz);
+    const float ax = fmaf(g.aabb_min[0], ix, -ox), ay = fmaf(g.aabb_min[1], iy, -oy), az = fmaf(g.aabb_min[2], iz, -oz);
+    const float bx = fmaf(g.aabb_max[0], ix, -ox), by = fmaf(g.aabb_max[1], iy, -oy), bz = fmaf(g.aabb_max[2], iz, -oz);
+    const float min_x = ax < bx ? ax : bx, max_x = ax < bx ? bx : ax;
+    const float min_y = ay < by ? ay : by, max_y = ay < by ? by : ay;
+    const float min_z = az < bz ? az : bz, max_z = az < bz ? bz : az;
+    t_near = fmaxf(min_x, fmaxf(min_y, min_z));
+    t_far = fminf(max_x, fminf(max_y, max_z));
+    return t_far > t_near && t_far > 0;
+}
+// GridVolumeMedium::sample -> delta tracking (vol_grid.cu:104-150)
+PT_DEV MediumSample grid_sample(const GridPOD &g, const MediumPOD &m, V3 o, V3 d, float hit_t, Rng &rng) {
+    MediumSample ds;
+    ds.local_thp = splat4(1.f);
+    ds.dist = hit_t;
+    ds.flag = 0;
+    float t_near = 0, t_far = 0;
+    if (grid_span(g, o, d, t_near, t_far)) {
+        t_near = fmaxf(0.f, t_near);
+        t_far = fminf(t_far, hit_t);
+        const float inv_maj = 1.f / (g.scale * g.majorant);
+        float t = t_near - logf(1.f - rng.next1d()) * inv_maj;
+        while (t < t_far) {
+            const V3 pos{fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)};
+            const float offset = rng.next1d() - 0.5f;
+            const float dens = grid_scalar(g.ch[0], pos, offset) * g.scale;
+            if (rng.next1d() < dens * inv_maj) { // real collision
+                ds.dist = t;
+                ds.local_thp = grid_albedo(g, m, pos, offset);
+                ds.flag = 1;
+                break;
+            }
+            t -= logf(1.f - rng.next1d()) * inv_maj;
+        }
+    }
+    return ds;
+}
+// GridVolumeMedium::transmittance -> ratio tracking with roulette below 0.1 (vol_grid.cu:117-127,179-199).  `far_cap`
+// is the ray's hit_t: the NEE march of the reference hands over a ray whose hit_t is still MAX_DIST, so the estimate
+// runs over the whole span of the grid's box in front of the origin (reproduced by the caller passing kMaxDist).
+PT_DEV V4 grid_transmittance(const GridPOD &g, V3 o, V3 d, float far_cap, Rng &rng) {
+    float Tr = 1.f, t_near = 0, t_far = 0;
+    if (grid_span(g, o, d, t_near, t_far)) {
+        t_near = fmaxf(0.f, t_near);
+        t_far = fminf(t_far, far_cap);
+        const float inv_maj = 1.f / (g.scale * g.majorant);
+        float t = t_near - logf(1.f - rng.next1d()) * inv_maj;
+        bool dead = false;
+        while (t < t_far) {
+            const V3 pos{fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)};
+            const float offset = rng.next1d() - 0.5f;
+            const float dens = grid_scalar(g.ch[0], pos, offset) * g.scale;
+            Tr *= fmaxf(0.f, 1.f - dens * inv_maj);
+            if (Tr < 0.1f) {
+                if (rng.next1d() >= Tr) {
+                    dead = true;
+                    break;
+                }
+                Tr = 1.f;
+            }
+            t -= logf(1.f - rng.next1d()) * inv_maj;
+        }
+        if (dead)
+            Tr = 0.f;
+    }
+    return mk4(Tr, Tr, Tr, 1.f);
+}
+// GridVolumeMedium::query_emission (vol_grid.cu:97-102): the jitter draw happens whether or not a temperature grid exists
+PT_DEV V4 grid_emission(const GridPOD &g, cudaTextureObject_t blackbody, V3 pos, Rng &rng) {
+    const float offset = rng.next1d() - 0.5f;
+    const float temp = g.ch[2].ncomp ? grid_scalar(g.ch[2], pos, offset) : 0.f;
+    return from_f4(tex1D<float4>(blackbody, temp * g.temp_scale)) * g.em_scale;
 }
 
 // ---- phase functions (henyey_greenstein.cuh) ----

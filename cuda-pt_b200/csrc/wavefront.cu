@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
 // medium events is the follow-up), S samples in flight, radiance to the path pool's L for k_splat.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-__device__ V4 nee_transmittance(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, BankStack nested, float max_dist,
+__device__ V4 nee_transmittance(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, BankStack nested, float max_dist, Rng &rng,
                                 unsigned int &segments) {
     float total_dist = 0;
     V4 Tr = splat4(1.f);
@@ -845,7 +845,9 @@ __device__ V4 nee_transmittance(const DevScene &sc, const uint4 *s_cached, V3 o,
             nested.push(active_medium);
             active_medium = old_active;
         }
-        Tr *= medium_transmittance(sc.media[active_medium], min_dist);
+        const MediumPOD &am = sc.media[active_medium];
+        // grid media: Medium::transmittance(ray, sp, dist) ignores `dist`; the march's ray keeps hit_t = MAX_DIST
+        Tr *= am.type == MEDIUM_GRID ? grid_transmittance(sc.grids[am.grid], o, d, kMaxDist, rng) : medium_transmittance(am, min_dist);
         total_dist += min_dist;
         o = advance(o, d, min_dist);
     }
@@ -895,7 +897,8 @@ __global__ void __launch_bounds__(kBlock, VPT_MIN_BLOCKS) k_vpt(DevScene sc, Cam
             const bool hit_emitter = emitter_id > 0;
             // ---- medium event or surface event
             const MediumPOD &medium = sc.media[nested.top()];
-            const MediumSample md = medium_sample(medium, h.t, rng);
+            const MediumSample md =
+                medium.type == MEDIUM_GRID ? grid_sample(sc.grids[medium.grid], medium, o, d, h.t, rng) : medium_sample(medium, h.t, rng);
             throughput *= md.local_thp;
             const bool alpha_mask = (obj_info & 0x40000000) == 0x40000000;
             if (alpha_mask && md.flag == 0) {
@@ -931,12 +934,13 @@ __global__ void __launch_bounds__(kBlock, VPT_MIN_BLOCKS) k_vpt(DevScene sc, Cam
             sd *= __frcp_rn(emit_len_mis);
             if (emit_id != 0) {
                 ++n_shadow;
-                nee_tr = nee_transmittance<MODE>(sc, s_cached, so, sd, nested, emit_len_mis - kEps, n_segments);
+                nee_tr = nee_transmittance<MODE>(sc, s_cached, so, sd, nested, emit_len_mis - kEps, rng, n_segments);
             }
             int lobe = LOBE_NONE;
             V4 nee_thp;
             if (md.flag > 0) { // medium event
-                radiance += throughput * splat4(0, 1); // Medium::query_emission: homogeneous media do not emit
+                // Medium::query_emission: homogeneous media do not emit; grid media look up the blackbody table
+                radiance += throughput * (medium.type == MEDIUM_GRID ? grid_emission(sc.grids[medium.grid], sc.blackbody, so, rng) : splat4(0, 1));
                 const float phase_pdf = phase_eval(medium, sd, d);
                 nee_thp = splat4(phase_pdf, 1.f);
                 emit_len_mis = direct_pdf + phase_pdf;
@@ -1152,6 +1156,9 @@ struct Renderer::Impl {
     DevBuf<ObjectPOD> objects;
     DevBuf<Material> mats;
     DevBuf<MediumPOD> media;
+    DevBuf<GridPOD> grids;
+    DevBuf<int> grid_bricks;
+    DevBuf<float> grid_data;
     int max_volume = 0;
     DevBuf<EmitterPOD> emitters;
     DevScene dev{};
@@ -1391,7 +1398,7 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
             mp.type = -1; // vacuum
             if (i > 0 && i < scene.media.size()) {
                 const CptsMedium &c = scene.media[i];
-                mp.type = c.type, mp.phase_type = c.phase_type;
+                mp.type = c.type, mp.phase_type = c.phase_type, mp.grid = c.grid;
                 mp.sigma_a = make_float4(c.sigma_a[0], c.sigma_a[1], c.sigma_a[2], c.sigma_a[3]);
                 mp.sigma_s = make_float4(c.sigma_s[0], c.sigma_s[1], c.sigma_s[2], c.sigma_s[3]);
                 mp.sigma_t = make_float4(c.sigma_a[0] + c.sigma_s[0], c.sigma_a[1] + c.sigma_s[1], c.sigma_a[2] + c.sigma_s[2],
@@ -1406,37 +1413,69 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         m.dev.cam_vol = scene.config[CPTS_CFG_CAM_VOL];
         m.max_volume = scene.config[CPTS_CFG_MAX_VOLUME];
     }
+    m.dev.grids = nullptr;
+    m.dev.blackbody = 0;
+    if (!scene.grids.empty()) { // grid media: brick tables + pools as two flat device arrays, channels point into them
+        m.grid_bricks.upload(scene.grid_bricks);
+        m.grid_data.upload(scene.grid_data);
+        std::vector<GridPOD> gp(scene.grids.size());
+        for (size_t i = 0; i < gp.size(); i++) {
+            const CptsGrid &c = scene.grids[i];
+            GridPOD g{};
+            g.scale = c.scale, g.temp_scale = c.temp_scale, g.em_scale = c.em_scale, g.majorant = c.majorant;
+            for (int k = 0; k < 3; k++)
+                g.aabb_min[k] = c.aabb_min[k], g.aabb_max[k] = c.aabb_max[k];
+            for (int ch = 0; ch < 3; ch++) {
+                const CptsGridChannel &cc = c.ch[ch];
+                GridChannelPOD &d = g.ch[ch];
+                memcpy(d.inv_mat, cc.inv_mat, sizeof(d.inv_mat));
+                memcpy(d.vec, cc.vec, sizeof(d.vec));
+                memcpy(d.bmin, cc.bmin, sizeof(d.bmin));
+                memcpy(d.nb, cc.nb, sizeof(d.nb));
+                memcpy(d.bg, cc.background, sizeof(d.bg));
+                d.ncomp = cc.ncomp;
+                d.bricks = m.grid_bricks.p + cc.brick_offset;
+                d.data = m.grid_data.p + cc.data_offset;
+            }
+            gp[i] = g;
+        }
+        m.grids.upload(gp);
+        m.dev.grids = m.grids.p;
+        m.scene_bytes += scene.grid_bricks.size() * 4 + scene.grid_data.size() * 4;
+    }
     m.dev.num_nodes = scene.num_nodes();
     m.dev.num_cache = int(scene.cache_nodes.size());
     m.dev.num_prims = scene.num_prims();
     m.dev.num_emitters = int(scene.emitters.size()) - 1;
     m.dev.envmap_id = scene.config[CPTS_CFG_ENVMAP_ID];
     m.dev.cie = m.dev.d65 = 0;
+    // 1-D array textures, linear filter, clamp, normalised coordinates (reference: src/core/xyz.cuh:60-84)
+    auto make1d = [&](const void *src, size_t count, bool four) {
+        cudaChannelFormatDesc desc = four ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float>();
+        cudaArray_t arr;
+        CUDA_OK(cudaMallocArray(&arr, &desc, count));
+        const size_t bytes = count * (four ? 16 : 4);
+        CUDA_OK(cudaMemcpy2DToArray(arr, 0, 0, src, bytes, bytes, 1, cudaMemcpyHostToDevice));
+        m.tex_arrays.push_back(arr);
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 1;
+        cudaTextureObject_t obj = 0;
+        CUDA_OK(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+        m.tex_objs.push_back(obj);
+        return obj;
+    };
     if (!scene.cie_xyz.empty()) {
-        // 1-D array textures, linear filter, clamp, normalised coordinates (reference: src/core/xyz.cuh:60-84)
-        auto make1d = [&](const void *src, size_t count, bool four) {
-            cudaChannelFormatDesc desc = four ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float>();
-            cudaArray_t arr;
-            CUDA_OK(cudaMallocArray(&arr, &desc, count));
-            const size_t bytes = count * (four ? 16 : 4);
-            CUDA_OK(cudaMemcpy2DToArray(arr, 0, 0, src, bytes, bytes, 1, cudaMemcpyHostToDevice));
-            m.tex_arrays.push_back(arr);
-            cudaResourceDesc res{};
-            res.resType = cudaResourceTypeArray;
-            res.res.array.array = arr;
-            cudaTextureDesc td{};
-            td.addressMode[0] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModeLinear;
-            td.readMode = cudaReadModeElementType;
-            td.normalizedCoords = 1;
-            cudaTextureObject_t obj = 0;
-            CUDA_OK(cudaCreateTextureObject(&obj, &res, &td, nullptr));
-            m.tex_objs.push_back(obj);
-            return obj;
-        };
         m.dev.cie = make1d(scene.cie_xyz.data(), scene.cie_xyz.size(), true);
         m.dev.d65 = make1d(scene.d65_spd.data(), scene.d65_spd.size(), false);
     }
+    if (!scene.grids.empty()) // vol_grid.cu:304-326
+        m.dev.blackbody = make1d(scene.blackbody.data(), scene.blackbody.size(), true);
     m.cam = camera_from_floats(scene.camera);
 
     const size_t P = size_t(w_) * h_;

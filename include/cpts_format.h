@@ -152,8 +152,51 @@ typedef struct CptsMedium {
     float sigma_a[4];   /* already multiplied by the density scale (vol_homo.cu:26-32) */
     float sigma_s[4];
     float phase[4];     /* hg: g; duo-hg: g1, g2, weight */
-    int32_t pad[2];
+    int32_t grid;       /* grid media: index into the "grids" section; 0 otherwise */
+    int32_t pad;
 } CptsMedium;
+
+/* Grid media (reference: GridVolumeMedium, src/volume/grid.cuh:34-121, src/impl/vol_grid.cu:82-211).  A grid medium keeps
+ * its constant albedo in CptsMedium::sigma_a and (emission scale, temperature scale) in CptsMedium::sigma_s[0..1]
+ * (MediumInfo::MediumParams, core/dynamic_bsdf.cuh:55-60); everything else is one CptsGrid in the "grids" section.
+ *
+ * A grid has up to three channels (density: float, albedo: 3 floats, temperature: float), each the image of one NanoVDB
+ * grid under nearest-voxel lookup (`getValue(Coord)`), stored as a two-level brick grid instead of the NanoVDB tree:
+ *   "grid_bricks"  int32   one entry per 8x8x8 brick of the channel's index bounding box, x-major
+ *                          ((bx * nb[1] + by) * nb[2] + bz), value = brick number in the channel's pool or -1 (every
+ *                          voxel of the brick holds the background value)
+ *   "grid_data"    float   brick pools: brick b of a channel starts at data_offset + b * 512 * ncomp; inside a brick a
+ *                          voxel sits at (((i & 7) << 6) | ((j & 7) << 3) | (k & 7)) * ncomp  (NanoVDB leaf order)
+ * Lookups outside the index bounding box return the background.  `inv_mat` / `vec` are the float copies of the grid's
+ * affine map (NanoVDB Map::mInvMatF / mVecF): index = inv_mat * (world - vec), evaluated as in math::matMult. */
+typedef struct CptsGridChannel {
+    float inv_mat[9];
+    float vec[3];
+    int32_t bmin[3];     /* index bounding box minimum (a multiple of 8 per axis) */
+    int32_t nb[3];       /* bricks per axis */
+    float background[3];
+    int32_t ncomp;       /* 0: channel absent, 1 or 3 */
+    uint64_t brick_offset; /* into "grid_bricks" (entries) */
+    uint64_t data_offset;  /* into "grid_data" (floats) */
+} CptsGridChannel;       /* 104 B */
+
+enum { CPTS_GRID_DENSITY = 0, CPTS_GRID_ALBEDO = 1, CPTS_GRID_TEMPERATURE = 2 };
+typedef struct CptsGrid {
+    int32_t medium;       /* index of the medium that owns this grid */
+    int32_t pad;
+    float scale;          /* density scale */
+    float temp_scale;
+    float em_scale;
+    float majorant;       /* maximum of the density grid (Tree::extrema), unscaled */
+    float avg_density;    /* mean of the positive density voxels (residual tracking; unused by the served estimators) */
+    float pad1;
+    float aabb_min[3];    /* world bounding box of the density grid, as floats (GridVolumeMedium::grid_aabb) */
+    float aabb_max[3];
+    CptsGridChannel ch[3];
+} CptsGrid;               /* 368 B */
+
+/* "blackbody" section: float[4] x N, the emission colour table indexed by normalised temperature (the reference reads
+ * scene/data/blackbody.bin into a linear-filtered, clamped, normalised 1D texture: vol_grid.cu:304-326). */
 
 /* "tex_desc" section: one per texture; texels live in "tex_data" (float) at `offset` floats. */
 typedef struct CptsTexDesc {

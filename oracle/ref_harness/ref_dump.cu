@@ -21,6 +21,9 @@
  *          listed (1-based) frame counts as <out_prefix>_fNNNN.bin, and the
  *          scene as <out_prefix>.cpts (same in-process Scene => same BVH /
  *          emitter primitive order, SURVEY.md §7 "hard parts").
+ *   mkvdb  <prefix> [n]
+ *          write synthetic <prefix>_{density,albedo,temperature}.nvdb with the vendored NanoVDB tools (the reference's
+ *          own volume assets are not distributed); no scene is loaded.
  *   bench  <xml> <mode> <warmup> <frames> [seed_offset]
  *          time `frames` render_raw() calls with CUDA events; prints one JSON line.
  */
@@ -41,6 +44,12 @@
 #include "renderer/volume_pt.cuh"
 
 #include "cpts_format.h"
+
+#include <nanovdb/io/IO.h>
+#include <nanovdb/tools/CreateNanoGrid.h>
+#include <nanovdb/tools/GridBuilder.h>
+#include <cmath>
+#include <fstream>
 
 extern CPT_GPU_CONST Emitter *c_emitter[9];
 extern CPT_GPU_CONST BSDF *c_material[48];
@@ -168,6 +177,10 @@ int grab_texture(cudaTextureObject_t obj, std::vector<CptsTexDesc> &descs, std::
     descs.push_back(d);
     return int(descs.size()) - 1;
 }
+
+struct Writer;
+void dump_grids(const Scene &scene, const tinyxml2::XMLElement *root, const std::string &xml_path, std::vector<CptsMedium> &media,
+                Writer &w);
 
 void dump_scene(const Scene &scene, const std::string &xml_path, const std::string &out_path) {
     Writer w(out_path);
@@ -372,6 +385,7 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
             }
             media[i] = m;
         }
+        dump_grids(scene, root, xml_path, media, w);
         w.section("media", media.data(), sizeof(CptsMedium), media.size());
     }
     if (!tex_descs.empty()) {
@@ -398,6 +412,182 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
         cudaFree(d_d65);
     }
     w.close();
+}
+
+
+// ---- grid media: the image of a NanoVDB grid under nearest-voxel lookups, as the brick grid of cpts_format.h.
+// Values are read through the grid's own host accessor (what GridVolumeMedium::sample_density does on the device,
+// src/volume/grid.cuh:51-58), never by walking the tree ourselves.
+template <typename GridT, int NC>
+void append_channel(const GridT *grid, CptsGridChannel &ch, std::vector<int32_t> &bricks, std::vector<float> &data) {
+    const auto &map = grid->map();
+    for (int k = 0; k < 9; k++)
+        ch.inv_mat[k] = map.mInvMatF[k];
+    for (int k = 0; k < 3; k++)
+        ch.vec[k] = map.mVecF[k];
+    const auto bbox = grid->indexBBox();
+    const auto bg = grid->tree().background();
+    for (int k = 0; k < 3; k++) {
+        if constexpr (NC == 1)
+            ch.background[k] = k == 0 ? float(bg) : 0.f;
+        else
+            ch.background[k] = float(bg[k]);
+        ch.bmin[k] = bbox.min()[k] & ~7;
+        ch.nb[k] = ((bbox.max()[k] - ch.bmin[k]) >> 3) + 1;
+    }
+    ch.ncomp = NC;
+    ch.brick_offset = bricks.size();
+    ch.data_offset = data.size();
+    auto acc = grid->getAccessor();
+    int32_t next = 0;
+    std::vector<float> tmp(512 * NC);
+    for (int bx = 0; bx < ch.nb[0]; bx++)
+        for (int by = 0; by < ch.nb[1]; by++)
+            for (int bz = 0; bz < ch.nb[2]; bz++) {
+                bool any = false;
+                for (int v = 0; v < 512; v++) {
+                    const nanovdb::Coord c(ch.bmin[0] + bx * 8 + (v >> 6), ch.bmin[1] + by * 8 + ((v >> 3) & 7), ch.bmin[2] + bz * 8 + (v & 7));
+                    const auto val = acc.getValue(c);
+                    if constexpr (NC == 1) {
+                        tmp[v] = float(val);
+                        any |= val != bg;
+                    } else {
+                        for (int k = 0; k < 3; k++)
+                            tmp[v * 3 + k] = float(val[k]);
+                        any |= val != bg;
+                    }
+                }
+                if (any) {
+                    bricks.push_back(next++);
+                    data.insert(data.end(), tmp.begin(), tmp.end());
+                } else {
+                    bricks.push_back(-1);
+                }
+            }
+}
+
+void dump_grids(const Scene &scene, const tinyxml2::XMLElement *root, const std::string &xml_path, std::vector<CptsMedium> &media,
+                Writer &w) {
+    std::string folder = xml_path.substr(0, xml_path.find_last_of("/\\") + 1); // scene.cu: folder_prefix
+    std::vector<CptsGrid> grids;
+    std::vector<int32_t> bricks;
+    std::vector<float> data;
+    int idx = 1;
+    for (auto me = root->FirstChildElement("medium"); me; me = me->NextSiblingElement("medium"), idx++) {
+        if (strcmp(me->Attribute("type"), "grid") != 0 || size_t(idx) >= media.size())
+            continue;
+        std::string den, alb, ems;
+        for (auto e = me->FirstChildElement("string"); e; e = e->NextSiblingElement("string")) {
+            const char *n = e->Attribute("name");
+            if (strcmp(n, "density") == 0)
+                den = folder + e->Attribute("value");
+            else if (strcmp(n, "albedo") == 0)
+                alb = folder + e->Attribute("value");
+            else if (strcmp(n, "emission") == 0)
+                ems = folder + e->Attribute("value");
+        }
+        const MediumInfo &mi = scene.medium_infos[idx];
+        CptsGrid g{};
+        g.medium = idx;
+        g.scale = mi.med_param.scale;
+        g.em_scale = mi.med_param.emission_scale();
+        g.temp_scale = mi.med_param.temperature_scale();
+        auto hd = nanovdb::io::readGrid(den);
+        const nanovdb::FloatGrid *dg = hd.grid<float>();
+        float lo = 0, hi = 0;
+        dg->tree().extrema(lo, hi);
+        g.majorant = hi;
+        const auto wb = dg->worldBBox();
+        for (int k = 0; k < 3; k++) {
+            g.aabb_min[k] = float(wb.min()[k]); // GridVolumeMedium ctor: Vec3(bbox.min()[0], ...) (vol_grid.cu:90-94)
+            g.aabb_max[k] = float(wb.max()[k]);
+        }
+        append_channel<nanovdb::FloatGrid, 1>(dg, g.ch[CPTS_GRID_DENSITY], bricks, data);
+        { // mean of the positive voxels (compute_volume_sum, vol_grid.cu:45-80; only the unused residual estimator reads it)
+            double sum = 0;
+            size_t cnt = 0;
+            const CptsGridChannel &c = g.ch[CPTS_GRID_DENSITY];
+            for (size_t i = c.data_offset; i < data.size(); i++)
+                if (data[i] > 0)
+                    sum += data[i], cnt++;
+            g.avg_density = cnt ? float(sum / double(cnt)) : 0.f;
+        }
+        if (!alb.empty()) {
+            auto ha = nanovdb::io::readGrid(alb);
+            append_channel<nanovdb::Vec3fGrid, 3>(ha.grid<nanovdb::Vec3f>(), g.ch[CPTS_GRID_ALBEDO], bricks, data);
+        }
+        if (!ems.empty()) {
+            auto he = nanovdb::io::readGrid(ems);
+            append_channel<nanovdb::FloatGrid, 1>(he.grid<float>(), g.ch[CPTS_GRID_TEMPERATURE], bricks, data);
+        }
+        media[idx].grid = int(grids.size());
+        grids.push_back(g);
+    }
+    if (grids.empty())
+        return;
+    w.section("grids", grids.data(), sizeof(CptsGrid), grids.size());
+    w.section("grid_bricks", bricks.data(), 4, bricks.size());
+    w.section("grid_data", data.data(), 4, data.size());
+    // the emission colour table, read the way GridVolumeManager::load_black_body_data does (vol_grid.cu:304-326)
+    std::ifstream file(folder + "../data/blackbody.bin", std::ios::binary);
+    std::vector<float> bb;
+    float p[3];
+    while (file.read(reinterpret_cast<char *>(p), sizeof(p))) {
+        bb.insert(bb.end(), {p[0], p[1], p[2], 1.f});
+    }
+    w.section("blackbody", bb.data(), 16, bb.size() / 4);
+}
+
+// `mkvdb <prefix> <n>`: synthetic NanoVDB assets (the reference's .nvdb files are not distributed): a smoke puff of n
+// voxels in height over the tall box of the cornell scene, written with the vendored NanoVDB tools.
+int make_vdb(const std::string &prefix, int n) {
+    using namespace nanovdb;
+    const double height = 3.2, vs = height / n;
+    const int nx = int(std::ceil(1.9 / vs)), ny = n, nz = int(std::ceil(1.9 / vs));
+    const Vec3d origin(3.685 - 0.5 * nx * vs, 0.06, 3.515 - 0.5 * nz * vs);
+    const CoordBBox box(Coord(0), Coord(nx - 1, ny - 1, nz - 1));
+    auto shape = [=](const Coord &c, float &r2) {
+        const float x = (float(c[0]) + 0.5f) / float(nx) * 2.f - 1.f, y = (float(c[1]) + 0.5f) / float(ny) * 2.f - 1.f,
+                    z = (float(c[2]) + 0.5f) / float(nz) * 2.f - 1.f;
+        r2 = x * x + y * y + z * z;
+        return Vec3f(x, y, z);
+    };
+    auto density = [=](const Coord &c) -> float {
+        float r2;
+        const Vec3f p = shape(c, r2);
+        if (r2 >= 1.f)
+            return 0.f;
+        const float wisp = 0.55f + 0.45f * std::sin(9.f * p[0] + 2.f * std::sin(5.f * p[1])) * std::cos(7.f * p[2] + 3.f * p[1]);
+        const float v = (1.f - r2) * wisp * (0.35f + 0.65f * (0.5f - 0.5f * p[1]));
+        return v > 0.02f ? v : 0.f;
+    };
+    auto albedo = [=](const Coord &c) -> Vec3f {
+        float r2;
+        const Vec3f p = shape(c, r2);
+        if (r2 >= 1.f)
+            return Vec3f(0.f);
+        return Vec3f(0.55f + 0.4f * std::sin(4.f * p[1]), 0.6f + 0.3f * std::cos(5.f * p[0]), 0.7f + 0.25f * std::sin(3.f * p[2] + 1.f));
+    };
+    auto temperature = [=](const Coord &c) -> float {
+        float r2;
+        const Vec3f p = shape(c, r2);
+        const float q = p[0] * p[0] * 6.f + (p[1] + 0.55f) * (p[1] + 0.55f) * 3.f + p[2] * p[2] * 6.f;
+        return q < 1.f ? (1.f - q) * 0.9f : 0.f;
+    };
+    tools::build::Grid<float> gd(0.f, "density", GridClass::FogVolume);
+    gd.setTransform(vs, origin);
+    gd(density, box);
+    io::writeGrid(prefix + "_density.nvdb", tools::createNanoGrid(gd));
+    tools::build::Grid<Vec3f> ga(Vec3f(0.f), "albedo", GridClass::Unknown);
+    ga.setTransform(vs, origin);
+    ga(albedo, box);
+    io::writeGrid(prefix + "_albedo.nvdb", tools::createNanoGrid(ga));
+    tools::build::Grid<float> gt(0.f, "temperature", GridClass::FogVolume);
+    gt.setTransform(vs, origin);
+    gt(temperature, box);
+    io::writeGrid(prefix + "_temperature.nvdb", tools::createNanoGrid(gt));
+    printf("[ref_dump] wrote %s_{density,albedo,temperature}.nvdb (%d x %d x %d voxels of %.5f)\n", prefix.c_str(), nx, ny, nz, vs);
+    return 0;
 }
 
 std::unique_ptr<TracerBase> make_renderer(const Scene &scene, const std::string &mode) {
@@ -432,6 +622,8 @@ int main(int argc, char **argv) {
         return 1;
     }
     std::string cmd = argv[1], xml = argv[2];
+    if (cmd == "mkvdb")
+        return make_vdb(argv[2], argc > 3 ? atoi(argv[3]) : 64);
     CUDA_CHECK_RETURN(cudaFree(nullptr));
     ColorSpaceXYZ xyz_host;
     Scene scene(xml);

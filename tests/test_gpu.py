@@ -183,6 +183,34 @@ def test_volumetric_path_bit_exact_vs_reference_vpt(traversal):
     r.close()
 
 
+@pytest.mark.parametrize("traversal", [1, 2])
+def test_grid_media_bit_exact_vs_reference(traversal):
+    """Grid (NanoVDB) media: delta-tracking distance sampling, ratio-tracking transmittance with
+    its roulette, nearest-voxel density / albedo / temperature lookups through the grid's float map, blackbody
+    emission - on brick grids instead of the NanoVDB tree, against the reference's VPT frames (RGB, alpha, variance)."""
+    r = cpt.WavefrontRenderer(os.path.join(GOLDEN, "grid_cbox_256.cpts"), 0, 0)
+    assert r.get_option("rules") == 2
+    r.set_option("traversal", traversal)
+    r.enable_variance(True)
+    r.render_raw(False)
+    assert bit_exact_fraction(r.download_output(), load_frame("grid_cbox_256_vpt_f0001.bin")) == 1.0
+    for _ in range(15):
+        r.render_raw(False)
+    out, ref = r.download_output(), load_frame("grid_cbox_256_vpt_f0016.bin")
+    assert rel_l2(out, ref) <= 1e-4
+    assert bit_exact_fraction(out, ref) == 1.0
+    assert np.array_equal(out[..., 3].view(np.uint32), ref[..., 3].view(np.uint32))
+    var_ref = np.fromfile(os.path.join(GOLDEN, "grid_cbox_256_vpt_var_f0016.bin"), dtype=np.float32).reshape(256, 256, 1)
+    assert np.array_equal(r.download_variance().view(np.uint32), var_ref.view(np.uint32))
+    r.close()
+    # constant-albedo grid without a temperature grid (the emission jitter draw and table lookup still happen)
+    q = cpt.WavefrontRenderer(os.path.join(GOLDEN, "grid_cbox_const_256.cpts"), 0, 0)
+    q.set_option("traversal", traversal)
+    out = q.render_to_host(16, False)
+    assert bit_exact_fraction(out, load_frame("grid_cbox_const_256_vpt_f0016.bin")) == 1.0
+    q.close()
+
+
 @pytest.mark.skipif(not have_meshes(), reason="cornell meshes not on this box")
 def test_xml_loader_media_scene_statistically_equal_reference():
     """Our XML loader on the medium scene (media / phase / cullable parsing): a different BVH gives different light
