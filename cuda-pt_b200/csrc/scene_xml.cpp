@@ -12,6 +12,7 @@
 // TRIANGLE_ONLY), JPEG / HDR images, grid (NanoVDB) media.
 #include "image_io.h"
 #include "scene_host.h"
+#include "nvdb_read.h"
 
 #include <dlfcn.h>
 
@@ -572,19 +573,42 @@ int linearize(const Builder &b, int id, int depth, int cache_levels, std::vector
 // observer 360-830 nm and D65 300-830 nm at 1 nm.  The numbers ship as data/spectral_tables.bin next to the library
 // (read back at run time from the reference's own device textures by the golden-vector harness, tests/golden/README.md);
 // CPTB200_DATA overrides the directory.
-void load_spectral_tables(HostScene &out) {
+std::string data_dir() {
     std::string dir;
     if (const char *e = getenv("CPTB200_DATA"))
         dir = e;
     else {
         Dl_info info{};
-        if (dladdr(reinterpret_cast<const void *>(&load_spectral_tables), &info) && info.dli_fname) {
+        if (dladdr(reinterpret_cast<const void *>(&data_dir), &info) && info.dli_fname) {
             dir = info.dli_fname;
             const size_t slash = dir.find_last_of('/');
             dir = (slash == std::string::npos ? std::string(".") : dir.substr(0, slash)) + "/data";
         }
     }
-    const std::string path = dir + "/spectral_tables.bin";
+    return dir;
+}
+
+// emission colour of grid media by normalised temperature: 1024 x (r, g, b, 1), data/blackbody_table.bin next to the
+// library (the table the reference ships as scene/data/blackbody.bin, carried over through a scene dump)
+void load_blackbody_table(HostScene &out) {
+    const std::string path = data_dir() + "/blackbody_table.bin";
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp)
+        throw std::runtime_error("scene: grid media need the blackbody table, cannot open '" + path + "'");
+    char magic[8];
+    int32_t n[2] = {0, 0};
+    bool ok = fread(magic, 1, 8, fp) == 8 && memcmp(magic, "CPTBBDY1", 8) == 0 && fread(n, 4, 2, fp) == 2 && n[0] > 0 && n[0] <= 65536;
+    if (ok) {
+        out.blackbody.resize(size_t(n[0]));
+        ok = fread(out.blackbody.data(), sizeof(F4), out.blackbody.size(), fp) == out.blackbody.size();
+    }
+    fclose(fp);
+    if (!ok)
+        throw std::runtime_error("scene: malformed blackbody table file '" + path + "'");
+}
+
+void load_spectral_tables(HostScene &out) {
+    const std::string path = data_dir() + "/spectral_tables.bin";
     FILE *fp = fopen(path.c_str(), "rb");
     if (!fp)
         throw std::runtime_error("scene: dispersion BSDF needs the spectral tables, cannot open '" + path + "'");
@@ -766,8 +790,8 @@ void load_xml(const std::string &path, HostScene &out) {
         int idx = 1;
         for (auto md : root.children("medium")) {
             const std::string id = md->attr_or("id", ""), type = md->attr_or("type", "homogeneous");
-            if (type != "homogeneous")
-                throw std::runtime_error("scene: medium '" + id + "' is a grid (NanoVDB) volume; only homogeneous media are supported");
+            if (type != "homogeneous" && type != "grid")
+                throw std::runtime_error("scene: medium '" + id + "' has an unknown type '" + type + "'");
             int phase_id = 0;
             if (auto r = md->first("ref"))
                 if (r->attr_or("type", "") == "phase") {
@@ -794,6 +818,61 @@ void load_xml(const std::string &path, HostScene &out) {
             for (int k = 0; k < 4; k++) {
                 rec.sigma_a[k] = sa[k] * scale, rec.sigma_s[k] = ss[k] * scale; // create_homogeneous_volume (vol_homo.cu:26-32)
                 rec.phase[k] = phases[phase_id].second[k];
+            }
+            if (type == "grid") { // scene.cu:850-892, GridVolumeManager::push / to_gpu (vol_grid.cu:226-302)
+                std::string den, alb, ems;
+                for (auto c : md->children("string")) {
+                    const std::string n = c->attr_or("name", "");
+                    if (n == "density")
+                        den = folder + c->attr_or("value", "");
+                    else if (n == "albedo")
+                        alb = folder + c->attr_or("value", "");
+                    else if (n == "emission")
+                        ems = folder + c->attr_or("value", "");
+                }
+                if (den.empty())
+                    throw std::runtime_error("scene: grid medium '" + id + "' has no density grid");
+                float albedo[4] = {1, 1, 1, 1}, temp_scale = 1.f, em_scale = 1.f;
+                if (auto c = md->first("rgb")) // only the first <rgb> is looked at (scene.cu:866-868)
+                    if (c->attr_or("name", "") == "albedo")
+                        parse_color(c->attr_or("value", "1"), albedo);
+                get_float(*md, {"temp-scale", "temp_scale"}, temp_scale);
+                get_float(*md, {"emission-scale", "em-scale"}, em_scale);
+                rec.type = CPTS_MEDIUM_GRID;
+                for (int k = 0; k < 4; k++) // MediumParams(albedo, (emission scale, temperature scale, 0), phase, scale)
+                    rec.sigma_a[k] = albedo[k];
+                rec.sigma_s[0] = em_scale, rec.sigma_s[1] = temp_scale, rec.sigma_s[2] = 0.f, rec.sigma_s[3] = 1.f;
+                rec.grid = int(out.grids.size());
+                CptsGrid g{};
+                g.medium = idx;
+                g.scale = scale, g.temp_scale = temp_scale, g.em_scale = em_scale;
+                auto append = [&](const std::string &file, int ncomp, int slot) -> NvdbGrid {
+                    NvdbGrid ng;
+                    read_nvdb(file, ncomp, ng);
+                    ng.channel.brick_offset = out.grid_bricks.size();
+                    ng.channel.data_offset = out.grid_data.size();
+                    out.grid_bricks.insert(out.grid_bricks.end(), ng.bricks.begin(), ng.bricks.end());
+                    out.grid_data.insert(out.grid_data.end(), ng.data.begin(), ng.data.end());
+                    g.ch[slot] = ng.channel;
+                    return ng;
+                };
+                {
+                    const NvdbGrid d = append(den, 1, CPTS_GRID_DENSITY);
+                    g.majorant = d.value_max; // Tree::extrema (vol_grid.cu:131-133)
+                    for (int k = 0; k < 3; k++)
+                        g.aabb_min[k] = float(d.world_bbox[k]), g.aabb_max[k] = float(d.world_bbox[3 + k]);
+                    double sum = 0;
+                    size_t cnt = 0;
+                    for (float v : d.data)
+                        if (v > 0)
+                            sum += v, cnt++;
+                    g.avg_density = cnt ? float(sum / double(cnt)) : 0.f;
+                }
+                if (!alb.empty())
+                    append(alb, 3, CPTS_GRID_ALBEDO);
+                if (!ems.empty())
+                    append(ems, 1, CPTS_GRID_TEMPERATURE);
+                out.grids.push_back(g);
             }
             out.media.push_back(rec);
             medium_ids[id] = idx++;
@@ -1176,6 +1255,8 @@ void load_xml(const std::string &path, HostScene &out) {
             load_spectral_tables(out);
             break;
         }
+    if (!out.grids.empty() && out.blackbody.empty())
+        load_blackbody_table(out);
     validate_scene(out);
 }
 

@@ -24,7 +24,7 @@
  *                      host loop src/pt_impl/wf_path_tracer.cu:175-230, emitter pick tracing_func.cuh:210-225
  *   megakernel rules   src/pt_impl/megakernel_pt.cu:59-186 ("pt": lobe caps, throughput cut-off, RR from bounce 1)
  *   participating media src/pt_impl/megakernel_vpt.cu:59-456, src/volume/homogeneous.cuh:45-88,
- *                      src/volume/henyey_greenstein.cuh:28-108, src/core/medium.cuh:72-112 (homogeneous media only)
+ *                      src/volume/henyey_greenstein.cuh:28-108, src/core/medium.cuh:72-112 ; grid media src/volume/grid.cuh:51-92, src/impl/vol_grid.cu:97-211
  *
  * It is a TOLERANCE oracle: the reference runs on the GPU with --use_fast_math (approximate
  * rcp/sqrt/div, flush-to-zero), which cannot be reproduced bit-for-bit on a CPU.
@@ -157,6 +157,9 @@ struct Scene {
     std::vector<float> tris; // 12 floats per primitive
     std::vector<float> cie, d65;
     std::vector<CptsMedium> media;     // [0] = vacuum (volumetric path)
+    std::vector<CptsGrid> grids;       // grid media: brick tables + pools (cpts_format.h), emission colour table
+    std::vector<int32_t> grid_bricks;
+    std::vector<float> grid_data, blackbody;
     std::vector<CptsTexDesc> tex_desc; // image textures as the reference decoded them (float texels)
     std::vector<float> tex_data;
     float env_rot[4] = {0, 0, 0, 1};   // environment-map rotation quaternion (emitter.cuh:349-353)
@@ -233,6 +236,14 @@ Scene *load_scene(const char *path) {
             read_vec(fp, s, sc->emitters);
         else if (name == "media")
             read_vec(fp, s, sc->media);
+        else if (name == "grids")
+            read_vec(fp, s, sc->grids);
+        else if (name == "grid_bricks")
+            read_vec(fp, s, sc->grid_bricks);
+        else if (name == "grid_data")
+            read_vec(fp, s, sc->grid_data);
+        else if (name == "blackbody")
+            read_vec(fp, s, sc->blackbody);
         else if (name == "tex_desc")
             read_vec(fp, s, sc->tex_desc);
         else if (name == "tex_data")
@@ -1050,6 +1061,99 @@ V3 medium_scatter(const CptsMedium &m, V3 raydir, V4 &thp, Rng &rng, float &pdf)
     pdf = weight;
     return to_world(raydir, local);
 }
+
+// ---- grid media (src/volume/grid.cuh:51-92 nearest-voxel lookups, src/impl/vol_grid.cu:97-211 delta / ratio tracking,
+// blackbody emission).  The NanoVDB grids arrive as brick grids (include/cpts_format.h): same values, one table read.
+long long grid_voxel(const Scene &sc, const CptsGridChannel &c, V3 pos, float offset) {
+    const float x = pos.x - c.vec[0], y = pos.y - c.vec[1], z = pos.z - c.vec[2];
+    float f[3];
+    for (int r = 0; r < 3; r++) // NanoVDB math::matMult(float*): fmaf(x, m0, fmaf(y, m1, z * m2))
+        f[r] = std::fmaf(x, c.inv_mat[3 * r], std::fmaf(y, c.inv_mat[3 * r + 1], z * c.inv_mat[3 * r + 2])) + offset;
+    const int i = int(std::round(f[0])) - c.bmin[0], j = int(std::round(f[1])) - c.bmin[1], k = int(std::round(f[2])) - c.bmin[2];
+    if (unsigned(i) >= unsigned(c.nb[0] * 8) || unsigned(j) >= unsigned(c.nb[1] * 8) || unsigned(k) >= unsigned(c.nb[2] * 8))
+        return -1;
+    const int b = sc.grid_bricks[c.brick_offset + size_t((i >> 3) * c.nb[1] + (j >> 3)) * c.nb[2] + (k >> 3)];
+    if (b < 0)
+        return -1;
+    return (long long)c.data_offset + ((long long)b * 512 + (((i & 7) << 6) | ((j & 7) << 3) | (k & 7))) * c.ncomp;
+}
+float grid_scalar(const Scene &sc, const CptsGridChannel &c, V3 pos, float offset) {
+    const long long a = grid_voxel(sc, c, pos, offset);
+    return a < 0 ? c.background[0] : sc.grid_data[a];
+}
+bool grid_span(const CptsGrid &g, V3 o, V3 d, float &t_near, float &t_far) { // AABB::intersect (aabb.cuh:78-85)
+    const float od[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    t_near = -INFINITY, t_far = INFINITY;
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        const float inv = 1.f / dd[k], od_inv = od[k] * inv;
+        const float a = std::fmaf(g.aabb_min[k], inv, -od_inv), b = std::fmaf(g.aabb_max[k], inv, -od_inv);
+        lo[k] = a < b ? a : b, hi[k] = a < b ? b : a;
+    }
+    t_near = std::fmax(lo[0], std::fmax(lo[1], lo[2]));
+    t_far = std::fmin(hi[0], std::fmin(hi[1], hi[2]));
+    return t_far > t_near && t_far > 0;
+}
+MediumSampleO grid_sample(const Scene &sc, const CptsMedium &m, V3 o, V3 d, float hit_t, Rng &rng) {
+    const CptsGrid &g = sc.grids[m.grid];
+    MediumSampleO ds{v4(1.f), hit_t, 0};
+    float t_near = 0, t_far = 0;
+    if (!grid_span(g, o, d, t_near, t_far))
+        return ds;
+    t_near = std::max(0.f, t_near), t_far = std::min(t_far, hit_t);
+    const float inv_maj = 1.f / (g.scale * g.majorant);
+    float t = t_near - std::log(1.f - rng.f()) * inv_maj;
+    while (t < t_far) {
+        const V3 pos = o + d * t;
+        const float offset = rng.f() - 0.5f;
+        const float dens = grid_scalar(sc, g.ch[CPTS_GRID_DENSITY], pos, offset) * g.scale;
+        if (rng.f() < dens * inv_maj) { // real collision: throughput = albedo
+            ds.dist = t, ds.flag = 1;
+            const CptsGridChannel &ac = g.ch[CPTS_GRID_ALBEDO];
+            if (ac.ncomp == 0) {
+                ds.local_thp = {m.sigma_a[0], m.sigma_a[1], m.sigma_a[2], 1.f};
+            } else {
+                const long long a = grid_voxel(sc, ac, pos, offset);
+                ds.local_thp = a < 0 ? V4{ac.background[0], ac.background[1], ac.background[2], 1.f}
+                                     : V4{sc.grid_data[a], sc.grid_data[a + 1], sc.grid_data[a + 2], 1.f};
+            }
+            break;
+        }
+        t -= std::log(1.f - rng.f()) * inv_maj;
+    }
+    return ds;
+}
+// ratio tracking with roulette below 0.1; `far_cap` = the ray's hit_t (MAX_DIST in the NEE march)
+V4 grid_transmittance(const Scene &sc, const CptsMedium &m, V3 o, V3 d, float far_cap, Rng &rng) {
+    const CptsGrid &g = sc.grids[m.grid];
+    float Tr = 1.f, t_near = 0, t_far = 0;
+    if (grid_span(g, o, d, t_near, t_far)) {
+        t_near = std::max(0.f, t_near), t_far = std::min(t_far, far_cap);
+        const float inv_maj = 1.f / (g.scale * g.majorant);
+        float t = t_near - std::log(1.f - rng.f()) * inv_maj;
+        while (t < t_far) {
+            const V3 pos = o + d * t;
+            const float offset = rng.f() - 0.5f;
+            const float dens = grid_scalar(sc, g.ch[CPTS_GRID_DENSITY], pos, offset) * g.scale;
+            Tr *= std::max(0.f, 1.f - dens * inv_maj);
+            if (Tr < 0.1f) {
+                if (rng.f() >= Tr)
+                    return {0, 0, 0, 1};
+                Tr = 1.f;
+            }
+            t -= std::log(1.f - rng.f()) * inv_maj;
+        }
+    }
+    return {Tr, Tr, Tr, 1.f};
+}
+V4 grid_emission(const Scene &sc, const CptsMedium &m, V3 pos, Rng &rng) { // query_emission: the draw always happens
+    const CptsGrid &g = sc.grids[m.grid];
+    const float offset = rng.f() - 0.5f;
+    const float temp = g.ch[CPTS_GRID_TEMPERATURE].ncomp ? grid_scalar(sc, g.ch[CPTS_GRID_TEMPERATURE], pos, offset) : 0.f;
+    const float x = temp * g.temp_scale;
+    return V4{table_lookup(sc.blackbody, 4, 0, x), table_lookup(sc.blackbody, 4, 1, x), table_lookup(sc.blackbody, 4, 2, x),
+              table_lookup(sc.blackbody, 4, 3, x)} * g.em_scale;
+}
 struct BankStackO {
     int depth = 0, v[3] = {0, 0, 0};
     int top() const { return depth > 0 ? v[depth - 1] : 0; }
@@ -1065,7 +1169,7 @@ V3 interp_normal(const Scene &sc, int prim, float u, float v) {
     return normalize(at(0) * (1.f - u - v) + at(1) * u + at(2) * v);
 }
 // occlusion_transmittance_estimate (megakernel_vpt.cu:104-201)
-V4 nee_transmittance(const Scene &sc, V3 o, V3 d, BankStackO nested, float max_dist) {
+V4 nee_transmittance(const Scene &sc, V3 o, V3 d, BankStackO nested, float max_dist, Rng &rng) {
     float total = 0;
     V4 Tr = v4(1.f);
     while (total < max_dist) {
@@ -1083,7 +1187,8 @@ V4 nee_transmittance(const Scene &sc, V3 o, V3 d, BankStackO nested, float max_d
             nested.push(active);
             active = old;
         }
-        Tr = Tr * medium_transmittance(medium_of(sc, active), seg);
+        const CptsMedium *am = medium_of(sc, active);
+        Tr = Tr * (am && am->type == CPTS_MEDIUM_GRID ? grid_transmittance(sc, *am, o, d, MAX_DIST, rng) : medium_transmittance(am, seg));
         total += seg;
         o = o + d * seg;
     }
@@ -1122,7 +1227,7 @@ V4 trace_path_megakernel(const Scene &sc, int px, int py, int accum, int seed_of
         const CptsMedium *medium = rules == 2 ? medium_of(sc, nested.top()) : nullptr;
         MediumSampleO md{v4(1.f), h.t, 0};
         if (rules == 2) {
-            md = medium_sample(medium, h.t, rng);
+            md = medium && medium->type == CPTS_MEDIUM_GRID ? grid_sample(sc, *medium, o, d, h.t, rng) : medium_sample(medium, h.t, rng);
             thp = thp * md.local_thp;
             if ((info & 0x40000000) && md.flag == 0) { // cullable boundary: step through, no shading
                 o = o + d * md.dist;
@@ -1176,11 +1281,11 @@ V4 trace_path_megakernel(const Scene &sc, int px, int py, int accum, int seed_of
             V4 nee_tr{0, 0, 0, 1}, nee_thp;
             if (eid != 0) {
                 cnt.shadow++;
-                nee_tr = nee_transmittance(sc, so, sd, nested, dist - EPS);
+                nee_tr = nee_transmittance(sc, so, sd, nested, dist - EPS, rng);
             }
             float mis;
             if (md.flag > 0) { // medium event
-                radiance = radiance + thp * V4{0, 0, 0, 1};
+                radiance = radiance + thp * (medium->type == CPTS_MEDIUM_GRID ? grid_emission(sc, *medium, so, rng) : V4{0, 0, 0, 1});
                 const float pp = phase_eval(*medium, sd, d);
                 nee_thp = v4(pp, 1.f);
                 mis = direct_pdf + pp;

@@ -227,6 +227,22 @@ def test_xml_loader_media_scene_statistically_equal_reference():
     assert abs(ours.mean() / ref.mean() - 1) < 0.02
 
 
+@pytest.mark.skipif(not have_meshes(), reason="cornell meshes not on this box")
+def test_xml_loader_grid_scene_statistically_equal_reference():
+    """`<medium type="grid">` through our XML loader and NanoVDB reader: the grids are byte-identical to the reference's
+    (test_host), the BVH differs, so block statistics against the reference's 16-spp frame."""
+    r = cpt.WavefrontRenderer(os.path.join(SCENES, "grid_cbox_vpt_256.xml"), 0, 0)
+    assert r.get_option("rules") == 2
+    r.render_batch(64, False)
+    ours = np.minimum(r.download_output()[..., :3].astype(np.float64), 4.0)
+    r.close()
+    ref = np.minimum(load_frame("grid_cbox_256_vpt_f0016.bin")[..., :3].astype(np.float64), 4.0)
+    bo, br = ours.reshape(16, 16, 16, 16, 3).mean((1, 3)), ref.reshape(16, 16, 16, 16, 3).mean((1, 3))
+    rel = np.abs(bo - br).sum(-1) / np.maximum(br.sum(-1), 1e-2)
+    assert np.median(rel) < 0.08, np.median(rel)
+    assert abs(ours.mean() / ref.mean() - 1) < 0.03
+
+
 def test_megakernel_rules_bit_exact_vs_reference_pt():
     """`renderer type="pt"` scenes: the megakernel's termination rules (lobe caps, throughput cut-off, Russian
     roulette from bounce 1 with an exactly rounded 1/max, per-bounce NaN scrub, emission-before-NEE accumulation)

@@ -188,8 +188,81 @@ def test_xml_loader_media_match_the_reference_dump(tmp_path):
     x = tmp_path / "g.xml"
     x.write_text('<scene version="1.2"><sensor><film/></sensor><phase type="isotropic" id="p"/>'
                  '<medium type="grid" id="m"><ref type="phase" id="p"/></medium></scene>')
-    with pytest.raises(cpt.CptError, match="grid"):
+    with pytest.raises(cpt.CptError, match="no density grid"):
         cpt.Scene(str(x))
+
+
+VOLUMES = os.path.join(os.path.dirname(SCENES), "volume")
+
+
+@needs_meshes
+@pytest.mark.parametrize("xml,gold", [("grid_cbox_vpt_256.xml", "grid_cbox_256.cpts"), ("grid_cbox_const_vpt_256.xml", "grid_cbox_const_256.cpts")])
+def test_xml_loader_grid_media_match_the_reference_dump(tmp_path, xml, gold):
+    """Our NanoVDB reader (nvdb_read.cpp: leaves -> bricks, float map, root extrema, world box) + `<medium type="grid">`
+    parsing against what the reference's loader + NanoVDB's own accessor produced for the same files: byte-identical
+    media records, grid records (incl. majorant, box, mean density), brick tables, brick pools and blackbody table."""
+    sc = cpt.Scene(os.path.join(SCENES, xml))
+    out = tmp_path / "g.cpts"
+    sc.save(str(out))
+    a, b = read_cpts(str(out)), read_cpts(os.path.join(GOLDEN, gold))
+    for k in ("media", "grids", "grid_bricks", "grid_data", "blackbody"):
+        assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
+
+
+def test_cpts_grid_sections_are_validated(tmp_path):
+    """A brick number past the end of the pool, or a grid record pointing past the brick table, is refused at load."""
+    import struct
+    data = bytearray(open(os.path.join(GOLDEN, "grid_cbox_const_256.cpts"), "rb").read())
+    def section(name):
+        n, = struct.unpack_from("<I", data, 8)
+        off = 16
+        for _ in range(n):
+            nm = bytes(data[off:off + 24]).split(b"\0")[0].decode()
+            elem, _r, count = struct.unpack_from("<IIQ", data, off + 24)
+            off += 40
+            if nm == name:
+                return off, elem * count
+            off += elem * count + (16 - (elem * count) % 16) % 16
+        raise KeyError(name)
+    off, nbytes = section("grid_bricks")
+    bricks = np.frombuffer(bytes(data[off:off + nbytes]), dtype=np.int32)
+    first = int(np.nonzero(bricks >= 0)[0][0])
+    bad = bytearray(data)
+    struct.pack_into("<i", bad, off + 4 * first, 1 << 20)
+    p = tmp_path / "bad.cpts"
+    p.write_bytes(bytes(bad))
+    with pytest.raises(cpt.CptError, match="grid brick outside"):
+        cpt.Scene(str(p))
+    goff, _ = section("grids")
+    bad = bytearray(data)
+    struct.pack_into("<Q", bad, goff + 56 + 88, 1 << 40)  # density channel's brick_offset
+    p.write_bytes(bytes(bad))
+    with pytest.raises(cpt.CptError, match="brick table outside"):
+        cpt.Scene(str(p))
+
+
+def test_nvdb_reader_rejects_what_it_cannot_read(tmp_path):
+    src = open(os.path.join(VOLUMES, "puff64_density.nvdb"), "rb").read()
+    def scene_with(data, kind="density"):
+        (tmp_path / "v.nvdb").write_bytes(data)
+        x = tmp_path / "g.xml"
+        x.write_text('<scene version="1.2"><sensor><film/></sensor><phase type="isotropic" id="p"/><medium type="grid" id="m">'
+                     '<string name="density" value="v.nvdb"/><ref type="phase" id="p"/></medium></scene>')
+        return str(x)
+    with pytest.raises(cpt.CptError, match="truncated"):
+        cpt.Scene(scene_with(src[:100000]))
+    with pytest.raises(cpt.CptError, match="not a NanoVDB file"):
+        cpt.Scene(scene_with(b"\0" * 8 + src[8:]))
+    zipped = bytearray(src)
+    zipped[16 + 168] = 1  # metadata codec = ZIP
+    with pytest.raises(cpt.CptError, match="compressed"):
+        cpt.Scene(scene_with(bytes(zipped)))
+    with pytest.raises(cpt.CptError, match="expected a float grid"):
+        cpt.Scene(scene_with(open(os.path.join(VOLUMES, "puff64_albedo.nvdb"), "rb").read()))
+    old = bytearray(src)
+    old[8:12] = (31 << 21).to_bytes(4, "little")
+    with pytest.raises(cpt.CptError, match="format version 31"):
+        cpt.Scene(scene_with(bytes(old)))
 
 
 def test_image_errors(tmp_path):

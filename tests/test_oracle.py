@@ -175,6 +175,24 @@ def test_oracle_volumetric_rules_pinned_to_reference():
         sc.render(1, rules=3)
 
 
+def test_oracle_grid_media_pinned_to_reference():
+    """Grid media in the oracle (delta tracking, ratio tracking + roulette, nearest-voxel lookups through the float map,
+    blackbody table; vol_grid.cu:97-211) against the reference's VPT frames of the two grid scenes."""
+    sc = oracle.OracleScene(os.path.join(GOLDEN, "grid_cbox_256.cpts"))
+    one, _ = sc.render(1, rules=2)
+    ref1 = load_frame("grid_cbox_256_vpt_f0001.bin")
+    d1 = np.abs(one[..., :3] - ref1[..., :3]).max(-1)
+    assert (d1 < 1e-3 * np.maximum(ref1[..., :3].max(-1), 1e-3)).mean() > 0.98
+    for name, lo, hi in (("grid_cbox_256", 9.0, 9.6), ("grid_cbox_const_256", 9.3, 9.9)):
+        sc = oracle.OracleScene(os.path.join(GOLDEN, name + ".cpts"))
+        s, st = sc.render(16, rules=2)
+        ref, mean = load_frame(name + "_vpt_f0016.bin"), s / 16
+        assert np.median(np.abs(mean[..., :3] - ref[..., :3]).max(-1)) < 1e-5
+        assert abs(mean[..., :3].mean() / ref[..., :3].mean() - 1) < 1e-3
+        assert rel_l2(mean, ref) < 1e-2
+        assert lo < st["rays"] / st["samples"] < hi
+
+
 def test_oracle_rows_subset_matches_full():
     sc = oracle.OracleScene(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"))
     full, _ = sc.render(2)

@@ -2,7 +2,8 @@
 import struct
 import numpy as np
 
-DT = {"config": np.int32, "camera": np.float32, "obj_idxs": np.int32, "emitter_prims": np.int32, "d65_spd": np.float32}
+DT = {"config": np.int32, "camera": np.float32, "obj_idxs": np.int32, "emitter_prims": np.int32, "d65_spd": np.float32,
+      "grid_bricks": np.int32, "grid_data": np.float32}
 
 
 def read_cpts(path):
@@ -21,7 +22,7 @@ def read_cpts(path):
             arr = np.frombuffer(raw, dtype=DT[name]).copy()
         elif name in ("cache_nodes",):
             arr = np.frombuffer(raw, dtype=np.uint32).reshape(-1, 4).copy()
-        elif name in ("bsdfs", "emitters", "objects", "tex_desc"):
+        elif name in ("bsdfs", "emitters", "objects", "tex_desc", "media", "grids"):
             arr = np.frombuffer(raw, dtype=np.uint8).reshape(count, elem).copy()
         else:
             arr = np.frombuffer(raw, dtype=np.float32).reshape(count, elem // 4).copy()
