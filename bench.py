@@ -36,10 +36,35 @@ METRIC = "Mrays/s (primary + closest-hit + shadow traversals), wavefront PT, 192
 
 WORKLOADS = {"c1": "vader_wfpt_1080p.xml",       # BASELINE config 1 (default): vader geometry, no image assets
              "c2": "vader_tex_wfpt_1080p.xml",    # texture-heavy stand-in: + 2K glossy/roughness/normal/albedo maps + envmap
-             "vpt": "medium_cbox_vpt_1080p.xml"}  # participating media (homogeneous), volumetric path tracer
+             "vpt": "medium_cbox_vpt_1080p.xml",  # participating media (homogeneous), volumetric path tracer
+             "grid": "grid_cbox_vpt_1080p.xml"}   # BASELINE config 4 stand-in: grid (NanoVDB) medium, 304x512x304 voxels
+
+
+def ensure_volumes():
+    """The grid workload's .nvdb files (~0.5 GB) are synthetic and too large to ship: written on first use with the
+    vendored NanoVDB tools of the reference harness (`ref_dump mkvdb`, no GPU involved).  Both arms read the same files."""
+    vol = os.path.join(ROOT, "scenes", "volume")
+    done = os.path.join(vol, "puff512.done")
+    if os.path.exists(done):
+        return
+    if int(os.environ.get("RANK", "0")) != 0:  # rank 0 writes them
+        t0 = time.time()
+        while not os.path.exists(done):
+            if time.time() - t0 > 300:
+                raise SystemExit("bench.py --scene grid: timed out waiting for rank 0 to write the volumes")
+            time.sleep(0.5)
+        return
+    tool = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+    if not os.path.exists(tool):
+        raise SystemExit("bench.py --scene grid: scenes/volume/puff512_*.nvdb missing and oracle/_ref/ref_dump (which writes them) not built")
+    os.makedirs(vol, exist_ok=True)
+    subprocess.run([tool, "mkvdb", os.path.join(vol, "puff512"), "512"], check=True, stdout=subprocess.DEVNULL)
+    open(done, "w").write("ok\n")
 
 
 def pick_scene(arg):
+    if arg == "grid":
+        ensure_volumes()
     if arg in WORKLOADS:
         return os.path.join(ROOT, "scenes", "xml", WORKLOADS[arg]), WORKLOADS[arg]
     if arg:
@@ -140,7 +165,8 @@ def run_reference(args, scene, workload):
     ref_dump = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
     base = {"metric": METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "impl": "reference",
-            "data": ("cornell box geometry bundled with the reference + three homogeneous media" if "vpt" in workload else
+            "data": ("cornell box geometry bundled with the reference + a synthetic 304x512x304 NanoVDB smoke volume (density, albedo, temperature grids) + two homogeneous media" if "grid" in workload else
+                     "cornell box geometry bundled with the reference + three homogeneous media" if "vpt" in workload else
                      "vader geometry bundled with the reference; textures/envmap not shipped upstream, removed" if "tex" not in workload else
                      "vader geometry + seeded placeholder 2K textures and environment map (tools/make_assets.py)"),
             "config": {"workload": workload, "width": 1920, "height": 1080, "spp_per_step": S}}
@@ -360,7 +386,10 @@ def main():
 
     out = {"metric": METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (args.split == "tiles" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
-           "data": ("cornell box geometry bundled with the reference + three homogeneous media (the reference's medium-cbox scene); fixed seeds"
+           "data": ("cornell box geometry bundled with the reference + a synthetic 304x512x304 NanoVDB smoke volume (density, albedo, temperature "
+                    "grids; `ref_dump mkvdb`) read by our own .nvdb reader + two homogeneous media; fixed seeds"
+                    if "grid" in workload else
+                    "cornell box geometry bundled with the reference + three homogeneous media (the reference's medium-cbox scene); fixed seeds"
                     if "vpt" in workload else
                     "vader geometry bundled with the reference + seeded placeholder 2K textures and environment map (tools/make_assets.py); fixed seeds"
                     if "tex" in workload else
