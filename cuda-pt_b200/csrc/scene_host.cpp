@@ -285,9 +285,8 @@ void validate_scene(const HostScene &sc) {
                 fail("grid medium without a matching entry in the 'grids' section");
         } else if (sc.media[i].type != CPTS_MEDIUM_HOMOGENEOUS)
             fail("unknown medium type");
-        if (sc.media[i].phase_type != CPTS_PHASE_ISOTROPIC && sc.media[i].phase_type != CPTS_PHASE_HG &&
-            sc.media[i].phase_type != CPTS_PHASE_DUO_HG)
-            fail("unsupported phase function (isotropic, hg and hg-duo are)");
+        if (sc.media[i].phase_type < CPTS_PHASE_ISOTROPIC || sc.media[i].phase_type > CPTS_PHASE_SGGX)
+            fail("unknown phase function type");
     }
     for (const auto &g : sc.grids) { // every brick table and every brick pool must lie inside its section
         if (g.ch[CPTS_GRID_DENSITY].ncomp != 1)

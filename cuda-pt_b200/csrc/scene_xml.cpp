@@ -781,7 +781,7 @@ void load_xml(const std::string &path, HostScene &out) {
             }
             rec.first = CPTS_PHASE_DUO_HG, rec.second = {g1, g2, w, 1.f}; // Vec4(g1, g2, weight): w = 1
         } else if (type == "rayleigh") {
-            throw std::runtime_error("scene: the Rayleigh phase function is not supported (isotropic, hg, hg-duo are)");
+            rec.first = CPTS_PHASE_RAYLEIGH;
         } // "isotropic", "sggx" and unknown types fall back to isotropic upstream
         phase_ids[ph->attr_or("id", "")] = int(phases.size());
         phases.push_back(rec);

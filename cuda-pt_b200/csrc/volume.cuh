@@ -40,7 +40,7 @@ struct GridPOD {
 };
 enum : int { MEDIUM_HOMOGENEOUS = 0, MEDIUM_GRID = 1 };
 
-enum : int { PHASE_NULL = 0, PHASE_ISOTROPIC = 1, PHASE_HG = 2, PHASE_DUO_HG = 3 };
+enum : int { PHASE_NULL = 0, PHASE_ISOTROPIC = 1, PHASE_HG = 2, PHASE_DUO_HG = 3, PHASE_RAYLEIGH = 4, PHASE_SGGX = 5 };
 
 // ---- nested volumes: one 4-byte bank, x = depth, y/z/w = medium ids (megakernel_vpt.cu:59-94) ----
 struct BankStack {
@@ -235,7 +235,9 @@ PT_DEV V3 hg_sample(Rng &rng, float g, float g2) {
 }
 PT_DEV float phase_eval(const MediumPOD &m, V3 indir, V3 outdir) {
     switch (m.phase_type) {
+    case PHASE_SGGX: // "works the same as IsotropicPhase" upstream (sggx.cuh:30-45)
     case PHASE_ISOTROPIC: return kInvPi * 0.25f;
+    case PHASE_RAYLEIGH: return 3.f / 16.f * kInvPi * (1.f + dot(indir, outdir)); // rayleigh.cuh:35-37
     case PHASE_HG: return hg_phase(dot(indir, outdir), m.phase.x, sq_rn(m.phase.x));
     case PHASE_DUO_HG: {
         const float c = dot(indir, outdir);
@@ -251,9 +253,20 @@ PT_DEV V3 medium_scatter(const MediumPOD &m, V3 raydir, V4 &throughput, Rng &rng
     V3 local{0, 0, 1};
     float weight = 1.f;
     switch (m.phase_type) {
+    case PHASE_SGGX:
     case PHASE_ISOTROPIC: {
         float dummy = 0;
         local = sample_sphere_uniform(rng.next2d(), dummy);
+        break;
+    }
+    case PHASE_RAYLEIGH: { // analytic inversion, weight 1 (rayleigh.cuh:39-48)
+        const V2 uv = rng.next2d();
+        const float u_rs = uv.x * 2.f - 1.f;
+        const float cos_theta = cbrtf(2.f * u_rs + sqrtf(4.f * u_rs * u_rs + 1.f));
+        const float sin_theta = sqrtf(fmaxf(0, 1 - cos_theta * cos_theta));
+        float sin_phi = 0, cos_phi = 0;
+        sincospif(2.f * uv.y, &sin_phi, &cos_phi);
+        local = V3{cos_phi * sin_theta, sin_phi * sin_theta, cos_theta};
         break;
     }
     case PHASE_HG: local = hg_sample(rng, m.phase.x, sq_rn(m.phase.x)); break;

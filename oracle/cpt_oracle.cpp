@@ -1036,7 +1036,9 @@ V3 hg_sample(Rng &rng, float g) {
 float phase_eval(const CptsMedium &m, V3 a, V3 b) {
     const float c = dot(a, b);
     switch (m.phase_type) {
+    case CPTS_PHASE_SGGX: // same as isotropic upstream (sggx.cuh:30-45)
     case CPTS_PHASE_ISOTROPIC: return INV_PI * 0.25f;
+    case CPTS_PHASE_RAYLEIGH: return 3.f / 16.f * INV_PI * (1.f + c); // rayleigh.cuh:35-37
     case CPTS_PHASE_HG: return hg_phase(c, m.phase[0]);
     case CPTS_PHASE_DUO_HG: return hg_phase(c, m.phase[0]) * m.phase[2] + hg_phase(c, m.phase[1]) * (1.f - m.phase[2]);
     default: return 0.f;
@@ -1045,8 +1047,12 @@ float phase_eval(const CptsMedium &m, V3 a, V3 b) {
 V3 medium_scatter(const CptsMedium &m, V3 raydir, V4 &thp, Rng &rng, float &pdf) {
     V3 local{0, 0, 1};
     float weight = 1.f;
-    if (m.phase_type == CPTS_PHASE_ISOTROPIC) {
+    if (m.phase_type == CPTS_PHASE_ISOTROPIC || m.phase_type == CPTS_PHASE_SGGX) {
         const float ux = rng.f(), uy = rng.f(), ct = 2.f * ux - 1.f, st = std::sqrt(1.f - ct * ct);
+        local = {std::cos(2.f * uy * PI) * st, std::sin(2.f * uy * PI) * st, ct};
+    } else if (m.phase_type == CPTS_PHASE_RAYLEIGH) { // rayleigh.cuh:39-48, weight 1
+        const float ux = rng.f(), uy = rng.f(), u = ux * 2.f - 1.f;
+        const float ct = std::cbrt(2.f * u + std::sqrt(4.f * u * u + 1.f)), st = std::sqrt(std::max(0.f, 1.f - ct * ct));
         local = {std::cos(2.f * uy * PI) * st, std::sin(2.f * uy * PI) * st, ct};
     } else if (m.phase_type == CPTS_PHASE_HG) {
         local = hg_sample(rng, m.phase[0]);

@@ -14,4 +14,4 @@ $R render $X/texroom_wfpt_256.xml gpurun_out/ref/texroom_256 wfpt 0 1,64 > gpuru
 $R render $X/medium_cbox_vpt_256.xml gpurun_out/ref/medium_cbox_256 vpt 0 1,64 > gpurun_out/ref/medium.log 2>&1
 ls -la gpurun_out/ref | head -60
 $R render $X/grid_cbox_vpt_256.xml gpurun_out/ref/grid_cbox_256 vpt 0 1,16 > gpurun_out/ref/grid.log 2>&1
-$R render $X/grid_cbox_const_vpt_256.xml gpurun_out/ref/grid_cbox_const_256 vpt 0 16 >> gpurun_out/ref/grid.log 2>&1
+$R render $X/grid_cbox_rayleigh_vpt_256.xml gpurun_out/ref/grid_cbox_rayleigh_256 vpt 0 16 >> gpurun_out/ref/grid.log 2>&1

@@ -203,11 +203,12 @@ def test_grid_media_bit_exact_vs_reference(traversal):
     var_ref = np.fromfile(os.path.join(GOLDEN, "grid_cbox_256_vpt_var_f0016.bin"), dtype=np.float32).reshape(256, 256, 1)
     assert np.array_equal(r.download_variance().view(np.uint32), var_ref.view(np.uint32))
     r.close()
-    # constant-albedo grid without a temperature grid (the emission jitter draw and table lookup still happen)
-    q = cpt.WavefrontRenderer(os.path.join(GOLDEN, "grid_cbox_const_256.cpts"), 0, 0)
+    # constant-albedo grid without a temperature grid (the emission jitter draw and table lookup still happen), Rayleigh
+    # phase function, "sggx" falling back to isotropic
+    q = cpt.WavefrontRenderer(os.path.join(GOLDEN, "grid_cbox_rayleigh_256.cpts"), 0, 0)
     q.set_option("traversal", traversal)
     out = q.render_to_host(16, False)
-    assert bit_exact_fraction(out, load_frame("grid_cbox_const_256_vpt_f0016.bin")) == 1.0
+    assert bit_exact_fraction(out, load_frame("grid_cbox_rayleigh_256_vpt_f0016.bin")) == 1.0
     q.close()
 
 

@@ -196,7 +196,7 @@ VOLUMES = os.path.join(os.path.dirname(SCENES), "volume")
 
 
 @needs_meshes
-@pytest.mark.parametrize("xml,gold", [("grid_cbox_vpt_256.xml", "grid_cbox_256.cpts"), ("grid_cbox_const_vpt_256.xml", "grid_cbox_const_256.cpts")])
+@pytest.mark.parametrize("xml,gold", [("grid_cbox_vpt_256.xml", "grid_cbox_256.cpts"), ("grid_cbox_rayleigh_vpt_256.xml", "grid_cbox_rayleigh_256.cpts")])
 def test_xml_loader_grid_media_match_the_reference_dump(tmp_path, xml, gold):
     """Our NanoVDB reader (nvdb_read.cpp: leaves -> bricks, float map, root extrema, world box) + `<medium type="grid">`
     parsing against what the reference's loader + NanoVDB's own accessor produced for the same files: byte-identical
@@ -212,7 +212,7 @@ def test_xml_loader_grid_media_match_the_reference_dump(tmp_path, xml, gold):
 def test_cpts_grid_sections_are_validated(tmp_path):
     """A brick number past the end of the pool, or a grid record pointing past the brick table, is refused at load."""
     import struct
-    data = bytearray(open(os.path.join(GOLDEN, "grid_cbox_const_256.cpts"), "rb").read())
+    data = bytearray(open(os.path.join(GOLDEN, "grid_cbox_rayleigh_256.cpts"), "rb").read())
     def section(name):
         n, = struct.unpack_from("<I", data, 8)
         off = 16

@@ -183,7 +183,7 @@ def test_oracle_grid_media_pinned_to_reference():
     ref1 = load_frame("grid_cbox_256_vpt_f0001.bin")
     d1 = np.abs(one[..., :3] - ref1[..., :3]).max(-1)
     assert (d1 < 1e-3 * np.maximum(ref1[..., :3].max(-1), 1e-3)).mean() > 0.98
-    for name, lo, hi in (("grid_cbox_256", 9.0, 9.6), ("grid_cbox_const_256", 9.3, 9.9)):
+    for name, lo, hi in (("grid_cbox_256", 9.0, 9.6), ("grid_cbox_rayleigh_256", 9.3, 9.9)):
         sc = oracle.OracleScene(os.path.join(GOLDEN, name + ".cpts"))
         s, st = sc.render(16, rules=2)
         ref, mean = load_frame(name + "_vpt_f0016.bin"), s / 16
