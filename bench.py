@@ -37,7 +37,8 @@ METRIC = "Mrays/s (primary + closest-hit + shadow traversals), wavefront PT, 192
 WORKLOADS = {"c1": "vader_wfpt_1080p.xml",       # BASELINE config 1 (default): vader geometry, no image assets
              "c2": "vader_tex_wfpt_1080p.xml",    # texture-heavy stand-in: + 2K glossy/roughness/normal/albedo maps + envmap
              "vpt": "medium_cbox_vpt_1080p.xml",  # participating media (homogeneous), volumetric path tracer
-             "grid": "grid_cbox_vpt_1080p.xml"}   # BASELINE config 4 stand-in: grid (NanoVDB) medium, 304x512x304 voxels
+             "grid": "grid_cbox_vpt_1080p.xml",   # BASELINE config 4 stand-in: grid (NanoVDB) medium, 304x512x304 voxels
+             "fog": "vader_fog_vpt_1080p.xml"}    # volumetric path on the 320k-triangle vader geometry inside a thin fog
 
 
 def ensure_volumes():
@@ -166,6 +167,7 @@ def run_reference(args, scene, workload):
     base = {"metric": METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "impl": "reference",
             "data": ("cornell box geometry bundled with the reference + a synthetic 304x512x304 NanoVDB smoke volume (density, albedo, temperature grids) + two homogeneous media" if "grid" in workload else
+                     "vader geometry bundled with the reference inside a homogeneous fog bounded by a cullable box" if "fog" in workload else
                      "cornell box geometry bundled with the reference + three homogeneous media" if "vpt" in workload else
                      "vader geometry bundled with the reference; textures/envmap not shipped upstream, removed" if "tex" not in workload else
                      "vader geometry + seeded placeholder 2K textures and environment map (tools/make_assets.py)"),
@@ -389,6 +391,8 @@ def main():
            "data": ("cornell box geometry bundled with the reference + a synthetic 304x512x304 NanoVDB smoke volume (density, albedo, temperature "
                     "grids; `ref_dump mkvdb`) read by our own .nvdb reader + two homogeneous media; fixed seeds"
                     if "grid" in workload else
+                    "vader geometry bundled with the reference inside a homogeneous fog bounded by a cullable box (scenes/assets/fogbox); fixed seeds"
+                    if "fog" in workload else
                     "cornell box geometry bundled with the reference + three homogeneous media (the reference's medium-cbox scene); fixed seeds"
                     if "vpt" in workload else
                     "vader geometry bundled with the reference + seeded placeholder 2K textures and environment map (tools/make_assets.py); fixed seeds"

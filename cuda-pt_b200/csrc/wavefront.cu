@@ -59,7 +59,8 @@ struct PathState {
     float4 *isect; // n.xyz, half2 uv
     uint2 *rng;
     float *pdf;
-    uint32_t *lobes; // megakernel-rules mode: diffuse | specular << 8 | transmit << 16 bounce counters
+    uint32_t *lobes; // megakernel-rules mode: diffuse | specular << 8 | transmit << 16 (| volume << 24) bounce counters
+    uint2 *vstate;   // volumetric wavefront: x = nested-volume BankStack, y = emitter id | medium-event flag << 8
 };
 
 struct BatchParams {
@@ -150,6 +151,8 @@ __global__ void __launch_bounds__(kBlock)
             st.rng[slot] = make_uint2(rng.d0, rng.d1);
             if (bp.rules)
                 st.lobes[slot] = 0u;
+            if (bp.rules == 2)
+                st.vstate[slot] = make_uint2(BankStack::make(sc.cam_vol).bits, 0u);
         }
         const Hit h = closest_hit<MODE>(sc, s_cached, o, d, inside); // all 32 lanes call (warp-synchronous modes)
         if (inside) {
@@ -1006,6 +1009,251 @@ __global__ void __launch_bounds__(kBlock, VPT_MIN_BLOCKS) k_vpt(DevScene sc, Cam
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Volumetric path, wavefront form: the loop body of render_vpt_kernel (megakernel_vpt.cu:242-452) cut
+// at its two traversal points, so that every kernel runs one kind of work over a compacted queue:
+//   k_raygen / k_trace      closest hit of bounce b (miss: environment, path ends)                     [traversal]
+//   k_vpt_pre               distance sampling in the current medium (delta tracking for grids); cullable boundary
+//                           reached -> step through and go straight to the next trace; otherwise pick the emitter and
+//                           the point on it, build the shadow ray                                       [no traversal]
+//   k_vpt_march             transmittance march along the shadow ray (bounded closest hits + medium
+//                           transmittance / ratio tracking)                                             [traversal]
+//   k_vpt_post              medium event: emission, phase function; surface event: emitter hit with MIS, BSDF; NEE
+//                           contribution, lobe caps, throughput cut-off, Russian roulette                [no traversal]
+// Each path draws from its own sampler in the megakernel's order (distance sampling, emitter pick, march, emission
+// jitter, scattering, roulette), so the frames are the megakernel's frames bit for bit.
+// ------------------------------------------------------------------------------------------------
+struct VptBufs {
+    float4 *sh_o;  // shadow origin = event position, emit_len_mis (distance to the sampled emitter point)
+    float4 *sh_d;  // shadow direction, direct_pdf
+    float4 *dcomp; // emitter sample's radiance term (direct_comp)
+    float4 *tr;    // result of the march
+};
+
+__global__ void __launch_bounds__(kBlock, SHADE_MIN_BLOCKS)
+    k_vpt_pre(DevScene sc, PathState st, VptBufs vb, const uint32_t *__restrict__ queue, const int *__restrict__ q_count, int *work,
+              uint32_t *q_shade, int *q_shade_count, uint32_t *q_march, int *q_march_count, uint32_t *q_next, int *q_next_count) {
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        bool to_shade = false, to_march = false, to_next = false;
+        uint32_t slot = 0;
+        if (i < count) {
+            slot = queue[i];
+            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            V3 o = xyz(ro);
+            const V3 d = xyz(rd);
+            const float hit_t = ro.w;
+            const uint32_t tag = __float_as_uint(rd.w);
+            const int prim = int(tag & TAG_INDEX);
+            const int obj_info = __ldg(sc.obj_idxs + prim);
+            const int hit_med_idx = (obj_info >> 20) & 0xff, object_id = obj_info & 0x000fffff;
+            uint2 vs = st.vstate[slot];
+            BankStack nested{vs.x};
+            const uint2 rs = st.rng[slot];
+            Rng rng{rs.x, rs.y};
+            V4 throughput = from_f4(st.thp[slot]);
+            const MediumPOD &medium = sc.media[nested.top()];
+            const MediumSample md =
+                medium.type == MEDIUM_GRID ? grid_sample(sc.grids[medium.grid], medium, o, d, hit_t, rng) : medium_sample(medium, hit_t, rng);
+            throughput *= md.local_thp;
+            st.thp[slot] = to_f4(throughput);
+            const bool alpha_mask = (obj_info & 0x40000000) == 0x40000000;
+            if (alpha_mask && md.flag == 0) { // cullable boundary reached: step through it, no NEE, next bounce
+                o = advance(o, d, md.dist);
+                const float4 it = st.isect[slot];
+                if (dot(d, xyz(it)) > 0)
+                    nested.pop();
+                else
+                    nested.push(hit_med_idx);
+                st.ray_o[slot] = make_float4(o.x, o.y, o.z, hit_t);
+                st.vstate[slot] = make_uint2(nested.bits, 0u);
+                st.rng[slot] = make_uint2(rng.d0, rng.d1);
+                to_next = true;
+            } else {
+                const ObjectPOD ob = sc.objects[object_id];
+                const int emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+                V4 direct_comp = splat4(0, 1);
+                float direct_pdf = 1;
+                const int no_sample = md.flag > 0 ? 0 : emitter_id; // the hit emitter is excluded only for surface events
+                int num = sc.num_emitters;
+                num -= no_sample > 0 && num > 1;
+                uint32_t emit_id = (rng.next_u32() % uint32_t(num)) + 1;
+                emit_id += emit_id >= uint32_t(no_sample) && no_sample > 0;
+                direct_pdf = 1.f / float(num);
+                emit_id = emit_id * uint32_t(no_sample == 0 || num > 1);
+                const EmitterPOD &em = sc.emitters[emit_id];
+                const ObjectPOD eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
+                direct_pdf *= eo.inv_area;
+                int emit_prim = int(rng.next_u32() % uint32_t(eo.prim_num)) + eo.prim_offset;
+                emit_prim = __ldg(sc.emitter_prims + emit_prim);
+                const V3 so = advance(o, d, md.dist);
+                V3 sd = emitter_sample(sc, em, so, V3{0, 0, 1}, direct_comp, direct_pdf, rng.next2d(), emit_prim) - so;
+                const float emit_len_mis = length(sd);
+                sd *= __frcp_rn(emit_len_mis);
+                vb.sh_o[slot] = make_float4(so.x, so.y, so.z, emit_len_mis);
+                vb.sh_d[slot] = make_float4(sd.x, sd.y, sd.z, direct_pdf);
+                vb.dcomp[slot] = to_f4(direct_comp);
+                st.vstate[slot] = make_uint2(nested.bits, emit_id | (md.flag << 8));
+                st.rng[slot] = make_uint2(rng.d0, rng.d1);
+                to_shade = true;
+                to_march = emit_id != 0;
+            }
+        }
+        warp_push(q_next, q_next_count, to_next, slot, lane);
+        warp_push(q_shade, q_shade_count, to_shade, slot, lane);
+        warp_push(q_march, q_march_count, to_march, slot, lane);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_vpt_march(DevScene sc, PathState st, VptBufs vb, const uint32_t *__restrict__ queue,
+                                                      const int *__restrict__ q_count, int *work, unsigned long long *stats) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    unsigned int n_segments = 0;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        if (i < count) {
+            const uint32_t slot = queue[i];
+            const float4 a = vb.sh_o[slot], b = vb.sh_d[slot];
+            const uint2 rs = st.rng[slot];
+            Rng rng{rs.x, rs.y};
+            const V4 tr = nee_transmittance<MODE>(sc, s_cached, xyz(a), xyz(b), BankStack{st.vstate[slot].x}, a.w - kEps, rng, n_segments);
+            vb.tr[slot] = to_f4(tr);
+            st.rng[slot] = make_uint2(rng.d0, rng.d1);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1)
+        n_segments += __shfl_down_sync(0xffffffffu, n_segments, off);
+    if (lane == 0 && n_segments)
+        atomicAdd(stats + 3, (unsigned long long)n_segments);
+}
+
+__global__ void __launch_bounds__(kBlock, SHADE_MIN_BLOCKS)
+    k_vpt_post(DevScene sc, PathState st, VptBufs vb, BatchParams bp, const uint32_t *__restrict__ queue, const int *__restrict__ q_count,
+               int *work, uint32_t *q_next, int *q_next_count, int b) {
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        bool alive = false;
+        uint32_t slot = 0;
+        if (i < count) {
+            slot = queue[i];
+            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            V3 d = xyz(rd);
+            const float hit_t = ro.w;
+            const uint32_t tag = __float_as_uint(rd.w);
+            const int prim = int(tag & TAG_INDEX);
+            bool delta = (tag & TAG_DELTA) != 0;
+            const int obj_info = __ldg(sc.obj_idxs + prim);
+            const int hit_med_idx = (obj_info >> 20) & 0xff, object_id = obj_info & 0x000fffff;
+            const ObjectPOD ob = sc.objects[object_id];
+            const int material_id = ob.bsdf_emitter >> 16, emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+            const bool hit_emitter = emitter_id > 0;
+            const uint2 vs = st.vstate[slot];
+            BankStack nested{vs.x};
+            const uint32_t emit_id = vs.y & 0xffu;
+            const bool medium_event = (vs.y >> 8) & 1u;
+            const uint2 rs = st.rng[slot];
+            Rng rng{rs.x, rs.y};
+            V4 throughput = from_f4(st.thp[slot]), radiance = from_f4(st.L[slot]);
+            float emission_weight = st.pdf[slot];
+            const float4 so4 = vb.sh_o[slot], sd4 = vb.sh_d[slot];
+            const V3 so = xyz(so4), sd = xyz(sd4);
+            float emit_len_mis = so4.w;
+            const float direct_pdf = sd4.w;
+            const V4 direct_comp = from_f4(vb.dcomp[slot]);
+            const V4 nee_tr = emit_id != 0 ? from_f4(vb.tr[slot]) : splat4(0, 1);
+            const MediumPOD &medium = sc.media[nested.top()];
+            const EmitterPOD &em = sc.emitters[emit_id];
+            int lobe = LOBE_NONE;
+            V4 nee_thp;
+            if (medium_event) {
+                radiance += throughput * (medium.type == MEDIUM_GRID ? grid_emission(sc.grids[medium.grid], sc.blackbody, so, rng) : splat4(0, 1));
+                const float phase_pdf = phase_eval(medium, sd, d);
+                nee_thp = splat4(phase_pdf, 1.f);
+                emit_len_mis = direct_pdf + phase_pdf;
+                lobe = LOBE_VOLUME;
+                d = medium_scatter(medium, d, throughput, rng, emission_weight);
+                delta = false;
+            } else {
+                const float4 it = st.isect[slot];
+                const Material &mat = sc.mats[material_id];
+                emission_weight = emission_weight / (emission_weight + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, hit_t) *
+                                                                           hit_emitter * (b > 0) * (!delta));
+                {
+                    const V4 tl = throughput * emitter_eval(sc.emitters[emitter_id], d, it, true);
+                    radiance = V4{fmaf(tl.x, emission_weight, radiance.x), fmaf(tl.y, emission_weight, radiance.y),
+                                  fmaf(tl.z, emission_weight, radiance.z), fmaf(tl.w, emission_weight, radiance.w)};
+                }
+                emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
+                nee_thp = bsdf_eval(sc, mat, it, sd, d);
+                const bool same_hemisphere = dot(d, xyz(it)) > 0;
+                d = bsdf_sample(sc, mat, d, it, throughput, emission_weight, rng, lobe);
+                delta = (lobe & LOBE_SPECULAR) > 0;
+                if (((dot(xyz(it), d) > 0) ^ same_hemisphere) == false) {
+                    if (same_hemisphere)
+                        nested.pop();
+                    else
+                        nested.push(hit_med_idx);
+                }
+            }
+            radiance += nee_tr * throughput * direct_comp *
+                        (nee_thp * float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+            if (bad_rgb(radiance))
+                radiance = splat4(0);
+            uint32_t c = st.lobes[slot];
+            c += uint32_t((lobe & LOBE_DIFFUSE) > 0) | (uint32_t((lobe & LOBE_SPECULAR) > 0) << 8) | (uint32_t((lobe & LOBE_TRANSMIT) > 0) << 16) |
+                 (uint32_t((lobe & LOBE_VOLUME) > 0) << 24);
+            alive = !(int(c & 0xff) >= bp.max_diffuse || int((c >> 8) & 0xff) >= bp.max_specular || int((c >> 16) & 0xff) >= bp.max_transmit ||
+                      int(c >> 24) >= bp.max_volume);
+            if (alive) {
+                const float max_value = max3(throughput);
+                if (max_value < kThpEps) {
+                    alive = false;
+                } else if (b >= kRRBounce && max_value < kRRThreshold) {
+                    if (rng.next1d() > max_value)
+                        alive = false;
+                    else
+                        throughput *= float(1. / max_value);
+                }
+            }
+            st.L[slot] = to_f4(radiance);
+            if (alive) {
+                st.lobes[slot] = c;
+                st.thp[slot] = to_f4(throughput);
+                st.pdf[slot] = emission_weight;
+                st.rng[slot] = make_uint2(rng.d0, rng.d1);
+                st.vstate[slot] = make_uint2(nested.bits, 0u);
+                st.ray_o[slot] = make_float4(so.x, so.y, so.z, hit_t);
+                st.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(TAG_ACTIVE | (delta ? TAG_DELTA : 0u)));
+            }
+        }
+        warp_push(q_next, q_next_count, alive, slot, lane);
+    }
+}
+
+// ray accounting of the volumetric wavefront: closest-hit rays = paths entering a trace after bounce 0, shadow rays =
+// marches, shaded = events that ran NEE
+__global__ void k_fold_vpt_stats(const int *__restrict__ cnt_t, const int *__restrict__ cnt_m, const int *__restrict__ cnt_s, int depth,
+                                 unsigned long long *stats) {
+    if (threadIdx.x == 0) {
+        unsigned long long closest = 0, shadow = 0, shaded = 0;
+        for (int b = 0; b < depth; b++) {
+            closest += b > 0 ? (unsigned long long)cnt_t[b] : 0ull;
+            shadow += (unsigned long long)cnt_m[b];
+            shaded += (unsigned long long)cnt_s[b];
+        }
+        stats[0] += closest, stats[1] += shadow, stats[2] += shaded;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_splat — reference: radiance_splat (wavefront_pt.cu:476-503), estimate_variance
 // (tracing_func.cuh:194-208), Vec4::gamma_corr (vec4.cuh:213-217)
@@ -1171,6 +1419,9 @@ struct Renderer::Impl {
     int caps[3] = {16, 16, 16};
     DevBuf<uint32_t> queue[2], shadow_queue;
     DevBuf<float4> sh_o, sh_d, hit; // dynamic-fetch pipeline: shadow rays and hit records
+    DevBuf<float4> vtr;             // volumetric wavefront: march results
+    DevBuf<uint2> vstate;           // volumetric wavefront: nested-volume stack + event word
+    DevBuf<uint32_t> queue3;        // volumetric wavefront: fourth queue (hit / trace ping-pong, shade, march)
     DevBuf<int> counters;                 // [0..D] queue sizes, [D+1 ..] work counters
     DevBuf<unsigned long long> stats;     // closest, shadow, shaded
     std::vector<cudaTextureObject_t> tex_objs;
@@ -1538,7 +1789,9 @@ void Renderer::enable_variance(bool on) {
 
 void Renderer::ensure_capacity(int samples) {
     Impl &m = *impl_;
-    if (samples <= m.capacity_samples && int(m.counters.n) >= 8 * (max_depth_ + 2) + 8 && (pipeline_ < 2 || m.hit.n > 0))
+    const bool vpt_wave = rules_ == 2 && pipeline_ != 0;
+    if (samples <= m.capacity_samples && int(m.counters.n) >= 8 * (max_depth_ + 2) + 8 && (pipeline_ < 2 || m.hit.n > 0) &&
+        (!vpt_wave || (m.vstate.n > 0 && m.hit.n > 0)))
         return;
     CUDA_OK(cudaStreamSynchronize(stream_));
     const size_t slots = size_t(w_) * h_ * size_t(std::max(samples, m.capacity_samples));
@@ -1552,7 +1805,12 @@ void Renderer::ensure_capacity(int samples) {
     m.lobes.alloc(slots);
     m.queue[0].alloc(slots);
     m.queue[1].alloc(slots);
-    if (pipeline_ >= 2) {
+    if (vpt_wave) {
+        m.vtr.alloc(slots);
+        m.vstate.alloc(slots);
+        m.queue3.alloc(slots);
+    }
+    if (pipeline_ >= 2 || vpt_wave) {
         m.shadow_queue.alloc(slots);
         m.sh_o.alloc(slots);
         m.sh_d.alloc(slots);
@@ -1569,7 +1827,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         throw std::runtime_error("cpt_b200: empty row range (row_begin >= row_end)");
     ensure_capacity(samples);
     const int P = w_ * h_, D = max_depth_;
-    PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p, m.lobes.p};
+    PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p, m.lobes.p, m.vstate.p};
     BatchParams bp{w_, h_, P, samples, first_accum, seed_offset_, row0_, row1_ > 0 ? std::min(row1_, h_) : h_, rules_,
                    max_depth_, m.caps[0], m.caps[1], m.caps[2], m.max_volume > 0 ? m.max_volume : max_depth_};
     int *q_counts = m.counters.p;          // D + 1 entries
@@ -1613,7 +1871,45 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             m.kev_bounce.push_back(bounce);
         }
     };
-    if (rules_ == 2) { // volumetric path: one kernel per batch + the splat
+    if (rules_ == 2 && this->pipeline_ != 0) { // volumetric path, wavefront form (see k_vpt_pre)
+        int *cnt_h = m.counters.p, *cnt_m = cnt_h + (D + 2), *cnt_s = cnt_h + 2 * (D + 2), *cnt_t = cnt_h + 3 * (D + 2);
+        int *wkv = cnt_h + 4 * (D + 2);
+        VptBufs vb{m.sh_o.p, m.sh_d.p, m.hit.p, m.vtr.p};
+        uint32_t *q_hit = m.queue[0].p, *q_trace = m.queue[1].p, *q_shade = m.shadow_queue.p, *q_march = m.queue3.p;
+        mark(0, 0);
+        LAUNCH_MODE(k_raygen, m.dev, m.cam, st, bp, q_hit, cnt_h, wkv + wk);
+        ++wk;
+        int launches = 1;
+        for (int b = 0; b < D; b++) {
+            mark(1, b);
+            k_vpt_pre<<<grid, kBlock, 0, stream_>>>(m.dev, st, vb, q_hit, cnt_h + b, wkv + wk, q_shade, cnt_s + b, q_march, cnt_m + b, q_trace,
+                                                    cnt_t + b + 1);
+            ++wk;
+            mark(4, b);
+            LAUNCH_MODE(k_vpt_march, m.dev, st, vb, q_march, cnt_m + b, wkv + wk, m.stats.p);
+            ++wk;
+            mark(1, b);
+            k_vpt_post<<<grid, kBlock, 0, stream_>>>(m.dev, st, vb, bp, q_shade, cnt_s + b, wkv + wk, q_trace, cnt_t + b + 1, b);
+            ++wk;
+            launches += 3;
+            if (b + 1 >= D)
+                break;
+            mark(2, b);
+            LAUNCH_MODE(k_trace, m.dev, st, q_trace, cnt_t + b + 1, wkv + wk, q_hit, cnt_h + b + 1, b + 1, 1);
+            ++wk, ++launches;
+        }
+        mark(3, 0);
+        k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples, first_accum,
+                                                   write_output ? 1 : 0, gamma ? 1 : 0, 0, row0_ * w_, row_end() * w_);
+        mark(-1, 0);
+        k_fold_vpt_stats<<<1, 32, 0, stream_>>>(cnt_t, cnt_m, cnt_s, D, m.stats.p);
+        CUDA_OK(cudaEventRecord(m.ev1, stream_));
+        CUDA_OK(cudaGetLastError());
+        host_stats_.samples += uint64_t(w_) * uint64_t(row_end() - row_begin()) * samples;
+        host_stats_.launches += launches + 2;
+        return;
+    }
+    if (rules_ == 2) { // volumetric path, megakernel form (pipeline 0): one kernel per batch + the splat
         mark(0, 0);
         LAUNCH_MODE(k_vpt, m.dev, m.cam, st, bp, work, m.stats.p);
         mark(3, 0);
