@@ -47,6 +47,12 @@ constexpr int kBlock = 128;
 #ifndef VPT_MIN_BLOCKS
 #define VPT_MIN_BLOCKS 8 // register budget of the volumetric megakernel: 8 CTAs/SM (64 registers) measured best of 1/4/6/8
 #endif
+#ifndef VPTW_SHADE_MIN_BLOCKS
+#define VPTW_SHADE_MIN_BLOCKS 6 // volumetric wavefront, traversal-free kernels (k_vpt_pre / k_vpt_post)
+#endif
+#ifndef VPTW_MARCH_MIN_BLOCKS
+#define VPTW_MARCH_MIN_BLOCKS 10 // volumetric wavefront, transmittance march: 48 registers (fog scene: march 6.04 -> 5.60 ms; 8: 6.00, 12: 5.67)
+#endif
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 6 // register budget of the traversal-free shading kernels: 6 CTAs/SM -> <= 85 registers
 #endif
@@ -1031,7 +1037,7 @@ struct VptBufs {
     float4 *tr;    // result of the march
 };
 
-__global__ void __launch_bounds__(kBlock, SHADE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, VPTW_SHADE_MIN_BLOCKS)
     k_vpt_pre(DevScene sc, PathState st, VptBufs vb, const uint32_t *__restrict__ queue, const int *__restrict__ q_count, int *work,
               uint32_t *q_shade, int *q_shade_count, uint32_t *q_march, int *q_march_count, uint32_t *q_next, int *q_next_count) {
     const int lane = threadIdx.x & 31;
@@ -1109,7 +1115,7 @@ __global__ void __launch_bounds__(kBlock, SHADE_MIN_BLOCKS)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_vpt_march(DevScene sc, PathState st, VptBufs vb, const uint32_t *__restrict__ queue,
+__global__ void __launch_bounds__(kBlock, VPTW_MARCH_MIN_BLOCKS) k_vpt_march(DevScene sc, PathState st, VptBufs vb, const uint32_t *__restrict__ queue,
                                                       const int *__restrict__ q_count, int *work, unsigned long long *stats) {
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
@@ -1134,7 +1140,7 @@ __global__ void __launch_bounds__(kBlock) k_vpt_march(DevScene sc, PathState st,
         atomicAdd(stats + 3, (unsigned long long)n_segments);
 }
 
-__global__ void __launch_bounds__(kBlock, SHADE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, VPTW_SHADE_MIN_BLOCKS)
     k_vpt_post(DevScene sc, PathState st, VptBufs vb, BatchParams bp, const uint32_t *__restrict__ queue, const int *__restrict__ q_count,
                int *work, uint32_t *q_next, int *q_next_count, int b) {
     const int lane = threadIdx.x & 31;
@@ -1621,6 +1627,16 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     m.dev.mats = m.mats.p;
     m.dev.emitters = m.emitters.p;
     m.dev.wnodes = m.arena.p;
+    // DRAM -> L2 fetch granularity (env CPTB200_L2_FETCH = 32 / 64 / 128 bytes): the path pool is read through compacted
+    // queues, 16 B per field per path, so a large fetch granularity multiplies DRAM traffic
+    if (const char *e = getenv("CPTB200_L2_FETCH")) {
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(e)));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        cudaGetLastError();
+        fprintf(stderr, "[cpt_b200] L2 fetch granularity %zu -> %zu\n", before, after);
+    }
     // L2 residency for the traversal arena (env CPTB200_L2_PERSIST=0 turns it off)
     {
         const char *e = getenv("CPTB200_L2_PERSIST");
