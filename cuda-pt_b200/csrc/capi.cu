@@ -253,9 +253,9 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
         } else if (k == "split_shadow") {
             r->impl->set_pipeline(value != 0 ? 1 : 0);
         } else if (k == "pipeline") {
-            if (value < 0 || value > 4)
-                throw std::runtime_error("pipeline must be 0 (fused), 1 (split shadow kernel), 2 (dynamic-fetch traversal kernels), 3 (deferred NEE) "
-                                         "or 4 (deferred NEE + dynamic-fetch traversal kernels)");
+            if (value < 0 || value > 5)
+                throw std::runtime_error("pipeline must be 0 (fused), 1 (split shadow kernel), 2 (dynamic-fetch traversal kernels), 3 (deferred NEE), "
+                                         "4 (deferred NEE + dynamic-fetch traversal kernels) or 5 (deferred NEE over dense path records)");
             r->impl->set_pipeline(int(value));
         } else if (k == "row_begin" || k == "row_end") {
             const int h = r->impl->height();

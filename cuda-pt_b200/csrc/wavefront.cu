@@ -112,6 +112,19 @@ __device__ __forceinline__ void warp_push(uint32_t *queue, int *count, bool pred
         queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+// warp-aggregated allocation of one output index per predicated lane; must be called by the full warp
+__device__ __forceinline__ int warp_alloc(int *count, bool pred, int lane) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0)
+        return -1;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader)
+        base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
+}
+
 __device__ __forceinline__ V4 null_or_env(const DevScene &sc, V3 dir) {
     // c_emitter[envmap_id]->eval_le(&ray.d): envmap_id == 0 selects the null emitter -> (0,0,0,1)
     if (sc.envmap_id > 0)
@@ -466,11 +479,20 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anyhit(DevScene sc, PathState 
 // two differ (in any bit) are queued for k_shadow_apply.  NEE samples that cannot change the pixel (emitter
 // facing away, BSDF value zero, delta lobes) therefore never cost a traversal, and the result stays exact.
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
+// DENSE (deferred-NEE pipeline only): the path records themselves are kept compact instead of a queue of slot ids - the
+// kernel reads generation `st` at indices [0, count) (entries whose path ended in the last trace are skipped) and writes
+// the shaded paths compactly into generation `dn.out`, shadow rays and Lvis at the new index (see k_vptd_post for why)
+struct DenseIO {
+    PathState out;
+    const uint32_t *pix_in;
+    uint32_t *pix_out;
+    int *n_out;
+};
+template <int MODE, bool DENSE = false>
 __global__ void __launch_bounds__(kBlock, (MODE < 0 ? SHADE_MIN_BLOCKS : 1)) k_shade(DevScene sc, PathState st, const uint32_t *__restrict__ queue,
                                                   const int *__restrict__ q_count, int *work,
                                                   unsigned long long *shadow_counter, int secondary_bounce, PtRules pt,
-                                                  RayBufs rb, uint32_t *sq, int *sq_count) {
+                                                  RayBufs rb, uint32_t *sq, int *sq_count, DenseIO dn = DenseIO{}) {
     extern __shared__ uint4 s_cached[];
     if constexpr (MODE >= 0)
         stage_cached_nodes(sc, s_cached);
@@ -479,9 +501,16 @@ __global__ void __launch_bounds__(kBlock, (MODE < 0 ? SHADE_MIN_BLOCKS : 1)) k_s
     unsigned int local_shadow = 0;
     for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
         const int i = chunk * 32 + lane;
-        const bool valid = i < count;
+        bool valid = i < count;
         // ---- part 1 (per lane): load the path, pick an emitter + primitive, sample it, set up the shadow ray
         uint32_t slot = 0, tag = 0, emit_id = 0;
+        int oslot = 0; // where the path's state goes: its slot, or (DENSE) a fresh compact index of the next generation
+        if constexpr (DENSE) {
+            slot = uint32_t(i);
+            valid = valid && (__float_as_uint(st.ray_d[valid ? i : 0].w) & TAG_ACTIVE) != 0;
+            oslot = warp_alloc(dn.n_out, valid, lane);
+        }
+        PathState &so = DENSE ? dn.out : st;
         V4 thp = mk4(0, 0, 0, 0), rdc = thp, direct_comp = mk4(0, 0, 0, 1);
         V3 o{0, 0, 0}, d{0, 0, 1}, hit_pos{0, 0, 0}, sd{0, 0, 1};
         float4 it = make_float4(0, 0, 1, 0);
@@ -490,7 +519,10 @@ __global__ void __launch_bounds__(kBlock, (MODE < 0 ? SHADE_MIN_BLOCKS : 1)) k_s
         int material_id = 0, emitter_id = 0;
         ObjectPOD ob{0, 0, 1, 0.f};
         if (valid) {
-            slot = queue[i];
+            if constexpr (!DENSE) {
+                slot = queue[i];
+                oslot = int(slot);
+            }
             thp = from_f4(st.thp[slot]);
             rdc = from_f4(st.L[slot]);
             const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
@@ -567,7 +599,7 @@ __global__ void __launch_bounds__(kBlock, (MODE < 0 ? SHADE_MIN_BLOCKS : 1)) k_s
                 uint32_t c = st.lobes[slot];
                 c += uint32_t((lobe & LOBE_DIFFUSE) > 0) + (uint32_t((lobe & LOBE_SPECULAR) > 0) << 8) +
                      (uint32_t((lobe & LOBE_TRANSMIT) > 0) << 16);
-                st.lobes[slot] = c;
+                so.lobes[oslot] = c;
                 bool go_on = !(int(c & 0xFF) >= pt.max_diffuse || int((c >> 8) & 0xFF) >= pt.max_specular ||
                                int((c >> 16) & 0xFF) >= pt.max_transmit);
                 const float max_value = max3(thp);
@@ -586,23 +618,25 @@ __global__ void __launch_bounds__(kBlock, (MODE < 0 ? SHADE_MIN_BLOCKS : 1)) k_s
                 queue_shadow = need_shadow && (__float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y) ||
                                                __float_as_uint(a.z) != __float_as_uint(b.z) || __float_as_uint(a.w) != __float_as_uint(b.w));
                 if (queue_shadow) {
-                    rb.sh_o[slot] = make_float4(hit_pos.x, hit_pos.y, hit_pos.z, shadow_range);
-                    rb.sh_d[slot] = make_float4(sd.x, sd.y, sd.z, 0.f);
-                    rb.hit[slot] = b;
+                    rb.sh_o[oslot] = make_float4(hit_pos.x, hit_pos.y, hit_pos.z, shadow_range);
+                    rb.sh_d[oslot] = make_float4(sd.x, sd.y, sd.z, 0.f);
+                    rb.hit[oslot] = b;
                 }
-                st.L[slot] = a;
+                so.L[oslot] = a;
             } else {
-                st.L[slot] = to_f4(Lv);
+                so.L[oslot] = to_f4(Lv);
             }
 
-            st.thp[slot] = to_f4(thp);
-            st.rng[slot] = make_uint2(rng.d0, rng.d1);
-            st.ray_o[slot] = make_float4(o.x, o.y, o.z, hit_t);
-            st.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
-            st.pdf[slot] = pdf;
+            so.thp[oslot] = to_f4(thp);
+            so.rng[oslot] = make_uint2(rng.d0, rng.d1);
+            so.ray_o[oslot] = make_float4(o.x, o.y, o.z, hit_t);
+            so.ray_d[oslot] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
+            so.pdf[oslot] = pdf;
+            if constexpr (DENSE)
+                dn.pix_out[oslot] = dn.pix_in[slot];
         }
         if constexpr (MODE == -2)
-            warp_push(sq, sq_count, queue_shadow, slot, lane);
+            warp_push(sq, sq_count, queue_shadow, uint32_t(oslot), lane);
     }
     // per-warp ray statistics (Mrays/s accounting)
     for (int off = 16; off > 0; off >>= 1)
@@ -1245,6 +1279,354 @@ __global__ void __launch_bounds__(kBlock, VPTW_SHADE_MIN_BLOCKS)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Volumetric wavefront, dense form (default): same cuts as above, but the path RECORDS are kept dense instead of the
+// queue of slot ids.  ncu on the slot form (profiles/r01_ncu_volumetric_summary.md): by bounce 5 only ~30 % of the slots
+// are alive, every 16 B field read lands in its own sector, DRAM moves 6x the useful bytes and the traversal-free
+// kernels wait on it.  Here generation g of the path arrays holds the n alive paths at indices [0, n): k_vptd_post
+// writes the survivors of generation g compactly into generation g^1 (warp-aggregated allocation), every kernel
+// reads and writes fully coalesced SoA, a path carries its slot (sample x pixel) in `pix` and deposits its final
+// radiance into Lout[slot] when it ends.  The image is indexed by slot, each path uses its own sampler: order-free,
+// so the frames stay the megakernel's (and the reference's) bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t VK_SHADE = 0u, VK_CONTINUE = 1u, VK_DEAD = 2u; // event word bits 16-17 (k_vptd_pre -> k_vptd_post)
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+    k_vptd_raygen(DevScene sc, CameraPOD cam, PathState out, uint32_t *pix, float4 *Lout, BatchParams bp, int *n_out, int *work) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int ty0 = bp.row0 >> 2;
+    const int tiles_x = (bp.W + 7) >> 3, tiles_y = ((bp.row1 + 3) >> 2) - ty0, tiles = tiles_x * tiles_y;
+    const int total = tiles * bp.S;
+    for (int task = warp_next_chunk(work, lane); task < total; task = warp_next_chunk(work, lane)) {
+        const int s = task / tiles, tile = task - s * tiles;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int px = (tx << 3) + (lane & 7), py = ((ty + ty0) << 2) + (lane >> 3);
+        const bool inside = px < bp.W && py >= bp.row0 && py < bp.row1;
+        uint32_t slot = 0;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        Rng rng{0, 0};
+        if (inside) {
+            const int gidx = px + py * bp.W;
+            slot = uint32_t(s) * uint32_t(bp.P) + uint32_t(gidx);
+            rng.seed(gidx, bp.seed_offset + (bp.first_accum + s) * kSeedScaler);
+            camera_ray(cam, px, py, rng, o, d);
+        }
+        const Hit h = closest_hit<MODE>(sc, s_cached, o, d, inside);
+        const bool alive = inside && h.prim >= 0;
+        const int j = warp_alloc(n_out, alive, lane);
+        if (alive) {
+            out.ray_o[j] = make_float4(o.x, o.y, o.z, h.t);
+            out.ray_d[j] = make_float4(d.x, d.y, d.z, __uint_as_float(TAG_ACTIVE | TAG_HIT | uint32_t(h.prim)));
+            out.thp[j] = make_float4(1, 1, 1, 1);
+            out.L[j] = make_float4(0, 0, 0, 1);
+            out.isect[j] = make_interaction(sc, h.prim, h.u, h.v);
+            out.rng[j] = make_uint2(rng.d0, rng.d1);
+            out.pdf[j] = 1.f;
+            if (bp.rules)
+                out.lobes[j] = 0u;
+            if (bp.rules == 2)
+                out.vstate[j] = make_uint2(BankStack::make(sc.cam_vol).bits, 0u);
+            pix[j] = slot;
+        } else if (inside) {
+            V4 L = mk4(0, 0, 0, 1);
+            if (bp.rules)
+                L += mk4(1, 1, 1, 1) * null_or_env(sc, d); // megakernel_pt.cu:181-184: radiance(0,0,0,1) += throughput * Le
+            else
+                L = null_or_env(sc, d);
+            Lout[slot] = to_f4(L);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock, VPTW_SHADE_MIN_BLOCKS)
+    k_vptd_pre(DevScene sc, PathState st, VptBufs vb, const int *__restrict__ n_ptr, int *work, uint32_t *q_march, int *n_march,
+               unsigned long long *stats) {
+    const int lane = threadIdx.x & 31;
+    const int count = *n_ptr;
+    unsigned int n_shaded = 0;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        bool to_march = false;
+        if (i < count) {
+            const float4 ro = st.ray_o[i], rd = st.ray_d[i];
+            const uint32_t tag = __float_as_uint(rd.w);
+            uint2 vs = st.vstate[i];
+            if (!(tag & TAG_ACTIVE)) { // ended at the trace (miss): its radiance is already deposited
+                st.vstate[i] = make_uint2(vs.x, VK_DEAD << 16);
+            } else {
+                V3 o = xyz(ro);
+                const V3 d = xyz(rd);
+                const float hit_t = ro.w;
+                const int prim = int(tag & TAG_INDEX);
+                const int obj_info = __ldg(sc.obj_idxs + prim);
+                const int hit_med_idx = (obj_info >> 20) & 0xff, object_id = obj_info & 0x000fffff;
+                BankStack nested{vs.x};
+                const uint2 rs = st.rng[i];
+                Rng rng{rs.x, rs.y};
+                V4 throughput = from_f4(st.thp[i]);
+                const MediumPOD &medium = sc.media[nested.top()];
+                const MediumSample md = medium.type == MEDIUM_GRID ? grid_sample(sc.grids[medium.grid], medium, o, d, hit_t, rng)
+                                                                   : medium_sample(medium, hit_t, rng);
+                throughput *= md.local_thp;
+                st.thp[i] = to_f4(throughput);
+                const bool alpha_mask = (obj_info & 0x40000000) == 0x40000000;
+                if (alpha_mask && md.flag == 0) { // cullable boundary reached: step through it, no NEE, next bounce
+                    o = advance(o, d, md.dist);
+                    const float4 it = st.isect[i];
+                    if (dot(d, xyz(it)) > 0)
+                        nested.pop();
+                    else
+                        nested.push(hit_med_idx);
+                    st.ray_o[i] = make_float4(o.x, o.y, o.z, hit_t);
+                    st.vstate[i] = make_uint2(nested.bits, VK_CONTINUE << 16);
+                } else {
+                    ++n_shaded;
+                    const ObjectPOD ob = sc.objects[object_id];
+                    const int emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+                    V4 direct_comp = splat4(0, 1);
+                    float direct_pdf = 1;
+                    const int no_sample = md.flag > 0 ? 0 : emitter_id;
+                    int num = sc.num_emitters;
+                    num -= no_sample > 0 && num > 1;
+                    uint32_t emit_id = (rng.next_u32() % uint32_t(num)) + 1;
+                    emit_id += emit_id >= uint32_t(no_sample) && no_sample > 0;
+                    direct_pdf = 1.f / float(num);
+                    emit_id = emit_id * uint32_t(no_sample == 0 || num > 1);
+                    const EmitterPOD &em = sc.emitters[emit_id];
+                    const ObjectPOD eo = sc.objects[em.obj_ref * (em.obj_ref >= 0)];
+                    direct_pdf *= eo.inv_area;
+                    int emit_prim = int(rng.next_u32() % uint32_t(eo.prim_num)) + eo.prim_offset;
+                    emit_prim = __ldg(sc.emitter_prims + emit_prim);
+                    const V3 so = advance(o, d, md.dist);
+                    V3 sd = emitter_sample(sc, em, so, V3{0, 0, 1}, direct_comp, direct_pdf, rng.next2d(), emit_prim) - so;
+                    const float emit_len_mis = length(sd);
+                    sd *= __frcp_rn(emit_len_mis);
+                    vb.sh_o[i] = make_float4(so.x, so.y, so.z, emit_len_mis);
+                    vb.sh_d[i] = make_float4(sd.x, sd.y, sd.z, direct_pdf);
+                    vb.dcomp[i] = to_f4(direct_comp);
+                    st.vstate[i] = make_uint2(nested.bits, emit_id | (md.flag << 8) | (VK_SHADE << 16));
+                    to_march = emit_id != 0;
+                }
+                st.rng[i] = make_uint2(rng.d0, rng.d1);
+            }
+        }
+        warp_push(q_march, n_march, to_march, uint32_t(i), lane);
+    }
+    for (int off = 16; off > 0; off >>= 1)
+        n_shaded += __shfl_down_sync(0xffffffffu, n_shaded, off);
+    if (lane == 0 && n_shaded)
+        atomicAdd(stats + 2, (unsigned long long)n_shaded);
+}
+
+__global__ void __launch_bounds__(kBlock, VPTW_SHADE_MIN_BLOCKS)
+    k_vptd_post(DevScene sc, PathState st, PathState out, const uint32_t *__restrict__ pix, uint32_t *pix_out, VptBufs vb, float4 *Lout,
+                BatchParams bp, const int *__restrict__ n_ptr, int *n_out, int *work, int b) {
+    const int lane = threadIdx.x & 31;
+    const int count = *n_ptr;
+    const bool last = b + 1 >= bp.max_depth;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        bool alive = false;
+        float4 n_o, n_d, n_thp, n_L, n_isect;
+        uint2 n_rng, n_vs;
+        float n_pdf = 0;
+        uint32_t n_lobes = 0, slot = 0;
+        if (i < count) {
+            const uint2 vs = st.vstate[i];
+            const uint32_t kind = vs.y >> 16;
+            if (kind != VK_DEAD) {
+                slot = pix[i];
+                const float4 ro = st.ray_o[i], rd = st.ray_d[i];
+                n_L = st.L[i];
+                if (kind == VK_CONTINUE) { // stepped through a cullable boundary in k_vptd_pre: unchanged, on to the next trace
+                    alive = true;
+                    n_o = ro, n_d = rd, n_thp = st.thp[i], n_isect = st.isect[i], n_rng = st.rng[i], n_vs = make_uint2(vs.x, 0u);
+                    n_pdf = st.pdf[i], n_lobes = st.lobes[i];
+                } else {
+                    V3 d = xyz(rd);
+                    const float hit_t = ro.w;
+                    const uint32_t tag = __float_as_uint(rd.w);
+                    const int prim = int(tag & TAG_INDEX);
+                    bool delta = (tag & TAG_DELTA) != 0;
+                    const int obj_info = __ldg(sc.obj_idxs + prim);
+                    const int hit_med_idx = (obj_info >> 20) & 0xff, object_id = obj_info & 0x000fffff;
+                    const ObjectPOD ob = sc.objects[object_id];
+                    const int material_id = ob.bsdf_emitter >> 16, emitter_id = ((ob.bsdf_emitter & 0xFFFF) ^ 0x8000) - 0x8000;
+                    const bool hit_emitter = emitter_id > 0;
+                    BankStack nested{vs.x};
+                    const uint32_t emit_id = vs.y & 0xffu;
+                    const bool medium_event = (vs.y >> 8) & 1u;
+                    const uint2 rs = st.rng[i];
+                    Rng rng{rs.x, rs.y};
+                    V4 throughput = from_f4(st.thp[i]), radiance = from_f4(n_L);
+                    float emission_weight = st.pdf[i];
+                    const float4 so4 = vb.sh_o[i], sd4 = vb.sh_d[i];
+                    const V3 so = xyz(so4), sd = xyz(sd4);
+                    float emit_len_mis = so4.w;
+                    const float direct_pdf = sd4.w;
+                    const V4 direct_comp = from_f4(vb.dcomp[i]);
+                    const V4 nee_tr = emit_id != 0 ? from_f4(vb.tr[i]) : splat4(0, 1);
+                    const MediumPOD &medium = sc.media[nested.top()];
+                    const EmitterPOD &em = sc.emitters[emit_id];
+                    int lobe = LOBE_NONE;
+                    V4 nee_thp;
+                    if (medium_event) {
+                        radiance += throughput * (medium.type == MEDIUM_GRID ? grid_emission(sc.grids[medium.grid], sc.blackbody, so, rng) : splat4(0, 1));
+                        const float phase_pdf = phase_eval(medium, sd, d);
+                        nee_thp = splat4(phase_pdf, 1.f);
+                        emit_len_mis = direct_pdf + phase_pdf;
+                        lobe = LOBE_VOLUME;
+                        d = medium_scatter(medium, d, throughput, rng, emission_weight);
+                        delta = false;
+                        n_isect = make_float4(0, 0, 0, 0);
+                    } else {
+                        const float4 it = st.isect[i];
+                        n_isect = it;
+                        const Material &mat = sc.mats[material_id];
+                        emission_weight = emission_weight / (emission_weight + solid_angle_pdf(ob.inv_area, shading_normal_world(mat, it), d, hit_t) *
+                                                                                   hit_emitter * (b > 0) * (!delta));
+                        {
+                            const V4 tl = throughput * emitter_eval(sc.emitters[emitter_id], d, it, true);
+                            radiance = V4{fmaf(tl.x, emission_weight, radiance.x), fmaf(tl.y, emission_weight, radiance.y),
+                                          fmaf(tl.z, emission_weight, radiance.z), fmaf(tl.w, emission_weight, radiance.w)};
+                        }
+                        emit_len_mis = direct_pdf + bsdf_pdf(sc, mat, it, sd, d) * float(em.is_sphere != 0);
+                        nee_thp = bsdf_eval(sc, mat, it, sd, d);
+                        const bool same_hemisphere = dot(d, xyz(it)) > 0;
+                        d = bsdf_sample(sc, mat, d, it, throughput, emission_weight, rng, lobe);
+                        delta = (lobe & LOBE_SPECULAR) > 0;
+                        if (((dot(xyz(it), d) > 0) ^ same_hemisphere) == false) {
+                            if (same_hemisphere)
+                                nested.pop();
+                            else
+                                nested.push(hit_med_idx);
+                        }
+                    }
+                    radiance += nee_tr * throughput * direct_comp *
+                                (nee_thp * float(emit_len_mis > kEps) * __frcp_rn(emit_len_mis < kEps ? 1.f : emit_len_mis));
+                    if (bad_rgb(radiance))
+                        radiance = splat4(0);
+                    uint32_t c = st.lobes[i];
+                    c += uint32_t((lobe & LOBE_DIFFUSE) > 0) | (uint32_t((lobe & LOBE_SPECULAR) > 0) << 8) |
+                         (uint32_t((lobe & LOBE_TRANSMIT) > 0) << 16) | (uint32_t((lobe & LOBE_VOLUME) > 0) << 24);
+                    alive = !(int(c & 0xff) >= bp.max_diffuse || int((c >> 8) & 0xff) >= bp.max_specular ||
+                              int((c >> 16) & 0xff) >= bp.max_transmit || int(c >> 24) >= bp.max_volume);
+                    if (alive) {
+                        const float max_value = max3(throughput);
+                        if (max_value < kThpEps) {
+                            alive = false;
+                        } else if (b >= kRRBounce && max_value < kRRThreshold) {
+                            if (rng.next1d() > max_value)
+                                alive = false;
+                            else
+                                throughput *= float(1. / max_value);
+                        }
+                    }
+                    n_L = to_f4(radiance);
+                    n_o = make_float4(so.x, so.y, so.z, hit_t);
+                    n_d = make_float4(d.x, d.y, d.z, __uint_as_float(TAG_ACTIVE | (delta ? TAG_DELTA : 0u)));
+                    n_thp = to_f4(throughput), n_rng = make_uint2(rng.d0, rng.d1), n_vs = make_uint2(nested.bits, 0u);
+                    n_pdf = emission_weight, n_lobes = c;
+                }
+                if (!alive || last) { // the path ends here (or the bounce loop does): final radiance of its slot
+                    Lout[slot] = n_L;
+                    alive = false;
+                }
+            }
+        }
+        const int j = warp_alloc(n_out, alive, lane);
+        if (alive) {
+            out.ray_o[j] = n_o, out.ray_d[j] = n_d, out.thp[j] = n_thp, out.L[j] = n_L, out.isect[j] = n_isect;
+            out.rng[j] = n_rng, out.vstate[j] = n_vs, out.pdf[j] = n_pdf, out.lobes[j] = n_lobes;
+            pix_out[j] = slot;
+        }
+    }
+}
+
+// closest hit of the dense generation, in place: hit -> interaction + hit record; miss -> environment, final radiance
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_vptd_trace(DevScene sc, PathState st, const uint32_t *__restrict__ pix, float4 *Lout,
+                                                       const int *__restrict__ n_ptr, int *work) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *n_ptr;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        const bool valid = i < count;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        uint32_t tag = 0;
+        if (valid) {
+            const float4 ro = st.ray_o[i], rd = st.ray_d[i];
+            o = xyz(ro), d = xyz(rd);
+            tag = __float_as_uint(rd.w) & (TAG_ACTIVE | TAG_DELTA);
+        }
+        const Hit h = closest_hit<MODE>(sc, s_cached, o, d, valid);
+        if (valid) {
+            if (h.prim >= 0) {
+                st.isect[i] = make_interaction(sc, h.prim, h.u, h.v);
+                st.ray_o[i].w = h.t;
+                st.ray_d[i].w = __uint_as_float(tag | TAG_HIT | uint32_t(h.prim));
+            } else {
+                V4 L = from_f4(st.L[i]);
+                L += from_f4(st.thp[i]) * null_or_env(sc, d);
+                Lout[pix[i]] = to_f4(L);
+                st.ray_d[i].w = __uint_as_float(0u);
+            }
+        }
+    }
+}
+
+// k_trace over a dense generation, in place (surface path, deferred-NEE pipeline): hit -> interaction, Russian roulette;
+// the path ends (miss, roulette, or ended by k_shade under the megakernel rules) -> final radiance to Lout[slot]
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_trace_dense(DevScene sc, PathState st, const uint32_t *__restrict__ pix, float4 *Lout,
+                                                        const int *__restrict__ n_ptr, int *work, int bounce, int pt_rules) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *n_ptr;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        bool valid = i < count, ended = false;
+        uint32_t tag = 0;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        if (valid) {
+            const float4 ro = st.ray_o[i], rd = st.ray_d[i];
+            o = xyz(ro), d = xyz(rd);
+            tag = __float_as_uint(rd.w) & 0x50000000u;
+            ended = (tag & TAG_ACTIVE) == 0; // megakernel rules: k_shade ended the path
+            valid = !ended;
+        }
+        const Hit h = closest_hit<MODE>(sc, s_cached, o, d, valid); // all 32 lanes call
+        if (valid)
+            ended = !resolve_hit(sc, st, uint32_t(i), tag, d, h.t, h.u, h.v, h.prim, bounce, pt_rules);
+        if (ended)
+            Lout[pix[i]] = st.L[i];
+    }
+}
+
+// final radiance of the paths still in flight after the last bounce
+__global__ void k_deposit(PathState st, const uint32_t *__restrict__ pix, float4 *Lout, const int *__restrict__ n_ptr) {
+    const int count = *n_ptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        Lout[pix[i]] = st.L[i];
+}
+
+__global__ void k_fold_vptd_stats(const int *__restrict__ cnt_n, const int *__restrict__ cnt_m, int depth, unsigned long long *stats) {
+    if (threadIdx.x == 0) {
+        unsigned long long closest = 0, shadow = 0;
+        for (int b = 0; b < depth; b++) {
+            closest += b > 0 ? (unsigned long long)cnt_n[b] : 0ull;
+            shadow += (unsigned long long)cnt_m[b];
+        }
+        stats[0] += closest, stats[1] += shadow;
+    }
+}
+
 // ray accounting of the volumetric wavefront: closest-hit rays = paths entering a trace after bounce 0, shadow rays =
 // marches, shaded = events that ran NEE
 __global__ void k_fold_vpt_stats(const int *__restrict__ cnt_t, const int *__restrict__ cnt_m, const int *__restrict__ cnt_s, int depth,
@@ -1428,6 +1810,17 @@ struct Renderer::Impl {
     DevBuf<float4> vtr;             // volumetric wavefront: march results
     DevBuf<uint2> vstate;           // volumetric wavefront: nested-volume stack + event word
     DevBuf<uint32_t> queue3;        // volumetric wavefront: fourth queue (hit / trace ping-pong, shade, march)
+    struct PathGen {                // volumetric wavefront, dense form: one generation of the compact path arrays
+        DevBuf<float4> ray_o, ray_d, thp, L, isect;
+        DevBuf<uint2> rng, vstate;
+        DevBuf<float> pdf;
+        DevBuf<uint32_t> lobes, pix;
+        void alloc(size_t n) {
+            ray_o.alloc(n), ray_d.alloc(n), thp.alloc(n), L.alloc(n), isect.alloc(n), rng.alloc(n), vstate.alloc(n), pdf.alloc(n), lobes.alloc(n),
+                pix.alloc(n);
+        }
+        PathState view() { return PathState{ray_o.p, ray_d.p, thp.p, L.p, isect.p, rng.p, pdf.p, lobes.p, vstate.p}; }
+    } gen[2];
     DevBuf<int> counters;                 // [0..D] queue sizes, [D+1 ..] work counters
     DevBuf<unsigned long long> stats;     // closest, shadow, shaded
     std::vector<cudaTextureObject_t> tex_objs;
@@ -1807,7 +2200,7 @@ void Renderer::ensure_capacity(int samples) {
     Impl &m = *impl_;
     const bool vpt_wave = rules_ == 2 && pipeline_ != 0;
     if (samples <= m.capacity_samples && int(m.counters.n) >= 8 * (max_depth_ + 2) + 8 && (pipeline_ < 2 || m.hit.n > 0) &&
-        (!vpt_wave || (m.vstate.n > 0 && m.hit.n > 0)))
+        (!vpt_wave || (m.vstate.n > 0 && m.hit.n > 0)) && (!((vpt_wave && pipeline_ >= 2) || (rules_ != 2 && pipeline_ == 5)) || m.gen[1].pix.n > 0))
         return;
     CUDA_OK(cudaStreamSynchronize(stream_));
     const size_t slots = size_t(w_) * h_ * size_t(std::max(samples, m.capacity_samples));
@@ -1825,6 +2218,10 @@ void Renderer::ensure_capacity(int samples) {
         m.vtr.alloc(slots);
         m.vstate.alloc(slots);
         m.queue3.alloc(slots);
+    }
+    if ((vpt_wave && pipeline_ >= 2) || (rules_ != 2 && pipeline_ == 5)) {
+        m.gen[0].alloc(slots);
+        m.gen[1].alloc(slots);
     }
     if (pipeline_ >= 2 || vpt_wave) {
         m.shadow_queue.alloc(slots);
@@ -1887,7 +2284,47 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             m.kev_bounce.push_back(bounce);
         }
     };
-    if (rules_ == 2 && this->pipeline_ != 0) { // volumetric path, wavefront form (see k_vpt_pre)
+    if (rules_ == 2 && this->pipeline_ >= 2) { // volumetric path, wavefront with dense path records (see k_vptd_post)
+        int *cnt_n = m.counters.p, *cnt_m = cnt_n + (D + 2), *wkv = cnt_n + 4 * (D + 2);
+        VptBufs vb{m.sh_o.p, m.sh_d.p, m.hit.p, m.vtr.p};
+        PathState g[2] = {m.gen[0].view(), m.gen[1].view()};
+        uint32_t *gp[2] = {m.gen[0].pix.p, m.gen[1].pix.p};
+        uint32_t *q_march = m.queue3.p;
+        mark(0, 0);
+        LAUNCH_MODE(k_vptd_raygen, m.dev, m.cam, g[0], gp[0], m.L.p, bp, cnt_n, wkv + wk);
+        ++wk;
+        int launches = 1, cur = 0;
+        for (int b = 0; b < D; b++) {
+            mark(1, b);
+            k_vptd_pre<<<grid, kBlock, 0, stream_>>>(m.dev, g[cur], vb, cnt_n + b, wkv + wk, q_march, cnt_m + b, m.stats.p);
+            ++wk;
+            mark(4, b);
+            LAUNCH_MODE(k_vpt_march, m.dev, g[cur], vb, q_march, cnt_m + b, wkv + wk, m.stats.p);
+            ++wk;
+            mark(1, b);
+            k_vptd_post<<<grid, kBlock, 0, stream_>>>(m.dev, g[cur], g[cur ^ 1], gp[cur], gp[cur ^ 1], vb, m.L.p, bp, cnt_n + b, cnt_n + b + 1,
+                                                      wkv + wk, b);
+            ++wk;
+            launches += 3;
+            cur ^= 1;
+            if (b + 1 >= D)
+                break;
+            mark(2, b);
+            LAUNCH_MODE(k_vptd_trace, m.dev, g[cur], gp[cur], m.L.p, cnt_n + b + 1, wkv + wk);
+            ++wk, ++launches;
+        }
+        mark(3, 0);
+        k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples, first_accum,
+                                                   write_output ? 1 : 0, gamma ? 1 : 0, 0, row0_ * w_, row_end() * w_);
+        mark(-1, 0);
+        k_fold_vptd_stats<<<1, 32, 0, stream_>>>(cnt_n, cnt_m, D, m.stats.p);
+        CUDA_OK(cudaEventRecord(m.ev1, stream_));
+        CUDA_OK(cudaGetLastError());
+        host_stats_.samples += uint64_t(w_) * uint64_t(row_end() - row_begin()) * samples;
+        host_stats_.launches += launches + 2;
+        return;
+    }
+    if (rules_ == 2 && this->pipeline_ != 0) { // volumetric path, wavefront over slot queues (pipeline 1; see k_vpt_pre)
         int *cnt_h = m.counters.p, *cnt_m = cnt_h + (D + 2), *cnt_s = cnt_h + 2 * (D + 2), *cnt_t = cnt_h + 3 * (D + 2);
         int *wkv = cnt_h + 4 * (D + 2);
         VptBufs vb{m.sh_o.p, m.sh_d.p, m.hit.p, m.vtr.p};
@@ -1936,6 +2373,43 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         CUDA_OK(cudaGetLastError());
         host_stats_.samples += uint64_t(w_) * uint64_t(row_end() - row_begin()) * samples;
         host_stats_.launches += 2;
+        return;
+    }
+    if (this->pipeline_ == 5) { // deferred NEE over dense path records (see DenseIO / k_vptd_post): surface path
+        int *ent = m.counters.p, *sqc = ent + (D + 2), *wkd = ent + 2 * (D + 2);
+        PathState g[2] = {m.gen[0].view(), m.gen[1].view()};
+        uint32_t *gp[2] = {m.gen[0].pix.p, m.gen[1].pix.p};
+        unsigned long long *shadow_counter = m.stats.p + 1;
+        mark(0, 0);
+        LAUNCH_MODE(k_vptd_raygen, m.dev, m.cam, g[0], gp[0], m.L.p, bp, ent, wkd + wk);
+        ++wk;
+        int launches = 1, traced = 0, shaded = 0, cur = 0;
+        for (int b = 0; b < D; b++) {
+            const PtRules pt{rules_, b, m.caps[0], m.caps[1], m.caps[2]};
+            mark(1, b);
+            k_shade<-2, true><<<grid, kBlock, 0, stream_>>>(m.dev, g[cur], nullptr, ent + b, wkd + wk, shadow_counter, b > 0, pt, rb, m.shadow_queue.p,
+                                                             sqc + b, DenseIO{g[cur ^ 1], gp[cur], gp[cur ^ 1], ent + b + 1});
+            ++wk, ++launches, ++shaded;
+            cur ^= 1;
+            mark(4, b);
+            LAUNCH_MODE(k_shadow_apply, m.dev, g[cur], rb, m.shadow_queue.p, sqc + b, wkd + wk);
+            ++wk, ++launches;
+            if (b + 1 >= D)
+                break;
+            mark(2, b);
+            LAUNCH_MODE(k_trace_dense, m.dev, g[cur], gp[cur], m.L.p, ent + b + 1, wkd + wk, b, rules_);
+            ++wk, ++launches, ++traced;
+        }
+        mark(3, 0);
+        k_deposit<<<num_sms_ * 8, 256, 0, stream_>>>(g[cur], gp[cur], m.L.p, ent + D);
+        k_splat<<<num_sms_ * 4, 256, 0, stream_>>>(m.L.p, d_image_, d_out_, use_variance ? d_var_ : nullptr, P, samples, first_accum,
+                                                   write_output ? 1 : 0, gamma ? 1 : 0, rules_ == 0 ? 1 : 0, row0_ * w_, row_end() * w_);
+        mark(-1, 0);
+        k_fold_stats<<<1, 32, 0, stream_>>>(ent + 1, traced, shaded, m.stats.p, sqc, shaded);
+        CUDA_OK(cudaEventRecord(m.ev1, stream_));
+        CUDA_OK(cudaGetLastError());
+        host_stats_.samples += uint64_t(w_) * uint64_t(row_end() - row_begin()) * samples;
+        host_stats_.launches += launches + 3;
         return;
     }
     mark(0, 0);

@@ -94,22 +94,52 @@ def test_xml_loader_textures_statistically_equal_reference():
 @pytest.mark.parametrize("scene,frame", [("cbox_mats_256.cpts", "cbox_mats_256_wfpt_f0016.bin"), ("texroom_256.cpts", None)])
 def test_pipelines_agree(scene, frame):
     """"pipeline" 0: NEE ray traced inside the shading kernel; 1: own shadow kernel; 2: dynamic-fetch traversal kernels;
-    3: deferred NEE (only the shadow rays that can change the radiance are traced); 4: 3 + dynamic-fetch kernels."""
+    3: deferred NEE (only the shadow rays that can change the radiance are traced); 4: 3 + dynamic-fetch kernels;
+    5: 3 over dense path records (the shading kernel compacts the paths themselves, not a queue of slot ids)."""
     outs = []
-    for pipeline in (0, 1, 2, 3, 4):
+    for pipeline in (0, 1, 2, 3, 4, 5):
         r = cpt.WavefrontRenderer(os.path.join(GOLDEN, scene), 0, 0)
         r.set_option("pipeline", pipeline)
         assert r.get_option("pipeline") == pipeline
         r.render_batch(16, False)
         outs.append(r.download_output())
         st = r.stats()
-        assert st["launches"] == 1 + 8 * (1, 2, 3, 2, 2)[pipeline] + 7 * (1, 1, 2, 1, 2)[pipeline] + 2
+        assert st["launches"] == 1 + 8 * (1, 2, 3, 2, 2, 2)[pipeline] + 7 * (1, 1, 2, 1, 2, 1)[pipeline] + 2 + (pipeline == 5)
         assert st["shadow_traced"] <= st["shadow_rays"] and (pipeline >= 2 or st["shadow_traced"] == st["shadow_rays"])
         r.close()
     for o in outs[1:]:
         assert np.array_equal(outs[0].view(np.uint32), o.view(np.uint32))
     if frame:
         assert bit_exact_fraction(outs[1], load_frame(frame)) == 1.0
+
+
+def test_dense_pipeline_megakernel_rules_and_rows():
+    """pipeline 5 under the megakernel termination rules (paths ended by the shading kernel), with a row window, and with
+    several samples in flight: bit-identical to the slot-queue pipeline / the reference's pt frame."""
+    r = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), 0, 0)
+    r.set_option("rules", 1)
+    r.set_option("pipeline", 5)
+    out = r.render_to_host(64, False)
+    assert bit_exact_fraction(out, load_frame("cbox_pt_256_pt_f0064.bin")) == 1.0
+    st = r.stats()
+    r.close()
+    q = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), 0, 0)
+    q.set_option("rules", 1)
+    q.render_batch(64, False)
+    qs = q.stats()
+    assert (st["closest_rays"], st["shadow_rays"], st["shaded"]) == (qs["closest_rays"], qs["shadow_rays"], qs["shaded"])
+    q.close()
+    imgs = []
+    for pipeline in (3, 5):
+        w = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_mats_256.cpts"), 0, 0)
+        w.set_option("pipeline", pipeline)
+        w.set_option("row_end", 200)
+        w.set_option("row_begin", 96)
+        w.set_option("samples_in_flight", 5)
+        w.render_batch(16, False)
+        imgs.append(w.download_output())
+        w.close()
+    assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
 
 
 def test_row_range_tiles_reproduce_the_full_frame():
@@ -150,13 +180,14 @@ def test_xml_loader_all_materials_incl_dispersion_statistically_equal_reference(
     assert abs(ours.mean() / ref.mean() - 1) < 0.05
 
 
-@pytest.mark.parametrize("pipeline", [0, 3])
+@pytest.mark.parametrize("pipeline", [0, 1, 3])
 @pytest.mark.parametrize("traversal", [1, 2])
 def test_volumetric_path_bit_exact_vs_reference_vpt(traversal, pipeline):
     """Participating media: homogeneous media with HG / isotropic / two-lobe HG phase functions, nested
     volume stack, transmittance march through cullable boundaries - against the reference's megakernel VPT frames
     (RGB, alpha and variance).  Includes the reference's signed `discrete1D() % 3` channel pick.  pipeline 0 = the
-    megakernel form (k_vpt), 3 = the wavefront form (k_vpt_pre / k_vpt_march / k_vpt_post + k_trace, the default)."""
+    megakernel form (k_vpt), 1 = wavefront over slot queues (k_vpt_pre / k_vpt_march / k_vpt_post + k_trace), 3 = wavefront
+    with dense path records (k_vptd_*, the default)."""
     r = cpt.WavefrontRenderer(os.path.join(GOLDEN, "medium_cbox_256.cpts"), 0, 0)
     assert r.get_option("rules") == 2 and "volumetric" in r.info() and r.get_option("pipeline") == 3
     r.set_option("traversal", traversal)
@@ -189,7 +220,7 @@ def test_volumetric_path_bit_exact_vs_reference_vpt(traversal, pipeline):
     r.close()
 
 
-@pytest.mark.parametrize("pipeline", [0, 3])
+@pytest.mark.parametrize("pipeline", [0, 1, 3])
 @pytest.mark.parametrize("traversal", [1, 2])
 def test_grid_media_bit_exact_vs_reference(traversal, pipeline):
     """Grid (NanoVDB) media: delta-tracking distance sampling, ratio-tracking transmittance with
@@ -432,7 +463,7 @@ def test_live_reference_vader_fog_volumetric(tmp_path):
     subprocess.run([REF_DUMP, "render", os.path.join(SCENES, "vader_fog_vpt_256.xml"), prefix, "vpt", "0", "1,8"],
                    check=True, capture_output=True, cwd=ROOT)
     for traversal in (1, 2):
-        for pipeline in (0, 3):
+        for pipeline in (0, 1, 3):
             r = cpt.WavefrontRenderer(prefix + ".cpts", 0, 0)
             assert r.get_option("rules") == 2
             r.set_option("traversal", traversal)

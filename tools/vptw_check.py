@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cuda_pt_b200 as cpt
 g = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref")
 for name, frames in (("medium_cbox_256", (1, 64)), ("grid_cbox_256", (1, 16)), ("grid_cbox_rayleigh_256", (16,))):
-    for pipe in (0, 3):
+    for pipe in (1, 3):
         for trav in (1, 2):
             r = cpt.WavefrontRenderer(os.path.join(g, name + ".cpts"), 0, 0)
             r.set_option("traversal", trav)
@@ -25,11 +25,11 @@ for name, frames in (("medium_cbox_256", (1, 64)), ("grid_cbox_256", (1, 16)), (
                         print("   ", y, x, out[y, x], ref[y, x])
             print("   ", r.stats())
             r.close()
-for scene in ("medium_cbox_vpt_1080p.xml", "grid_cbox_vpt_1080p.xml"):
+for scene in ("medium_cbox_vpt_1080p.xml", "grid_cbox_vpt_1080p.xml", "vader_fog_vpt_1080p.xml"):
     path = os.path.join(os.path.dirname(g), "..", "..", "scenes", "xml", scene)
     if "grid" in scene and not os.path.exists(os.path.join(os.path.dirname(path), "..", "volume", "puff512.done")):
         continue
-    for pipe in (0, 3):
+    for pipe in (0, 1, 3):
         r = cpt.WavefrontRenderer(path, 0, 0)
         r.set_option("pipeline", pipe)
         r.set_option("samples_in_flight", 16)
