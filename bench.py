@@ -360,7 +360,7 @@ def main():
     if sh_ms > 0:
         stages["shade"]["of_which_shadow_kernels_ms_per_step"] = sh_ms / K
         stages["shade"]["shadow_rays_traced_per_step"] = sh_traced / K
-    if "vpt" in workload and "raygen" in stages:  # rules=2: the whole path runs in k_vpt, timed in the raygen slot;
+    if "vpt" in workload and args.pipeline == 0 and "raygen" in stages:  # megakernel form: the whole path runs in k_vpt, timed in the raygen slot;
         stages["vpt"] = stages.pop("raygen")       # per path it reads the camera sample and writes 16 B of radiance,
         v = stages["vpt"]                          # everything else stays in registers
         v["bytes_per_unit"] = 16
@@ -374,7 +374,10 @@ def main():
             traffic = json.load(open(prof)).get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": {"vpt": "k_vpt", "raygen": "k_raygen", "shade": "k_shade+k_shadow_apply", "trace": "k_trace", "splat": "k_splat"}[dom],
+    vol = "vpt" in workload
+    roofline = {"bound": "hbm", "kernel": {"vpt": "k_vpt", "raygen": "k_vptd_raygen" if vol else "k_raygen",
+                                            "shade": "k_vptd_pre+k_vptd_post+k_vpt_march" if vol else "k_shade+k_shadow_apply",
+                                            "trace": "k_vptd_trace" if vol else "k_trace", "splat": "k_splat"}[dom],
                 "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
                 "traffic": traffic, "peak_source": peak_src,
                 "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; BVH/triangle reads are L2-served "
@@ -403,7 +406,10 @@ def main():
                                       if world > 1 else "1 GPU"),
                       "l2_note": f"path-state pool {S * W * H * 92 / 1e6:.0f} MB per step >> 126 MB L2 (no flush needed)",
                       "traversal": {0: "ordered pair-node", 1: "reference DFS order", 2: "ordered pair-node, 256-bit node loads", 3: "ordered, warp-vote"}[args.traversal],
-                      "pipeline": {0: "fused", 1: "split shadow kernel", 2: "dynamic-fetch traversal", 3: "deferred NEE"}[args.pipeline],
+                      "pipeline": ({0: "volumetric megakernel", 1: "volumetric wavefront over slot queues"}.get(args.pipeline, "volumetric wavefront, dense path records")
+                                   if "vpt" in workload else
+                                   {0: "fused", 1: "split shadow kernel", 2: "dynamic-fetch traversal", 3: "deferred NEE", 4: "deferred NEE + dynamic fetch",
+                                    5: "deferred NEE, dense path records"}[args.pipeline]),
                       "ray_accounting": "rays = primary + closest-hit + NEE shadow rays of the algorithm (SURVEY.md 8d, one shadow ray per shaded "
                                         "segment whose sampled emitter is not the null emitter); shadow rays that provably cannot change the "
                                         "radiance are not traversed (shadow_traced_frac)"},

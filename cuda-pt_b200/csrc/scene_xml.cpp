@@ -428,7 +428,12 @@ struct Builder {
     std::vector<BuildNode> nodes;
     int max_leaf = 16;
     int max_depth = 0;
-    static constexpr int kBins = 16;
+    static constexpr int kMaxBins = 64;
+    int kBins = 16;
+    int sweep_below = 0;    // exact (sorted sweep) SAH for nodes with at most this many references (0 = binned only)
+    const int *prim_obj = nullptr; // object of each primitive: near the root, "these objects | those objects" is a split candidate
+    int object_split_depth = 0;
+    float object_bias = 1.f;
     float kTraverse = 0.2f; // SAH cost of one inner-node visit relative to one triangle test
 
     int build(int base, int count, int depth) {
@@ -458,8 +463,8 @@ struct Builder {
             const float ext = cb.hi[axis] - cb.lo[axis];
             if (!(ext > 1e-7f))
                 continue;
-            Box bins[kBins];
-            int cnt[kBins] = {0};
+            Box bins[kMaxBins];
+            int cnt[kMaxBins] = {0};
             for (auto &b : bins)
                 b.clear();
             const float scale = float(kBins) / ext;
@@ -468,8 +473,8 @@ struct Builder {
                 bins[b].grow(refs[i].box);
                 cnt[b]++;
             }
-            float right_area[kBins];
-            int right_cnt[kBins];
+            float right_area[kMaxBins];
+            int right_cnt[kMaxBins];
             Box acc;
             acc.clear();
             int c = 0;
@@ -492,7 +497,63 @@ struct Builder {
             }
         }
         int mid = -1;
-        if (best_axis >= 0 && (best_cost < float(count) || count > max_leaf)) {
+        if (count <= sweep_below) { // exact SAH: sort by centroid on each axis, evaluate every split
+            float sweep_cost = 1e30f;
+            int sweep_axis = -1, sweep_pos = -1;
+            std::vector<float> ra(size_t(count) + 1);
+            for (int axis = 0; axis < 3; axis++) {
+                std::sort(refs.begin() + base, refs.begin() + base + count,
+                          [axis](const PrimRef &a, const PrimRef &b) { return a.ctr[axis] < b.ctr[axis]; });
+                Box acc;
+                acc.clear();
+                for (int i = count - 1; i > 0; i--) {
+                    acc.grow(refs[base + i].box);
+                    ra[i] = acc.area();
+                }
+                acc.clear();
+                for (int i = 1; i < count; i++) {
+                    acc.grow(refs[base + i - 1].box);
+                    const float cost = kTraverse + (acc.area() * float(i) + ra[i] * float(count - i)) / parent_area;
+                    if (cost < sweep_cost)
+                        sweep_cost = cost, sweep_axis = axis, sweep_pos = i;
+                }
+            }
+            if (sweep_axis >= 0 && (sweep_cost < float(count) || count > max_leaf)) {
+                if (sweep_axis != 2)
+                    std::sort(refs.begin() + base, refs.begin() + base + count,
+                              [sweep_axis](const PrimRef &a, const PrimRef &b) { return a.ctr[sweep_axis] < b.ctr[sweep_axis]; });
+                mid = base + sweep_pos;
+            } else if (count <= max_leaf) {
+                return id;
+            }
+        }
+        if (mid < 0 && prim_obj && depth < object_split_depth && count > max_leaf) {
+            // object candidate: references in input order (objects are contiguous there), split at an object boundary.
+            // The greedy SAH estimate of the two sides is compared with the best spatial candidate.
+            std::sort(refs.begin() + base, refs.begin() + base + count, [](const PrimRef &a, const PrimRef &b) { return a.prim < b.prim; });
+            std::vector<float> ra(size_t(count) + 1);
+            Box acc;
+            acc.clear();
+            for (int i = count - 1; i > 0; i--) {
+                acc.grow(refs[base + i].box);
+                ra[i] = acc.area();
+            }
+            acc.clear();
+            float obj_cost = 1e30f;
+            int obj_pos = -1;
+            for (int i = 1; i < count; i++) {
+                acc.grow(refs[base + i - 1].box);
+                if (prim_obj[refs[base + i].prim] == prim_obj[refs[base + i - 1].prim])
+                    continue;
+                const float cost = kTraverse + (acc.area() * float(i) + ra[i] * float(count - i)) / parent_area;
+                if (cost < obj_cost)
+                    obj_cost = cost, obj_pos = i;
+            }
+            if (obj_pos > 0 && obj_cost < object_bias * best_cost)
+                mid = base + obj_pos;
+        }
+        if (mid >= 0) {
+        } else if (best_axis >= 0 && (best_cost < float(count) || count > max_leaf)) {
             const float ext = cb.hi[best_axis] - cb.lo[best_axis], scale = float(kBins) / ext, lo = cb.lo[best_axis];
             const int axis = best_axis, bin = best_bin;
             auto it = std::partition(refs.begin() + base, refs.begin() + base + count, [&](const PrimRef &r) {
@@ -1179,6 +1240,14 @@ void load_xml(const std::string &path, HostScene &out) {
     bld.max_leaf = max_node_num;
     if (const char *e = getenv("CPTB200_SAH_TRAVERSE")) // builder tuning knob (experiments)
         bld.kTraverse = float(atof(e));
+    if (const char *e = getenv("CPTB200_SAH_BINS"))
+        bld.kBins = std::min(Builder::kMaxBins, std::max(4, atoi(e)));
+    if (const char *e = getenv("CPTB200_SAH_SWEEP"))
+        bld.sweep_below = std::max(0, atoi(e));
+    if (const char *e = getenv("CPTB200_SAH_OBJDEPTH"))
+        bld.object_split_depth = std::max(0, atoi(e));
+    if (const char *e = getenv("CPTB200_SAH_OBJBIAS"))
+        bld.object_bias = float(atof(e));
     bld.refs.resize(P0);
     {
         // primitive -> object word (bvh.cu:85-92; no media, triangles only)
@@ -1197,6 +1266,7 @@ void load_xml(const std::string &path, HostScene &out) {
             }
         }
         bld.nodes.reserve(2 * P0);
+        bld.prim_obj = prim_obj.data();
         bld.build(0, int(P0), 0);
         const int cache_levels = std::min(std::max(bld.max_depth - 1, 0), cache_level);
         linearize(bld, 0, 0, cache_levels, out.nodes, out.cache_nodes);

@@ -1548,7 +1548,7 @@ __global__ void __launch_bounds__(kBlock, VPTW_SHADE_MIN_BLOCKS)
 
 // closest hit of the dense generation, in place: hit -> interaction + hit record; miss -> environment, final radiance
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_vptd_trace(DevScene sc, PathState st, const uint32_t *__restrict__ pix, float4 *Lout,
+__global__ void __launch_bounds__(kBlock, 12) k_vptd_trace(DevScene sc, PathState st, const uint32_t *__restrict__ pix, float4 *Lout,
                                                        const int *__restrict__ n_ptr, int *work) {
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
@@ -1583,7 +1583,7 @@ __global__ void __launch_bounds__(kBlock) k_vptd_trace(DevScene sc, PathState st
 // k_trace over a dense generation, in place (surface path, deferred-NEE pipeline): hit -> interaction, Russian roulette;
 // the path ends (miss, roulette, or ended by k_shade under the megakernel rules) -> final radiance to Lout[slot]
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_trace_dense(DevScene sc, PathState st, const uint32_t *__restrict__ pix, float4 *Lout,
+__global__ void __launch_bounds__(kBlock, 12) k_trace_dense(DevScene sc, PathState st, const uint32_t *__restrict__ pix, float4 *Lout,
                                                         const int *__restrict__ n_ptr, int *work, int bounce, int pt_rules) {
     extern __shared__ uint4 s_cached[];
     stage_cached_nodes(sc, s_cached);
@@ -2020,16 +2020,6 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     m.dev.mats = m.mats.p;
     m.dev.emitters = m.emitters.p;
     m.dev.wnodes = m.arena.p;
-    // DRAM -> L2 fetch granularity (env CPTB200_L2_FETCH = 32 / 64 / 128 bytes): the path pool is read through compacted
-    // queues, 16 B per field per path, so a large fetch granularity multiplies DRAM traffic
-    if (const char *e = getenv("CPTB200_L2_FETCH")) {
-        size_t before = 0, after = 0;
-        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(e)));
-        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
-        cudaGetLastError();
-        fprintf(stderr, "[cpt_b200] L2 fetch granularity %zu -> %zu\n", before, after);
-    }
     // L2 residency for the traversal arena (env CPTB200_L2_PERSIST=0 turns it off)
     {
         const char *e = getenv("CPTB200_L2_PERSIST");

@@ -95,7 +95,10 @@ int cpt_b200_height(const cpt_b200_renderer *r);
  * "max_depth" (MaxDepthParams::max_depth, src/core/max_depth.h:26-42), "kernel_timing" (0/1: CUDA events
  * around every launch, read back with cpt_b200_kernel_times), "pipeline" (0: the NEE visibility ray is traced
  * inside the shading kernel; 1: in its own traversal kernel before shading; 2: dynamic-fetch traversal
- * kernels; 3: deferred NEE - shade first, then trace only the shadow rays that can change the radiance),
+ * kernels; 3: deferred NEE - shade first, then trace only the shadow rays that can change the radiance; 4: 3 with the
+ * dynamic-fetch kernels; 5: 3 over dense path records - the shading kernel compacts the paths themselves instead of a
+ * queue of slot ids.  Volumetric scenes (rules 2): 0 = megakernel form, 1 = wavefront over slot queues, >= 2 =
+ * wavefront with dense path records),
  * "split_shadow" (legacy alias: 0 -> pipeline 0, 1 -> pipeline 1), "row_begin" / "row_end" (tile split across GPUs:
  * only rows [row_begin,row_end) are traced and accumulated, pixel indices and therefore sample streams stay those of
  * the full frame; set row_end first when moving the window down) */
