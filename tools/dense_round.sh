@@ -2,8 +2,8 @@
 python -c "
 import sys; sys.argv=['bench.py']
 import bench; bench.ensure_volumes()"
-timeout 300 python tools/dense_check.py 2>&1 | grep -v "^    {" | cut -c1-200 | tee gpurun_out/dense.log
-python - <<PY 2>&1 | tee gpurun_out/vptw3.log
+timeout 300 python -m pytest tests -m gpu -x -q -k "volumetric or grid_media or fog" 2>&1 | tail -3
+python - <<PY 2>&1 | tee gpurun_out/vptw4.log
 import os, time, cuda_pt_b200 as cpt
 for scene in ("medium_cbox_vpt_1080p.xml", "grid_cbox_vpt_1080p.xml", "vader_fog_vpt_1080p.xml"):
     for pipe in (1, 3):
