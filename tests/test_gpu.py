@@ -452,6 +452,29 @@ def test_full_size_properties():
         q.close()
 
 
+WHISKEY = os.path.join(ROOT, "scenes", "ref_xml", "whiskey.xml")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_DUMP) and os.path.exists(WHISKEY) and os.path.exists(os.path.join(ROOT, "scenes", "meshes", "whiskey", "wine.obj"))),
+                    reason="reference harness / whiskey scene not on this box")
+def test_live_reference_whiskey_unmodified_scene(tmp_path):
+    """The reference's own wavefront demo scene, UNMODIFIED (scene/xml/whiskey.xml: 1024 x 1024, 16 bounces, nested glass +
+    liquid dielectrics, 68 k triangles, cache level 8), rendered by the unmodified reference right now; our kernels render
+    from the scene it dumped.  Bit-identical in the reference's traversal order and with the ordered traversal."""
+    prefix = str(tmp_path / "whiskey")
+    subprocess.run([REF_DUMP, "render", WHISKEY, prefix, "wfpt", "0", "1,4"], check=True, capture_output=True, cwd=ROOT)
+    for traversal in (1, 2):
+        r = cpt.WavefrontRenderer(prefix + ".cpts", 0, 0)
+        assert r.get_option("rules") == 0 and (r.width, r.height) == (1024, 1024)
+        r.set_option("traversal", traversal)
+        for n in (1, 4):
+            r.render_batch(n - r.counter(), False)
+            ref = np.fromfile(f"{prefix}_wfpt_f{n:04d}.bin", dtype=np.float32).reshape(1024, 1024, 4)
+            frac = bit_exact_fraction(r.download_output(), ref)
+            assert frac == 1.0 if traversal == 1 else frac >= 0.9999, (traversal, n, frac)
+        r.close()
+
+
 @pytest.mark.skipif(not (os.path.exists(REF_DUMP) and have_vader()), reason="reference harness / vader mesh not on this box")
 def test_live_reference_vader_fog_volumetric(tmp_path):
     """Volumetric path on a traversal-heavy scene: the vader geometry (reference-built SBVH) inside a homogeneous fog
