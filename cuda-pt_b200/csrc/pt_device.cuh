@@ -77,6 +77,7 @@ struct DevScene {
     const float4 *nodes;       // 2 float4 per DFS node {min.xyz, base}{max.xyz, cnt | -subtree}
     const uint4 *cache_nodes;  // fp16 near-root nodes
     const int *obj_idxs;       // per primitive object word
+    const int *prim_orig;      // reference index of each primitive when refined leaves re-ordered them (nullptr: identity)
     const float4 *tris;        // 3 float4 per primitive {v0,a20}{e1,a21}{e2,a22}
     const float4 *norms;       // 3 float4 per primitive
     const uint4 *uvs;          // 3 half2 per primitive (+pad)

@@ -4,6 +4,7 @@
 #include "scene_host.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -378,9 +379,14 @@ void build_normals_uvs(const HostScene &sc, std::vector<F4> &norms, std::vector<
 // ------------------------------------------------------------------------------------------------
 // pair-node layout
 // ------------------------------------------------------------------------------------------------
-void build_pair_layout(const HostScene &sc, PairLayout &out) {
+void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
     const int N = sc.num_nodes();
     out = PairLayout();
+    if (refine_above > 0) {
+        out.perm.resize(size_t(sc.num_prims()));
+        for (size_t i = 0; i < out.perm.size(); i++)
+            out.perm[i] = int32_t(i);
+    }
     auto node_cnt = [&](int k) {
         int32_t c;
         memcpy(&c, &sc.nodes[2 * k + 1].w, 4);
@@ -434,6 +440,94 @@ void build_pair_layout(const HostScene &sc, PairLayout &out) {
         return c;
     };
 
+    // ---- leaf refinement.  A reference leaf of many primitives (the reference builds leaves of up to 16 / 32) costs one
+    // triangle test per primitive for every ray that enters its box.  Its primitives get a median-split tree of their own:
+    // boxes = triangle bounds padded like the reference pads them (AABB_EPS); a ray that hits a triangle passes through that
+    // triangle's bounds, so the closest hit is unchanged and only misses are skipped.  Primitives move inside the leaf's own
+    // range only; ties keep resolving by the reference's index (perm).
+    struct Tri {
+        float lo[3], hi[3], ctr[3];
+        int32_t orig;
+    };
+    bool any_outside = false;
+    auto tri_of = [&](int32_t prim, const F4 &blo, const F4 &bhi) {
+        Tri t;
+        t.orig = prim;
+        const float leaf_lo[3] = {blo.x, blo.y, blo.z}, leaf_hi[3] = {bhi.x, bhi.y, bhi.z};
+        bool inside = true;
+        for (int a = 0; a < 3; a++) {
+            const float p0 = (&sc.verts[0][prim].x)[a], p1 = (&sc.verts[1][prim].x)[a], p2 = (&sc.verts[2][prim].x)[a];
+            t.lo[a] = std::min(p0, std::min(p1, p2)) - 1e-5f, t.hi[a] = std::max(p0, std::max(p1, p2)) + 1e-5f;
+            inside = inside && t.lo[a] >= leaf_lo[a] && t.hi[a] <= leaf_hi[a];
+        }
+        // A reference that sticks out of its leaf's box (SBVH: a triangle clipped to the node it was split into) makes the
+        // whole leaf ineligible: the reference tests every primitive of a leaf it enters, wherever the hit lies - also
+        // BEFORE the ray enters the leaf's box - and with its start-at-the-cached-frontier quirk such a hit may be the only
+        // way a triangle is found at all (cornell C0).  Distance culling between the parts of such a leaf would drop
+        // those hits; only leaves whose primitives all lie inside the leaf's box are refined.
+        if (!inside)
+            any_outside = true;
+        for (int a = 0; a < 3; a++)
+            t.ctr[a] = 0.5f * (t.lo[a] + t.hi[a]);
+        return t;
+    };
+    std::function<Child(int, std::vector<Tri> &, int, int, int, int)> refine = [&](int k, std::vector<Tri> &tris, int lo, int hi, int base,
+                                                                                    int depth) -> Child {
+        // child covering tris[lo, hi) = primitives [base + lo, base + hi) after the permutation
+        float blo[3] = {1e30f, 1e30f, 1e30f}, bhi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int i = lo; i < hi; i++)
+            for (int a = 0; a < 3; a++)
+                blo[a] = std::min(blo[a], tris[i].lo[a]), bhi[a] = std::max(bhi[a], tris[i].hi[a]);
+        out.max_depth = std::max(out.max_depth, depth);
+        Child c;
+        const int cnt = hi - lo;
+        if (cnt <= 2) {
+            const int32_t ref = ~int32_t((base + lo) | (cnt << 26));
+            c.lo = F4{blo[0], blo[1], blo[2], as_float(ref)};
+            c.hi = F4{bhi[0], bhi[1], bhi[2], as_float(k + 1)};
+            return c;
+        }
+        int axis = 0;
+        float ext = -1.f;
+        for (int a = 0; a < 3; a++) {
+            float clo = 1e30f, chi = -1e30f;
+            for (int i = lo; i < hi; i++)
+                clo = std::min(clo, tris[i].ctr[a]), chi = std::max(chi, tris[i].ctr[a]);
+            if (chi - clo > ext)
+                ext = chi - clo, axis = a;
+        }
+        const int mid = lo + cnt / 2;
+        std::nth_element(tris.begin() + lo, tris.begin() + mid, tris.begin() + hi,
+                         [axis](const Tri &a, const Tri &b) { return a.ctr[axis] < b.ctr[axis] || (a.ctr[axis] == b.ctr[axis] && a.orig < b.orig); });
+        const int idx = new_node();
+        const Child a = refine(k, tris, lo, mid, base, depth + 1), b = refine(k, tris, mid, hi, base, depth + 1);
+        out.wnodes[4 * idx + 0] = a.lo, out.wnodes[4 * idx + 1] = a.hi;
+        out.wnodes[4 * idx + 2] = b.lo, out.wnodes[4 * idx + 3] = b.hi;
+        c.lo = F4{blo[0], blo[1], blo[2], as_float(idx)};
+        c.hi = F4{bhi[0], bhi[1], bhi[2], as_float(k + 1)};
+        return c;
+    };
+    auto refined_leaf_child = [&](int k, int base, int cnt, int depth) -> Child {
+        if (base + cnt - 1 > kBaseMask)
+            throw std::runtime_error("pair layout: primitive index exceeds 26 bits");
+        const F4 lo = sc.nodes[2 * k], hi = sc.nodes[2 * k + 1];
+        std::vector<Tri> tris;
+        tris.reserve(size_t(cnt));
+        any_outside = false;
+        for (int i = 0; i < cnt; i++)
+            tris.push_back(tri_of(base + i, lo, hi));
+        if (any_outside)
+            return leaf_child(k, base, cnt);
+        Child c = refine(k, tris, 0, cnt, base, depth);
+        for (int i = 0; i < cnt; i++)
+            out.perm[size_t(base) + i] = tris[i].orig;
+        // the child keeps the LEAF's own box: the reference enters the leaf on that test, so do we
+        c.lo.x = lo.x, c.lo.y = lo.y, c.lo.z = lo.z;
+        c.hi.x = hi.x, c.hi.y = hi.y, c.hi.z = hi.z;
+        out.refined_leaves++;
+        return c;
+    };
+
     auto contained = [&](int child, int parent) {
         const F4 cl = sc.nodes[2 * child], ch = sc.nodes[2 * child + 1], pl = sc.nodes[2 * parent], ph = sc.nodes[2 * parent + 1];
         const float over = std::max(std::max(std::max(pl.x - cl.x, pl.y - cl.y), pl.z - cl.z),
@@ -460,7 +554,10 @@ void build_pair_layout(const HostScene &sc, PairLayout &out) {
         const int pair_idx = it.slot >> 1, which = it.slot & 1;
         Child c;
         if (node_cnt(it.k) > 0) {
-            c = leaf_child(it.k, node_base(it.k), node_cnt(it.k));
+            if (refine_above > 0 && node_cnt(it.k) > refine_above)
+                c = refined_leaf_child(it.k, node_base(it.k), node_cnt(it.k), it.depth);
+            else
+                c = leaf_child(it.k, node_base(it.k), node_cnt(it.k));
         } else {
             const int idx = new_node();
             const F4 lo = sc.nodes[2 * it.k], hi = sc.nodes[2 * it.k + 1];

@@ -83,7 +83,12 @@ struct PairLayout {
     int nesting_violations = 0; // child boxes that are not contained in their parent's box
     float max_overshoot = 0.f;  // by how much at most (the reference's SBVH pads clipped child boxes by AABB_EPS = 1e-5)
     int oversize_leaves = 0;
+    // leaf refinement: reference leaves with more than `refine_above` primitives get a small tree of their own inside the
+    // pair layout; their primitives are re-ordered INSIDE the leaf's range, perm[new index] = reference index (empty =
+    // identity).  The reference tree, its leaf ranges and the cached nodes are untouched.
+    std::vector<int32_t> perm;
+    int refined_leaves = 0;
 };
-void build_pair_layout(const HostScene &scene, PairLayout &out);
+void build_pair_layout(const HostScene &scene, PairLayout &out, int refine_above = 0);
 
 } // namespace cptb

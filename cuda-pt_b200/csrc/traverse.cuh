@@ -26,6 +26,14 @@
 namespace cptb {
 
 // slab test, same fma/min/max structure as AABB::intersect (aabb.cuh:58-65, vec3.cuh:263-276)
+// tie rule of the closest hit: the reference keeps the first hit in its DFS order = the smaller reference primitive index.
+// Refined leaves (scene_host.cpp build_pair_layout) re-order primitives inside a leaf; prim_orig maps back.
+PT_DEV bool prim_before(const DevScene &sc, int a, int b) {
+    if (b < 0)
+        return false;
+    return sc.prim_orig ? __ldg(sc.prim_orig + a) < __ldg(sc.prim_orig + b) : a < b;
+}
+
 PT_DEV bool slab_test(float minx, float miny, float minz, float maxx, float maxy, float maxz, V3 inv_d, V3 o_div,
                       float &t_near) {
     const float ax = fmaf(minx, inv_d.x, -o_div.x), ay = fmaf(miny, inv_d.y, -o_div.y), az = fmaf(minz, inv_d.z, -o_div.z);
@@ -103,7 +111,7 @@ PT_DEV Hit closest_hit_dfs(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d
         for (int idx = beg; idx < end; idx++) {
             float u, v;
             const float dist = hit_triangle(sc.tris, idx, o, d, u, v, __int_as_float(0x7f800000));
-            const bool valid = dist > kEps && dist < h.t;
+            const bool valid = dist > kEps && (dist < h.t || (dist == h.t && h.prim >= 0 && prim_before(sc, idx, h.prim)));
             h.t = valid ? dist : h.t;
             h.u = valid ? u : h.u;
             h.v = valid ? v : h.v;
@@ -206,7 +214,7 @@ PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, 
                 float u, v;
                 const float dist = hit_triangle(sc.tris, idx, o, d, u, v, inf);
                 // equal distances: the reference keeps the first hit in DFS order == the smaller primitive index
-                const bool valid = dist > kEps && (dist < h.t || (dist == h.t && idx < h.prim));
+                const bool valid = dist > kEps && (dist < h.t || (dist == h.t && prim_before(sc, idx, h.prim)));
                 h.t = valid ? dist : h.t;
                 h.u = valid ? u : h.u;
                 h.v = valid ? v : h.v;
@@ -321,7 +329,7 @@ PT_DEV Hit closest_hit_vote(const DevScene &sc, const uint4 *s_cached, V3 o, V3 
         } else if (want_tri) {
             float u, v;
             const float dist = hit_triangle(sc.tris, ti, o, d, u, v, inf);
-            const bool valid = dist > kEps && (dist < h.t || (dist == h.t && ti < h.prim));
+            const bool valid = dist > kEps && (dist < h.t || (dist == h.t && prim_before(sc, ti, h.prim)));
             h.t = valid ? dist : h.t;
             h.u = valid ? u : h.u;
             h.v = valid ? v : h.v;

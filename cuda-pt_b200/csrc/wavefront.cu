@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_intersect(DevScene sc, PathSta
                         float u, v;
                         const float dist = hit_triangle(sc.tris, idx, o, d, u, v, inf);
                         // equal distances: the reference keeps the first hit in DFS order == the smaller primitive index
-                        const bool better = dist > kEps && (dist < ht || (dist == ht && idx < hprim));
+                        const bool better = dist > kEps && (dist < ht || (dist == ht && prim_before(sc, idx, hprim)));
                         ht = better ? dist : ht;
                         hu = better ? u : hu;
                         hv = better ? v : hv;
@@ -1802,7 +1802,8 @@ struct Renderer::Impl {
     DevBuf<float4> nodes, norms, arena; // arena = [pair nodes | triangles]
     size_t arena_nodes = 0, l2_window_bytes = 0;
     DevBuf<uint4> cache_nodes, uvs;
-    DevBuf<int> obj_idxs, emitter_prims;
+    DevBuf<int> obj_idxs, emitter_prims, prim_orig;
+    int refined_leaves = 0;
     DevBuf<ObjectPOD> objects;
     DevBuf<Material> mats;
     DevBuf<MediumPOD> media;
@@ -1928,10 +1929,35 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         memcpy(n4.data(), norms.data(), n4.size() * sizeof(float4));
         std::vector<uint4> u4(uvs.size());
         memcpy(u4.data(), uvs.data(), u4.size() * sizeof(uint4));
+        // reference leaves larger than this get a tree of their own in the pair layout (CPTB200_REFINE_LEAVES, 0 = off); their
+        // primitives are re-ordered inside the leaf's range, every per-primitive array follows the permutation
+        int refine_above = 2;
+        if (const char *e = getenv("CPTB200_REFINE_LEAVES"))
+            refine_above = atoi(e);
+        PairLayout pl;
+        build_pair_layout(scene, pl, refine_above);
+        std::vector<int> prim_obj_words(scene.obj_idxs.begin(), scene.obj_idxs.end());
+        std::vector<int> inv_perm;
+        if (pl.refined_leaves > 0) {
+            const std::vector<int32_t> &perm = pl.perm;
+            const size_t P = perm.size();
+            std::vector<float4> t2(t4.size()), n2(n4.size());
+            std::vector<uint4> u2(u4.size());
+            inv_perm.resize(P);
+            for (size_t i = 0; i < P; i++) {
+                const size_t o = size_t(perm[i]);
+                for (int k = 0; k < 3; k++)
+                    t2[3 * i + k] = t4[3 * o + k], n2[3 * i + k] = n4[3 * o + k];
+                u2[i] = u4[o];
+                prim_obj_words[i] = scene.obj_idxs[o];
+                inv_perm[o] = int(i);
+            }
+            t4.swap(t2), n4.swap(n2), u4.swap(u2);
+            m.prim_orig.upload(std::vector<int>(perm.begin(), perm.end()));
+        }
+        m.refined_leaves = pl.refined_leaves;
         m.norms.upload(n4);
         m.uvs.upload(u4);
-        PairLayout pl;
-        build_pair_layout(scene, pl);
         std::vector<float4> w4(pl.wnodes.size());
         memcpy(w4.data(), pl.wnodes.data(), w4.size() * sizeof(float4));
         // traversal arena: pair nodes and triangles in one allocation, so that one L2 access-policy window can pin both
@@ -1950,9 +1976,12 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         m.max_overshoot = pl.max_overshoot;
         if (pl.max_depth + 2 > kStackSize || pl.max_overshoot > 2.5e-5f)
             traversal_ = TRAVERSAL_DFS;
-        m.obj_idxs.upload(std::vector<int>(scene.obj_idxs.begin(), scene.obj_idxs.end()));
+        m.obj_idxs.upload(prim_obj_words);
         // emitter primitive map is padded like path_tracer.cu:76-87 (zero filled here)
         std::vector<int> ep(scene.emitter_prims.begin(), scene.emitter_prims.end());
+        if (!inv_perm.empty())
+            for (int &e : ep)
+                e = inv_perm[size_t(e)];
         ep.resize(std::max<size_t>(ep.size(), size_t(std::max(scene.objects.front().prim_num, 1))), 0);
         m.emitter_prims.upload(ep);
         std::vector<ObjectPOD> objs(scene.objects.size());
@@ -2026,6 +2055,7 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     m.dev.nodes = m.nodes.p;
     m.dev.cache_nodes = m.cache_nodes.p;
     m.dev.obj_idxs = m.obj_idxs.p;
+    m.dev.prim_orig = m.prim_orig.p; // nullptr: primitives are in the reference's order
     m.dev.tris = m.arena.p + m.arena_nodes;
     m.dev.norms = m.norms.p;
     m.dev.uvs = m.uvs.p;
@@ -2645,6 +2675,7 @@ std::string Renderer::info() const {
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
        << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : "ordered-vote")))
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations << " (max " << impl_->max_overshoot << ")"
+       << ", refined leaves " << impl_->refined_leaves
        << ", L2 window " << (impl_->l2_window_bytes >> 20) << " MB, pipeline " << pipeline_ << ", rules " << (rules_ == 2 ? "volumetric-pt" : (rules_ ? "megakernel-pt" : "wavefront")) << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();
 }
