@@ -38,7 +38,8 @@ WORKLOADS = {"c1": "vader_wfpt_1080p.xml",       # BASELINE config 1 (default): 
              "c2": "vader_tex_wfpt_1080p.xml",    # texture-heavy stand-in: + 2K glossy/roughness/normal/albedo maps + envmap
              "vpt": "medium_cbox_vpt_1080p.xml",  # participating media (homogeneous), volumetric path tracer
              "grid": "grid_cbox_vpt_1080p.xml",   # BASELINE config 4 stand-in: grid (NanoVDB) medium, 304x512x304 voxels
-             "fog": "vader_fog_vpt_1080p.xml"}    # volumetric path on the 320k-triangle vader geometry inside a thin fog
+             "fog": "vader_fog_vpt_1080p.xml",    # volumetric path on the 320k-triangle vader geometry inside a thin fog
+             "whiskey": "../ref_xml/whiskey.xml"}  # the reference's own wavefront demo scene, unmodified (1024 x 1024, 16 bounces)
 
 
 def ensure_volumes():
@@ -67,7 +68,7 @@ def pick_scene(arg):
     if arg == "grid":
         ensure_volumes()
     if arg in WORKLOADS:
-        return os.path.join(ROOT, "scenes", "xml", WORKLOADS[arg]), WORKLOADS[arg]
+        return os.path.normpath(os.path.join(ROOT, "scenes", "xml", WORKLOADS[arg])), os.path.basename(WORKLOADS[arg])
     if arg:
         return arg, os.path.basename(arg)
     vader = os.path.join(ROOT, "scenes", "xml", "vader_wfpt_1080p.xml")
@@ -164,9 +165,10 @@ def run_reference(args, scene, workload):
         return
     S = args.spp_per_step
     ref_dump = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
-    base = {"metric": METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    base = {"metric": (METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC).replace("1920x1080", "1024x1024" if "whiskey" in workload else "1920x1080"), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "impl": "reference",
             "data": ("cornell box geometry bundled with the reference + a synthetic 304x512x304 NanoVDB smoke volume (density, albedo, temperature grids) + two homogeneous media" if "grid" in workload else
+                     "the reference's whiskey scene, unmodified" if "whiskey" in workload else
                      "vader geometry bundled with the reference inside a homogeneous fog bounded by a cullable box" if "fog" in workload else
                      "cornell box geometry bundled with the reference + three homogeneous media" if "vpt" in workload else
                      "vader geometry bundled with the reference; textures/envmap not shipped upstream, removed" if "tex" not in workload else
@@ -389,11 +391,12 @@ def main():
         sc.save(tmp)
         cpu_baseline = cpu_oracle_rate(tmp, W, H, rules=int(r.get_option("rules")))
 
-    out = {"metric": METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
+    out = {"metric": (METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC).replace("1920x1080", f"{W}x{H}"), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (args.split == "tiles" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
            "data": ("cornell box geometry bundled with the reference + a synthetic 304x512x304 NanoVDB smoke volume (density, albedo, temperature "
                     "grids; `ref_dump mkvdb`) read by our own .nvdb reader + two homogeneous media; fixed seeds"
                     if "grid" in workload else
+                    "the reference's whiskey scene, unmodified (scene/xml/whiskey.xml + its meshes); fixed seeds" if "whiskey" in workload else
                     "vader geometry bundled with the reference inside a homogeneous fog bounded by a cullable box (scenes/assets/fogbox); fixed seeds"
                     if "fog" in workload else
                     "cornell box geometry bundled with the reference + three homogeneous media (the reference's medium-cbox scene); fixed seeds"
