@@ -448,6 +448,7 @@ void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
     struct Tri {
         float lo[3], hi[3], ctr[3];
         int32_t orig;
+        bool inside;
     };
     bool any_outside = false;
     auto tri_of = [&](int32_t prim, const F4 &blo, const F4 &bhi) {
@@ -460,13 +461,14 @@ void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
             t.lo[a] = std::min(p0, std::min(p1, p2)) - 1e-5f, t.hi[a] = std::max(p0, std::max(p1, p2)) + 1e-5f;
             inside = inside && t.lo[a] >= leaf_lo[a] && t.hi[a] <= leaf_hi[a];
         }
-        // A reference that sticks out of its leaf's box (SBVH: a triangle clipped to the node it was split into) makes the
-        // whole leaf ineligible: the reference tests every primitive of a leaf it enters, wherever the hit lies - also
+        // A reference that sticks out of its leaf's box (SBVH: a triangle clipped to the node it was split into) cannot be
+        // given bounds of its own: the reference tests every primitive of a leaf it enters, wherever the hit lies - also
         // BEFORE the ray enters the leaf's box - and with its start-at-the-cached-frontier quirk such a hit may be the only
-        // way a triangle is found at all (cornell C0).  Distance culling between the parts of such a leaf would drop
-        // those hits; only leaves whose primitives all lie inside the leaf's box are refined.
+        // way a triangle is found at all (cornell C0).  Distance culling would drop those hits; such references stay in a
+        // plain group that is tested on every entry of the leaf (refined_leaf_child), only the others are refined.
         if (!inside)
             any_outside = true;
+        t.inside = inside;
         for (int a = 0; a < 3; a++)
             t.ctr[a] = 0.5f * (t.lo[a] + t.hi[a]);
         return t;
@@ -516,9 +518,27 @@ void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
         any_outside = false;
         for (int i = 0; i < cnt; i++)
             tris.push_back(tri_of(base + i, lo, hi));
-        if (any_outside)
+        // references that stick out of the leaf's box first (reference order kept among them): they form a plain group
+        // with the LEAF's box, which the traversal visits first whenever it enters the leaf (same entry distance as the
+        // leaf, never farther than the refined part) - every one of them is tested exactly when the reference tests them.
+        const int n_out = int(std::stable_partition(tris.begin(), tris.end(), [](const Tri &t) { return !t.inside; }) - tris.begin());
+        const int n_in = cnt - n_out;
+        if (n_in <= 2 || n_out > kMaxLeaf)
             return leaf_child(k, base, cnt);
-        Child c = refine(k, tris, 0, cnt, base, depth);
+        Child c;
+        if (n_out == 0) {
+            c = refine(k, tris, 0, cnt, base, depth);
+        } else {
+            const int idx = new_node();
+            const int32_t ref = ~int32_t(base | (n_out << 26));
+            const Child in = refine(k, tris, n_out, cnt, base, depth + 1);
+            out.wnodes[4 * idx + 0] = F4{lo.x, lo.y, lo.z, as_float(ref)};
+            out.wnodes[4 * idx + 1] = F4{hi.x, hi.y, hi.z, as_float(k + 1)};
+            out.wnodes[4 * idx + 2] = in.lo, out.wnodes[4 * idx + 3] = in.hi;
+            c.lo = F4{lo.x, lo.y, lo.z, as_float(idx)};
+            c.hi = F4{hi.x, hi.y, hi.z, as_float(k + 1)};
+            out.max_depth = std::max(out.max_depth, depth + 1);
+        }
         for (int i = 0; i < cnt; i++)
             out.perm[size_t(base) + i] = tris[i].orig;
         // the child keeps the LEAF's own box: the reference enters the leaf on that test, so do we
