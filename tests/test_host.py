@@ -369,3 +369,26 @@ def test_xml_loader_vader_scale():
     assert abs(cam[16] - 0.19) < 1e-7 and abs(cam[17] - 5.4) < 1e-6  # thin lens
     sc.set_film(256, 128)
     assert sc.config["width"] == 256 and sc.camera[13] == 128.0 and sc.camera[14] == 64.0
+
+
+def test_pair_layout_and_leaf_refinement_invariants(tmp_path):
+    """build_pair_layout (the re-laid-out traversal structure) with and without leaf refinement on every golden scene:
+    each primitive in exactly one leaf record, refined records inside their reference leaf's range and box, the
+    permutation only moves primitives inside reference leaves.  Plain C++ against scene_host.cpp, no GPU."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "pair_layout_check")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "cuda-pt_b200", "csrc"),
+                    os.path.join(root, "tests", "cpp", "pair_layout_check.cpp"), os.path.join(root, "cuda-pt_b200", "csrc", "scene_host.cpp"), "-o", exe],
+                   check=True)
+    refined_any = 0
+    for scene in ("cbox_wfpt_256", "cbox_mats_256", "texroom_256", "medium_cbox_256", "grid_cbox_256"):
+        for refine in (0, 2, 4):
+            out = subprocess.run([exe, os.path.join(GOLDEN, scene + ".cpts"), str(refine)], capture_output=True, text=True)
+            assert out.returncode == 0, (scene, refine, out.stdout, out.stderr)
+            fields = dict(zip(out.stdout.split()[0::2], out.stdout.split()[1::2]))
+            assert int(fields["errors"]) == 0
+            if refine == 0:
+                assert int(fields["refined_leaves"]) == 0
+            refined_any += int(fields["refined_leaves"])
+    assert refined_any > 0
