@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <queue>
 #include <thread>
 #include <cmath>
 #include <cstdio>
@@ -577,6 +578,148 @@ struct Builder {
         return id;
     }
 };
+
+
+// ---- insertion-based optimisation of the finished tree (Bittner, Hapala, Havran 2013: "Fast insertion-based optimization
+// of bounding volume hierarchies"): take a subtree out, re-insert it where the surface area of the tree grows least
+// (branch-and-bound search from the root), most wasteful nodes first.  Greedy top-down SAH cannot undo an early split;
+// this can.  Leaves and their primitive ranges are untouched; afterwards the references are re-packed in DFS leaf order.
+struct TreeOptimizer {
+    std::vector<BuildNode> &n;
+    std::vector<int> parent;
+    explicit TreeOptimizer(std::vector<BuildNode> &nodes) : n(nodes), parent(nodes.size(), -1) {
+        for (size_t i = 0; i < n.size(); i++)
+            if (n[i].left >= 0)
+                parent[size_t(n[i].left)] = int(i), parent[size_t(n[i].right)] = int(i);
+    }
+    static Box merged(const Box &a, const Box &b) {
+        Box r = a;
+        r.grow(b);
+        return r;
+    }
+    void refit_up(int i) {
+        for (; i >= 0; i = parent[size_t(i)]) {
+            Box b = n[size_t(n[size_t(i)].left)].box;
+            b.grow(n[size_t(n[size_t(i)].right)].box);
+            n[size_t(i)].box = b;
+        }
+    }
+    double total_area() const {
+        double a = 0;
+        for (size_t i = 0; i < n.size(); i++)
+            if (n[i].left >= 0)
+                a += n[i].box.area();
+        return a;
+    }
+    // returns true if the tree changed
+    bool reinsert(int x) {
+        const int p = parent[size_t(x)];
+        if (p <= 0)
+            return false; // root or child of the root
+        const int g = parent[size_t(p)], s = n[size_t(p)].left == x ? n[size_t(p)].right : n[size_t(p)].left;
+        // detach x and p: s takes p's place
+        (n[size_t(g)].left == p ? n[size_t(g)].left : n[size_t(g)].right) = s;
+        parent[size_t(s)] = g;
+        refit_up(g);
+        // branch and bound for the cheapest new sibling
+        const Box xb = n[size_t(x)].box;
+        const float xa = xb.area();
+        struct Cand {
+            float induced;
+            int node;
+            bool operator<(const Cand &o) const { return induced > o.induced; } // min-heap on the induced cost
+        };
+        std::priority_queue<Cand> pq;
+        { // the root itself is not a candidate (node 0 stays the root): start from its children
+            const float root_induced = merged(n[0].box, xb).area() - n[0].box.area();
+            pq.push(Cand{root_induced, n[0].left});
+            pq.push(Cand{root_induced, n[0].right});
+        }
+        float best_cost = 1e30f;
+        int best = s;
+        while (!pq.empty()) {
+            const Cand c = pq.top();
+            pq.pop();
+            if (c.induced + xa >= best_cost)
+                break;
+            const BuildNode &nd = n[size_t(c.node)];
+            const float direct = merged(nd.box, xb).area(), cost = c.induced + direct;
+            if (cost < best_cost)
+                best_cost = cost, best = c.node;
+            const float child_induced = cost - nd.box.area();
+            if (nd.left >= 0 && child_induced + xa < best_cost) {
+                pq.push(Cand{child_induced, nd.left});
+                pq.push(Cand{child_induced, nd.right});
+            }
+        }
+        // p becomes the parent of (best, x) in best's place
+        const int bp = parent[size_t(best)];
+        n[size_t(p)].left = best, n[size_t(p)].right = x;
+        parent[size_t(best)] = p, parent[size_t(x)] = p;
+        parent[size_t(p)] = bp;
+        if (bp >= 0)
+            (n[size_t(bp)].left == best ? n[size_t(bp)].left : n[size_t(bp)].right) = p;
+        refit_up(p);
+        return best != s;
+    }
+    void run(int passes, float fraction) {
+        for (int pass = 0; pass < passes; pass++) {
+            // candidates: inner and leaf nodes, largest surface area first (the ones that cost the most when badly placed)
+            std::vector<int> order;
+            order.reserve(n.size());
+            for (size_t i = 1; i < n.size(); i++)
+                if (parent[i] > 0)
+                    order.push_back(int(i));
+            std::sort(order.begin(), order.end(), [&](int a, int b) {
+                const float aa = n[size_t(a)].box.area(), ab = n[size_t(b)].box.area();
+                return aa > ab || (aa == ab && a < b);
+            });
+            const size_t count = size_t(double(order.size()) * fraction);
+            for (size_t k = 0; k < count; k++)
+                reinsert(order[k]);
+        }
+    }
+};
+
+void optimize_tree(Builder &b, int passes, float fraction) {
+    const double before = TreeOptimizer(b.nodes).total_area();
+    std::vector<BuildNode> backup = b.nodes;
+    {
+        TreeOptimizer opt(b.nodes);
+        opt.run(passes, fraction);
+        if (!(opt.total_area() < before)) {
+            b.nodes.swap(backup);
+            return;
+        }
+    }
+    // depths, and references re-packed in DFS leaf order (leaf ranges ascend along the reference-order traversal)
+    std::vector<PrimRef> packed;
+    packed.reserve(b.refs.size());
+    int max_depth = 0;
+    std::vector<std::pair<int, int>> stack(1, {0, 0});
+    while (!stack.empty()) {
+        const auto [id, depth] = stack.back();
+        stack.pop_back();
+        BuildNode &nd = b.nodes[size_t(id)];
+        nd.depth = depth;
+        max_depth = std::max(max_depth, depth);
+        if (nd.left < 0) {
+            const int nb = int(packed.size());
+            for (int i = nd.base; i < nd.base + nd.count; i++)
+                packed.push_back(b.refs[size_t(i)]);
+            nd.base = nb;
+        } else {
+            stack.push_back({nd.right, depth + 1});
+            stack.push_back({nd.left, depth + 1});
+        }
+    }
+    if (max_depth > 40 || packed.size() != b.refs.size()) { // keep the traversal stack of the renderer safe
+        b.nodes.swap(backup);
+        return;
+    }
+    b.refs.swap(packed);
+    b.max_depth = max_depth;
+}
 
 uint16_t f2h(float f) { // round-to-nearest-even half (see scene_host.cpp); local copy to keep this TU independent
     uint32_t x;
@@ -1300,7 +1443,34 @@ void load_xml(const std::string &path, HostScene &out) {
             bld.nodes.reserve(2 * P0);
             bld.build(0, int(P0), 0);
         }
-        const int cache_levels = std::min(std::max(bld.max_depth - 1, 0), cache_level);
+        {
+            int passes = 2;
+            float fraction = 1.f;
+            if (const char *e = getenv("CPTB200_TREE_OPT"))
+                passes = atoi(e);
+            if (const char *e = getenv("CPTB200_TREE_OPT_FRACTION"))
+                fraction = float(atof(e));
+            if (passes > 0 && P0 > 64)
+                optimize_tree(bld, passes, fraction);
+        }
+        // The cached near-root nodes hold fp16 boxes rounded to nearest (bvh.cuh:182-251, reproduced by the kernels): the
+        // bounds of a large axis-aligned triangle (a wall: 2e-5 thick) collapse to zero thickness there and are never
+        // entered, so a LEAF inside the cached levels loses its hits - the holes of the reference's own cornell image.
+        // Our trees keep every leaf below the cached levels (the optimised tree lifts big triangles close to the root).
+        int min_leaf_depth = bld.max_depth;
+        {
+            std::vector<std::pair<int, int>> st(1, {0, 0});
+            while (!st.empty()) {
+                const auto [id, depth] = st.back();
+                st.pop_back();
+                const BuildNode &nd = bld.nodes[size_t(id)];
+                if (nd.left < 0)
+                    min_leaf_depth = std::min(min_leaf_depth, depth);
+                else if (depth + 1 < min_leaf_depth)
+                    st.push_back({nd.left, depth + 1}), st.push_back({nd.right, depth + 1});
+            }
+        }
+        const int cache_levels = std::min(std::min(std::max(bld.max_depth - 1, 0), cache_level), min_leaf_depth);
         linearize(bld, 0, 0, cache_levels, out.nodes, out.cache_nodes);
         cache_level = cache_levels;
         // reorder primitives into leaf order, build the emitter primitive map (bvh.cu:325-401)
