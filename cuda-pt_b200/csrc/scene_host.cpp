@@ -489,18 +489,43 @@ void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
             c.hi = F4{bhi[0], bhi[1], bhi[2], as_float(k + 1)};
             return c;
         }
-        int axis = 0;
-        float ext = -1.f;
-        for (int a = 0; a < 3; a++) {
-            float clo = 1e30f, chi = -1e30f;
-            for (int i = lo; i < hi; i++)
-                clo = std::min(clo, tris[i].ctr[a]), chi = std::max(chi, tris[i].ctr[a]);
-            if (chi - clo > ext)
-                ext = chi - clo, axis = a;
+        // split: exact SAH over the centroid-sorted order of each axis (a leaf holds at most a few dozen primitives);
+        // falls back to the median of the widest axis when no split beats keeping the range together
+        int mid = lo + cnt / 2;
+        {
+            float best_cost = 1e30f;
+            int best_axis = -1, best_pos = -1;
+            std::vector<float> right_area(size_t(cnt) + 1);
+            for (int a = 0; a < 3; a++) {
+                std::sort(tris.begin() + lo, tris.begin() + hi,
+                          [a](const Tri &x, const Tri &y) { return x.ctr[a] < y.ctr[a] || (x.ctr[a] == y.ctr[a] && x.orig < y.orig); });
+                float rl[3] = {1e30f, 1e30f, 1e30f}, rh[3] = {-1e30f, -1e30f, -1e30f};
+                auto area_of = [](const float *l, const float *h) {
+                    const float dx = h[0] - l[0], dy = h[1] - l[1], dz = h[2] - l[2];
+                    return 2.f * (dx * dy + dy * dz + dx * dz);
+                };
+                for (int i = cnt - 1; i > 0; i--) {
+                    for (int q = 0; q < 3; q++)
+                        rl[q] = std::min(rl[q], tris[lo + i].lo[q]), rh[q] = std::max(rh[q], tris[lo + i].hi[q]);
+                    right_area[size_t(i)] = area_of(rl, rh);
+                }
+                float ll[3] = {1e30f, 1e30f, 1e30f}, lh[3] = {-1e30f, -1e30f, -1e30f};
+                for (int i = 1; i < cnt; i++) {
+                    for (int q = 0; q < 3; q++)
+                        ll[q] = std::min(ll[q], tris[lo + i - 1].lo[q]), lh[q] = std::max(lh[q], tris[lo + i - 1].hi[q]);
+                    const float cost = area_of(ll, lh) * float(i) + right_area[size_t(i)] * float(cnt - i);
+                    if (cost < best_cost)
+                        best_cost = cost, best_axis = a, best_pos = i;
+                }
+            }
+            if (best_axis >= 0) {
+                const int a = best_axis;
+                if (a != 2)
+                    std::sort(tris.begin() + lo, tris.begin() + hi,
+                              [a](const Tri &x, const Tri &y) { return x.ctr[a] < y.ctr[a] || (x.ctr[a] == y.ctr[a] && x.orig < y.orig); });
+                mid = lo + best_pos;
+            }
         }
-        const int mid = lo + cnt / 2;
-        std::nth_element(tris.begin() + lo, tris.begin() + mid, tris.begin() + hi,
-                         [axis](const Tri &a, const Tri &b) { return a.ctr[axis] < b.ctr[axis] || (a.ctr[axis] == b.ctr[axis] && a.orig < b.orig); });
         const int idx = new_node();
         const Child a = refine(k, tris, lo, mid, base, depth + 1), b = refine(k, tris, mid, hi, base, depth + 1);
         out.wnodes[4 * idx + 0] = a.lo, out.wnodes[4 * idx + 1] = a.hi;

@@ -3,7 +3,7 @@ O=gpurun_out/refine; mkdir -p $O
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $O/pytest.log
 oracle/_ref/ref_dump dump scenes/ref_xml/whiskey.xml $O/w.cpts > /dev/null 2>&1
 oracle/_ref/ref_dump dump scenes/xml/vader_wfpt_1080p.xml $O/v.cpts > /dev/null 2>&1
-for rf in 0 2; do
+for rf in 2; do
 CPTB200_REFINE_LEAVES=$rf python - <<PY 2>&1 | tee -a $O/ours.log
 import time, numpy as np, cuda_pt_b200 as cpt
 for name, path in (("whiskey ref-built", "$O/w.cpts"), ("vader ref-built", "$O/v.cpts"), ("vader own", "scenes/xml/vader_wfpt_1080p.xml")):
