@@ -1413,7 +1413,8 @@ void load_xml(const std::string &path, HostScene &out) {
         // Greedy top-down SAH is sensitive to where the bins fall near the root (a big floor under a dense model): the
         // total SAH cost of the finished tree is bimodal in the bin count (vader: 9.62 with 16 / 48 / 64 bins, 8.99 with
         // 24 / 32 / 40; whiskey 7.26 vs 6.43) and traversal time follows it (-2.5 % / -11 %).  So the tree is built with
-        // several bin counts in parallel and the cheapest one is kept (CPTB200_SAH_BINS pins a single count).
+        // several bin counts in parallel, each one optimised (optimize_tree), and the cheapest result is kept
+        // (CPTB200_SAH_BINS pins a single count).
         auto sah_total = [](const Builder &b) {
             const float root = std::max(b.nodes[0].box.area(), 1e-20f);
             double cost = 0;
@@ -1421,16 +1422,25 @@ void load_xml(const std::string &path, HostScene &out) {
                 cost += double(n.box.area()) / root * (n.left < 0 ? double(n.count) : double(b.kTraverse));
             return cost;
         };
+        int opt_passes = 2;
+        float opt_fraction = 1.f;
+        if (const char *e = getenv("CPTB200_TREE_OPT"))
+            opt_passes = atoi(e);
+        if (const char *e = getenv("CPTB200_TREE_OPT_FRACTION"))
+            opt_fraction = float(atof(e));
+        auto build_one = [P0, opt_passes, opt_fraction](Builder &b) {
+            b.nodes.reserve(2 * P0);
+            b.build(0, int(P0), 0);
+            if (opt_passes > 0 && P0 > 64)
+                optimize_tree(b, opt_passes, opt_fraction);
+        };
         if (!getenv("CPTB200_SAH_BINS") && P0 > 64) {
             const int candidates[4] = {16, 24, 32, 40};
             std::vector<Builder> trial(4, bld);
             std::vector<std::thread> workers;
             for (int c = 0; c < 4; c++) {
                 trial[c].kBins = candidates[c];
-                workers.emplace_back([&trial, c, P0]() {
-                    trial[c].nodes.reserve(2 * P0);
-                    trial[c].build(0, int(P0), 0);
-                });
+                workers.emplace_back([&trial, &build_one, c]() { build_one(trial[c]); });
             }
             for (auto &w : workers)
                 w.join();
@@ -1440,18 +1450,7 @@ void load_xml(const std::string &path, HostScene &out) {
                     best = c;
             bld = std::move(trial[best]);
         } else {
-            bld.nodes.reserve(2 * P0);
-            bld.build(0, int(P0), 0);
-        }
-        {
-            int passes = 2;
-            float fraction = 1.f;
-            if (const char *e = getenv("CPTB200_TREE_OPT"))
-                passes = atoi(e);
-            if (const char *e = getenv("CPTB200_TREE_OPT_FRACTION"))
-                fraction = float(atof(e));
-            if (passes > 0 && P0 > 64)
-                optimize_tree(bld, passes, fraction);
+            build_one(bld);
         }
         // The cached near-root nodes hold fp16 boxes rounded to nearest (bvh.cuh:182-251, reproduced by the kernels): the
         // bounds of a large axis-aligned triangle (a wall: 2e-5 thick) collapse to zero thickness there and are never
