@@ -57,6 +57,7 @@ int main(int argc, char **argv) {
                 for (int i = node_i(k, 0); i < node_i(k, 0) + node_i(k, 1); i++)
                     if (pl.perm[i] < node_i(k, 0) || pl.perm[i] >= node_i(k, 0) + node_i(k, 1)) errors++;
     }
-    printf("prims %d leaf_records %d refined_leaves %d depth %d errors %d\n", P, leaf_records, pl.refined_leaves, pl.max_depth, errors);
+    printf("prims %d leaf_records %d refined_leaves %d depth %d nesting_violations %d errors %d\n", P, leaf_records, pl.refined_leaves, pl.max_depth,
+           pl.nesting_violations, errors);
     return errors ? 1 : 0;
 }

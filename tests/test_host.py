@@ -392,3 +392,19 @@ def test_pair_layout_and_leaf_refinement_invariants(tmp_path):
                 assert int(fields["refined_leaves"]) == 0
             refined_any += int(fields["refined_leaves"])
     assert refined_any > 0
+    # trees built by our own loader (binned SAH, best of four bin counts, insertion-based optimisation): same invariants,
+    # every child box inside its parent's, shallow enough for the traversal stack, no leaf inside the cached levels
+    if have_meshes():
+        for xml in ("cbox_mats_wfpt_256.xml", "medium_cbox_vpt_256.xml", "texroom_wfpt_256.xml"):
+            sc = cpt.Scene(os.path.join(SCENES, xml))
+            path = str(tmp_path / "own.cpts")
+            sc.save(path)
+            out = subprocess.run([exe, path, "2"], capture_output=True, text=True)
+            assert out.returncode == 0, (xml, out.stdout, out.stderr)
+            fields = dict(zip(out.stdout.split()[0::2], out.stdout.split()[1::2]))
+            assert int(fields["errors"]) == 0 and int(fields["nesting_violations"]) == 0 and int(fields["depth"]) <= 46, (xml, fields)
+            d = read_cpts(path)
+            nodes = d["nodes"].reshape(-1, 2, 4)
+            cnt = nodes[:, 1, 3].copy().view(np.int32)
+            cached_idx = (d["cache_nodes"][:, 3] >> 8).astype(np.int64)
+            assert not (cnt[cached_idx] > 0).any(), xml  # no leaf among the fp16-cached nodes
