@@ -24,6 +24,9 @@
  *   mkvdb  <prefix> [n]
  *          write synthetic <prefix>_{density,albedo,temperature}.nvdb with the vendored NanoVDB tools (the reference's
  *          own volume assets are not distributed); no scene is loaded.
+ *   vdbdump <file.nvdb> <out.cpts>
+ *          brick-grid image of one float grid read voxel by voxel through NanoVDB's host accessor (no scene, no GPU):
+ *          the reference answer for tests of our own .nvdb reader.
  *   bench  <xml> <mode> <warmup> <frames> [seed_offset]
  *          time `frames` render_raw() calls with CUDA events; prints one JSON line.
  */
@@ -587,6 +590,48 @@ int make_vdb(const std::string &prefix, int n) {
     gt(temperature, box);
     io::writeGrid(prefix + "_temperature.nvdb", tools::createNanoGrid(gt));
     printf("[ref_dump] wrote %s_{density,albedo,temperature}.nvdb (%d x %d x %d voxels of %.5f)\n", prefix.c_str(), nx, ny, nz, vs);
+    // a grid with constant regions: full 8^3 leaves of one value are pruned into tile values by the NanoVDB builder, so this
+    // file exercises the tile paths of a reader (lower-level tiles) next to ordinary leaves; negative index coordinates too
+    auto blocks = [=](const Coord &c) -> float {
+        const bool core = c[0] >= -16 && c[0] < 24 && c[1] >= 0 && c[1] < 32 && c[2] >= -8 && c[2] < 16;
+        if (core)
+            return 0.75f;
+        const bool shell = c[0] >= -19 && c[0] < 27 && c[1] >= -3 && c[1] < 35 && c[2] >= -11 && c[2] < 19;
+        return shell ? 0.1f + 0.01f * float((c[0] * 7 + c[1] * 3 + c[2] * 5) & 15) : 0.f;
+    };
+    tools::build::Grid<float> gb(0.f, "blocks", GridClass::FogVolume);
+    gb.setTransform(0.05, Vec3d(1.0, 0.5, 2.0));
+    gb(blocks, CoordBBox(Coord(-24, -8, -16), Coord(31, 39, 23)));
+    io::writeGrid(prefix + "_blocks.nvdb", tools::createNanoGrid(gb));
+    return 0;
+}
+
+// `vdbdump <file.nvdb> <out.cpts>`: the brick-grid image of one float grid, every voxel read through NanoVDB's own host
+// accessor (append_channel) - the reference answer for readers of the .nvdb container.  No scene, no GPU.
+int dump_vdb(const std::string &path, const std::string &out_path) {
+    auto h = nanovdb::io::readGrid(path);
+    const nanovdb::FloatGrid *g = h.grid<float>();
+    if (!g) {
+        fprintf(stderr, "vdbdump: %s holds no float grid\n", path.c_str());
+        return 1;
+    }
+    CptsGrid rec{};
+    std::vector<int32_t> bricks;
+    std::vector<float> data;
+    append_channel<nanovdb::FloatGrid, 1>(g, rec.ch[CPTS_GRID_DENSITY], bricks, data);
+    float lo = 0, hi = 0;
+    g->tree().extrema(lo, hi);
+    rec.majorant = hi;
+    const auto wb = g->worldBBox();
+    for (int k = 0; k < 3; k++)
+        rec.aabb_min[k] = float(wb.min()[k]), rec.aabb_max[k] = float(wb.max()[k]);
+    Writer w(out_path);
+    w.section("grids", &rec, sizeof(CptsGrid), 1);
+    w.section("grid_bricks", bricks.data(), 4, bricks.size());
+    w.section("grid_data", data.data(), 4, data.size());
+    w.close();
+    printf("[ref_dump] wrote %s (%zu bricks, %zu values, tiles in tree: %u lower, %u upper)\n", out_path.c_str(), bricks.size(), data.size(),
+           g->tree().nodeCount(1) ? unsigned(h.gridMetaData()->activeTileCount(1)) : 0u, unsigned(h.gridMetaData()->activeTileCount(2)));
     return 0;
 }
 
@@ -624,6 +669,8 @@ int main(int argc, char **argv) {
     std::string cmd = argv[1], xml = argv[2];
     if (cmd == "mkvdb")
         return make_vdb(argv[2], argc > 3 ? atoi(argv[3]) : 64);
+    if (cmd == "vdbdump")
+        return argc > 3 ? dump_vdb(argv[2], argv[3]) : 1;
     CUDA_CHECK_RETURN(cudaFree(nullptr));
     ColorSpaceXYZ xyz_host;
     Scene scene(xml);

@@ -408,3 +408,35 @@ def test_pair_layout_and_leaf_refinement_invariants(tmp_path):
             cnt = nodes[:, 1, 3].copy().view(np.int32)
             cached_idx = (d["cache_nodes"][:, 3] >> 8).astype(np.int64)
             assert not (cnt[cached_idx] > 0).any(), xml  # no leaf among the fp16-cached nodes
+
+
+REF_DUMP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_dump")
+
+
+@needs_meshes
+@pytest.mark.skipif(not os.path.exists(REF_DUMP), reason="reference harness (NanoVDB tools) not built")
+def test_nvdb_reader_matches_nanovdb_accessor_incl_tiles(tmp_path):
+    """Our .nvdb reader against NanoVDB's own host accessor (`ref_dump vdbdump`, no GPU) on a grid whose constant regions
+    the NanoVDB builder pruned into tile values (60 lower-level tiles), with negative index coordinates, and on the
+    ordinary puff: identical float map, index box, brick table and brick pool."""
+    import subprocess
+    prefix = str(tmp_path / "t")
+    subprocess.run([REF_DUMP, "mkvdb", prefix, "32"], check=True, capture_output=True)
+    mesh = lambda n: os.path.relpath(os.path.join(os.path.dirname(SCENES), "meshes", "cbox", n), str(tmp_path))
+    for kind, min_tiles in (("blocks", 1), ("density", 0)):
+        out = subprocess.run([REF_DUMP, "vdbdump", f"{prefix}_{kind}.nvdb", f"{prefix}_{kind}.cpts"], check=True, capture_output=True, text=True)
+        tiles = int(out.stdout.split("tiles in tree:")[1].split()[0])
+        assert tiles >= min_tiles
+        x = tmp_path / f"{kind}.xml"
+        x.write_text(f'''<scene version="1.2"><renderer type="vpt"/><sensor><film/></sensor><phase type="isotropic" id="p"/>
+<medium type="grid" id="m"><string name="density" value="t_{kind}.nvdb"/><ref type="phase" id="p"/></medium>
+<brdf type="lambertian" id="w"/><emitter type="area" id="a"><rgb name="emission" value="1,1,1"/><string name="bind_type" value="triangle"/></emitter>
+<shape type="obj"><string name="filename" value="{mesh("light.obj")}"/><ref type="material" id="w"/><ref type="emitter" id="a"/></shape>
+<shape type="obj"><string name="filename" value="{mesh("floor.obj")}"/><ref type="material" id="w"/></shape></scene>''')
+        sc = cpt.Scene(str(x))
+        sc.save(str(tmp_path / "own.cpts"))
+        a, b = read_cpts(str(tmp_path / "own.cpts")), read_cpts(f"{prefix}_{kind}.cpts")
+        ga, gb = a["grids"][0], b["grids"][0]
+        assert ga[56:160].tobytes() == gb[56:160].tobytes()          # density channel: map, index box, background
+        assert ga[20:24].tobytes() == gb[20:24].tobytes() and ga[32:56].tobytes() == gb[32:56].tobytes()  # majorant, world box
+        assert np.array_equal(a["grid_bricks"], b["grid_bricks"]) and a["grid_data"].tobytes() == b["grid_data"].tobytes()
