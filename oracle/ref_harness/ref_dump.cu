@@ -603,6 +603,14 @@ int make_vdb(const std::string &prefix, int n) {
     gb.setTransform(0.05, Vec3d(1.0, 0.5, 2.0));
     gb(blocks, CoordBBox(Coord(-24, -8, -16), Coord(31, 39, 23)));
     io::writeGrid(prefix + "_blocks.nvdb", tools::createNanoGrid(gb));
+    auto blocks3 = [=](const Coord &c) -> Vec3f {
+        const float v = blocks(c);
+        return v == 0.f ? Vec3f(0.f) : (v == 0.75f ? Vec3f(0.75f, 0.5f, 0.25f) : Vec3f(v, 1.f - v, 0.5f * v));
+    };
+    tools::build::Grid<Vec3f> gb3(Vec3f(0.f), "blocks3", GridClass::Unknown);
+    gb3.setTransform(0.05, Vec3d(1.0, 0.5, 2.0));
+    gb3(blocks3, CoordBBox(Coord(-24, -8, -16), Coord(31, 39, 23)));
+    io::writeGrid(prefix + "_blocks3.nvdb", tools::createNanoGrid(gb3));
     return 0;
 }
 
@@ -610,14 +618,25 @@ int make_vdb(const std::string &prefix, int n) {
 // accessor (append_channel) - the reference answer for readers of the .nvdb container.  No scene, no GPU.
 int dump_vdb(const std::string &path, const std::string &out_path) {
     auto h = nanovdb::io::readGrid(path);
-    const nanovdb::FloatGrid *g = h.grid<float>();
-    if (!g) {
-        fprintf(stderr, "vdbdump: %s holds no float grid\n", path.c_str());
-        return 1;
-    }
     CptsGrid rec{};
     std::vector<int32_t> bricks;
     std::vector<float> data;
+    if (const nanovdb::Vec3fGrid *g3 = h.grid<nanovdb::Vec3f>()) { // Vec3f grid: the albedo channel
+        append_channel<nanovdb::Vec3fGrid, 3>(g3, rec.ch[CPTS_GRID_ALBEDO], bricks, data);
+        Writer w3(out_path);
+        w3.section("grids", &rec, sizeof(CptsGrid), 1);
+        w3.section("grid_bricks", bricks.data(), 4, bricks.size());
+        w3.section("grid_data", data.data(), 4, data.size());
+        w3.close();
+        printf("[ref_dump] wrote %s (%zu bricks, %zu values, tiles in tree: %u lower, %u upper)\n", out_path.c_str(), bricks.size(), data.size(),
+               unsigned(h.gridMetaData()->activeTileCount(1)), unsigned(h.gridMetaData()->activeTileCount(2)));
+        return 0;
+    }
+    const nanovdb::FloatGrid *g = h.grid<float>();
+    if (!g) {
+        fprintf(stderr, "vdbdump: %s holds neither a float nor a Vec3f grid\n", path.c_str());
+        return 1;
+    }
     append_channel<nanovdb::FloatGrid, 1>(g, rec.ch[CPTS_GRID_DENSITY], bricks, data);
     float lo = 0, hi = 0;
     g->tree().extrema(lo, hi);

@@ -440,3 +440,18 @@ def test_nvdb_reader_matches_nanovdb_accessor_incl_tiles(tmp_path):
         assert ga[56:160].tobytes() == gb[56:160].tobytes()          # density channel: map, index box, background
         assert ga[20:24].tobytes() == gb[20:24].tobytes() and ga[32:56].tobytes() == gb[32:56].tobytes()  # majorant, world box
         assert np.array_equal(a["grid_bricks"], b["grid_bricks"]) and a["grid_data"].tobytes() == b["grid_data"].tobytes()
+    # Vec3f grid with tiles as the albedo channel of a medium whose density is the ordinary puff
+    out = subprocess.run([REF_DUMP, "vdbdump", f"{prefix}_blocks3.nvdb", f"{prefix}_blocks3.cpts"], check=True, capture_output=True, text=True)
+    assert int(out.stdout.split("tiles in tree:")[1].split()[0]) >= 1
+    x = tmp_path / "v3.xml"
+    x.write_text(open(str(tmp_path / "density.xml")).read().replace('<string name="density" value="t_density.nvdb"/>',
+                 '<string name="density" value="t_density.nvdb"/><string name="albedo" value="t_blocks3.nvdb"/>'))
+    sc = cpt.Scene(str(x))
+    sc.save(str(tmp_path / "own3.cpts"))
+    a, b, d = read_cpts(str(tmp_path / "own3.cpts")), read_cpts(f"{prefix}_blocks3.cpts"), read_cpts(f"{prefix}_density.cpts")
+    ga, gb = a["grids"][0], b["grids"][0]
+    alb_a, alb_b = ga[160:264].copy(), gb[160:264].copy()   # albedo channel record; offsets differ (it follows the density channel)
+    nb_d, nd_d = d["grid_bricks"].size, d["grid_data"].size
+    assert alb_a[:88].tobytes() == alb_b[:88].tobytes()
+    assert np.frombuffer(alb_a[88:104].tobytes(), dtype=np.uint64).tolist() == [nb_d, nd_d]
+    assert np.array_equal(a["grid_bricks"][nb_d:], b["grid_bricks"]) and a["grid_data"][nd_d:].tobytes() == b["grid_data"].tobytes()
