@@ -27,6 +27,8 @@
  *   vdbdump <file.nvdb> <out.cpts>
  *          brick-grid image of one float grid read voxel by voxel through NanoVDB's host accessor (no scene, no GPU):
  *          the reference answer for tests of our own .nvdb reader.
+ *   imgdump <image> <channels> <out.bin>
+ *          the pixels the reference's texture loader gets for an image file (its stb_image instance, no scene, no GPU).
  *   bench  <xml> <mode> <warmup> <frames> [seed_offset]
  *          time `frames` render_raw() calls with CUDA events; prints one JSON line.
  */
@@ -614,6 +616,27 @@ int make_vdb(const std::string &prefix, int n) {
     return 0;
 }
 
+// `imgdump <image> <channels> <out.bin>`: what the reference's texture loader gets from its image library for this file
+// (stbi_load as instantiated in src/impl/textures.cu:27-29, called like textures.cu:59,100): int32 width, height, channels
+// in file, channels requested, then the 8-bit pixels.  No scene, no GPU - the reference answer for our image decoders.
+extern "C" unsigned char *stbi_load(char const *filename, int *x, int *y, int *channels_in_file, int desired_channels);
+extern "C" void stbi_image_free(void *retval_from_stbi_load);
+int dump_image(const std::string &path, int req, const std::string &out_path) {
+    int w = 0, h = 0, n = 0;
+    unsigned char *px = stbi_load(path.c_str(), &w, &h, &n, req);
+    if (!px) {
+        fprintf(stderr, "imgdump: cannot decode %s\n", path.c_str());
+        return 1;
+    }
+    FILE *fp = fopen(out_path.c_str(), "wb");
+    const int32_t hdr[4] = {w, h, n, req};
+    fwrite(hdr, 4, 4, fp);
+    fwrite(px, 1, size_t(w) * h * (req ? req : n), fp);
+    fclose(fp);
+    stbi_image_free(px);
+    return 0;
+}
+
 // `vdbdump <file.nvdb> <out.cpts>`: the brick-grid image of one float grid, every voxel read through NanoVDB's own host
 // accessor (append_channel) - the reference answer for readers of the .nvdb container.  No scene, no GPU.
 int dump_vdb(const std::string &path, const std::string &out_path) {
@@ -690,6 +713,8 @@ int main(int argc, char **argv) {
         return make_vdb(argv[2], argc > 3 ? atoi(argv[3]) : 64);
     if (cmd == "vdbdump")
         return argc > 3 ? dump_vdb(argv[2], argv[3]) : 1;
+    if (cmd == "imgdump")
+        return argc > 4 ? dump_image(argv[2], atoi(argv[3]), argv[4]) : 1;
     CUDA_CHECK_RETURN(cudaFree(nullptr));
     ColorSpaceXYZ xyz_host;
     Scene scene(xml);

@@ -271,6 +271,10 @@ def test_image_errors(tmp_path):
     notpng.write_bytes(b"\xff\xd8\xff\xe0 not really a jpeg")
     x.write_text('<scene version="1.2"><sensor><film/></sensor><brdf type="lambertian" id="a">'
                  '<ref type="texture" id="t"/></brdf><texture id="t"><string name="diffuse" value="a.jpg"/></texture></scene>')
+    with pytest.raises(cpt.CptError, match="JPEG"):
+        cpt.Scene(str(x))
+    (tmp_path / "a.hdr").write_bytes(b"#?RADIANCE\n\n-Y 1 +X 1\n\x80\x80\x80\x80")
+    x.write_text(x.read_text().replace("a.jpg", "a.hdr"))
     with pytest.raises(cpt.CptError, match="PNG"):
         cpt.Scene(str(x))
     x.write_text('<scene version="1.2"><sensor><film/></sensor><brdf type="lambertian" id="a">'
@@ -455,3 +459,42 @@ def test_nvdb_reader_matches_nanovdb_accessor_incl_tiles(tmp_path):
     assert alb_a[:88].tobytes() == alb_b[:88].tobytes()
     assert np.frombuffer(alb_a[88:104].tobytes(), dtype=np.uint64).tolist() == [nb_d, nd_d]
     assert np.array_equal(a["grid_bricks"][nb_d:], b["grid_bricks"]) and a["grid_data"][nd_d:].tobytes() == b["grid_data"].tobytes()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DUMP), reason="reference harness not built")
+def test_image_decoders_match_the_reference_decoder_byte_for_byte(tmp_path):
+    """Our PNG and baseline-JPEG decoders against the decoder the reference links (`ref_dump imgdump` = its stb_image
+    instance, CPU only): 4:4:4 / 4:2:2 / 4:2:0 / 4:1:1 chroma, greyscale, restart markers, optimised Huffman tables, low and
+    high quality, odd and tiny sizes, 1 / 2 / 3 / 4 requested channels (1 / 2 from a colour JPEG = its luma plane).
+    Progressive files are refused with a clear message."""
+    import subprocess
+    Image = pytest.importorskip("PIL.Image")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "cuda-pt_b200", "csrc")
+    exe = str(tmp_path / "image_check")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + csrc, os.path.join(root, "tests", "cpp", "image_check.cpp"),
+                    os.path.join(csrc, "image_io.cpp"), os.path.join(csrc, "jpeg_read.cpp"), "-lz", "-o", exe], check=True)
+    rng = np.random.default_rng(2)
+    def img(w, h, amp=100):
+        y, x = np.mgrid[0:h, 0:w]
+        a = np.stack([128 + amp * np.sin(x / 3.0) * np.cos(y / 4.0), 128 + amp * np.cos(x / 2.0 + y / 5.0), 128 + amp * np.sin((x + y) / 3.0)], -1)
+        return Image.fromarray(np.clip(a + rng.normal(0, 25, a.shape), 0, 255).astype(np.uint8))
+    cases = [("a444.jpg", img(67, 45), dict(quality=92, subsampling=0)), ("a422.jpg", img(67, 45), dict(quality=75, subsampling=1)),
+             ("a420.jpg", img(67, 45), dict(quality=85, subsampling=2)), ("a411.jpg", img(97, 61, 140), dict(quality=80, subsampling="4:1:1")),
+             ("grey.jpg", img(128, 96).convert("L"), dict(quality=80)), ("rst.jpg", img(200, 130), dict(quality=70, subsampling=2, restart_marker_blocks=3)),
+             ("opt.jpg", img(33, 17), dict(quality=30, subsampling=2, optimize=True)), ("q100.jpg", img(97, 61, 140), dict(quality=100, subsampling=0)),
+             ("hard.jpg", img(97, 61, 140), dict(quality=15, subsampling=2)), ("t1.jpg", img(1, 1), dict(quality=70)), ("t2.jpg", img(2, 3), dict(quality=70)),
+             ("t17.jpg", img(17, 33), dict(quality=70)), ("rgb.png", img(31, 19), {}), ("grey.png", img(31, 19).convert("L"), {}),
+             ("rgba.png", img(31, 19).convert("RGBA"), {})]
+    for name, im, kw in cases:
+        path = str(tmp_path / name)
+        im.save(path, **kw)
+        for req in (1, 2, 3, 4):
+            dump = str(tmp_path / (name + f".{req}.bin"))
+            subprocess.run([REF_DUMP, "imgdump", path, str(req), dump], check=True, capture_output=True)
+            out = subprocess.run([exe, path, str(req), dump], capture_output=True, text=True)
+            assert out.returncode == 0 and "mismatching bytes 0 of" in out.stdout, (name, req, out.stdout)
+    prog = str(tmp_path / "prog.jpg")
+    img(64, 64).save(prog, quality=80, progressive=True)
+    out = subprocess.run([exe, prog, "4", prog], capture_output=True, text=True)
+    assert out.returncode == 2 and "progressive" in out.stdout
