@@ -4,8 +4,7 @@
 // maps and 1 channel for roughness / ior maps (src/impl/textures.cu:53-81,92-131).  To give the same
 // texels for the same file this reader follows the PNG specification for decoding and stb_image's
 // documented channel-conversion rules (grey = (77 r + 150 g + 29 b) >> 8, opaque alpha = 255, 16-bit
-// samples keep their high byte).  Baseline JPEG files go to jpeg_read.cpp; HDR, progressive JPEG and interlaced PNG
-// files are rejected with an error.
+// samples keep their high byte).  JPEG files go to jpeg_read.cpp; HDR and interlaced PNG files are rejected with an error.
 #include "image_io.h"
 
 #include <cstdio>

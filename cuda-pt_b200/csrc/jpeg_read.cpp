@@ -1,4 +1,4 @@
-// jpeg_read.cpp — baseline / extended-sequential Huffman JPEG (ITU-T T.81) decoder for the XML scene loader.
+// jpeg_read.cpp — Huffman JPEG (ITU-T T.81: baseline, extended sequential, progressive) decoder for the XML scene loader.
 //
 // The reference decodes its textures with stb_image (src/impl/textures.cu:27-29,59,100) and the kernels sample the
 // decoded bytes, so "the same file gives the same texels" needs the same integer arithmetic after entropy decoding:
@@ -10,7 +10,8 @@
 //   * YCbCr -> RGB runs in 20-bit fixed point with the 1.402 / 0.71414 / 0.34414 / 1.772 coefficients rounded to 12 bits,
 //   * a request for 1 or 2 channels from a colour file returns the luma plane itself.
 // tests/test_host.py checks every case byte for byte against the reference's own decoder (`ref_dump imgdump`).
-// Progressive, arithmetic-coded, lossless, 12-bit and 4-component files are refused.
+// Baseline, extended-sequential and progressive Huffman files; arithmetic-coded, lossless, 12-bit and 4-component files are
+// refused.
 #include "image_io.h"
 
 #include <algorithm>
@@ -34,6 +35,7 @@ struct Component {
     int x = 0, y = 0;          // size in samples
     int dc_pred = 0;
     std::vector<uint8_t> data; // decoded plane
+    std::vector<int16_t> coef; // progressive files: 64 coefficients per block of the padded plane, until the last scan
 };
 
 const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
@@ -49,7 +51,8 @@ struct Decoder {
     Huff dc[4], ac[4];
     Component comp[3];
     int ncomp = 0, width = 0, height = 0, hmax = 1, vmax = 1, restart_interval = 0;
-    bool is_rgb = false, saw_jfif = false;
+    bool is_rgb = false, saw_jfif = false, progressive = false;
+    int ss = 0, se = 63, ah = 0, al = 0, eobrun = 0; // progressive scan parameters
     int adobe_transform = -1;
     // bit reader
     uint32_t bitbuf = 0;
@@ -234,10 +237,117 @@ struct Decoder {
         }
         for (int i = 0; i < ncomp; i++)
             comp[i].dc_pred = 0;
+        eobrun = 0;
+    }
+
+    // ---- progressive scans (T.81 Annex G): coefficients accumulate in c.coef, spectral band [ss, se], successive
+    // approximation bit positions ah (previous) / al (this scan)
+    void decode_block_progressive(Component &c, int bx, int by) {
+        int16_t *d = c.coef.data() + 64 * (size_t(by) * (c.w2 >> 3) + size_t(bx));
+        if (ss == 0) { // DC scan
+            if (ah == 0) {
+                const int t = decode(dc[c.td]);
+                if (t > 15)
+                    fail("bad DC category");
+                const int diff = t ? extend(bits(t), t) : 0;
+                c.dc_pred += diff;
+                d[0] = int16_t(c.dc_pred * (1 << al));
+            } else if (bits(1)) {
+                d[0] = int16_t(d[0] + int16_t(1 << al));
+            }
+            return;
+        }
+        if (ah == 0) { // AC first scan of this band
+            if (eobrun) {
+                --eobrun;
+                return;
+            }
+            for (int k = ss; k <= se;) {
+                const int rs = decode(ac[c.ta]), r = rs >> 4, s = rs & 15;
+                if (s == 0) {
+                    if (r < 15) {
+                        eobrun = 1 << r;
+                        if (r)
+                            eobrun += bits(r);
+                        --eobrun;
+                        break;
+                    }
+                    k += 16;
+                } else {
+                    k += r;
+                    if (k > 63)
+                        fail("coefficient index past the block");
+                    d[kZigzag[k]] = int16_t(extend(bits(s), s) * (1 << al));
+                    k++;
+                }
+            }
+            return;
+        }
+        // AC refinement: one more bit for every coefficient that is already non-zero, new +-1 coefficients in between
+        const int16_t bit = int16_t(1 << al);
+        auto refine = [&](int16_t &p) {
+            if (bits(1) && (p & bit) == 0)
+                p = int16_t(p > 0 ? p + bit : p - bit);
+        };
+        if (eobrun) {
+            --eobrun;
+            for (int k = ss; k <= se; k++) {
+                int16_t &p = d[kZigzag[k]];
+                if (p != 0)
+                    refine(p);
+            }
+            return;
+        }
+        int k = ss;
+        do {
+            const int rs = decode(ac[c.ta]);
+            int r = rs >> 4;
+            const int s = rs & 15;
+            int value = 0;
+            if (s == 0) {
+                if (r < 15) {
+                    eobrun = (1 << r) - 1;
+                    if (r)
+                        eobrun += bits(r);
+                    r = 64; // run to the end of the band
+                }
+            } else {
+                if (s != 1)
+                    fail("bad refinement code");
+                value = bits(1) ? bit : -bit;
+            }
+            while (k <= se) {
+                int16_t &p = d[kZigzag[k++]];
+                if (p != 0) {
+                    refine(p);
+                } else {
+                    if (r == 0) {
+                        p = int16_t(value);
+                        break;
+                    }
+                    --r;
+                }
+            }
+        } while (k <= se);
+    }
+
+    void finish_progressive() {
+        for (int i = 0; i < ncomp; i++) {
+            Component &c = comp[i];
+            const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+            const uint16_t *q = quant[c.tq];
+            for (int by = 0; by < bh; by++)
+                for (int bx = 0; bx < bw; bx++) {
+                    int16_t *d = c.coef.data() + 64 * (size_t(by) * (c.w2 >> 3) + size_t(bx));
+                    for (int k = 0; k < 64; k++)
+                        d[kZigzag[k]] = int16_t(d[kZigzag[k]] * q[k]);
+                    idct(d, c.data.data() + size_t(by) * 8 * c.w2 + size_t(bx) * 8, c.w2);
+                }
+        }
     }
 
     void scan(int nscan, const int *order) {
-        bitbuf = 0, bitcnt = 0, hit_marker = false;
+        bitbuf = 0, bitcnt = 0, hit_marker = false, eobrun = 0;
         for (int i = 0; i < ncomp; i++)
             comp[i].dc_pred = 0;
         int todo = restart_interval ? restart_interval : 0x7fffffff;
@@ -246,7 +356,10 @@ struct Decoder {
             const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
             for (int by = 0; by < bh; by++)
                 for (int bx = 0; bx < bw; bx++) {
-                    decode_block(c, bx, by);
+                    if (progressive)
+                        decode_block_progressive(c, bx, by);
+                    else
+                        decode_block(c, bx, by);
                     if (--todo <= 0) {
                         restart();
                         todo = restart_interval;
@@ -261,8 +374,12 @@ struct Decoder {
                 for (int k = 0; k < nscan; k++) {
                     Component &c = comp[order[k]];
                     for (int y = 0; y < c.v; y++)
-                        for (int x = 0; x < c.h; x++)
-                            decode_block(c, i * c.h + x, j * c.v + y);
+                        for (int x = 0; x < c.h; x++) {
+                            if (progressive)
+                                decode_block_progressive(c, i * c.h + x, j * c.v + y);
+                            else
+                                decode_block(c, i * c.h + x, j * c.v + y);
+                        }
                 }
                 if (--todo <= 0) {
                     restart();
@@ -314,7 +431,8 @@ struct Decoder {
                     build(cls ? ac[id] : dc[id], counts, &buf[pos], total);
                     pos += size_t(total);
                 }
-            } else if (m == 0xC0 || m == 0xC1) { // SOF0 / SOF1
+            } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) { // SOF0 / SOF1 / SOF2 (progressive)
+                progressive = m == 0xC2;
                 if (have_frame)
                     fail("more than one frame");
                 if (byte() != 8)
@@ -344,10 +462,12 @@ struct Decoder {
                     c.x = (width * c.h + hmax - 1) / hmax, c.y = (height * c.v + vmax - 1) / vmax;
                     c.w2 = mx * c.h * 8, c.h2 = my * c.v * 8;
                     c.data.assign(size_t(c.w2) * c.h2, 0);
+                    if (progressive)
+                        c.coef.assign(size_t(c.w2) * c.h2, 0);
                 }
                 have_frame = true;
-            } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
-                fail(m == 0xC2 ? "progressive JPEG is not supported (re-save as baseline)" : "unsupported JPEG process");
+            } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+                fail("unsupported JPEG process (lossless, hierarchical or arithmetic coding)");
             } else if (m == 0xDD) {
                 restart_interval = be16();
             } else if (m == 0xE0) {
@@ -375,9 +495,15 @@ struct Decoder {
                         fail("scan refers to an undefined table");
                     order[k] = which;
                 }
-                const int ss = byte(), se = byte(), ah_al = byte();
-                if (ss != 0 || se != 63 || ah_al != 0)
-                    fail("unsupported spectral selection (progressive scan?)");
+                ss = byte(), se = byte();
+                const int ah_al = byte();
+                ah = ah_al >> 4, al = ah_al & 15;
+                if (progressive) {
+                    if (ss > 63 || se > 63 || ss > se || ah > 13 || al > 13 || (ss == 0 && se != 0) || (ss != 0 && ns != 1))
+                        fail("bad progressive scan parameters");
+                } else if (ss != 0 || se != 63 || ah_al != 0) {
+                    fail("bad scan parameters");
+                }
                 pos = seg + size_t(len);
                 scan(ns, order);
                 decoded = true;
@@ -390,6 +516,8 @@ struct Decoder {
         }
         if (!have_frame || !decoded)
             fail("no image data");
+        if (progressive)
+            finish_progressive();
     }
 };
 

@@ -465,8 +465,8 @@ def test_nvdb_reader_matches_nanovdb_accessor_incl_tiles(tmp_path):
 def test_image_decoders_match_the_reference_decoder_byte_for_byte(tmp_path):
     """Our PNG and baseline-JPEG decoders against the decoder the reference links (`ref_dump imgdump` = its stb_image
     instance, CPU only): 4:4:4 / 4:2:2 / 4:2:0 / 4:1:1 chroma, greyscale, restart markers, optimised Huffman tables, low and
-    high quality, odd and tiny sizes, 1 / 2 / 3 / 4 requested channels (1 / 2 from a colour JPEG = its luma plane).
-    Progressive files are refused with a clear message."""
+    high quality, odd and tiny sizes, progressive files (spectral selection + successive approximation, with restart
+    markers), 1 / 2 / 3 / 4 requested channels (1 / 2 from a colour JPEG = its luma plane)."""
     import subprocess
     Image = pytest.importorskip("PIL.Image")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -484,7 +484,11 @@ def test_image_decoders_match_the_reference_decoder_byte_for_byte(tmp_path):
              ("grey.jpg", img(128, 96).convert("L"), dict(quality=80)), ("rst.jpg", img(200, 130), dict(quality=70, subsampling=2, restart_marker_blocks=3)),
              ("opt.jpg", img(33, 17), dict(quality=30, subsampling=2, optimize=True)), ("q100.jpg", img(97, 61, 140), dict(quality=100, subsampling=0)),
              ("hard.jpg", img(97, 61, 140), dict(quality=15, subsampling=2)), ("t1.jpg", img(1, 1), dict(quality=70)), ("t2.jpg", img(2, 3), dict(quality=70)),
-             ("t17.jpg", img(17, 33), dict(quality=70)), ("rgb.png", img(31, 19), {}), ("grey.png", img(31, 19).convert("L"), {}),
+             ("t17.jpg", img(17, 33), dict(quality=70)), ("p1.jpg", img(64, 64), dict(quality=80, progressive=True)),
+             ("p2.jpg", img(97, 61, 140), dict(quality=90, progressive=True, subsampling=0)),
+             ("p3.jpg", img(200, 130), dict(quality=50, progressive=True, subsampling=2, restart_marker_blocks=5)),
+             ("p4.jpg", img(37, 29).convert("L"), dict(quality=75, progressive=True)),
+             ("p5.jpg", img(33, 17), dict(quality=20, progressive=True, subsampling=1, optimize=True)), ("rgb.png", img(31, 19), {}), ("grey.png", img(31, 19).convert("L"), {}),
              ("rgba.png", img(31, 19).convert("RGBA"), {})]
     for name, im, kw in cases:
         path = str(tmp_path / name)
@@ -494,7 +498,7 @@ def test_image_decoders_match_the_reference_decoder_byte_for_byte(tmp_path):
             subprocess.run([REF_DUMP, "imgdump", path, str(req), dump], check=True, capture_output=True)
             out = subprocess.run([exe, path, str(req), dump], capture_output=True, text=True)
             assert out.returncode == 0 and "mismatching bytes 0 of" in out.stdout, (name, req, out.stdout)
-    prog = str(tmp_path / "prog.jpg")
-    img(64, 64).save(prog, quality=80, progressive=True)
-    out = subprocess.run([exe, prog, "4", prog], capture_output=True, text=True)
-    assert out.returncode == 2 and "progressive" in out.stdout
+    cmyk = str(tmp_path / "cmyk.jpg")
+    img(16, 16).convert("CMYK").save(cmyk, quality=80)
+    out = subprocess.run([exe, cmyk, "4", cmyk], capture_output=True, text=True)
+    assert out.returncode == 2 and "3-component" in out.stdout
