@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("CPTB200_LIB", os.path.join(PKG_DIR, "libcpt_b200.so"))  # override: A/B builds of the kernels
-SOURCES = ["wavefront.cu", "capi.cu", "scene_host.cpp", "scene_xml.cpp", "image_io.cpp", "jpeg_read.cpp", "nvdb_read.cpp"]
+SOURCES = ["wavefront.cu", "capi.cu", "scene_host.cpp", "scene_xml.cpp", "image_io.cpp", "jpeg_read.cpp", "hdr_read.cpp", "nvdb_read.cpp"]
 NVCC_FLAGS = [
     "-O3", "--use_fast_math", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",

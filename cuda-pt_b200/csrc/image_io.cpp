@@ -4,7 +4,7 @@
 // maps and 1 channel for roughness / ior maps (src/impl/textures.cu:53-81,92-131).  To give the same
 // texels for the same file this reader follows the PNG specification for decoding and stb_image's
 // documented channel-conversion rules (grey = (77 r + 150 g + 29 b) >> 8, opaque alpha = 255, 16-bit
-// samples keep their high byte).  JPEG files go to jpeg_read.cpp; HDR and interlaced PNG files are rejected with an error.
+// samples keep their high byte).  JPEG files go to jpeg_read.cpp, Radiance .hdr files to hdr_read.cpp; interlaced PNG files are rejected with an error.
 #include "image_io.h"
 
 #include <cstdio>
@@ -211,11 +211,13 @@ std::vector<uint8_t> load_image8(const std::string &path, int want_channels, int
     {
         FILE *fp = fopen(path.c_str(), "rb");
         uint8_t magic[2] = {0, 0};
-        const bool jpeg = fp && fread(magic, 1, 2, fp) == 2 && magic[0] == 0xFF && magic[1] == 0xD8;
+        const bool got = fp && fread(magic, 1, 2, fp) == 2;
         if (fp)
             fclose(fp);
-        if (jpeg)
+        if (got && magic[0] == 0xFF && magic[1] == 0xD8)
             return decode_jpeg(read_file(path), path, want_channels, width, height);
+        if (got && magic[0] == '#' && magic[1] == '?')
+            return decode_hdr(read_file(path), path, want_channels, width, height);
     }
     const Image8 img = decode_png(path);
     width = img.width, height = img.height;

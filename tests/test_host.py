@@ -275,6 +275,10 @@ def test_image_errors(tmp_path):
         cpt.Scene(str(x))
     (tmp_path / "a.hdr").write_bytes(b"#?RADIANCE\n\n-Y 1 +X 1\n\x80\x80\x80\x80")
     x.write_text(x.read_text().replace("a.jpg", "a.hdr"))
+    with pytest.raises(cpt.CptError, match="HDR.*unsupported format"):
+        cpt.Scene(str(x))
+    (tmp_path / "a.bmp").write_bytes(b"BM" + bytes(64))
+    x.write_text(x.read_text().replace("a.hdr", "a.bmp"))
     with pytest.raises(cpt.CptError, match="PNG"):
         cpt.Scene(str(x))
     x.write_text('<scene version="1.2"><sensor><film/></sensor><brdf type="lambertian" id="a">'
@@ -463,7 +467,7 @@ def test_nvdb_reader_matches_nanovdb_accessor_incl_tiles(tmp_path):
 
 @pytest.mark.skipif(not os.path.exists(REF_DUMP), reason="reference harness not built")
 def test_image_decoders_match_the_reference_decoder_byte_for_byte(tmp_path):
-    """Our PNG and baseline-JPEG decoders against the decoder the reference links (`ref_dump imgdump` = its stb_image
+    """Our PNG, JPEG and Radiance-HDR decoders against the decoder the reference links (`ref_dump imgdump` = its stb_image
     instance, CPU only): 4:4:4 / 4:2:2 / 4:2:0 / 4:1:1 chroma, greyscale, restart markers, optimised Huffman tables, low and
     high quality, odd and tiny sizes, progressive files (spectral selection + successive approximation, with restart
     markers), 1 / 2 / 3 / 4 requested channels (1 / 2 from a colour JPEG = its luma plane)."""
@@ -473,7 +477,8 @@ def test_image_decoders_match_the_reference_decoder_byte_for_byte(tmp_path):
     csrc = os.path.join(root, "cuda-pt_b200", "csrc")
     exe = str(tmp_path / "image_check")
     subprocess.run(["g++", "-std=c++17", "-O1", "-I" + csrc, os.path.join(root, "tests", "cpp", "image_check.cpp"),
-                    os.path.join(csrc, "image_io.cpp"), os.path.join(csrc, "jpeg_read.cpp"), "-lz", "-o", exe], check=True)
+                    os.path.join(csrc, "image_io.cpp"), os.path.join(csrc, "jpeg_read.cpp"), os.path.join(csrc, "hdr_read.cpp"), "-lz", "-o", exe],
+                   check=True)
     rng = np.random.default_rng(2)
     def img(w, h, amp=100):
         y, x = np.mgrid[0:h, 0:w]
@@ -493,6 +498,51 @@ def test_image_decoders_match_the_reference_decoder_byte_for_byte(tmp_path):
     for name, im, kw in cases:
         path = str(tmp_path / name)
         im.save(path, **kw)
+        for req in (1, 2, 3, 4):
+            dump = str(tmp_path / (name + f".{req}.bin"))
+            subprocess.run([REF_DUMP, "imgdump", path, str(req), dump], check=True, capture_output=True)
+            out = subprocess.run([exe, path, str(req), dump], capture_output=True, text=True)
+            assert out.returncode == 0 and "mismatching bytes 0 of" in out.stdout, (name, req, out.stdout)
+    # Radiance .hdr through the 8-bit entry point (RGBE -> float -> gamma 1/2.2 bytes), run-length encoded and flat scanlines
+    def write_hdr(path, a, rle):
+        h, w = a.shape[:2]
+        m = a.max(-1)
+        px = np.zeros((h, w, 4), np.uint8)
+        nz = m > 1e-32
+        fr, ex = np.frexp(m[nz])
+        px[nz, :3] = (a[nz] * (fr * 256.0 / m[nz])[:, None]).astype(np.uint8)
+        px[nz, 3] = (ex + 128).astype(np.uint8)
+        with open(path, "wb") as f:
+            f.write(b"#?RADIANCE\nGAMMA=1\nFORMAT=32-bit_rle_rgbe\n\n" + f"-Y {h} +X {w}\n".encode())
+            if not rle:
+                f.write(px.tobytes())
+                return
+            for j in range(h):
+                f.write(bytes([2, 2, w >> 8, w & 255]))
+                for k in range(4):
+                    row, i = px[j, :, k], 0
+                    while i < w:
+                        r = 1
+                        while i + r < w and r < 127 and row[i + r] == row[i]:
+                            r += 1
+                        if r >= 3:
+                            f.write(bytes([128 + r, row[i]]))
+                            i += r
+                        else:
+                            n = 1
+                            while i + n < w and n < 128 and not (i + n + 2 < w and row[i + n] == row[i + n + 1] == row[i + n + 2]):
+                                n += 1
+                            f.write(bytes([n]) + row[i:i + n].tobytes())
+                            i += n
+    def hdr_img(w, h):
+        y, x = np.mgrid[0:h, 0:w]
+        a = np.stack([np.exp(np.sin(x / 5.0) * 3), np.exp(np.cos(y / 4.0) * 2) * 0.5, (x + y) % 7 / 7.0 * 4], -1) * rng.uniform(0.5, 1.5, (h, w, 1))
+        a[h // 2:h // 2 + 3, w // 3:w // 3 + 9] = 0.0
+        a[:2, :12] = 2.5
+        return a
+    for name, (w, h), rle in (("rle.hdr", (64, 20), True), ("flat.hdr", (40, 11), False), ("tiny.hdr", (5, 3), False)):
+        path = str(tmp_path / name)
+        write_hdr(path, hdr_img(w, h), rle)
         for req in (1, 2, 3, 4):
             dump = str(tmp_path / (name + f".{req}.bin"))
             subprocess.run([REF_DUMP, "imgdump", path, str(req), dump], check=True, capture_output=True)
