@@ -4,7 +4,7 @@
 // maps and 1 channel for roughness / ior maps (src/impl/textures.cu:53-81,92-131).  To give the same
 // texels for the same file this reader follows the PNG specification for decoding and stb_image's
 // documented channel-conversion rules (grey = (77 r + 150 g + 29 b) >> 8, opaque alpha = 255, 16-bit
-// samples keep their high byte).  JPEG files go to jpeg_read.cpp, Radiance .hdr files to hdr_read.cpp; interlaced PNG files are rejected with an error.
+// samples keep their high byte).  JPEG files go to jpeg_read.cpp, Radiance .hdr files to hdr_read.cpp.
 #include "image_io.h"
 
 #include <cstdio>
@@ -92,8 +92,8 @@ Image8 decode_png(const std::string &path) {
     }
     if (!have_hdr || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24))
         throw std::runtime_error("image: bad PNG dimensions in '" + path + "'");
-    if (interlace != 0)
-        throw std::runtime_error("image: interlaced PNG '" + path + "' is not supported");
+    if (interlace > 1)
+        throw std::runtime_error("image: bad PNG interlace method in '" + path + "'");
     int samples;
     switch (ctype) {
     case 0: samples = 1; break;
@@ -106,27 +106,66 @@ Image8 decode_png(const std::string &path) {
     if (!(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4))))
         throw std::runtime_error("image: unsupported PNG bit depth in '" + path + "'");
     const size_t bits_pp = size_t(samples) * depth, stride = (bits_pp * w + 7) / 8, bpp = bits_pp >= 8 ? bits_pp / 8 : 1;
-    std::vector<uint8_t> raw = inflate_all(idat, (stride + 1) * h, path);
 
-    // undo the per-scanline filters in place (PNG specification, section 9)
-    std::vector<uint8_t> pix(stride * h);
-    for (uint32_t y = 0; y < h; y++) {
-        const uint8_t ft = raw[y * (stride + 1)];
-        const uint8_t *in = &raw[y * (stride + 1) + 1];
-        uint8_t *cur = &pix[size_t(y) * stride];
-        const uint8_t *up = y ? cur - stride : nullptr;
-        for (size_t i = 0; i < stride; i++) {
-            const int a = i >= bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
-            int v = in[i];
-            switch (ft) {
-            case 0: break;
-            case 1: v += a; break;
-            case 2: v += b; break;
-            case 3: v += (a + b) >> 1; break;
-            case 4: v += paeth(a, b, c); break;
-            default: throw std::runtime_error("image: bad PNG filter in '" + path + "'");
+    // undo the per-scanline filters of one (sub-)image (PNG specification, section 9)
+    auto unfilter = [&](const uint8_t *raw, uint32_t pw, uint32_t ph, uint8_t *dst) {
+        const size_t ps = (bits_pp * pw + 7) / 8;
+        for (uint32_t y = 0; y < ph; y++) {
+            const uint8_t ft = raw[y * (ps + 1)];
+            const uint8_t *in = &raw[y * (ps + 1) + 1];
+            uint8_t *cur = dst + size_t(y) * ps;
+            const uint8_t *up = y ? cur - ps : nullptr;
+            for (size_t i = 0; i < ps; i++) {
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
+                int v = in[i];
+                switch (ft) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: v += paeth(a, b, c); break;
+                default: throw std::runtime_error("image: bad PNG filter in '" + path + "'");
+                }
+                cur[i] = uint8_t(v);
             }
-            cur[i] = uint8_t(v);
+        }
+    };
+    std::vector<uint8_t> pix(stride * h);
+    if (interlace == 0) {
+        std::vector<uint8_t> raw = inflate_all(idat, (stride + 1) * h, path);
+        unfilter(raw.data(), w, h, pix.data());
+    } else { // Adam7: seven reduced images, each filtered on its own, pixels scattered back to their places
+        static const int xo[7] = {0, 4, 0, 2, 0, 1, 0}, yo[7] = {0, 0, 4, 0, 2, 0, 1}, xs[7] = {8, 8, 4, 4, 2, 2, 1}, ys[7] = {8, 8, 8, 4, 4, 2, 2};
+        size_t total = 0;
+        uint32_t pw[7], ph[7];
+        for (int p = 0; p < 7; p++) {
+            pw[p] = (w > uint32_t(xo[p])) ? (w - xo[p] + xs[p] - 1) / xs[p] : 0;
+            ph[p] = (h > uint32_t(yo[p])) ? (h - yo[p] + ys[p] - 1) / ys[p] : 0;
+            if (pw[p] && ph[p])
+                total += ((bits_pp * pw[p] + 7) / 8 + 1) * ph[p];
+        }
+        std::vector<uint8_t> raw = inflate_all(idat, total, path);
+        size_t off = 0;
+        for (int p = 0; p < 7; p++) {
+            if (!pw[p] || !ph[p])
+                continue;
+            const size_t ps = (bits_pp * pw[p] + 7) / 8;
+            std::vector<uint8_t> sub(ps * ph[p]);
+            unfilter(raw.data() + off, pw[p], ph[p], sub.data());
+            off += (ps + 1) * ph[p];
+            for (uint32_t j = 0; j < ph[p]; j++)
+                for (uint32_t i = 0; i < pw[p]; i++) {
+                    const size_t x = size_t(xo[p]) + size_t(i) * xs[p], y = size_t(yo[p]) + size_t(j) * ys[p];
+                    if (bits_pp >= 8) {
+                        memcpy(&pix[y * stride + x * bpp], &sub[size_t(j) * ps + size_t(i) * bpp], bpp);
+                    } else {
+                        const size_t sb = size_t(i) * depth, db = x * depth;
+                        const unsigned v = (sub[size_t(j) * ps + sb / 8] >> (8 - depth - sb % 8)) & ((1u << depth) - 1);
+                        uint8_t &d = pix[y * stride + db / 8];
+                        const int shift = int(8 - depth - db % 8);
+                        d = uint8_t((d & ~(((1u << depth) - 1) << shift)) | (v << shift));
+                    }
+                }
         }
     }
 

@@ -548,6 +548,51 @@ def test_image_decoders_match_the_reference_decoder_byte_for_byte(tmp_path):
             subprocess.run([REF_DUMP, "imgdump", path, str(req), dump], check=True, capture_output=True)
             out = subprocess.run([exe, path, str(req), dump], capture_output=True, text=True)
             assert out.returncode == 0 and "mismatching bytes 0 of" in out.stdout, (name, req, out.stdout)
+    # hand-written PNGs: Adam7 interlacing and the sub-byte / 16-bit / palette + tRNS layouts PIL does not write
+    import struct, zlib
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    def write_png(path, rows_fn, w, h, depth, ctype, interlace, palette=None, trns=None):
+        raw = b""
+        if interlace:
+            xo, yo, xs, ys = [0, 4, 0, 2, 0, 1, 0], [0, 0, 4, 0, 2, 0, 1], [8, 8, 4, 4, 2, 2, 1], [8, 8, 8, 4, 4, 2, 2]
+            for p in range(7):
+                xsel, ysel = list(range(xo[p], w, xs[p])), list(range(yo[p], h, ys[p]))
+                if xsel and ysel:
+                    for y in ysel:
+                        raw += b"\0" + rows_fn(xsel, y)
+        else:
+            for y in range(h):
+                raw += b"\0" + rows_fn(list(range(w)), y)
+        d = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace))
+        if palette is not None:
+            d += chunk(b"PLTE", palette)
+        if trns is not None:
+            d += chunk(b"tRNS", trns)
+        open(path, "wb").write(d + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+    def pack_bits(vals, depth):
+        out = bytearray((len(vals) * depth + 7) // 8)
+        for i, v in enumerate(vals):
+            b = i * depth
+            out[b // 8] |= (int(v) & ((1 << depth) - 1)) << (8 - depth - b % 8)
+        return bytes(out)
+    w, h = 37, 23
+    rgb8, rgba8 = rng.integers(0, 256, (h, w, 3), dtype=np.uint8), rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    g16, idx4, g1, g2 = rng.integers(0, 65536, (h, w), dtype=np.uint16), rng.integers(0, 16, (h, w)), rng.integers(0, 2, (h, w)), rng.integers(0, 4, (h, w))
+    pal, tr = rng.integers(0, 256, 48, dtype=np.uint8).tobytes(), rng.integers(0, 256, 9, dtype=np.uint8).tobytes()
+    pngs = [("i_rgb.png", lambda xs, y: rgb8[y, xs].tobytes(), w, h, 8, 2, 1, None, None), ("i_rgba.png", lambda xs, y: rgba8[y, xs].tobytes(), w, h, 8, 6, 1, None, None),
+            ("i_g16.png", lambda xs, y: g16[y, xs].astype(">u2").tobytes(), w, h, 16, 0, 1, None, None),
+            ("i_pal4.png", lambda xs, y: pack_bits(idx4[y, xs], 4), w, h, 4, 3, 1, pal, tr), ("n_pal4.png", lambda xs, y: pack_bits(idx4[y, xs], 4), w, h, 4, 3, 0, pal, tr),
+            ("i_g1.png", lambda xs, y: pack_bits(g1[y, xs], 1), w, h, 1, 0, 1, None, None), ("i_g2.png", lambda xs, y: pack_bits(g2[y, xs], 2), w, h, 2, 0, 1, None, None),
+            ("i_tiny.png", lambda xs, y: rgb8[y, xs].tobytes(), 3, 2, 8, 2, 1, None, None)]
+    for name, fn, pw, ph, depth, ctype, il, pl, tn in pngs:
+        path = str(tmp_path / name)
+        write_png(path, fn, pw, ph, depth, ctype, il, pl, tn)
+        for req in (1, 2, 3, 4):
+            dump = str(tmp_path / (name + f".{req}.bin"))
+            subprocess.run([REF_DUMP, "imgdump", path, str(req), dump], check=True, capture_output=True)
+            out = subprocess.run([exe, path, str(req), dump], capture_output=True, text=True)
+            assert out.returncode == 0 and "mismatching bytes 0 of" in out.stdout, (name, req, out.stdout)
     cmyk = str(tmp_path / "cmyk.jpg")
     img(16, 16).convert("CMYK").save(cmyk, quality=80)
     out = subprocess.run([exe, cmyk, "4", cmyk], capture_output=True, text=True)
