@@ -243,9 +243,14 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
         if (k == "samples_in_flight")
             r->impl->set_samples_in_flight(int(value));
         else if (k == "traversal") {
-            if (value < 0 || value > 3)
-                throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads) or 3 (warp vote)");
-            r->impl->set_traversal(int(value));
+            if (value < 0 || value > 4)
+                throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads), 3 (warp vote) or 4 "
+                                         "(warp-cooperative, wide layout)");
+            r->impl->set_traversal(int(value)); // modes the scene does not allow are replaced (see Renderer::set_traversal)
+        } else if (k == "coop_flush") {
+            r->impl->set_coop(int(value), int(cpt_b200_get_option(r, "coop_slab")));
+        } else if (k == "coop_slab") {
+            r->impl->set_coop(int(cpt_b200_get_option(r, "coop_flush")), int(value));
         } else if (k == "rules") {
             if (value < 0 || value > 2)
                 throw std::runtime_error("rules must be 0 (wavefront), 1 (megakernel pt) or 2 (volumetric pt)");
@@ -290,6 +295,12 @@ int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key) {
         return r->impl->pipeline() != 0 ? 1 : 0;
     if (k == "pipeline")
         return r->impl->pipeline();
+    if (k == "traversal")
+        return r->impl->traversal();
+    if (k == "coop_flush")
+        return r->impl->coop_flush();
+    if (k == "coop_slab")
+        return r->impl->coop_slab();
     if (k == "row_begin")
         return r->impl->row_begin();
     if (k == "row_end")

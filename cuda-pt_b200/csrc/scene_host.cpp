@@ -624,4 +624,104 @@ void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// wide layout: collapse of the pair tree (see scene_host.h)
+// ---------------------------------------------------------------------------------------------------------------------
+void build_wide_layout(const PairLayout &pl, int width, WideLayout &out) {
+    if (width != 2 && width != 4 && width != 8)
+        throw std::runtime_error("wide layout: width must be 2, 4 or 8");
+    out = WideLayout();
+    out.width = width;
+    auto as_int = [](float f) {
+        int32_t v;
+        memcpy(&v, &f, 4);
+        return v;
+    };
+    auto as_float = [](int32_t v) {
+        float f;
+        memcpy(&f, &v, 4);
+        return f;
+    };
+    struct Child {
+        F4 lo, hi;
+    };
+    auto area = [](const Child &c) {
+        const float dx = c.hi.x - c.lo.x, dy = c.hi.y - c.lo.y, dz = c.hi.z - c.lo.z;
+        return (dx < 0 || dy < 0 || dz < 0) ? -1.f : 2.f * (dx * dy + dy * dz + dx * dz);
+    };
+    auto is_empty = [&](const Child &c) { return as_int(c.lo.w) == ~0 && as_int(c.hi.w) == 0; };
+    auto pair_children = [&](int pair_idx, Child &a, Child &b) {
+        a = Child{pl.wnodes[4 * size_t(pair_idx) + 0], pl.wnodes[4 * size_t(pair_idx) + 1]};
+        b = Child{pl.wnodes[4 * size_t(pair_idx) + 2], pl.wnodes[4 * size_t(pair_idx) + 3]};
+    };
+    const Child empty{F4{1e30f, 1e30f, 1e30f, as_float(~0)}, F4{-1e30f, -1e30f, -1e30f, as_float(0)}};
+
+    // breadth-first construction: queue of (pair node to collapse, wide node index, depth, stack need of the path so far)
+    struct Item {
+        int pair_idx, wide_idx, depth, stack;
+    };
+    std::vector<Item> queue;
+    auto new_node = [&]() {
+        const int idx = out.num_nodes++;
+        out.nodes.resize(out.nodes.size() + 2 * size_t(width), F4{0, 0, 0, 0});
+        return idx;
+    };
+    queue.push_back(Item{pl.root, new_node(), 1, 0});
+    size_t filled = 0;
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        const Item it = queue[qi];
+        out.max_depth = std::max(out.max_depth, it.depth);
+        std::vector<Child> kids;
+        {
+            Child a, b;
+            pair_children(it.pair_idx, a, b);
+            if (!is_empty(a))
+                kids.push_back(a);
+            if (!is_empty(b))
+                kids.push_back(b);
+        }
+        // greedy collapse (Wald et al. 2008): open the inner child with the largest surface area until the node is full
+        while (int(kids.size()) < width) {
+            int best = -1;
+            float best_area = -1.f;
+            for (int i = 0; i < int(kids.size()); i++)
+                if (as_int(kids[size_t(i)].lo.w) >= 0 && area(kids[size_t(i)]) > best_area)
+                    best = i, best_area = area(kids[size_t(i)]);
+            if (best < 0)
+                break;
+            Child a, b;
+            pair_children(as_int(kids[size_t(best)].lo.w), a, b);
+            kids.erase(kids.begin() + best);
+            if (!is_empty(a))
+                kids.push_back(a);
+            if (!is_empty(b))
+                kids.push_back(b);
+        }
+        int inner = 0;
+        for (const Child &c : kids)
+            inner += as_int(c.lo.w) >= 0;
+        const int need = it.stack + std::max(inner - 1, 0);
+        out.max_stack = std::max(out.max_stack, need);
+        filled += kids.size();
+        for (int i = 0; i < width; i++) {
+            Child c = i < int(kids.size()) ? kids[size_t(i)] : empty;
+            const int ref = as_int(c.lo.w);
+            if (i < int(kids.size())) {
+                if (ref >= 0) {
+                    const int w = new_node();
+                    queue.push_back(Item{ref, w, it.depth + 1, need});
+                    c.lo.w = as_float(w);
+                    out.inner_slots++;
+                } else {
+                    out.leaf_slots++;
+                }
+            }
+            out.nodes[(size_t(it.wide_idx) * width + size_t(i)) * 2 + 0] = c.lo;
+            out.nodes[(size_t(it.wide_idx) * width + size_t(i)) * 2 + 1] = c.hi;
+        }
+    }
+    out.avg_children = out.num_nodes ? double(filled) / out.num_nodes : 0.0;
+}
+
 } // namespace cptb

@@ -91,4 +91,22 @@ struct PairLayout {
 };
 void build_pair_layout(const HostScene &scene, PairLayout &out, int refine_above = 0);
 
+// Wide re-layout for the warp-cooperative traversal (traverse_coop.cuh): the pair tree collapsed to `width` (4 or 8)
+// children per node.  One node = `width` child records of 32 B, {min.xyz, ref}{max.xyz, end} - the SAME fp32 boxes, leaf
+// references and DFS end indices as the pair layout, so that lane i of a ray's lane group loads child i with one 256-bit
+// load and tests it with the reference's slab arithmetic.  Collapsing only removes box tests of inner nodes whose
+// children's boxes are tested instead (children nest inside their parents), the set of leaves a ray can reach is the one
+// of the pair tree.  Nodes are numbered breadth-first, so that the first `n` records are the top of the tree: they form
+// the "treelet slab" the traversal kernels stage in shared memory with one bulk copy (TMA) per CTA.
+struct WideLayout {
+    int width = 8;
+    std::vector<F4> nodes; // 2 * width per node
+    int num_nodes = 0;
+    int max_depth = 0;     // wide levels
+    int max_stack = 0;     // worst-case number of deferred inner children along one root-to-leaf path
+    double avg_children = 0; // filled slots per node
+    int leaf_slots = 0, inner_slots = 0;
+};
+void build_wide_layout(const PairLayout &pairs, int width, WideLayout &out);
+
 } // namespace cptb

@@ -19,6 +19,7 @@
 //   * S samples are in flight at once (180 GB HBM3e) so late bounces still fill 148 SMs;
 //   * near-child-first traversal over a re-laid-out copy of the SAME tree (traverse.cuh).
 #include "traverse.cuh"
+#include "traverse_coop.cuh"
 #include "volume.cuh"
 #include "wavefront.cuh"
 
@@ -854,6 +855,172 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
         if (valid)
             alive = resolve_hit(sc, st, slot, tag, d, h.t, h.u, h.v, h.prim, bounce, pt_rules);
         warp_push(q_next, q_next_count, alive, slot, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-cooperative forms of the three traversal kernels of the default pipeline (traversal=4, traverse_coop.cuh):
+// same prologue / epilogue per path as k_raygen / k_shadow_apply / k_trace, one ray per lane; in between the warp's
+// 32 rays are traversed by lane groups over the wide layout.  Dynamic shared memory: coop_layout().
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoopBlock = 256;
+
+template <int G>
+__global__ void __launch_bounds__(kCoopBlock)
+    k_trace_coop(DevScene sc, CoopParams cp, PathState st, const uint32_t *__restrict__ queue, const int *__restrict__ q_count, int *work,
+                 uint32_t *q_next, int *q_next_count, int bounce, int pt_rules) {
+    extern __shared__ __align__(128) unsigned char coop_smem[];
+    const CoopShared S = coop_setup(coop_smem, sc, cp, G);
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        uint32_t slot = 0, tag = 0;
+        bool valid = i < count;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        int start = 0;
+        if (valid) {
+            slot = queue[i];
+            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            o = xyz(ro), d = xyz(rd);
+            tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index
+            valid = (tag & TAG_ACTIVE) != 0;           // megakernel rules: k_shade may have ended the path
+        }
+        float4 h0 = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(-1));
+        bool coop_ray = valid;
+        if (valid && !coop_ray_ok(d)) { // a (near-)zero direction component: per-thread traversal with the compare+select slab test
+            const Hit hh = closest_hit_ordered<true, false>(sc, S.cached, o, d);
+            h0 = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
+            coop_ray = false;
+        }
+        if (coop_ray) {
+            const V3 inv_d = rcp3(d), o_div = o * inv_d;
+            start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+        }
+        S.rays[2 * lane] = make_float4(o.x, o.y, o.z, __int_as_float(start));
+        S.rays[2 * lane + 1] = make_float4(d.x, d.y, d.z, coop_ray ? kMaxDist : -1.f);
+        S.hits[lane] = h0;
+        if (lane == 0)
+            *S.next = 0;
+        __syncwarp();
+        coop_traverse<G, false>(sc, cp, S, lane);
+        const float4 h = S.hits[lane];
+        bool alive = false;
+        if (valid)
+            alive = resolve_hit(sc, st, slot, tag, d, h.x, h.y, h.z, __float_as_int(h.w), bounce, pt_rules);
+        warp_push(q_next, q_next_count, alive, slot, lane);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kCoopBlock)
+    k_shadow_apply_coop(DevScene sc, CoopParams cp, PathState st, RayBufs rb, const uint32_t *__restrict__ sq, const int *__restrict__ sq_count, int *work) {
+    extern __shared__ __align__(128) unsigned char coop_smem[];
+    const CoopShared S = coop_setup(coop_smem, sc, cp, G);
+    const int lane = threadIdx.x & 31;
+    const int count = *sq_count;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        const bool valid = i < count;
+        uint32_t slot = 0;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        float range = -1.f;
+        int start = 0;
+        if (valid) {
+            slot = sq[i];
+            const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
+            o = xyz(a), d = xyz(b), range = a.w;
+        }
+        float vis0 = 1.f;
+        if (valid && !coop_ray_ok(d)) { // per-thread traversal with the compare+select slab test
+            vis0 = unoccluded_ordered<true, false>(sc, S.cached, o, d, range) ? 1.f : 0.f;
+            range = -1.f;
+        }
+        if (range > 0.f) {
+            const V3 inv_d = rcp3(d), o_div = o * inv_d;
+            start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, range, sc.num_nodes);
+        }
+        S.rays[2 * lane] = make_float4(o.x, o.y, o.z, __int_as_float(start));
+        S.rays[2 * lane + 1] = make_float4(d.x, d.y, d.z, range); // a range <= 0 cannot be occluded (no t in (EPSILON, range))
+        S.hits[lane] = make_float4(vis0, 0.f, 0.f, 0.f);
+        if (lane == 0)
+            *S.next = 0;
+        __syncwarp();
+        coop_traverse<G, true>(sc, cp, S, lane);
+        if (valid && S.hits[lane].x != 0.f)
+            st.L[slot] = rb.hit[slot];
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kCoopBlock)
+    k_raygen_coop(DevScene sc, CoopParams cp, CameraPOD cam, PathState st, BatchParams bp, uint32_t *q_out, int *q_count, int *work) {
+    extern __shared__ __align__(128) unsigned char coop_smem[];
+    const CoopShared S = coop_setup(coop_smem, sc, cp, G);
+    const int lane = threadIdx.x & 31;
+    const int ty0 = bp.row0 >> 2;
+    const int tiles_x = (bp.W + 7) >> 3, tiles_y = ((bp.row1 + 3) >> 2) - ty0, tiles = tiles_x * tiles_y;
+    const int total = tiles * bp.S;
+    for (int task = warp_next_chunk(work, lane); task < total; task = warp_next_chunk(work, lane)) {
+        const int s = task / tiles, tile = task - s * tiles;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int px = (tx << 3) + (lane & 7), py = ((ty + ty0) << 2) + (lane >> 3);
+        const bool inside = px < bp.W && py >= bp.row0 && py < bp.row1;
+        bool hit_any = false;
+        uint32_t slot = 0;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        int start = 0;
+        if (inside) {
+            const int gidx = px + py * bp.W;
+            slot = uint32_t(s) * uint32_t(bp.P) + uint32_t(gidx);
+            Rng rng;
+            rng.seed(gidx, bp.seed_offset + (bp.first_accum + s) * kSeedScaler);
+            camera_ray(cam, px, py, rng, o, d);
+            st.thp[slot] = make_float4(1, 1, 1, 1);
+            st.pdf[slot] = 1.f;
+            st.rng[slot] = make_uint2(rng.d0, rng.d1);
+            if (bp.rules)
+                st.lobes[slot] = 0u;
+            if (bp.rules == 2)
+                st.vstate[slot] = make_uint2(BankStack::make(sc.cam_vol).bits, 0u);
+        }
+        float4 h0 = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(-1));
+        bool coop_ray = inside;
+        if (inside && !coop_ray_ok(d)) {
+            const Hit hh = closest_hit_ordered<true, false>(sc, S.cached, o, d);
+            h0 = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
+            coop_ray = false;
+        }
+        if (coop_ray) {
+            const V3 inv_d = rcp3(d), o_div = o * inv_d;
+            start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+        }
+        S.rays[2 * lane] = make_float4(o.x, o.y, o.z, __int_as_float(start));
+        S.rays[2 * lane + 1] = make_float4(d.x, d.y, d.z, coop_ray ? kMaxDist : -1.f);
+        S.hits[lane] = h0;
+        if (lane == 0)
+            *S.next = 0;
+        __syncwarp();
+        coop_traverse<G, false>(sc, cp, S, lane);
+        if (inside) {
+            const float4 h = S.hits[lane];
+            const int prim = __float_as_int(h.w);
+            uint32_t tag = 0;
+            V4 L = mk4(0, 0, 0, 1);
+            if (prim >= 0) {
+                tag = TAG_ACTIVE | TAG_HIT | uint32_t(prim);
+                st.isect[slot] = make_interaction(sc, prim, h.y, h.z);
+                hit_any = true;
+            } else if (bp.rules) {
+                L += mk4(1, 1, 1, 1) * null_or_env(sc, d);
+            } else {
+                L = null_or_env(sc, d);
+            }
+            st.L[slot] = to_f4(L);
+            st.ray_o[slot] = make_float4(o.x, o.y, o.z, h.x);
+            st.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
+        }
+        warp_push(q_out, q_count, hit_any, slot, lane);
     }
 }
 
@@ -1799,8 +1966,12 @@ template <typename T> struct DevBuf {
 };
 
 struct Renderer::Impl {
-    DevBuf<float4> nodes, norms, arena; // arena = [pair nodes | triangles]
-    size_t arena_nodes = 0, l2_window_bytes = 0;
+    DevBuf<float4> nodes, norms, arena; // arena = [pair nodes | wide nodes | triangles]
+    size_t arena_nodes = 0, arena_wide = 0, l2_window_bytes = 0;
+    int wide_width = 4, wide_nodes = 0, wide_max_stack = 0, wide_depth = 0;
+    double wide_fill = 0;
+    int coop_blocks_per_sm = 0; // occupancy of the cooperative kernels with the current shared-memory carve-up
+    size_t coop_smem = 0;
     DevBuf<uint4> cache_nodes, uvs;
     DevBuf<int> obj_idxs, emitter_prims, prim_orig;
     int refined_leaves = 0;
@@ -1960,12 +2131,22 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         m.uvs.upload(u4);
         std::vector<float4> w4(pl.wnodes.size());
         memcpy(w4.data(), pl.wnodes.data(), w4.size() * sizeof(float4));
-        // traversal arena: pair nodes and triangles in one allocation, so that one L2 access-policy window can pin both
-        // (the 4-5 GB path-state pool streams through L2 every bounce and would otherwise keep evicting them)
-        m.arena.alloc(w4.size() + t4.size());
+        // wide layout for the cooperative traversal (traversal=4): the pair tree collapsed to 4 (CPTB200_COOP_WIDTH=8: 8) children
+        WideLayout wl;
+        if (const char *e = getenv("CPTB200_COOP_WIDTH"))
+            m.wide_width = atoi(e) == 8 ? 8 : 4;
+        build_wide_layout(pl, m.wide_width, wl);
+        std::vector<float4> ww(wl.nodes.size());
+        memcpy(ww.data(), wl.nodes.data(), ww.size() * sizeof(float4));
+        m.wide_nodes = wl.num_nodes, m.wide_max_stack = wl.max_stack, m.wide_depth = wl.max_depth, m.wide_fill = wl.avg_children;
+        // traversal arena: pair nodes, wide nodes and triangles in one allocation, so that one L2 access-policy window can pin
+        // them all (the 4-5 GB path-state pool streams through L2 every bounce and would otherwise keep evicting them)
+        m.arena.alloc(w4.size() + ww.size() + t4.size());
         CUDA_OK(cudaMemcpy(m.arena.p, w4.data(), w4.size() * sizeof(float4), cudaMemcpyHostToDevice));
-        CUDA_OK(cudaMemcpy(m.arena.p + w4.size(), t4.data(), t4.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(m.arena.p + w4.size(), ww.data(), ww.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(m.arena.p + w4.size() + ww.size(), t4.data(), t4.size() * sizeof(float4), cudaMemcpyHostToDevice));
         m.arena_nodes = w4.size();
+        m.arena_wide = ww.size();
         m.pair_depth = pl.max_depth;
         m.nesting_violations = pl.nesting_violations;
         m.dev.wroot = pl.root;
@@ -1974,8 +2155,10 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         // would have to lie within the padding of a box edge to be affected), anything larger falls back to the
         // reference's own visiting order
         m.max_overshoot = pl.max_overshoot;
-        if (pl.max_depth + 2 > kStackSize || pl.max_overshoot > 2.5e-5f)
+        if (pl.max_depth + 2 > kStackSize || pl.max_overshoot > 2.5e-5f) {
+            ordered_ok_ = false;
             traversal_ = TRAVERSAL_DFS;
+        }
         m.obj_idxs.upload(prim_obj_words);
         // emitter primitive map is padded like path_tracer.cu:76-87 (zero filled here)
         std::vector<int> ep(scene.emitter_prims.begin(), scene.emitter_prims.end());
@@ -1989,7 +2172,7 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
             objs[i] = ObjectPOD{scene.objects[i].bsdf_emitter, scene.objects[i].prim_offset, scene.objects[i].prim_num,
                                 scene.objects[i].inv_area};
         m.objects.upload(objs);
-        m.scene_bytes = (t4.size() + n4.size() + w4.size() + tmp.size()) * sizeof(float4) + u4.size() * sizeof(uint4);
+        m.scene_bytes = (t4.size() + n4.size() + w4.size() + ww.size() + tmp.size()) * sizeof(float4) + u4.size() * sizeof(uint4);
     }
     // ---- textures
     for (const auto &t : scene.textures)
@@ -2056,7 +2239,7 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     m.dev.cache_nodes = m.cache_nodes.p;
     m.dev.obj_idxs = m.obj_idxs.p;
     m.dev.prim_orig = m.prim_orig.p; // nullptr: primitives are in the reference's order
-    m.dev.tris = m.arena.p + m.arena_nodes;
+    m.dev.tris = m.arena.p + m.arena_nodes + m.arena_wide;
     m.dev.norms = m.norms.p;
     m.dev.uvs = m.uvs.p;
     m.dev.objects = m.objects.p;
@@ -2181,6 +2364,13 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     CUDA_OK(cudaMemsetAsync(m.stats.p, 0, 4 * sizeof(unsigned long long), stream_));
     if (const char *e = getenv("CPTB200_BLOCKS_PER_SM"))
         blocks_per_sm_ = std::max(1, atoi(e));
+    if (const char *e = getenv("CPTB200_COOP_FLUSH"))
+        coop_flush_ = std::min(32, std::max(1, atoi(e)));
+    if (const char *e = getenv("CPTB200_COOP_SLAB"))
+        coop_slab_ = std::max(0, atoi(e));
+    set_coop(coop_flush_, coop_slab_);
+    if (const char *e = getenv("CPTB200_TRAVERSAL"))
+        set_traversal(atoi(e));
     if (const char *e = getenv("CPTB200_DYN_REFILL"))
         dyn_refill_ = std::min(32, std::max(1, atoi(e)));
     if (const char *e = getenv("CPTB200_DYN_STEPS"))
@@ -2210,6 +2400,52 @@ Renderer::~Renderer() {
     cudaFree(d_var_);
     impl_.reset();
     cudaStreamDestroy(stream_);
+}
+
+// shared memory and occupancy of the cooperative kernels for the current knobs; decides whether traversal=4 may be used
+void Renderer::set_coop(int flush_lanes, int slab_nodes) {
+    Impl &m = *impl_;
+    CUDA_OK(cudaSetDevice(device_));
+    coop_flush_ = std::min(32, std::max(1, flush_lanes));
+    coop_slab_ = std::min(std::max(0, slab_nodes), m.wide_nodes);
+    const int G = m.wide_width;
+    coop_ok_ = false;
+    m.coop_blocks_per_sm = 0;
+    int max_optin = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
+    for (;; coop_slab_ /= 2) { // shrink the slab until the carve-up fits
+        const int cap = std::max(8, (m.wide_max_stack + 7) / 8 * 8);
+        const CoopLayout L = coop_layout(m.dev.num_cache, coop_slab_, G, cap, kCoopBlock / 32);
+        if (L.total <= max_optin) {
+            m.coop_smem = size_t(L.total);
+            break;
+        }
+        if (coop_slab_ == 0)
+            return; // the stacks alone do not fit: the tree is too deep for the cooperative kernels
+    }
+    auto prep = [&](auto kernel) {
+        CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m.coop_smem)));
+        int nb = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kCoopBlock, m.coop_smem));
+        return nb;
+    };
+    int nb;
+    if (G == 8)
+        nb = std::min(std::min(prep(k_trace_coop<8>), prep(k_shadow_apply_coop<8>)), prep(k_raygen_coop<8>));
+    else
+        nb = std::min(std::min(prep(k_trace_coop<4>), prep(k_shadow_apply_coop<4>)), prep(k_raygen_coop<4>));
+    m.coop_blocks_per_sm = nb;
+    coop_ok_ = nb >= 1 && ordered_ok_; // same preconditions as the ordered traversal (nesting), plus the stack carve-up
+}
+
+void Renderer::set_traversal(int t) {
+    if (t < 0 || t > 4)
+        throw std::runtime_error("traversal must be 0..4");
+    if (t == 4 && !coop_ok_)
+        t = 2;
+    if (t != TRAVERSAL_DFS && !ordered_ok_)
+        t = TRAVERSAL_DFS;
+    traversal_ = t;
 }
 
 void Renderer::set_samples_in_flight(int s) {
@@ -2286,8 +2522,20 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     const size_t smem_dyn = smem + size_t(kSmemTop) * kBlock * sizeof(uint2); // dynamic-fetch kernels: + shared-memory stack
     const size_t smem_any = size_t(kSmemTop) * kBlock * sizeof(uint2);
     const int grid = num_sms_ * blocks_per_sm_;
-    const int mode = traversal_;
-    const int pipeline_ = (traversal_ == 1 || traversal_ == 3) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
+    // traversal=4: cooperative forms of k_raygen / k_shadow_apply / k_trace in the deferred-NEE surface pipeline; every other
+    // kernel (fused shading, volumetric path) keeps the ordered per-thread traversal
+    const bool coop = traversal_ == 4 && coop_ok_ && rules_ != 2 && this->pipeline_ == 3;
+    const int mode = traversal_ == 4 ? 2 : traversal_;
+    const int coop_grid = num_sms_ * std::max(1, m.coop_blocks_per_sm);
+    const CoopParams cpar{m.arena.p + m.arena_nodes, coop_slab_, std::max(8, (m.wide_max_stack + 7) / 8 * 8), coop_flush_};
+#define LAUNCH_COOP(kernel, ...)                                                                                       \
+    do {                                                                                                               \
+        if (m.wide_width == 8)                                                                                         \
+            kernel<8><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                                    \
+        else                                                                                                           \
+            kernel<4><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                                    \
+    } while (0)
+    const int pipeline_ = (traversal_ == 1 || traversal_ == 3 || traversal_ == 4) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
 #define LAUNCH_MODE(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (mode == 0)                                                                                                 \
@@ -2451,7 +2699,10 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         return;
     }
     mark(0, 0);
-    LAUNCH_MODE(k_raygen, m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
+    if (coop)
+        LAUNCH_COOP(k_raygen_coop, m.dev, cpar, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
+    else
+        LAUNCH_MODE(k_raygen, m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
     ++wk;
     unsigned long long *shadow_counter = m.stats.p + 1;
     int launches = 1, traced = 0, shaded = 0;
@@ -2464,7 +2715,9 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
                                                       m.shadow_queue.p, sq_counts + b);
             ++wk, ++launches;
             mark(4, b);
-            if (pipeline_ == 3)
+            if (pipeline_ == 3 && coop)
+                LAUNCH_COOP(k_shadow_apply_coop, m.dev, cpar, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+            else if (pipeline_ == 3)
                 LAUNCH_MODE(k_shadow_apply, m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (dyn_minb_ >= 12)
                 k_anyhit<12, true><<<grid, kBlock, smem_dyn, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, dyn_refill_, dyn_steps_);
@@ -2506,6 +2759,8 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             ++wk, ++launches;
             mark(2, b);
             k_resolve<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+        } else if (coop) {
+            LAUNCH_COOP(k_trace_coop, m.dev, cpar, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else {
             LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         }
@@ -2673,7 +2928,10 @@ std::string Renderer::info() const {
     std::ostringstream os;
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
-       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : "ordered-vote")))
+       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : "cooperative"))))
+       << ", wide layout " << impl_->wide_width << "-ary " << impl_->wide_nodes << " nodes (fill " << impl_->wide_fill << ", depth " << impl_->wide_depth
+       << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks_per_sm << " CTAs/SM x " << impl_->coop_smem
+       << " B smem, slab " << coop_slab_ << " nodes, flush " << coop_flush_ << " lanes)"
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations << " (max " << impl_->max_overshoot << ")"
        << ", refined leaves " << impl_->refined_leaves
        << ", L2 window " << (impl_->l2_window_bytes >> 20) << " MB, pipeline " << pipeline_ << ", rules " << (rules_ == 2 ? "volumetric-pt" : (rules_ ? "megakernel-pt" : "wavefront")) << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;

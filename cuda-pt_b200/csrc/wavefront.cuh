@@ -63,7 +63,16 @@ class Renderer {
     void update_camera(const float cam[CPTS_CAM_COUNT]);
     void set_max_depth(int d) { max_depth_ = d; }
     void set_samples_in_flight(int s);
-    void set_traversal(int t) { traversal_ = t; }
+    // 0 / 2 / 3: ordered pair traversal (128-bit / 256-bit loads / warp vote), 1: the reference's own DFS order, 4: warp-
+    // cooperative traversal of the wide layout (traverse_coop.cuh).  A mode whose preconditions the scene does not meet
+    // (ordered: stack depth and box nesting, checked at construction; cooperative: shared-memory stack) is replaced by the
+    // best mode that is allowed - the constructor's fallback cannot be overridden from outside.
+    void set_traversal(int t);
+    int traversal() const { return traversal_; }
+    // cooperative traversal knobs: triangle-phase threshold in lanes, treelet slab size in wide nodes
+    void set_coop(int flush_lanes, int slab_nodes);
+    int coop_flush() const { return coop_flush_; }
+    int coop_slab() const { return coop_slab_; }
     void enable_variance(bool on);
     void set_accum_count(int c) { accum_cnt_ = c; }
     void set_kernel_timing(bool on) { kernel_timing_ = on; }
@@ -99,6 +108,8 @@ class Renderer {
     int s_max_ = 1, traversal_ = 2 /* ordered pair-node traversal with 256-bit node loads */, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
     bool variance_on_ = false, kernel_timing_ = false;
     int pipeline_ = 3, row0_ = 0, row1_ = 0;
+    bool ordered_ok_ = true, coop_ok_ = false;
+    int coop_flush_ = 12, coop_slab_ = 64;
     int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);
