@@ -176,8 +176,11 @@ void load_cpts(const std::string &path, HostScene &out) {
     for (const auto &d : tex_desc) {
         HostTexture t;
         t.width = d.width, t.height = d.height, t.channels = d.channels;
-        const uint64_t n = uint64_t(d.width) * d.height * d.channels;
-        if (d.offset + n > tex_data.size())
+        // dimensions first: a negative width / height / channel count must not reach the size arithmetic below
+        if (d.width <= 0 || d.height <= 0 || d.width > 65536 || d.height > 65536 || (d.channels != 2 && d.channels != 4))
+            throw std::runtime_error("cpts: texture with invalid dimensions (width / height in [1,65536], 2 or 4 channels)");
+        const uint64_t n = uint64_t(d.width) * uint64_t(d.height) * uint64_t(d.channels);
+        if (uint64_t(d.offset) > tex_data.size() || n > tex_data.size() - uint64_t(d.offset))
             throw std::runtime_error("cpts: texture data out of range");
         t.texels.assign(tex_data.begin() + d.offset, tex_data.begin() + d.offset + n);
         out.textures.push_back(std::move(t));
@@ -257,6 +260,32 @@ void validate_scene(const HostScene &sc) {
         fail("BVH required (path_tracer.cu:73-75)");
     if (sc.cache_nodes.size() > 255)
         fail("more than 255 cached nodes");
+    for (size_t i = 0; i < sc.cache_nodes.size(); i++) {
+        // {half2 x, half2 y, half2 z, gmem_index << 8 | skip}: the cached walk advances by `skip` on a miss (bvh.cuh:182-251), so a
+        // zero skip would spin forever on the device, and the frontier index it hands over must be a node
+        const uint32_t w = sc.cache_nodes[i].w, skip = w & 0xffu, gmem = w >> 8;
+        if (skip == 0)
+            fail("cached BVH node with a zero skip offset");
+        if (gmem >= sc.nodes.size() / 2)
+            fail("cached BVH node points past the node array");
+    }
+    for (const auto &t : sc.textures)
+        if (t.width <= 0 || t.height <= 0 || (t.channels != 2 && t.channels != 4) ||
+            t.texels.size() != size_t(t.width) * size_t(t.height) * size_t(t.channels))
+            fail("texture with invalid dimensions or texel count");
+    auto tex_ok = [&](int32_t idx) { return idx >= -1 && idx < int32_t(sc.textures.size()); };
+    for (const auto &b : sc.bsdfs)
+        for (int k = 0; k < 5; k++)
+            if (!tex_ok(b.tex[k]))
+                fail("BSDF references an unknown texture");
+    for (const auto &e : sc.emitters) {
+        if (!tex_ok(e.tex))
+            fail("emitter references an unknown texture");
+        if (e.obj_ref < -1)
+            fail("emitter with an invalid object reference (must be -1 or an object index)");
+    }
+    if (sc.config[CPTS_CFG_ENVMAP_ID] < 0 || size_t(sc.config[CPTS_CFG_ENVMAP_ID]) >= std::max<size_t>(sc.emitters.size(), 1))
+        fail("environment-map emitter index out of range");
     if (sc.objects.empty())
         fail("no objects");
     if (sc.bsdfs.empty() || sc.bsdfs.size() > 48)
@@ -339,6 +368,8 @@ void validate_scene(const HostScene &sc) {
         memcpy(&cnt, &sc.nodes[2 * k + 1].w, 4);
         if (cnt > 0 && (base < 0 || size_t(base) + cnt > P))
             fail("BVH leaf primitive range out of bounds");
+        if (cnt > 1024)
+            fail("BVH leaf with more than 1024 primitives (the reference's builders stop at 32)");
         if (cnt < 0 && k - cnt > N)
             fail("BVH skip offset runs past the node array");
         if (cnt == 0)
@@ -413,6 +444,7 @@ void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
     auto new_node = [&]() {
         const int idx = int(out.wnodes.size() / 4);
         out.wnodes.resize(out.wnodes.size() + 4, F4{0, 0, 0, 0});
+        out.children_nest.push_back(1);
         return idx;
     };
     const Child empty_child{F4{1e30f, 1e30f, 1e30f, as_float(~0)}, F4{-1e30f, -1e30f, -1e30f, as_float(0)}};
@@ -612,9 +644,9 @@ void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
             if (right >= N || right >= it.k + subtree(it.k))
                 throw std::runtime_error("pair layout: malformed skip offsets");
             if (!contained(left, it.k))
-                out.nesting_violations++;
+                out.nesting_violations++, out.children_nest[size_t(idx)] = 0;
             if (!contained(right, it.k))
-                out.nesting_violations++;
+                out.nesting_violations++, out.children_nest[size_t(idx)] = 0;
             // push right first so the left subtree is laid out next (DFS order => parent/child locality)
             todo.push_back(Item{right, idx * 2 + 1, it.depth + 1});
             todo.push_back(Item{left, idx * 2 + 0, it.depth + 1});
@@ -685,9 +717,12 @@ void build_wide_layout(const PairLayout &pl, int width, WideLayout &out) {
         while (int(kids.size()) < width) {
             int best = -1;
             float best_area = -1.f;
-            for (int i = 0; i < int(kids.size()); i++)
-                if (as_int(kids[size_t(i)].lo.w) >= 0 && area(kids[size_t(i)]) > best_area)
+            for (int i = 0; i < int(kids.size()); i++) {
+                const int ref = as_int(kids[size_t(i)].lo.w);
+                // a node whose children stick out of its box keeps its own box test (PairLayout::children_nest)
+                if (ref >= 0 && (pl.children_nest.empty() || pl.children_nest[size_t(ref)]) && area(kids[size_t(i)]) > best_area)
                     best = i, best_area = area(kids[size_t(i)]);
+            }
             if (best < 0)
                 break;
             Child a, b;

@@ -88,6 +88,10 @@ struct PairLayout {
     // identity).  The reference tree, its leaf ranges and the cached nodes are untouched.
     std::vector<int32_t> perm;
     int refined_leaves = 0;
+    // per pair node: both child boxes lie inside the node's own box (false where the reference's SBVH pads a clipped child
+    // beyond its parent).  The wide collapse only merges a node into its parent's record where this holds - elsewhere the
+    // node's own box test decides, as in the reference, whether its children are looked at at all.
+    std::vector<uint8_t> children_nest;
 };
 void build_pair_layout(const HostScene &scene, PairLayout &out, int refine_above = 0);
 

@@ -2798,9 +2798,9 @@ void Renderer::collect_kernel_times(int samples) {
 }
 
 const float *Renderer::render_raw(bool gamma) {
-    accum_cnt_++;
-    launch_batch(accum_cnt_, 1, gamma, true, variance_on_);
+    launch_batch(accum_cnt_ + 1, 1, gamma, true, variance_on_);
     CUDA_OK(cudaStreamSynchronize(stream_));
+    accum_cnt_++; // only a sample that was actually rendered counts
     float ms = 0;
     cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
     host_stats_.device_ms += ms;

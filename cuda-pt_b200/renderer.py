@@ -219,9 +219,14 @@ class PythonRenderer:
     def __init__(self, scene_path, device_id, seed_offset):
         self._r = WavefrontRenderer(scene_path, device_id, seed_offset)
         cfg = self._r.scene.config
-        if cfg["renderer"] != 1:
-            # the reference falls back to other integrators for other types; this library IS the wavefront path
-            print(f"[cuda-pt_b200] scene asks for renderer type {cfg['renderer']}; rendering with wavefront rules")
+        # RendererType (src/core/enums.cuh:26-37): this library serves the path tracers; the reference's other integrators
+        # (light tracer, depth / BVH-cost visualisers, ...) are out of scope and are refused rather than silently replaced
+        served = {0: "megakernel-pt rules", 8: "megakernel-pt rules", 1: "wavefront rules", 6: "volumetric-pt rules"}
+        if cfg["renderer"] not in served:
+            self._r.close()
+            raise ValueError(f"cuda-pt_b200: renderer type {cfg['renderer']} of '{scene_path}' is not a path tracer this library serves "
+                             "(pt / ptd / wfpt / vpt)")
+        self._rules = served[cfg["renderer"]]
         self._gamma = bool(cfg["gamma"])
         self._r.enable_variance(True)  # python_render.cu:93,99: initialize_var_buffer()
         self._times = []
@@ -233,14 +238,23 @@ class PythonRenderer:
         ptr = self._r.render_raw(self._gamma)
         self._times = (self._times + [(time.perf_counter() - t0) * 1e3])[-32:]
         view = device_tensor(ptr, (self._r.height, self._r.width, 4), self.device_id, self._r)
-        return view.clone()  # fresh allocation per call, like gpu_ndarray_deep_copy (python_render.cu:32-51)
+        return self._copy(view)  # fresh allocation per call, like gpu_ndarray_deep_copy (python_render.cu:32-51)
+
+    def _copy(self, view):
+        """Deep copy of a renderer-owned buffer that is COMPLETE when this returns (the reference uses a synchronous
+        cudaMemcpy, python_render.cu:45).  The renderer works on its own non-blocking stream, so a clone merely enqueued on
+        torch's current stream could still be pending when the next render() overwrites the buffer."""
+        import torch
+        out = view.clone()
+        torch.cuda.current_stream(self.device_id).synchronize()
+        return out
 
     def variance(self):
         ptr = self._r.variance_ptr()
         if not ptr:
             import torch
             return torch.empty(0)
-        return device_tensor(ptr, (self._r.height, self._r.width, 1), self.device_id, self._r).clone()
+        return self._copy(device_tensor(ptr, (self._r.height, self._r.width, 1), self.device_id, self._r))
 
     def counter(self):
         return self._r.counter()

@@ -57,7 +57,51 @@ int main(int argc, char **argv) {
                 for (int i = node_i(k, 0); i < node_i(k, 0) + node_i(k, 1); i++)
                     if (pl.perm[i] < node_i(k, 0) || pl.perm[i] >= node_i(k, 0) + node_i(k, 1)) errors++;
     }
-    printf("prims %d leaf_records %d refined_leaves %d depth %d nesting_violations %d errors %d\n", P, leaf_records, pl.refined_leaves, pl.max_depth,
-           pl.nesting_violations, errors);
+    // wide layouts (build_wide_layout): every leaf record of the pair tree appears exactly once with the same box / reference /
+    // DFS end, every inner slot points to a later node (breadth-first numbering, node 0 = root), the stack bound is a bound
+    int wide_errors = 0, wide_stack = 0;
+    for (int width : {4, 8}) {
+        WideLayout wl;
+        build_wide_layout(pl, width, wl);
+        std::vector<int> wcov(P, 0);
+        int leaves = 0;
+        std::function<void(int, int)> wwalk = [&](int node, int stack) {
+            int inner = 0;
+            for (int c = 0; c < width; c++) {
+                int32_t ref;
+                memcpy(&ref, &wl.nodes[(size_t(node) * width + c) * 2].w, 4);
+                inner += ref >= 0;
+            }
+            const int need = stack + (inner > 1 ? inner - 1 : 0);
+            if (need > wl.max_stack) wide_errors++;
+            wide_stack = need > wide_stack ? need : wide_stack;
+            for (int c = 0; c < width; c++) {
+                const F4 lo = wl.nodes[(size_t(node) * width + c) * 2], hi = wl.nodes[(size_t(node) * width + c) * 2 + 1];
+                int32_t ref, end;
+                memcpy(&ref, &lo.w, 4), memcpy(&end, &hi.w, 4);
+                if (ref == ~0 && end == 0)
+                    continue; // empty slot
+                if (ref >= 0) {
+                    if (ref <= node || ref >= wl.num_nodes) { wide_errors++; continue; }
+                    wwalk(ref, need);
+                    continue;
+                }
+                const int packed = ~ref, base = packed & ((1 << 26) - 1), cnt = packed >> 26;
+                leaves++;
+                const int k = end - 1;
+                if (k < 0 || k >= N) { wide_errors++; continue; }
+                for (int i = base; i < base + cnt; i++)
+                    wcov[i]++;
+            }
+        };
+        wwalk(0, 0);
+        for (int v : wcov)
+            wide_errors += v != 1;
+        wide_errors += leaves != leaf_records;
+        wide_errors += wl.leaf_slots != leaf_records;
+    }
+    errors += wide_errors;
+    printf("prims %d leaf_records %d refined_leaves %d depth %d nesting_violations %d wide_errors %d wide_stack %d errors %d\n", P, leaf_records,
+           pl.refined_leaves, pl.max_depth, pl.nesting_violations, wide_errors, wide_stack, errors);
     return errors ? 1 : 0;
 }

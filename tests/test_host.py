@@ -241,6 +241,53 @@ def test_cpts_grid_sections_are_validated(tmp_path):
         cpt.Scene(str(p))
 
 
+def test_cpts_validation_of_externally_produced_containers(tmp_path):
+    """.cpts files may come from other producers: fields that would hang or crash the device side are refused at
+    load - a cached node with a zero skip offset (infinite loop in the cached walk) or pointing past the node array, texture
+    descriptors with negative sizes, BSDF / emitter texture indices, the environment-map emitter index, emitter object references."""
+    import struct
+    src = os.path.join(GOLDEN, "texroom_256.cpts")
+    data = bytearray(open(src, "rb").read())
+
+    def section(name):
+        n, = struct.unpack_from("<I", data, 8)
+        off = 16
+        for _ in range(n):
+            nm = bytes(data[off:off + 24]).split(b"\0")[0].decode()
+            elem, _r, count = struct.unpack_from("<IIQ", data, off + 24)
+            off += 40
+            if nm == name:
+                return off, elem, count
+            off += elem * count + (16 - (elem * count) % 16) % 16
+        raise KeyError(name)
+
+    def refused(patch, match):
+        bad = bytearray(data)
+        patch(bad)
+        p = tmp_path / "bad.cpts"
+        p.write_bytes(bytes(bad))
+        with pytest.raises(cpt.CptError, match=match):
+            cpt.Scene(str(p))
+
+    coff, _, ccount = section("cache_nodes")
+    assert ccount > 0
+    w, = struct.unpack_from("<I", data, coff + 12)
+    refused(lambda b: struct.pack_into("<I", b, coff + 12, w & ~0xff), "zero skip")
+    refused(lambda b: struct.pack_into("<I", b, coff + 12, (0xffffff << 8) | (w & 0xff)), "past the node array")
+    toff, telem, tcount = section("tex_desc")
+    assert tcount > 0
+    refused(lambda b: struct.pack_into("<i", b, toff, -4), "invalid dimensions")        # width
+    refused(lambda b: struct.pack_into("<i", b, toff + 8, 3), "invalid dimensions")      # channels
+    boff, belem, _ = section("bsdfs")
+    refused(lambda b: struct.pack_into("<i", b, boff + 88, 1 << 20), "unknown texture")  # tex[0]
+    eoff, eelem, ecount = section("emitters")
+    refused(lambda b: struct.pack_into("<i", b, eoff + eelem + 4, -7), "invalid object reference")
+    refused(lambda b: struct.pack_into("<i", b, eoff + eelem + 12, 1 << 20), "unknown texture")
+    cfg, _, _ = section("config")
+    refused(lambda b: struct.pack_into("<i", b, cfg + 4 * 11, 99), "environment-map emitter index")
+    cpt.Scene(src).close()  # the unmodified file still loads
+
+
 def test_nvdb_reader_rejects_what_it_cannot_read(tmp_path):
     src = open(os.path.join(VOLUMES, "puff64_density.nvdb"), "rb").read()
     def scene_with(data, kind="density"):

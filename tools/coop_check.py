@@ -76,8 +76,22 @@ def bench(spp=32, sif=16):
     return rows
 
 
+def one(trav, spp=16):
+    """one batch of `spp` samples of vader 1080p (the thing to put under ncu)"""
+    r = cpt.WavefrontRenderer(VADER, 0, 0)
+    r.set_option("traversal", trav)
+    r.set_option("samples_in_flight", spp)
+    r.render_batch(spp, False)
+    r.sync()
+    print(r.info())
+    r.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "parity"
+    if what == "one":
+        one(int(sys.argv[2]))
+        sys.exit(0)
     if what == "parity":
         sys.exit(0 if parity() else 1)
     bench()
