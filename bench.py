@@ -13,7 +13,17 @@ One JSON line is printed by rank 0.  Keys beyond the base contract:
   roofline     dominant kernel, algorithmic bytes (SURVEY §8d figures) / CUDA-event time vs the measured HBM peak
   stages       the same for every kernel of the pipeline
   cpu_baseline the CPU oracle (a port: the reference has no CPU renderer) timed on a bounded sample (N=1 only)
-  e2e          the same metric through the C-ABI call with HOST buffers (camera H2D + frame D2H every step)
+  e2e          the same metric through the C-ABI call with HOST buffers: camera H2D + frame D2H every step; at N>1 the frame is
+               the REDUCED one (the per-step NCCL reduce to rank 0 is inside the timed region, the D2H happens on rank 0)
+  traced_mrays the rays that were actually traversed (deferred NEE skips shadow rays that cannot change the radiance; `value`
+               counts the algorithm's rays, like the reference arm)
+  dropin       the same step on the scene the REFERENCE's loader builds for this XML (its SBVH; the drop-in case of
+               INTEGRATION.md) - N=1 only, when oracle/_ref/ref_dump is on the box
+  megakernel_rules  the same step under the reference megakernel's termination rules (rules=1), the like-for-like partner
+               of the reference arm's `megakernel_pt` block (the reference's README calls its megakernel the faster renderer)
+
+Reference arm at N>1: every rank drives the unmodified reference on its own GPU (ddp_render.py semantics: full frame per
+rank, seed_offset = rank * 4201), value = all ranks' samples / slowest rank's time.
 """
 import argparse
 import json
@@ -88,11 +98,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def physical_gpu(local_index):
+    """nvidia-smi index of CUDA device `local_index` (CUDA_VISIBLE_DEVICES may renumber the devices)."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").strip()
+    if vis:
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if local_index < len(ids):
+            return ids[local_index]
+    return str(local_index)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index = [], None, physical_gpu(index)
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -157,15 +177,29 @@ def cpu_oracle_rate(scene_cpts, width, height, budget_s=12.0, rules=0):
             "msamples_per_s": st["samples"] / dt / 1e6, "rays_per_sample": st["rays"] / st["samples"]}
 
 
+def _ref_bench(ref_dump, scene, mode, warm, frames, seed_offset, gpu):
+    """one `ref_dump bench` process = the reference's own render_raw loop on one GPU; returns its JSON record"""
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+    out = subprocess.run([ref_dump, "bench", scene, mode, str(warm), str(frames), str(seed_offset)], capture_output=True, text=True, timeout=3000,
+                         cwd=ROOT, env=env)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{\"ref_bench\"")]
+    if not line:
+        raise RuntimeError("ref_dump bench produced no record: " + (out.stderr or out.stdout)[-300:])
+    return json.loads(line[-1])
+
+
 def run_reference(args, scene, workload):
-    """--impl reference: the UNMODIFIED reference (its GPU kernels driven by its own host loop: thrust sort +
-    per-bounce D2H count) through oracle/_ref/ref_dump on this box; CPU-oracle port if that binary is unavailable."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    """--impl reference: the UNMODIFIED reference (its GPU kernels driven by its own host loop: thrust sort + per-bounce D2H
+    count) through oracle/_ref/ref_dump.  N>1: every rank runs it on its own GPU with seed_offset = rank * 4201 (the reference's
+    multi-GPU scheme, scripts/ddp_render.py:141-143: full frame per rank, different seeds); value = all ranks' samples / the
+    slowest rank's device time.  The reference's reduce (one all_reduce of the frame every 128 frames, ddp_render.py:161-166) is
+    not inside this number - it would add < 0.2 ms per 128 frames.  CPU-oracle port if the binary is unavailable (rank 0 only)."""
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     S = args.spp_per_step
     ref_dump = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
-    base = {"metric": (METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC).replace("1920x1080", "1024x1024" if "whiskey" in workload else "1920x1080"), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    base = {"metric": (METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC).replace("1920x1080", "1024x1024" if "whiskey" in workload else "1920x1080"), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "impl": "reference",
             "data": ("cornell box geometry bundled with the reference + a synthetic 304x512x304 NanoVDB smoke volume (density, albedo, temperature grids) + two homogeneous media" if "grid" in workload else
                      "the reference's whiskey scene, unmodified" if "whiskey" in workload else
@@ -175,28 +209,64 @@ def run_reference(args, scene, workload):
                      "vader geometry + seeded placeholder 2K textures and environment map (tools/make_assets.py)"),
             "config": {"workload": workload, "width": 1920, "height": 1080, "spp_per_step": S}}
     tbl = rays_table().get(workload)
-    if scene.endswith(".xml") and os.path.exists(ref_dump):
+    have_ref = scene.endswith(".xml") and os.path.exists(ref_dump)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")  # host-side exchange of the per-rank records only
+    if have_ref:
+        err = None
+        rec = {}
         try:
             mode = "vpt" if "vpt" in workload else "wfpt"
-            out = subprocess.run([ref_dump, "bench", scene, mode, str(args.warmup * S), str(args.steps * S)],
-                                 capture_output=True, text=True, timeout=3000, cwd=ROOT)
-            line = [l for l in out.stdout.splitlines() if l.startswith("{\"ref_bench\"")][-1]
-            rb = json.loads(line)
+            gpu = physical_gpu(local_rank)
+            rec["main"] = _ref_bench(ref_dump, scene, mode, args.warmup * S, args.steps * S, rank * 4201, gpu)
+            if mode == "wfpt" and not args.no_extras:  # the reference's megakernel on the same scene (its README: the faster of its two)
+                rec["pt"] = _ref_bench(ref_dump, scene, "pt", args.warmup * S, max(S, args.steps * S // 2), rank * 4201, gpu)
+        except Exception as e:
+            err = str(e)[:300]
+        allrec = [(rec, err)]
+        if world > 1:
+            allrec = [None] * world
+            dist.all_gather_object(allrec, (rec, err))
+            dist.destroy_process_group()
+        if rank != 0:
+            return
+        errs = [e for _, e in allrec if e]
+        if not errs:
+            mains = [r["main"] for r, _ in allrec]
             rps = tbl.get("reference_scene_rays_per_sample", tbl["rays_per_sample"]) if tbl else None
-            ms_step = rb["ms_per_frame"] * S
-            msamples = rb["width"] * rb["height"] / rb["ms_per_frame"] / 1e3
+            px = mains[0]["width"] * mains[0]["height"]
+            t_max = max(m["total_ms"] for m in mains)
+            samples = sum(px * m["frames"] for m in mains)
+            msamples = samples / t_max / 1e3
             value = msamples * rps if rps else None
-            base.update({"value": value, "ms_per_step": ms_step, "msamples_per_s": msamples,
-                         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "reference",
-                                          "sample": f"{args.steps * S} x {'VolumePathTracer' if mode == 'vpt' else 'WavefrontPathTracer'}::render_raw (1 spp each) on 1 GPU of this box, "
-                                                    "reference kernels + its host loop (one host thread); rays/sample of the "
-                                                    "reference-built scene (its SBVH) from profiles/workload_rays.json, counts parity-checked"},
+            base.update({"value": value, "ms_per_step": t_max / args.steps, "msamples_per_s": msamples,
+                         "per_rank_ms_per_frame": [round(m["ms_per_frame"], 3) for m in mains],
+                         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": world, "kind": "reference",
+                                          "sample": f"{args.steps * S} x {'VolumePathTracer' if mode == 'vpt' else 'WavefrontPathTracer'}::render_raw (1 spp each) on each of {world} GPU(s) of this box "
+                                                    "(seed_offset = rank * 4201), reference kernels + its host loop (one host thread per GPU); Mrays/s = measured "
+                                                    "Msamples/s x rays/sample of the reference-built scene (its SBVH) from profiles/workload_rays.json, i.e. the ratio "
+                                                    "between the two arms is the Msamples/s ratio"},
                          "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                         "reference_kind": "reference GPU kernels (sm_100a rebuild) + reference host loop"})
+                         "reference_kind": "reference GPU kernels (sm_100a rebuild) + reference host loop, one process per GPU"})
+            pts = [r.get("pt") for r, _ in allrec]
+            if all(pts):
+                t_pt = max(m["total_ms"] for m in pts)
+                ms_pt = sum(px * m["frames"] for m in pts) / t_pt / 1e3
+                base["megakernel_pt"] = {"msamples_per_s": ms_pt, "ms_per_frame": [round(m["ms_per_frame"], 3) for m in pts],
+                                          "note": "PathTracer<SingleTileScheduler>::render_raw on the same scene (what `pt` runs for type=\"pt\" XMLs): "
+                                                  "Russian roulette from bounce 1 and per-lobe caps, so fewer rays per sample than the wavefront renderer; "
+                                                  "compare Msamples/s with the `megakernel_rules` block of our arm"}
+                base["best_msamples_per_s"] = max(msamples, ms_pt)
             print(json.dumps(base))
             return
-        except Exception as e:  # fall through to the CPU port
-            base["reference_error"] = str(e)[:200]
+        base["reference_error"] = "; ".join(errs)[:300]
+    elif world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     import cuda_pt_b200 as cpt
     sc = cpt.Scene(scene)
     if not scene.endswith(".xml"):
@@ -204,7 +274,7 @@ def run_reference(args, scene, workload):
     tmp = os.path.join(tempfile.gettempdir(), "bench_scene_ref.cpts")
     sc.save(tmp)
     cb = cpu_oracle_rate(tmp, 1920, 1080, budget_s=20.0, rules={6: 2, 0: 1, 8: 1}.get(sc.config["renderer"], 0))
-    base.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
+    base.update({"n_gpus": 0, "value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
                  "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(base))
 
@@ -217,8 +287,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default=None)
     ap.add_argument("--spp-per-step", type=int, default=16)
-    ap.add_argument("--traversal", type=int, default=2)
-    ap.add_argument("--pipeline", type=int, default=3)
+    ap.add_argument("--traversal", type=int, default=None, help="traversal mode (default: the library's; modes the scene does not allow are replaced)")
+    ap.add_argument("--pipeline", type=int, default=None)
+    ap.add_argument("--no-extras", action="store_true", help="skip the dropin / megakernel-rules legs (and the reference arm's megakernel run)")
+    ap.add_argument("--no-balance", action="store_true", help="tile split with static row bands")
     ap.add_argument("--split", default="samples", choices=["samples", "tiles"],
                     help="multi-GPU partition: samples (weak scaling, default) or tiles = bands of rows (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -250,20 +322,20 @@ def main():
     W, H, S, K, Wm = cfg["width"], cfg["height"], args.spp_per_step, args.steps, args.warmup
     r = cpt.WavefrontRenderer(sc, local_rank, 0)
     r.set_option("samples_in_flight", S)
-    r.set_option("traversal", args.traversal)
-    r.set_option("pipeline", args.pipeline)
+    if args.traversal is not None:
+        r.set_option("traversal", args.traversal)
+    if args.pipeline is not None:
+        r.set_option("pipeline", args.pipeline)
+    traversal, pipeline = int(r.get_option("traversal")), int(r.get_option("pipeline"))
     r.set_option("kernel_timing", 1)
-    if args.split == "tiles" and world > 1:
-        # strong scaling: the frame is cut into bands of rows, every rank traces all S samples of its band
-        from cuda_pt_b200.distributed import row_range
-        lo, hi = row_range(H, world, rank)
-        r.set_option("row_end", hi)
-        r.set_option("row_begin", lo)
-    else:
-        # weak scaling: every rank renders its own K*S sample numbers of the same seed stream
-        r.set_counter(rank * (K + Wm) * S * 2)
+    from cuda_pt_b200.distributed import DistributedRenderer
+    tiles = args.split == "tiles" and world > 1
+    # weak scaling (default): a step = S samples PER RANK (rank r renders the r-th block of S of every step's world*S samples of the
+    # same seed stream); strong scaling (--split tiles): a step = S samples of the frame, cut into row bands that follow the
+    # measured batch times.  Either way ONE reduce of the fp32 accumulator to rank 0 per step, overlapped with the next step.
+    dr = DistributedRenderer(r, split="tiles" if tiles else "samples", dst=0, balance=not args.no_balance)
+    step_spp = S if tiles else S * world
     ext = torch.cuda.ExternalStream(r.stream(), device=dev)
-    acc = cpt.device_tensor(r.accumulator_ptr(), (H, W, 4), local_rank, r)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -271,15 +343,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step():
-        r.render_batch(S, False)
-        if world > 1:  # one NCCL reduce of the HDR accumulator per sample batch (ddp_render.py:70-81)
-            total = acc.clone()
-            dist.all_reduce(total)
-            torch.cuda.current_stream(dev).synchronize()
-
     for _ in range(Wm):
-        step()
+        dr.step(step_spp)
+    dr.finish()
     barrier()
     st0, kt0 = r.stats(), r.kernel_times()
     clocks = ClockSampler(local_rank)
@@ -288,11 +354,16 @@ def main():
     e0.record(ext)
     t_wall = time.perf_counter()
     for _ in range(K):
-        step()
-    e1.record(ext)
+        dr.step(step_spp)
+    if world > 1:
+        dr.finish()  # current stream now waits for the last reduce: the timed region ends when the reduced frame exists on rank 0
+        e1.record(torch.cuda.current_stream(dev))
+    else:
+        e1.record(ext)
     barrier()
     t_wall = time.perf_counter() - t_wall
     ms = e0.elapsed_time(e1)
+    rows_final = list(dr.rows) if tiles else None
     clk = clocks.stop()
     st1, kt1 = r.stats(), r.kernel_times()
     rays = st1["rays"] - st0["rays"]
@@ -307,18 +378,29 @@ def main():
         samples = float(tvec[2])
     value = rays / (ms * 1e-3) / 1e6
 
-    # ---- end-to-end through the C ABI with host buffers: camera in (H2D), frame out (D2H) every step
+    # ---- end-to-end through the C ABI with host buffers: camera in (H2D) on every rank, frame out (D2H) every step.
+    # N>1: the frame that leaves the device is the REDUCED one - the per-step reduce to rank 0 and its D2H (rank 0) are timed
     pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     cam = sc.camera
-    for _ in range(2):
+    if world > 1:
+        dr.host_out = pinned
+
+    def e2e_step():
         r.update_camera(cam)
-        r.render_to_host(S, False, out=pinned)
+        if world > 1:
+            dr.step(step_spp)
+        else:
+            r.render_to_host(S, False, out=pinned)
+
+    for _ in range(2):
+        e2e_step()
+    dr.finish()
     barrier()
     s0 = r.stats()
     t0 = time.perf_counter()
     for _ in range(K):
-        r.update_camera(cam)
-        r.render_to_host(S, False, out=pinned)
+        e2e_step()
+    dr.finish()
     barrier()
     t_e2e = time.perf_counter() - t0
     e2e_rays = float(r.stats()["rays"] - s0["rays"])
@@ -329,8 +411,11 @@ def main():
         b = tv.clone()
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
         t_e2e, e2e_rays = float(a[0]), float(b[1])
-    e2e = {"value": e2e_rays / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 72, "d2h_bytes_per_step": W * H * 16,
-           "ms_per_step": t_e2e / K * 1e3, "timing": "host wall clock around K x (cpt_b200_update_camera + cpt_b200_render_to_host into pinned memory)"}
+    e2e = {"value": e2e_rays / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 72 * world, "d2h_bytes_per_step": W * H * 16,
+           "ms_per_step": t_e2e / K * 1e3,
+           "timing": ("host wall clock (max over ranks) around K x (cpt_b200_update_camera + render of the step + NCCL reduce of the fp32 accumulator to "
+                      "rank 0 + D2H of the reduced frame into pinned memory on rank 0), drained at the end" if world > 1 else
+                      "host wall clock around K x (cpt_b200_update_camera + cpt_b200_render_to_host into pinned memory)")}
 
     if rank != 0:
         if world > 1:
@@ -362,7 +447,7 @@ def main():
     if sh_ms > 0:
         stages["shade"]["of_which_shadow_kernels_ms_per_step"] = sh_ms / K
         stages["shade"]["shadow_rays_traced_per_step"] = sh_traced / K
-    if "vpt" in workload and args.pipeline == 0 and "raygen" in stages:  # megakernel form: the whole path runs in k_vpt, timed in the raygen slot;
+    if "vpt" in workload and pipeline == 0 and "raygen" in stages:  # megakernel form: the whole path runs in k_vpt, timed in the raygen slot;
         stages["vpt"] = stages.pop("raygen")       # per path it reads the camera sample and writes 16 B of radiance,
         v = stages["vpt"]                          # everything else stays in registers
         v["bytes_per_unit"] = 16
@@ -385,6 +470,41 @@ def main():
                 "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; BVH/triangle reads are L2-served "
                         "(scene fits the 126 MB L2) and traversal is latency/issue bound, so the HBM fraction is small by nature"}
 
+    # ---- extra legs (N=1): the reference megakernel's termination rules; the scene as the reference's loader builds it
+    extras = {}
+    if world == 1 and not args.no_extras and "vpt" not in workload:
+        def leg(rr, steps):
+            rr.set_option("samples_in_flight", S)
+            rr.render_batch(2 * S, False)
+            a = rr.stats()
+            rr.render_batch(steps * S, False)
+            rr.sync()
+            b = rr.stats()
+            dev_s = (b["device_us"] - a["device_us"]) / 1e6
+            return {"value": (b["rays"] - a["rays"]) / dev_s / 1e6, "unit": "Mrays/s", "msamples_per_s": (b["samples"] - a["samples"]) / dev_s / 1e6,
+                    "ms_per_step": dev_s / steps * 1e3, "rays_per_sample": (b["rays"] - a["rays"]) / max(1, b["samples"] - a["samples"]), "steps": steps}
+        try:
+            r.set_option("rules", 1)
+            extras["megakernel_rules"] = dict(leg(r, max(2, K // 2)), note="rules=1: lobe caps, throughput cut-off, Russian roulette from bounce 1 "
+                                              "(megakernel_pt.cu:162-180), same kernels; compare msamples_per_s with the reference arm's megakernel_pt block")
+            r.set_option("rules", 0 if cfg["renderer"] == 1 else 1)
+        except Exception as e:
+            extras["megakernel_rules"] = {"error": str(e)[:200]}
+        ref_dump = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+        if scene.endswith(".xml") and os.path.exists(ref_dump):
+            try:
+                tmpc = os.path.join(tempfile.gettempdir(), "bench_dropin.cpts")
+                subprocess.run([ref_dump, "dump", scene, tmpc], check=True, capture_output=True, timeout=900, cwd=ROOT)
+                rd = cpt.WavefrontRenderer(tmpc, local_rank, 0)
+                if args.traversal is not None:
+                    rd.set_option("traversal", args.traversal)
+                extras["dropin"] = dict(leg(rd, max(2, K // 2)), traversal=int(rd.get_option("traversal")),
+                                        note="the same step on the scene the reference's own loader builds for this XML (SBVH, leaves of up to 16, dumped by "
+                                             "`ref_dump dump`): what a host application that keeps the reference's loader gets (INTEGRATION.md)")
+                rd.close()
+            except Exception as e:
+                extras["dropin"] = {"error": str(e)[:200]}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         tmp = os.path.join(tempfile.gettempdir(), "bench_scene.cpts")
@@ -392,7 +512,7 @@ def main():
         cpu_baseline = cpu_oracle_rate(tmp, W, H, rules=int(r.get_option("rules")))
 
     out = {"metric": (METRIC.replace("wavefront PT", "volumetric PT") if "vpt" in workload else METRIC).replace("1920x1080", f"{W}x{H}"), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
-           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (args.split == "tiles" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32",
            "data": ("cornell box geometry bundled with the reference + a synthetic 304x512x304 NanoVDB smoke volume (density, albedo, temperature "
                     "grids; `ref_dump mkvdb`) read by our own .nvdb reader + two homogeneous media; fixed seeds"
                     if "grid" in workload else
@@ -405,21 +525,27 @@ def main():
                     if "tex" in workload else
                     "vader geometry bundled with the reference (textures/envmap not shipped upstream, removed); fixed seeds"),
            "config": {"workload": workload, "width": W, "height": H, "spp_per_step": S, "max_depth": cfg["max_depth"],
-                      "triangles": cfg["num_prims"], "parallelism": (f"{'row-band tile' if args.split == 'tiles' else 'sample'}-split x{world}, 1 NCCL all-reduce of the fp32 accumulator per step"
+                      "triangles": cfg["num_prims"], "parallelism": (f"{'row-band tile' if tiles else 'sample'}-split x{world}, 1 NCCL reduce of the fp32 accumulator to rank 0 per step, "
+                                                                     "issued from a snapshot on a side stream (overlaps the next step; drained inside the timed region)"
                                       if world > 1 else "1 GPU"),
+                      "samples_per_step": step_spp, "row_bands_at_the_end": rows_final,
+                      "steady_state_note": f"{K} steps x {step_spp} spp = {K * step_spp} spp timed (a steady-state rate; BASELINE's 1024 spp is the same loop run longer)",
                       "l2_note": f"path-state pool {S * W * H * 92 / 1e6:.0f} MB per step >> 126 MB L2 (no flush needed)",
-                      "traversal": {0: "ordered pair-node", 1: "reference DFS order", 2: "ordered pair-node, 256-bit node loads", 3: "ordered, warp-vote"}[args.traversal],
-                      "pipeline": ({0: "volumetric megakernel", 1: "volumetric wavefront over slot queues"}.get(args.pipeline, "volumetric wavefront, dense path records")
+                      "traversal": {0: "ordered pair-node", 1: "reference DFS order", 2: "ordered pair-node, 256-bit node loads", 3: "ordered, warp-vote",
+                                    4: "warp-cooperative, wide layout"}.get(traversal, str(traversal)),
+                      "pipeline": ({0: "volumetric megakernel", 1: "volumetric wavefront over slot queues"}.get(pipeline, "volumetric wavefront, dense path records")
                                    if "vpt" in workload else
                                    {0: "fused", 1: "split shadow kernel", 2: "dynamic-fetch traversal", 3: "deferred NEE", 4: "deferred NEE + dynamic fetch",
-                                    5: "deferred NEE, dense path records"}[args.pipeline]),
+                                    5: "deferred NEE, dense path records"}.get(pipeline, str(pipeline))),
                       "ray_accounting": "rays = primary + closest-hit + NEE shadow rays of the algorithm (SURVEY.md 8d, one shadow ray per shaded "
                                         "segment whose sampled emitter is not the null emitter); shadow rays that provably cannot change the "
                                         "radiance are not traversed (shadow_traced_frac)"},
            "msamples_per_s": samples / (ms * 1e-3) / 1e6, "rays_per_sample": rays / samples,
            "shadow_traced_frac": (st1["shadow_traced"] - st0["shadow_traced"]) / max(1, st1["shadow_rays"] - st0["shadow_rays"]),
+           "traced_mrays": value * (1.0 - ((st1["shadow_rays"] - st0["shadow_rays"]) - (st1["shadow_traced"] - st0["shadow_traced"])) / max(1.0, float(st1["rays"] - st0["rays"]))) if world == 1 else None,
            "gpu_launches": int((st1["launches"] - st0["launches"])), "wall_s": t_wall,
            "clocks": clk, "e2e": e2e, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline}
+    out.update(extras)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

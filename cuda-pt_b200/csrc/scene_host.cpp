@@ -614,6 +614,13 @@ void build_pair_layout(const HostScene &sc, PairLayout &out, int refine_above) {
         return !(over > 0.f);
     };
 
+    for (int k = 0; k < N; k++) { // clipped references (see PairLayout::clipped_refs)
+        if (node_cnt(k) <= 0)
+            continue;
+        const F4 lo = sc.nodes[2 * k], hi = sc.nodes[2 * k + 1];
+        for (int i = node_base(k); i < node_base(k) + node_cnt(k); i++)
+            out.clipped_refs += !tri_of(i, lo, hi).inside;
+    }
     // explicit stack: (reference node k, slot to fill = pair node index * 2 + child id, depth)
     struct Item {
         int k, slot, depth;

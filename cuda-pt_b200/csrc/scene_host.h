@@ -92,6 +92,11 @@ struct PairLayout {
     // beyond its parent).  The wide collapse only merges a node into its parent's record where this holds - elsewhere the
     // node's own box test decides, as in the reference, whether its children are looked at at all.
     std::vector<uint8_t> children_nest;
+    // primitive references that stick out of their leaf's box (SBVH: a triangle clipped to the node it was split into).  The
+    // reference finds hits of such a triangle only through leaves whose box the ray enters while no closer hit is known, so
+    // its result depends on the order in which leaves are tested; traversal modes that test leaves in batches (traversal=4)
+    // are not used on such scenes.
+    int clipped_refs = 0;
 };
 void build_pair_layout(const HostScene &scene, PairLayout &out, int refine_above = 0);
 

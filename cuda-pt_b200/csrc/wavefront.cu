@@ -865,12 +865,12 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
 // ------------------------------------------------------------------------------------------------
 constexpr int kCoopBlock = 256;
 
-template <int G>
+template <int G, bool SLAB>
 __global__ void __launch_bounds__(kCoopBlock)
     k_trace_coop(DevScene sc, CoopParams cp, PathState st, const uint32_t *__restrict__ queue, const int *__restrict__ q_count, int *work,
                  uint32_t *q_next, int *q_next_count, int bounce, int pt_rules) {
     extern __shared__ __align__(128) unsigned char coop_smem[];
-    const CoopShared S = coop_setup(coop_smem, sc, cp, G);
+    const CoopShared S = coop_setup(coop_smem, sc, cp, G, SLAB);
     const int lane = threadIdx.x & 31;
     const int count = *q_count;
     for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
@@ -888,22 +888,20 @@ __global__ void __launch_bounds__(kCoopBlock)
         }
         float4 h0 = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(-1));
         bool coop_ray = valid;
-        if (valid && !coop_ray_ok(d)) { // a (near-)zero direction component: per-thread traversal with the compare+select slab test
+        const V3 inv_d = rcp3(d), o_div = o * inv_d;
+        if (valid && !coop_ray_ok(inv_d)) { // a (near-)zero direction component: per-thread traversal with the compare+select slab test
             const Hit hh = closest_hit_ordered<true, false>(sc, S.cached, o, d);
             h0 = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
             coop_ray = false;
         }
-        if (coop_ray) {
-            const V3 inv_d = rcp3(d), o_div = o * inv_d;
+        if (coop_ray)
             start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
-        }
-        S.rays[2 * lane] = make_float4(o.x, o.y, o.z, __int_as_float(start));
-        S.rays[2 * lane + 1] = make_float4(d.x, d.y, d.z, coop_ray ? kMaxDist : -1.f);
+        coop_store_ray(S, lane, o, d, inv_d, o_div, start, coop_ray ? kMaxDist : -1.f);
         S.hits[lane] = h0;
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
-        coop_traverse<G, false>(sc, cp, S, lane);
+        coop_traverse<G, false, SLAB>(sc, cp, S, lane);
         const float4 h = S.hits[lane];
         bool alive = false;
         if (valid)
@@ -912,11 +910,11 @@ __global__ void __launch_bounds__(kCoopBlock)
     }
 }
 
-template <int G>
+template <int G, bool SLAB>
 __global__ void __launch_bounds__(kCoopBlock)
     k_shadow_apply_coop(DevScene sc, CoopParams cp, PathState st, RayBufs rb, const uint32_t *__restrict__ sq, const int *__restrict__ sq_count, int *work) {
     extern __shared__ __align__(128) unsigned char coop_smem[];
-    const CoopShared S = coop_setup(coop_smem, sc, cp, G);
+    const CoopShared S = coop_setup(coop_smem, sc, cp, G, SLAB);
     const int lane = threadIdx.x & 31;
     const int count = *sq_count;
     for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
@@ -932,31 +930,29 @@ __global__ void __launch_bounds__(kCoopBlock)
             o = xyz(a), d = xyz(b), range = a.w;
         }
         float vis0 = 1.f;
-        if (valid && !coop_ray_ok(d)) { // per-thread traversal with the compare+select slab test
+        const V3 inv_d = rcp3(d), o_div = o * inv_d;
+        if (valid && !coop_ray_ok(inv_d)) { // per-thread traversal with the compare+select slab test
             vis0 = unoccluded_ordered<true, false>(sc, S.cached, o, d, range) ? 1.f : 0.f;
             range = -1.f;
         }
-        if (range > 0.f) {
-            const V3 inv_d = rcp3(d), o_div = o * inv_d;
+        if (range > 0.f)
             start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, range, sc.num_nodes);
-        }
-        S.rays[2 * lane] = make_float4(o.x, o.y, o.z, __int_as_float(start));
-        S.rays[2 * lane + 1] = make_float4(d.x, d.y, d.z, range); // a range <= 0 cannot be occluded (no t in (EPSILON, range))
+        coop_store_ray(S, lane, o, d, inv_d, o_div, start, range); // a range <= 0 cannot be occluded (no t in (EPSILON, range))
         S.hits[lane] = make_float4(vis0, 0.f, 0.f, 0.f);
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
-        coop_traverse<G, true>(sc, cp, S, lane);
+        coop_traverse<G, true, SLAB>(sc, cp, S, lane);
         if (valid && S.hits[lane].x != 0.f)
             st.L[slot] = rb.hit[slot];
     }
 }
 
-template <int G>
+template <int G, bool SLAB>
 __global__ void __launch_bounds__(kCoopBlock)
     k_raygen_coop(DevScene sc, CoopParams cp, CameraPOD cam, PathState st, BatchParams bp, uint32_t *q_out, int *q_count, int *work) {
     extern __shared__ __align__(128) unsigned char coop_smem[];
-    const CoopShared S = coop_setup(coop_smem, sc, cp, G);
+    const CoopShared S = coop_setup(coop_smem, sc, cp, G, SLAB);
     const int lane = threadIdx.x & 31;
     const int ty0 = bp.row0 >> 2;
     const int tiles_x = (bp.W + 7) >> 3, tiles_y = ((bp.row1 + 3) >> 2) - ty0, tiles = tiles_x * tiles_y;
@@ -986,22 +982,20 @@ __global__ void __launch_bounds__(kCoopBlock)
         }
         float4 h0 = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(-1));
         bool coop_ray = inside;
-        if (inside && !coop_ray_ok(d)) {
+        const V3 inv_d = rcp3(d), o_div = o * inv_d;
+        if (inside && !coop_ray_ok(inv_d)) {
             const Hit hh = closest_hit_ordered<true, false>(sc, S.cached, o, d);
             h0 = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
             coop_ray = false;
         }
-        if (coop_ray) {
-            const V3 inv_d = rcp3(d), o_div = o * inv_d;
+        if (coop_ray)
             start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
-        }
-        S.rays[2 * lane] = make_float4(o.x, o.y, o.z, __int_as_float(start));
-        S.rays[2 * lane + 1] = make_float4(d.x, d.y, d.z, coop_ray ? kMaxDist : -1.f);
+        coop_store_ray(S, lane, o, d, inv_d, o_div, start, coop_ray ? kMaxDist : -1.f);
         S.hits[lane] = h0;
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
-        coop_traverse<G, false>(sc, cp, S, lane);
+        coop_traverse<G, false, SLAB>(sc, cp, S, lane);
         if (inside) {
             const float4 h = S.hits[lane];
             const int prim = __float_as_int(h.w);
@@ -2012,7 +2006,7 @@ struct Renderer::Impl {
     std::vector<cudaTextureObject_t> tex_objs;
     std::vector<cudaArray_t> tex_arrays;
     int capacity_samples = 0;
-    int pair_depth = 0, nesting_violations = 0;
+    int pair_depth = 0, nesting_violations = 0, clipped_refs = 0;
     float max_overshoot = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     size_t scene_bytes = 0;
@@ -2149,6 +2143,7 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         m.arena_wide = ww.size();
         m.pair_depth = pl.max_depth;
         m.nesting_violations = pl.nesting_violations;
+        m.clipped_refs = pl.clipped_refs;
         m.dev.wroot = pl.root;
         // ordered traversal's preconditions: stack depth, and child boxes inside their parents' boxes.  The
         // reference's SBVH pads clipped child boxes by AABB_EPS (1e-5) beyond the parent; that much is tolerated (a hit
@@ -2413,6 +2408,8 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
     m.coop_blocks_per_sm = 0;
     int max_optin = 0;
     CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
+    if (G == 8)
+        coop_slab_ = 0; // the slab variant is instantiated for groups of 4 only
     for (;; coop_slab_ /= 2) { // shrink the slab until the carve-up fits
         const int cap = std::max(8, (m.wide_max_stack + 7) / 8 * 8);
         const CoopLayout L = coop_layout(m.dev.num_cache, coop_slab_, G, cap, kCoopBlock / 32);
@@ -2431,11 +2428,15 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
     };
     int nb;
     if (G == 8)
-        nb = std::min(std::min(prep(k_trace_coop<8>), prep(k_shadow_apply_coop<8>)), prep(k_raygen_coop<8>));
+        nb = std::min(std::min(prep(k_trace_coop<8, false>), prep(k_shadow_apply_coop<8, false>)), prep(k_raygen_coop<8, false>));
+    else if (coop_slab_ > 0)
+        nb = std::min(std::min(prep(k_trace_coop<4, true>), prep(k_shadow_apply_coop<4, true>)), prep(k_raygen_coop<4, true>));
     else
-        nb = std::min(std::min(prep(k_trace_coop<4>), prep(k_shadow_apply_coop<4>)), prep(k_raygen_coop<4>));
+        nb = std::min(std::min(prep(k_trace_coop<4, false>), prep(k_shadow_apply_coop<4, false>)), prep(k_raygen_coop<4, false>));
     m.coop_blocks_per_sm = nb;
-    coop_ok_ = nb >= 1 && ordered_ok_; // same preconditions as the ordered traversal (nesting), plus the stack carve-up
+    // preconditions of the ordered traversal, plus: the stack carve-up fits, and no leaf holds a clipped (SBVH) reference - the
+    // reference's result on those depends on the order in which single leaves are tested (PairLayout::clipped_refs)
+    coop_ok_ = nb >= 1 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0;
 }
 
 void Renderer::set_traversal(int t) {
@@ -2527,13 +2528,15 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     const bool coop = traversal_ == 4 && coop_ok_ && rules_ != 2 && this->pipeline_ == 3;
     const int mode = traversal_ == 4 ? 2 : traversal_;
     const int coop_grid = num_sms_ * std::max(1, m.coop_blocks_per_sm);
-    const CoopParams cpar{m.arena.p + m.arena_nodes, coop_slab_, std::max(8, (m.wide_max_stack + 7) / 8 * 8), coop_flush_};
+    const CoopParams cpar{m.arena.p + m.arena_nodes, m.wide_width == 8 ? 0 : coop_slab_, std::max(8, (m.wide_max_stack + 7) / 8 * 8)};
 #define LAUNCH_COOP(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (m.wide_width == 8)                                                                                         \
-            kernel<8><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                                    \
+            kernel<8, false><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                             \
+        else if (coop_slab_ > 0)                                                                                       \
+            kernel<4, true><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                              \
         else                                                                                                           \
-            kernel<4><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                                    \
+            kernel<4, false><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                             \
     } while (0)
     const int pipeline_ = (traversal_ == 1 || traversal_ == 3 || traversal_ == 4) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
 #define LAUNCH_MODE(kernel, ...)                                                                                       \
@@ -2932,7 +2935,7 @@ std::string Renderer::info() const {
        << ", wide layout " << impl_->wide_width << "-ary " << impl_->wide_nodes << " nodes (fill " << impl_->wide_fill << ", depth " << impl_->wide_depth
        << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks_per_sm << " CTAs/SM x " << impl_->coop_smem
        << " B smem, slab " << coop_slab_ << " nodes, flush " << coop_flush_ << " lanes)"
-       << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations << " (max " << impl_->max_overshoot << ")"
+       << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations << " (max " << impl_->max_overshoot << "), clipped references " << impl_->clipped_refs
        << ", refined leaves " << impl_->refined_leaves
        << ", L2 window " << (impl_->l2_window_bytes >> 20) << " MB, pipeline " << pipeline_ << ", rules " << (rules_ == 2 ? "volumetric-pt" : (rules_ ? "megakernel-pt" : "wavefront")) << ", samples in flight " << s_max_ << ", device " << device_ << ", counter " << accum_cnt_;
     return os.str();

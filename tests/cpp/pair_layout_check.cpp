@@ -101,7 +101,7 @@ int main(int argc, char **argv) {
         wide_errors += wl.leaf_slots != leaf_records;
     }
     errors += wide_errors;
-    printf("prims %d leaf_records %d refined_leaves %d depth %d nesting_violations %d wide_errors %d wide_stack %d errors %d\n", P, leaf_records,
-           pl.refined_leaves, pl.max_depth, pl.nesting_violations, wide_errors, wide_stack, errors);
+    printf("prims %d leaf_records %d refined_leaves %d depth %d nesting_violations %d clipped_refs %d wide_errors %d wide_stack %d errors %d\n", P, leaf_records,
+           pl.refined_leaves, pl.max_depth, pl.nesting_violations, pl.clipped_refs, wide_errors, wide_stack, errors);
     return errors ? 1 : 0;
 }

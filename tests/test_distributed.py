@@ -44,6 +44,33 @@ def test_row_range_partitions_exactly():
         cd.row_range(100, 2, 2)
 
 
+def test_balanced_rows_partition_and_follow_the_cost():
+    """Dynamic tile split (DistributedRenderer, split="tiles"): the new bands always partition the frame into multiples of 4
+    rows with at least one unit per rank, and the cumulative cost (time per row of the previous bands) is cut into equal parts."""
+    rng = np.random.default_rng(0)
+    for height in (8, 256, 1080):
+        for world in (1, 2, 4, 8):
+            if height // 4 < world:
+                continue
+            rows = [cd.row_range(height, world, r) for r in range(world)]
+            for _ in range(5):
+                times = list(rng.uniform(1.0, 10.0, size=world))
+                new = cd.balanced_rows(height, rows, times)
+                assert new[0][0] == 0 and new[-1][1] == height
+                for (a, b), (c, d) in zip(new[:-1], new[1:]):
+                    assert b == c and a % 4 == 0 and b > a
+                assert new[-1][1] > new[-1][0]
+                rows = new
+    # equal densities: bands stay (nearly) equal; a rank that took 3x as long per row gets about a third of the rows
+    rows = [cd.row_range(1080, 4, r) for r in range(4)]
+    same = cd.balanced_rows(1080, rows, [5.0] * 4)
+    assert all(abs((b - a) - 270) <= 8 for a, b in same)
+    skew = cd.balanced_rows(1080, rows, [10.0, 30.0, 30.0, 10.0])
+    cost = lambda lo, hi: sum((10.0 if (y < 272 or y >= 812) else 30.0) / 270.0 for y in range(lo, hi))
+    costs = [cost(a, b) for a, b in skew]
+    assert max(costs) / min(costs) < 1.1, costs
+
+
 def _tile_worker(rank, world, port, total_spp, out_dir):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
     import oracle

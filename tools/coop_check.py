@@ -28,7 +28,7 @@ def parity():
     for scene, gold, spp in (("cbox_wfpt_256.cpts", "cbox_wfpt_256_wfpt_f0004.bin", 4), ("cbox_mats_256.cpts", "cbox_mats_256_wfpt_f0016.bin", 16),
                              ("texroom_256.cpts", "texroom_256_wfpt_f0064.bin", 64)):
         ref = np.fromfile(os.path.join(GOLD, gold), dtype=np.float32).reshape(256, 256, 4)
-        for opts in ((), (("coop_flush", 1),), (("coop_flush", 32), ("coop_slab", 0))):
+        for opts in ((), (("coop_slab", 16),)):
             out, st, eff, info = frame(os.path.join(GOLD, scene), spp, 4, opts)
             ex = float((out.view(np.uint32) == ref.view(np.uint32)).all(-1).mean())
             print(f"[parity] {scene} trav=4 (effective {eff}) opts={opts}: bit-exact pixels vs reference frame {ex * 100:.4f}%  rays {st['rays']}", flush=True)
@@ -47,11 +47,7 @@ def parity():
 
 def bench(spp=32, sif=16):
     rows = []
-    configs = [(2, ())]
-    for flush in (8, 12, 16, 24):
-        configs.append((4, (("coop_flush", flush), ("coop_slab", 64))))
-    for slab in (0, 16, 256):
-        configs.append((4, (("coop_flush", 12), ("coop_slab", slab))))
+    configs = [(2, ()), (4, (("coop_slab", 0),)), (4, (("coop_slab", 64),))]
     for trav, opts in configs:
         r = cpt.WavefrontRenderer(VADER, 0, 0)
         r.set_option("traversal", trav)
