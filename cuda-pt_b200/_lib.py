@@ -61,6 +61,7 @@ def lib():
         "cpt_b200_version": (cp, []),
         "cpt_b200_scene_load_xml": (i32, [cp, C.POINTER(vp)]),
         "cpt_b200_scene_load": (i32, [cp, C.POINTER(vp)]),
+        "cpt_b200_scene_load_memory": (i32, [vp, u64, C.POINTER(vp)]),
         "cpt_b200_scene_save": (i32, [vp, cp]),
         "cpt_b200_scene_config": (i32, [vp, C.POINTER(C.c_int32)]),
         "cpt_b200_scene_set_film": (i32, [vp, i32, i32]),

@@ -57,6 +57,22 @@ int cpt_b200_scene_load_xml(const char *xml_path, cpt_b200_scene **out) {
     });
 }
 
+int cpt_b200_scene_load_memory(const void *cpts_image, uint64_t bytes, cpt_b200_scene **out) {
+    REQUIRE(cpts_image);
+    REQUIRE(out);
+    *out = nullptr;
+    return guarded([&] {
+        auto s = new cpt_b200_scene();
+        try {
+            cptb::load_cpts_memory(cpts_image, size_t(bytes), s->host);
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        *out = s;
+    });
+}
+
 int cpt_b200_scene_load(const char *cpts_path, cpt_b200_scene **out) {
     REQUIRE(cpts_path);
     REQUIRE(out);

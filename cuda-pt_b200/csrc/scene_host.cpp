@@ -92,10 +92,25 @@ uint16_t float_to_half_rn(float f) {
 
 } // namespace
 
+static void load_cpts_stream(FILE *fp, const std::string &path, HostScene &out);
+
 void load_cpts(const std::string &path, HostScene &out) {
     FILE *fp = fopen(path.c_str(), "rb");
     if (!fp)
         throw std::runtime_error("cpts: cannot open '" + path + "'");
+    load_cpts_stream(fp, path, out);
+}
+
+void load_cpts_memory(const void *image, size_t bytes, HostScene &out) {
+    if (!image || bytes < sizeof(CptsHeader))
+        throw std::runtime_error("cpts: empty in-memory container");
+    FILE *fp = fmemopen(const_cast<void *>(image), bytes, "rb");
+    if (!fp)
+        throw std::runtime_error("cpts: cannot open the in-memory container");
+    load_cpts_stream(fp, "<memory>", out);
+}
+
+static void load_cpts_stream(FILE *fp, const std::string &path, HostScene &out) {
     FileCloser closer{fp};
     CptsHeader h{};
     if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, CPTS_MAGIC, 8) != 0)

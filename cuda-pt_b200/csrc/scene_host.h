@@ -61,6 +61,8 @@ struct HostScene {
 
 // ---- .cpts container (include/cpts_format.h) ----
 void load_cpts(const std::string &path, HostScene &out); // throws std::runtime_error
+// the same container handed over in memory (reference-side adapter: integration/b200_wavefront.cuh); the image is only read
+void load_cpts_memory(const void *image, size_t bytes, HostScene &out);
 void save_cpts(const HostScene &scene, const std::string &path);
 
 // ---- XML scene loader (scene format v1.2; reference behaviour: src/impl/scene.cu:937-1192) ----

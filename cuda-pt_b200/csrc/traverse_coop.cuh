@@ -152,7 +152,7 @@ template <int G> __device__ __forceinline__ unsigned group_min(unsigned v) {
 // Control flow is warp-uniform wherever lanes talk to each other (ballots, shuffles use the full mask); what differs
 // between the groups of a warp is predicated.  One loop iteration = one node visit per group; everything else (triangle
 // phase, retiring a ray, taking the next) sits in a "service" block the warp enters only when some group needs it.
-template <int G, bool ANYHIT, bool SLAB> __device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopParams &cp, const CoopShared &S, int lane) {
+template <int G, bool ANYHIT, bool SLAB, int UNROLL = 2> __device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopParams &cp, const CoopShared &S, int lane) {
     static_assert(G == 4 || G == 8, "lane group of 4 or 8");
     constexpr unsigned GM = (1u << G) - 1u, FULL = 0xffffffffu;
     const int li = lane & (G - 1), gbase = lane & ~(G - 1);
@@ -194,9 +194,11 @@ template <int G, bool ANYHIT, bool SLAB> __device__ __forceinline__ void coop_tr
 
     while (true) {
         __syncwarp();
-        // ---- node visit (groups without a node to visit run along with every test predicated off)
-        const bool walk = cur >= 0 && npend <= G;
-        {
+        // ---- node visits (groups without a node to visit run along with every test predicated off).  UNROLL visits per look at
+        // the service conditions: a group that gets blocked or finishes in between idles for at most UNROLL - 1 visits
+#pragma unroll
+        for (int rep = 0; rep < UNROLL; rep++) {
+            const bool walk = cur >= 0 && npend <= G;
             const int node = cur > 0 ? cur : 0;
             float4 lo, hi;
             if (SLAB && node < cp.slab_nodes)
@@ -240,6 +242,8 @@ template <int G, bool ANYHIT, bool SLAB> __device__ __forceinline__ void coop_tr
                     }
                 }
             }
+            if (rep + 1 < UNROLL)
+                __syncwarp();
         }
         // ---- service: a group that cannot go on without a triangle phase (pending list above G, or traversal finished with
         // leaves pending), or that finished its ray

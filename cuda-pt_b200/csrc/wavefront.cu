@@ -2363,6 +2363,8 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         coop_flush_ = std::min(32, std::max(1, atoi(e)));
     if (const char *e = getenv("CPTB200_COOP_SLAB"))
         coop_slab_ = std::max(0, atoi(e));
+    if (const char *e = getenv("CPTB200_COOP_RAYGEN"))
+        coop_raygen_ = atoi(e) != 0;
     set_coop(coop_flush_, coop_slab_);
     if (const char *e = getenv("CPTB200_TRAVERSAL"))
         set_traversal(atoi(e));
@@ -2702,7 +2704,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         return;
     }
     mark(0, 0);
-    if (coop)
+    if (coop && coop_raygen_) // primary rays are coherent: the per-thread kernel runs them at 15 of 32 lanes and is the faster one
         LAUNCH_COOP(k_raygen_coop, m.dev, cpar, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
     else
         LAUNCH_MODE(k_raygen, m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);

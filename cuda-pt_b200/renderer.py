@@ -27,6 +27,11 @@ class Scene:
 
     def __init__(self, path):
         self._h = C.c_void_p()
+        if isinstance(path, (bytes, bytearray, memoryview)):  # a .cpts container image in memory
+            buf = bytes(path)
+            check(lib().cpt_b200_scene_load_memory(buf, len(buf), C.byref(self._h)))
+            self.path = "<memory>"
+            return
         p = str(path).encode()
         if str(path).endswith(".cpts"):
             check(lib().cpt_b200_scene_load(p, C.byref(self._h)))

@@ -37,6 +37,10 @@ int cpt_b200_scene_load_xml(const char *xml_path, cpt_b200_scene **out);
 /* Flat container written by cpt_b200_scene_save() or by the reference-side adapter
  * (include/cpts_format.h): the exact arrays of a reference `Scene`. */
 int cpt_b200_scene_load(const char *cpts_path, cpt_b200_scene **out);
+/* The same container handed over IN MEMORY (no file): what the reference-side adapter integration/b200_wavefront.cuh does
+ * with the `Scene` the reference's own loader built (src/core/scene.cuh:49-107 -> integration/cpts_flatten.cuh).  The image
+ * is only read during the call and may be freed afterwards. */
+int cpt_b200_scene_load_memory(const void *cpts_image, uint64_t bytes, cpt_b200_scene **out);
 int cpt_b200_scene_save(const cpt_b200_scene *scene, const char *cpts_path);
 /* config[CPTS_CFG_COUNT] as in cpts_format.h (width, height, spp, max_depth, gamma, renderer ...) */
 int cpt_b200_scene_config(const cpt_b200_scene *scene, int32_t *config32);

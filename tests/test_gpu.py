@@ -5,6 +5,7 @@
   (4) the live reference (oracle/_ref/ref_dump) when that binary travelled to the box."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -35,7 +36,7 @@ def render_frames(scene, frames, seed=0, traversal=0, variance=True):
     return out, st
 
 
-@pytest.mark.parametrize("traversal", [0, 1, 2, 3])
+@pytest.mark.parametrize("traversal", [0, 1, 2, 3, 4])
 def test_cornell_c0_bit_exact_vs_reference(traversal):
     """BASELINE config C0: cornell box 256x256, seed 0, samples 1..64 (rel-L2 bar is 1e-4; we get identity)."""
     out, st = render_frames("cbox_wfpt_256.cpts", [1, 4, 64], traversal=traversal)
@@ -53,7 +54,7 @@ def test_seed_offset_bit_exact_vs_reference():
     assert bit_exact_fraction(out[3][0], load_frame("cbox_wfpt_256_s7_wfpt_f0003.bin")) == 1.0
 
 
-@pytest.mark.parametrize("traversal", [0, 1, 2, 3])
+@pytest.mark.parametrize("traversal", [0, 1, 2, 3, 4])
 def test_all_materials_bit_exact_vs_reference(traversal):
     """Lambert, specular, det-refraction, plastic, plastic-forward, GGX conductor (anisotropic), dispersion,
     area + point emitters, 8 bounces, Russian roulette."""
@@ -64,7 +65,7 @@ def test_all_materials_bit_exact_vs_reference(traversal):
     assert np.array_equal(out[16][1].view(np.uint32), var_ref.view(np.uint32))
 
 
-@pytest.mark.parametrize("traversal", [0, 1])
+@pytest.mark.parametrize("traversal", [0, 1, 4])
 def test_textures_and_envmap_vs_reference(traversal):
     """Every texture slot (diffuse, specular, glossy/sigma_a, normal, roughness x/y, ior, emission) and a rotated
     lat-long environment map, on UV-mapped geometry; texels are the ones the reference decoded (scene dump)."""
@@ -522,3 +523,71 @@ def test_live_reference_vader_bit_exact(tmp_path, xml):
         gold = load_frame("vader_256_wfpt_f0008.bin")
         assert rel_l2(r.download_output(), gold) <= 1e-4  # the SBVH build is threaded: allow a different primitive order
     r.close()
+
+
+def test_cooperative_traversal_is_used_where_allowed_and_replaced_where_not():
+    """traversal=4 (warp-cooperative, wide layout) runs on scenes without clipped SBVH references and gives the frames of the
+    ordered per-thread traversal bit for bit; on the SBVH cornell scene (29 clipped references: the reference's result there
+    depends on the order in which single leaves are tested) the request is replaced by the ordered traversal, and the
+    constructor's fall-back to the reference's own order cannot be overridden from outside."""
+    r = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_mats_256.cpts"), 0, 0)
+    r.set_option("traversal", 4)
+    assert r.get_option("traversal") == 4 and "coop ok" in r.info()
+    a = r.render_to_host(8, False)
+    r.set_option("coop_slab", 16)  # treelet slab in shared memory (TMA bulk copy): same frames
+    r.reset()
+    assert np.array_equal(a.view(np.uint32), r.render_to_host(8, False).view(np.uint32))
+    r.close()
+    q = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_mats_256.cpts"), 0, 0)
+    q.set_option("traversal", 2)
+    assert np.array_equal(a.view(np.uint32), q.render_to_host(8, False).view(np.uint32))
+    q.close()
+    s = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), 0, 0)
+    s.set_option("traversal", 4)
+    assert s.get_option("traversal") == 2 and "coop unavailable" in s.info()
+    s.close()
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_DUMP) and have_vader()), reason="reference harness / vader mesh not on this box")
+def test_benchmark_configuration_parity_vs_live_reference_1080p(tmp_path):
+    """BASELINE config 1 as bench.py runs it - vader_wfpt_1080p.xml, 1920 x 1080, 16 bounces - against the unmodified
+    reference rendering the same XML right now on this GPU (3 spp):
+      * drop-in case, the scene the reference's loader built (its SBVH): reference-order traversal 100 % bit-identical pixels,
+        the default ordered traversal >= 99.999 % (DESIGN.md 2: hits inside the 1e-5 padding of clipped SBVH boxes);
+      * the tree of our own loader (what the headline number is measured on): a different, valid primitive order, hence other
+        random streams per light sample - block statistics against the reference's frame."""
+    xml = os.path.join(SCENES, "vader_wfpt_1080p.xml")
+    prefix = str(tmp_path / "v1080")
+    subprocess.run([REF_DUMP, "render", xml, prefix, "wfpt", "0", "3"], check=True, capture_output=True, cwd=ROOT)
+    ref = np.fromfile(f"{prefix}_wfpt_f0003.bin", dtype=np.float32).reshape(1080, 1920, 4)
+    for traversal, bar in ((1, 1.0), (2, 0.99999)):
+        r = cpt.WavefrontRenderer(prefix + ".cpts", 0, 0)
+        r.set_option("traversal", traversal)
+        out = r.render_to_host(3, False)
+        r.close()
+        frac = bit_exact_fraction(out, ref)
+        assert frac >= bar and rel_l2(out, ref) <= 1e-6, (traversal, frac)
+    # own loader, own BVH: the benchmarked tree.  64 spp of ours against 64 spp of the reference would be the clean comparison;
+    # the reference needs ~3 s for those, affordable here
+    subprocess.run([REF_DUMP, "render", xml, prefix + "b", "wfpt", "0", "32"], check=True, capture_output=True, cwd=ROOT)
+    ref32 = np.fromfile(f"{prefix}b_wfpt_f0032.bin", dtype=np.float32).reshape(1080, 1920, 4)[..., :3].astype(np.float64)
+    r = cpt.WavefrontRenderer(xml, 0, 0)
+    ours = r.render_to_host(32, False)[..., :3].astype(np.float64)
+    st = r.stats()
+    r.close()
+    bo, br = ours.reshape(45, 24, 80, 24, 3).mean((1, 3)), ref32.reshape(45, 24, 80, 24, 3).mean((1, 3))
+    rel = np.abs(bo - br).sum(-1) / np.maximum(br.sum(-1), 1e-3)
+    assert np.median(rel) < 0.02 and np.quantile(rel, 0.95) < 0.10, (np.median(rel), np.quantile(rel, 0.95))
+    assert abs(ours.mean() / ref32.mean() - 1) < 0.01
+    assert abs(st["rays"] / st["samples"] - 6.31) < 0.05  # same work per sample as the reference's tree (profiles/workload_rays.json)
+
+
+def test_two_rank_distributed_render(tmp_path):
+    """Both multi-GPU partitions on two real GPUs (torchrun, NCCL): render_distributed and the streaming DistributedRenderer
+    (overlapped reduce, balanced tiles) reproduce the reference's committed 64-spp frame (tools/ddp_check.py asserts it)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with `gpurun --gpus 2`; log kept under profiles/)")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29731", os.path.join(ROOT, "tools", "ddp_check.py")], capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert out.returncode == 0 and "[ddp_check] OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
