@@ -177,6 +177,30 @@ def cpu_oracle_rate(scene_cpts, width, height, budget_s=12.0, rules=0):
             "msamples_per_s": st["samples"] / dt / 1e6, "rays_per_sample": st["rays"] / st["samples"]}
 
 
+def python_serial_rate(module_dir, scene, frames, gpu):
+    """BASELINE.md B5, the "Python serial path for plumbing": one process looping pyrender.PythonRenderer(xml, 0, 0).render()
+    (one sample + a deep copy into a fresh torch tensor per call, scripts/serial_render.py:181-192) on one GPU.  `module_dir`
+    holds the nanobind module: oracle/_ref/pyrender_ref (the unmodified reference) or oracle/_ref/b200_side (the same module
+    with its path-tracer cases routed to libcpt_b200.so through integration/b200_wavefront.cuh)."""
+    if not os.path.exists(os.path.join(module_dir, "pyrender.so")) or not scene.endswith(".xml"):
+        return None
+    code = ("import sys, time, json\nsys.path.insert(0, %r)\nimport torch, pyrender\nr = pyrender.PythonRenderer(%r, 0, 0)\n"
+            "for _ in range(4):\n    img = r.render()\ntorch.cuda.synchronize()\nt0 = time.perf_counter()\n"
+            "for _ in range(%d):\n    img = r.render()\ntorch.cuda.synchronize()\ndt = time.perf_counter() - t0\n"
+            "print(json.dumps({'py_serial': True, 'ms_per_frame': dt / %d * 1e3, 'pixels': int(img.shape[0] * img.shape[1])}))\nr.release()\n"
+            % (module_dir, scene, frames, frames))
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1800, cwd=ROOT, env=env)
+        line = [l for l in out.stdout.splitlines() if l.startswith('{"py_serial"')][-1]
+        rec = json.loads(line)
+        return {"ms_per_frame": rec["ms_per_frame"], "msamples_per_s": rec["pixels"] / rec["ms_per_frame"] / 1e3, "frames": frames,
+                "what": "wall clock of a Python loop of PythonRenderer.render() calls (1 spp + deep copy to a fresh CUDA tensor each), module " + os.path.relpath(module_dir, ROOT)}
+    except Exception as e:
+        return {"error": (str(e) + " " + (out.stderr[-200:] if 'out' in dir() else ""))[:300]}
+
+
 def _ref_bench(ref_dump, scene, mode, warm, frames, seed_offset, gpu):
     """one `ref_dump bench` process = the reference's own render_raw loop on one GPU; returns its JSON record"""
     env = dict(os.environ)
@@ -259,6 +283,10 @@ def run_reference(args, scene, workload):
                                                   "Russian roulette from bounce 1 and per-lobe caps, so fewer rays per sample than the wavefront renderer; "
                                                   "compare Msamples/s with the `megakernel_rules` block of our arm"}
                 base["best_msamples_per_s"] = max(msamples, ms_pt)
+            if not args.no_extras:
+                ps = python_serial_rate(os.path.join(ROOT, "oracle", "_ref", "pyrender_ref"), scene, max(16, args.steps * S // 4), physical_gpu(0))
+                if ps:
+                    base["python_serial"] = ps
             print(json.dumps(base))
             return
         base["reference_error"] = "; ".join(errs)[:300]
@@ -504,6 +532,12 @@ def main():
                 rd.close()
             except Exception as e:
                 extras["dropin"] = {"error": str(e)[:200]}
+
+    if world == 1 and not args.no_extras:
+        r.sync()
+        ps = python_serial_rate(os.path.join(ROOT, "oracle", "_ref", "b200_side"), scene, max(16, K * S // 4), physical_gpu(local_rank))
+        if ps:
+            extras["python_serial"] = ps
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -873,40 +873,56 @@ __global__ void __launch_bounds__(kCoopBlock)
     const CoopShared S = coop_setup(coop_smem, sc, cp, G, SLAB);
     const int lane = threadIdx.x & 31;
     const int count = *q_count;
-    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
-        const int i = chunk * 32 + lane;
-        uint32_t slot = 0, tag = 0;
-        bool valid = i < count;
-        V3 o{0, 0, 0}, d{0, 0, 1};
-        int start = 0;
-        if (valid) {
-            slot = queue[i];
-            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
-            o = xyz(ro), d = xyz(rd);
-            tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index
-            valid = (tag & TAG_ACTIVE) != 0;           // megakernel rules: k_shade may have ended the path
+    for (int chunk = warp_next_chunk(work, lane); chunk * kCoopChunk < count; chunk = warp_next_chunk(work, lane)) {
+        // ---- prologue, one ray per lane and round: fetch, fp16 cached phase, ray record for the lane groups
+#pragma unroll 1
+        for (int j = 0; j < kCoopChunk / 32; j++) {
+            const int r = j * 32 + lane, i = chunk * kCoopChunk + r;
+            uint32_t slot = 0, tag = 0;
+            bool valid = i < count;
+            V3 o{0, 0, 0}, d{0, 0, 1};
+            int start = 0;
+            if (valid) {
+                slot = queue[i];
+                const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+                o = xyz(ro), d = xyz(rd);
+                tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index
+                valid = (tag & TAG_ACTIVE) != 0;           // megakernel rules: k_shade may have ended the path
+            }
+            float4 h0 = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(-1));
+            bool coop_ray = valid;
+            const V3 inv_d = rcp3(d), o_div = o * inv_d;
+            if (valid && !coop_ray_ok(inv_d)) { // a (near-)zero direction component: per-thread traversal with the compare+select slab test
+                const Hit hh = closest_hit_ordered<true, false>(sc, S.cached, o, d);
+                h0 = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
+                coop_ray = false;
+            }
+            if (coop_ray)
+                start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+            coop_store_ray(S, r, o, d, inv_d, o_div, start, coop_ray ? kMaxDist : -1.f, slot, valid ? tag : 0u);
+            S.hits[r] = h0;
         }
-        float4 h0 = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(-1));
-        bool coop_ray = valid;
-        const V3 inv_d = rcp3(d), o_div = o * inv_d;
-        if (valid && !coop_ray_ok(inv_d)) { // a (near-)zero direction component: per-thread traversal with the compare+select slab test
-            const Hit hh = closest_hit_ordered<true, false>(sc, S.cached, o, d);
-            h0 = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
-            coop_ray = false;
-        }
-        if (coop_ray)
-            start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
-        coop_store_ray(S, lane, o, d, inv_d, o_div, start, coop_ray ? kMaxDist : -1.f);
-        S.hits[lane] = h0;
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
         coop_traverse<G, false, SLAB>(sc, cp, S, lane);
-        const float4 h = S.hits[lane];
-        bool alive = false;
-        if (valid)
-            alive = resolve_hit(sc, st, slot, tag, d, h.x, h.y, h.z, __float_as_int(h.w), bounce, pt_rules);
-        warp_push(q_next, q_next_count, alive, slot, lane);
+        // ---- epilogue, one ray per lane and round: interaction / miss, Russian roulette, compaction
+#pragma unroll 1
+        for (int j = 0; j < kCoopChunk / 32; j++) {
+            const int r = j * 32 + lane;
+            const float4 rd = S.rays[4 * r + 1];
+            const uint32_t slot = __float_as_uint(S.rays[4 * r + 2].w), tag = __float_as_uint(S.rays[4 * r + 3].w);
+            float4 h = S.hits[r];
+            if (__float_as_int(h.w) == kCoopRedo) { // deeper than the shared-memory stack (never on the bundled scenes)
+                const Hit hh = closest_hit_ordered<true, true>(sc, S.cached, xyz(S.rays[4 * r]), xyz(rd));
+                h = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
+            }
+            bool alive = false;
+            if (tag & TAG_ACTIVE)
+                alive = resolve_hit(sc, st, slot, tag, xyz(rd), h.x, h.y, h.z, __float_as_int(h.w), bounce, pt_rules);
+            warp_push(q_next, q_next_count, alive, slot, lane);
+        }
+        __syncwarp();
     }
 }
 
@@ -917,34 +933,51 @@ __global__ void __launch_bounds__(kCoopBlock)
     const CoopShared S = coop_setup(coop_smem, sc, cp, G, SLAB);
     const int lane = threadIdx.x & 31;
     const int count = *sq_count;
-    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
-        const int i = chunk * 32 + lane;
-        const bool valid = i < count;
-        uint32_t slot = 0;
-        V3 o{0, 0, 0}, d{0, 0, 1};
-        float range = -1.f;
-        int start = 0;
-        if (valid) {
-            slot = sq[i];
-            const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
-            o = xyz(a), d = xyz(b), range = a.w;
+    for (int chunk = warp_next_chunk(work, lane); chunk * kCoopChunk < count; chunk = warp_next_chunk(work, lane)) {
+#pragma unroll 1
+        for (int j = 0; j < kCoopChunk / 32; j++) {
+            const int r = j * 32 + lane, i = chunk * kCoopChunk + r;
+            const bool valid = i < count;
+            uint32_t slot = 0;
+            V3 o{0, 0, 0}, d{0, 0, 1};
+            float range = -1.f;
+            int start = 0;
+            if (valid) {
+                slot = sq[i];
+                const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
+                o = xyz(a), d = xyz(b), range = a.w;
+            }
+            float vis0 = 1.f;
+            const V3 inv_d = rcp3(d), o_div = o * inv_d;
+            if (valid && !coop_ray_ok(inv_d)) { // per-thread traversal with the compare+select slab test
+                vis0 = unoccluded_ordered<true, false>(sc, S.cached, o, d, range) ? 1.f : 0.f;
+                range = -1.f;
+            }
+            if (range > 0.f)
+                start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, range, sc.num_nodes);
+            // a range <= 0 cannot be occluded (no t in (EPSILON, range)); user1 = 1: a ray of the queue sits in this slot
+            coop_store_ray(S, r, o, d, inv_d, o_div, start, range, slot, valid ? 1u : 0u);
+            S.hits[r] = make_float4(vis0, 0.f, 0.f, 0.f);
         }
-        float vis0 = 1.f;
-        const V3 inv_d = rcp3(d), o_div = o * inv_d;
-        if (valid && !coop_ray_ok(inv_d)) { // per-thread traversal with the compare+select slab test
-            vis0 = unoccluded_ordered<true, false>(sc, S.cached, o, d, range) ? 1.f : 0.f;
-            range = -1.f;
-        }
-        if (range > 0.f)
-            start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, range, sc.num_nodes);
-        coop_store_ray(S, lane, o, d, inv_d, o_div, start, range); // a range <= 0 cannot be occluded (no t in (EPSILON, range))
-        S.hits[lane] = make_float4(vis0, 0.f, 0.f, 0.f);
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
         coop_traverse<G, true, SLAB>(sc, cp, S, lane);
-        if (valid && S.hits[lane].x != 0.f)
-            st.L[slot] = rb.hit[slot];
+#pragma unroll 1
+        for (int j = 0; j < kCoopChunk / 32; j++) {
+            const int r = j * 32 + lane;
+            const uint32_t slot = __float_as_uint(S.rays[4 * r + 2].w);
+            if (__float_as_uint(S.rays[4 * r + 3].w) == 0u)
+                continue;
+            float vis = S.hits[r].x;
+            if (vis == 2.f) { // deeper than the shared-memory stack: redone per thread
+                const float4 a = S.rays[4 * r], b = S.rays[4 * r + 1];
+                vis = unoccluded_ordered<true, true>(sc, S.cached, xyz(a), xyz(b), b.w) ? 1.f : 0.f;
+            }
+            if (vis != 0.f)
+                st.L[slot] = rb.hit[slot];
+        }
+        __syncwarp();
     }
 }
 
@@ -995,9 +1028,13 @@ __global__ void __launch_bounds__(kCoopBlock)
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
-        coop_traverse<G, false, SLAB>(sc, cp, S, lane);
+        coop_traverse<G, false, SLAB, 32>(sc, cp, S, lane);
         if (inside) {
-            const float4 h = S.hits[lane];
+            float4 h = S.hits[lane];
+            if (__float_as_int(h.w) == kCoopRedo) {
+                const Hit hh = closest_hit_ordered<true, true>(sc, S.cached, o, d);
+                h = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
+            }
             const int prim = __float_as_int(h.w);
             uint32_t tag = 0;
             V4 L = mk4(0, 0, 0, 1);
@@ -2365,6 +2402,8 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         coop_slab_ = std::max(0, atoi(e));
     if (const char *e = getenv("CPTB200_COOP_RAYGEN"))
         coop_raygen_ = atoi(e) != 0;
+    if (const char *e = getenv("CPTB200_COOP_STACK")) // shared-memory stack entries per lane group (tests: force the per-thread redo path)
+        coop_stack_ = std::min(kCoopStackMax, std::max(1, atoi(e)));
     set_coop(coop_flush_, coop_slab_);
     if (const char *e = getenv("CPTB200_TRAVERSAL"))
         set_traversal(atoi(e));
@@ -2413,7 +2452,7 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
     if (G == 8)
         coop_slab_ = 0; // the slab variant is instantiated for groups of 4 only
     for (;; coop_slab_ /= 2) { // shrink the slab until the carve-up fits
-        const int cap = std::max(8, (m.wide_max_stack + 7) / 8 * 8);
+        const int cap = std::min(coop_stack_, std::max(4, (m.wide_max_stack + 3) / 4 * 4));
         const CoopLayout L = coop_layout(m.dev.num_cache, coop_slab_, G, cap, kCoopBlock / 32);
         if (L.total <= max_optin) {
             m.coop_smem = size_t(L.total);
@@ -2530,7 +2569,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     const bool coop = traversal_ == 4 && coop_ok_ && rules_ != 2 && this->pipeline_ == 3;
     const int mode = traversal_ == 4 ? 2 : traversal_;
     const int coop_grid = num_sms_ * std::max(1, m.coop_blocks_per_sm);
-    const CoopParams cpar{m.arena.p + m.arena_nodes, m.wide_width == 8 ? 0 : coop_slab_, std::max(8, (m.wide_max_stack + 7) / 8 * 8)};
+    const CoopParams cpar{m.arena.p + m.arena_nodes, m.wide_width == 8 ? 0 : coop_slab_, std::min(coop_stack_, std::max(4, (m.wide_max_stack + 3) / 4 * 4))};
 #define LAUNCH_COOP(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (m.wide_width == 8)                                                                                         \

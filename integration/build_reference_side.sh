@@ -13,6 +13,8 @@
 # Outputs (travel to the GPU box with gpurun):
 #   oracle/_ref/b200_side/pyrender.so   import as `pyrender` with this directory on sys.path
 #   oracle/_ref/b200_side/pt            ./pt <scene.xml> -> render.png
+#   oracle/_ref/pyrender_ref/pyrender.so  the UNPATCHED reference module (same objects, its own switch cases): the baseline of
+#                                       the "Python serial path" timing in bench.py
 # Test infrastructure for the boundary (tests/test_gpu.py::test_reference_pyrender_*): it proves the adapter compiles and runs
 # inside the reference's build; it is not part of the product library.
 set -euo pipefail
@@ -51,7 +53,9 @@ patch_cases "$REF/app/pt_renderer.cu" "$OUT/pt_renderer_b200.cu" 'scene' 'xml_pa
 CORE_OBJS=$(ls "$OBJ"/*.o | grep -v ref_dump.o)
 MK="$OUT/obj/Makefile"
 {
-  echo "all: $OUT/pyrender.so $OUT/pt"
+  echo "all: $OUT/pyrender.so $OUT/pt $ROOT/oracle/_ref/pyrender_ref/pyrender.so"
+  echo "$OUT/obj/python_render_ref.o: $REF/src/pyrender/python_render.cu"
+  printf '\tnvcc %s %s -x cu -c $< -o $@\n' "$NVFLAGS" "$INC"
   PYOBJS=""
   for f in "$OUT/python_render_b200.cu" "$REF/src/pyrender/python_bind.cu"; do
     b=$(basename "$f"); o="$OUT/obj/${b%.*}.o"; PYOBJS="$PYOBJS $o"
@@ -68,6 +72,10 @@ MK="$OUT/obj/Makefile"
   echo "$OUT/pyrender.so: $PYOBJS"
   printf '\tnvcc -gencode arch=compute_100a,code=sm_100a -rdc=true -shared -Xcompiler -fPIC %s %s -o $@ -L%s -lcpt_b200 -lgomp -Xlinker -rpath=%s\n' \
          "$PYOBJS" "$(echo $CORE_OBJS)" "$ROOT/cuda-pt_b200" "\\\$\$ORIGIN/../../../cuda-pt_b200"
+  NBOBJS=$(for f in nb_func common error nb_internals nb_type nb_static_property implicit nb_ndarray; do printf '%s ' "$OUT/obj/$f.o"; done)
+  echo "$ROOT/oracle/_ref/pyrender_ref/pyrender.so: $OUT/obj/python_render_ref.o $OUT/obj/python_bind.o $NBOBJS"
+  printf '\tmkdir -p %s && nvcc -gencode arch=compute_100a,code=sm_100a -rdc=true -shared -Xcompiler -fPIC $^ %s -o $@ -lgomp\n' \
+         "$ROOT/oracle/_ref/pyrender_ref" "$(echo $CORE_OBJS)"
   echo "$OUT/pt: $OUT/obj/pt_renderer_b200.o"
   printf '\tnvcc -gencode arch=compute_100a,code=sm_100a -rdc=true $< %s -o $@ -L%s -lcpt_b200 -lgomp -Xlinker -rpath=%s\n' \
          "$(echo $CORE_OBJS)" "$ROOT/cuda-pt_b200" "\\\$\$ORIGIN/../../../cuda-pt_b200"

@@ -591,3 +591,53 @@ def test_two_rank_distributed_render(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29731", os.path.join(ROOT, "tools", "ddp_check.py")], capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert out.returncode == 0 and "[ddp_check] OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+
+
+B200_SIDE = os.path.join(ROOT, "oracle", "_ref", "b200_side")
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(B200_SIDE, "pyrender.so")) and have_meshes()), reason="reference-side build (integration/build_reference_side.sh) not on this box")
+def test_reference_pyrender_module_routed_to_the_library(tmp_path):
+    """The drop-in boundary for real: the REFERENCE'S OWN nanobind module `pyrender` (src/pyrender/python_bind.cu:61-70, its
+    PythonRenderer, its XML loader and SBVH builder), rebuilt with the path-tracer switch cases pointing at the adapter
+    integration/b200_wavefront.cuh -> libcpt_b200.so.  PythonRenderer(xml, 0, 0).render() x 4 must be the reference's own
+    4-sample frame, variance() its variance buffer shape, counter() 4 - and the scene crossed the ABI in memory."""
+    script = tmp_path / "drive.py"
+    script.write_text(f"""
+import sys
+sys.path.insert(0, {B200_SIDE!r})
+import numpy as np, torch, pyrender
+r = pyrender.PythonRenderer({os.path.join(SCENES, "cbox_wfpt_256.xml")!r}, 0, 0)
+for _ in range(4):
+    img = r.render()
+assert tuple(img.shape) == (256, 256, 4) and img.is_cuda and r.counter() == 4, (img.shape, r.counter())
+var = r.variance()
+assert tuple(var.shape) == (256, 256, 1)
+np.save({str(tmp_path / "frame.npy")!r}, img.cpu().numpy())
+print("avg frame time", r.avg_frame_time())
+r.release()
+""")
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert out.returncode == 0, (out.stdout[-800:], out.stderr[-1500:])
+    frame = np.load(tmp_path / "frame.npy")
+    ref = load_frame("cbox_wfpt_256_wfpt_f0004.bin")
+    assert bit_exact_fraction(frame, ref) == 1.0 and rel_l2(frame, ref) <= 1e-6
+    assert not [f for f in os.listdir(tmp_path) if f.endswith(".cpts")]  # no scene file was written anywhere near
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(B200_SIDE, "pt")) and have_meshes()), reason="reference-side build (integration/build_reference_side.sh) not on this box")
+def test_reference_pt_executable_routed_to_the_library(tmp_path):
+    """The reference's offline front end `pt <xml>` (app/pt_renderer.cu), same re-routing: its render.png (written by its own
+    stb encoder from the bytes the adapter returned) equals render_offline of the library on the scene its loader built."""
+    xml = os.path.join(SCENES, "cbox_pt_256.xml")
+    out = subprocess.run([os.path.join(B200_SIDE, "pt"), xml], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert out.returncode == 0 and os.path.exists(tmp_path / "render.png"), (out.stdout[-800:], out.stderr[-800:])
+    from PIL import Image
+    png = np.asarray(Image.open(tmp_path / "render.png").convert("RGBA"))
+    subprocess.run([REF_DUMP, "dump", xml, str(tmp_path / "s.cpts")], check=True, capture_output=True, cwd=ROOT)
+    sc = cpt.Scene(str(tmp_path / "s.cpts"))
+    cfg = sc.config
+    r = cpt.WavefrontRenderer(sc, 0, 0)
+    mine = r.render_offline(cfg["spp"], bool(cfg["gamma"]))
+    r.close()
+    assert png.shape == mine.shape and np.array_equal(png[..., :3], mine[..., :3])

@@ -575,7 +575,8 @@ struct DefStats {
     double inst = 0, thread_inst = 0, visits = 0, tri_tests = 0, tri_phases = 0, rays = 0, mismatches = 0, l1_wavefronts = 0;
 };
 static DefStats sim_coop_deferred(const Scene &sc, const WideLayout &w, const std::vector<Ray> &rays, const std::vector<Hit> &ref, const Cost &c,
-                                  int chunk, int flush_lanes, int slab_nodes /* nodes served from shared memory */) {
+                                  int chunk, int flush_lanes, int slab_nodes /* nodes served from shared memory */, int min_blocked = 1,
+                                  double visit_cost = 0, double tri_cost = 0) {
     DefStats S;
     const int G = w.width, NG = 32 / G;
     struct Group {
@@ -678,9 +679,10 @@ static DefStats sim_coop_deferred(const Scene &sc, const WideLayout &w, const st
                 if (!found)
                     q.cur = -1;
             }
-            if (walkers) {
-                S.inst += c.c_slab + c.c_sel + c.c_push + c.c_pop * 0.6;
-                S.thread_inst += (c.c_slab + c.c_sel + c.c_push * 0.5 + c.c_pop * 0.4) * walkers * G;
+            if (walkers || visit_cost > 0) {
+                const double vc = visit_cost > 0 ? visit_cost : c.c_slab + c.c_sel + c.c_push + c.c_pop * 0.6;
+                S.inst += vc;
+                S.thread_inst += vc * (visit_cost > 0 ? 32 : walkers * G);
             }
             // ---- triangle phase?
             int busy = 0, blocked = 0;
@@ -690,7 +692,7 @@ static DefStats sim_coop_deferred(const Scene &sc, const WideLayout &w, const st
                 busy += std::min(q.npend, G);
                 blocked += (!q.walking && q.npend > 0);
             }
-            if (busy >= flush_lanes || blocked > 0) {
+            if (busy >= flush_lanes || blocked >= min_blocked || (blocked > 0 && walkers - blocked <= 0)) {
                 int maxc = 0, act = 0;
                 double tsum = 0;
                 for (auto &q : g) {
@@ -715,7 +717,10 @@ static DefStats sim_coop_deferred(const Scene &sc, const WideLayout &w, const st
                         q.walking = true;
                 }
                 S.tri_phases++, S.tri_tests += tsum;
-                S.inst += c.c_tri0 + 12 + c.c_tri * maxc, S.thread_inst += (c.c_tri0 + 12) * act + c.c_tri * tsum;
+                if (tri_cost > 0)
+                    S.inst += 25 + tri_cost * maxc, S.thread_inst += 25 * act + tri_cost * tsum;
+                else
+                    S.inst += c.c_tri0 + 12 + c.c_tri * maxc, S.thread_inst += (c.c_tri0 + 12) * act + c.c_tri * tsum;
             }
             // ---- retire / refill
             int fetched = 0;
@@ -1020,6 +1025,12 @@ int main(int argc, char **argv) {
                            K, fl, rf, D.inst / D.rays, D.thread_inst / D.inst, D.visits / D.rays, D.tri_tests / D.rays, D.tri_phases / D.rays,
                            D.l1_wavefronts / D.rays, D.mismatches);
                 }
+        for (int mb : {1, 2, 3, 4, 6})
+            for (int ch : {32, 64}) {
+                const DefStats D = sim_coop_deferred(sc, sc.w4, rays, hits, cost, ch, 99, 0, mb, 107, 65);
+                printf("   coop G=4 measured costs, flush when >= %d groups blocked, chunk %d: warp-inst/ray %7.1f lanes/inst %5.2f visits/ray %5.1f "
+                       "tri-phases/ray %4.2f mismatches %g\n", mb, ch, D.inst / D.rays, D.thread_inst / D.inst, D.visits / D.rays, D.tri_phases / D.rays, D.mismatches);
+            }
         for (int G : {4, 8})
             for (int fl : {1, 12, 20, 28})
                 for (int slab_n : {0, 256}) {
