@@ -32,10 +32,6 @@
 
 namespace cptb {
 
-constexpr int kCoopChunk = 64;    // rays per warp and chunk (two per lane in the chunk prologue / epilogue)
-constexpr int kCoopStackMax = 20; // stack entries per group kept in shared memory; a ray that needs more is redone per thread
-constexpr int kCoopRedo = -2;     // hit record "primitive" of a ray the cooperative traversal gave up on
-
 struct CoopParams {
     const float4 *wide; // 2 * G float4 per node, node 0 = root
     int slab_nodes;     // nodes [0, slab_nodes) are resident in shared memory (kernels instantiated with SLAB only)
@@ -52,8 +48,8 @@ __host__ __device__ inline CoopLayout coop_layout(int num_cache, int slab_nodes,
     L.slab_off = L.cached_off + ((num_cache * 16 + 127) / 128) * 128;
     L.warp_off = L.slab_off + slab_nodes * G * 32;
     const int ng = 32 / G;
-    // rays 64 x 64 B, hits 64 x 16 B, next-ray counter 16 B, pending lists ng x 2G x 4 B, stacks ng x cap x 8 B
-    L.warp_bytes = kCoopChunk * 64 + kCoopChunk * 16 + 16 + ng * 2 * G * 4 + ng * stack_cap * 8;
+    // rays 32 x 64 B, hits 32 x 16 B, next-ray counter 16 B, pending lists ng x 2G x 4 B, stacks ng x cap x 8 B
+    L.warp_bytes = 2048 + 512 + 16 + ng * 2 * G * 4 + ng * stack_cap * 8;
     L.warp_bytes = (L.warp_bytes + 15) / 16 * 16;
     L.total = L.warp_off + warps * L.warp_bytes;
     return L;
@@ -113,10 +109,10 @@ __device__ __forceinline__ CoopShared coop_setup(unsigned char *smem, const DevS
     unsigned char *w = smem + L.warp_off + (threadIdx.x >> 5) * L.warp_bytes;
     const int ng = 32 / G;
     S.rays = reinterpret_cast<float4 *>(w);
-    S.hits = reinterpret_cast<float4 *>(w + kCoopChunk * 64);
-    S.next = reinterpret_cast<int *>(w + kCoopChunk * 80);
-    S.pend = reinterpret_cast<int *>(w + kCoopChunk * 80 + 16);
-    S.stack = reinterpret_cast<uint2 *>(w + kCoopChunk * 80 + 16 + ng * 2 * G * 4);
+    S.hits = reinterpret_cast<float4 *>(w + 2048);
+    S.next = reinterpret_cast<int *>(w + 2560);
+    S.pend = reinterpret_cast<int *>(w + 2576);
+    S.stack = reinterpret_cast<uint2 *>(w + 2576 + ng * 2 * G * 4);
     return S;
 }
 
@@ -132,14 +128,12 @@ __device__ __forceinline__ bool coop_ray_ok(V3 inv) {
     return fabsf(inv.x) < big && fabsf(inv.y) < big && fabsf(inv.z) < big;
 }
 
-// chunk prologue: the ray record the lane groups read (t_max <= 0: no ray in this slot).  `user0` / `user1` ride along for the
-// chunk epilogue (path slot, tag bits).
-__device__ __forceinline__ void coop_store_ray(const CoopShared &S, int r, V3 o, V3 d, V3 inv_d, V3 o_div, int start, float t_max, uint32_t user0 = 0,
-                                               uint32_t user1 = 0) {
-    S.rays[4 * r] = make_float4(o.x, o.y, o.z, __int_as_float(start));
-    S.rays[4 * r + 1] = make_float4(d.x, d.y, d.z, t_max);
-    S.rays[4 * r + 2] = make_float4(inv_d.x, inv_d.y, inv_d.z, __uint_as_float(user0));
-    S.rays[4 * r + 3] = make_float4(o_div.x, o_div.y, o_div.z, __uint_as_float(user1));
+// chunk prologue, one ray per lane: the ray record the lane groups read (t_max <= 0: no ray in this slot)
+__device__ __forceinline__ void coop_store_ray(const CoopShared &S, int lane, V3 o, V3 d, V3 inv_d, V3 o_div, int start, float t_max) {
+    S.rays[4 * lane] = make_float4(o.x, o.y, o.z, __int_as_float(start));
+    S.rays[4 * lane + 1] = make_float4(d.x, d.y, d.z, t_max);
+    S.rays[4 * lane + 2] = make_float4(inv_d.x, inv_d.y, inv_d.z, 0.f);
+    S.rays[4 * lane + 3] = make_float4(o_div.x, o_div.y, o_div.z, 0.f);
 }
 
 // minimum over the lanes of a group, every lane gets it.  Butterfly of full-mask shuffles: the exchange partners stay
@@ -158,8 +152,7 @@ template <int G> __device__ __forceinline__ unsigned group_min(unsigned v) {
 // Control flow is warp-uniform wherever lanes talk to each other (ballots, shuffles use the full mask); what differs
 // between the groups of a warp is predicated.  One loop iteration = one node visit per group; everything else (triangle
 // phase, retiring a ray, taking the next) sits in a "service" block the warp enters only when some group needs it.
-template <int G, bool ANYHIT, bool SLAB, int CHUNK = kCoopChunk, int UNROLL = 2>
-__device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopParams &cp, const CoopShared &S, int lane) {
+template <int G, bool ANYHIT, bool SLAB, int UNROLL = 2> __device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopParams &cp, const CoopShared &S, int lane) {
     static_assert(G == 4 || G == 8, "lane group of 4 or 8");
     constexpr unsigned GM = (1u << G) - 1u, FULL = 0xffffffffu;
     const int li = lane & (G - 1), gbase = lane & ~(G - 1);
@@ -173,17 +166,16 @@ __device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopPara
     int rcur = -1, cur = -1, sp = 0, npend = 0, start = 0, bprim = -1;
     V3 inv_d{0, 0, 0}, o_div{0, 0, 0};
     float ht = 0.f, bt = 0.f, bu = 0.f, bv = 0.f;
-    int more = 1;   // the chunk may still hold rays for this group
-    int waited = 0; // a blocked group has been kept waiting for company (warp-uniform)
+    int more = 1; // the chunk may still hold rays for this group
 
     auto take = [&](bool want) { // warp-uniform call; groups with `want` take the next ray of the chunk (or go idle)
-        int r = CHUNK;
+        int r = 32;
         if (want && more && li == 0)
             r = atomicAdd(S.next, 1);
         r = __shfl_sync(FULL, r, gbase);
         if (want) {
             rcur = -1, cur = -1, sp = 0, npend = 0;
-            if (r >= CHUNK) {
+            if (r >= 32) {
                 more = 0;
             } else {
                 rcur = r;
@@ -235,15 +227,10 @@ __device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopPara
             if (walk) {
                 if (im) {
                     const unsigned others = im & ~(1u << w);
-                    if (sp + __popc(others) > cp.stack_cap) { // deeper than the shared-memory stack: give the ray back (redone per thread)
-                        bprim = kCoopRedo, bt = ht;
-                        cur = -1, npend = 0, sp = 0;
-                    } else {
-                        if ((others >> li) & 1u)
-                            stack[sp + __popc(others & lt)] = make_uint2(uint32_t(ref), __float_as_uint(t));
-                        sp += __popc(others);
-                        cur = next;
-                    }
+                    if ((others >> li) & 1u)
+                        stack[sp + __popc(others & lt)] = make_uint2(uint32_t(ref), __float_as_uint(t));
+                    sp += __popc(others);
+                    cur = next;
                 } else {
                     cur = -1;
                     while (sp > 0) { // LIFO; every lane of the group reads the same entry (broadcast)
@@ -261,16 +248,10 @@ __device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopPara
         // ---- service: a group that cannot go on without a triangle phase (pending list above G, or traversal finished with
         // leaves pending), or that finished its ray
         const bool blocked = npend > 0 && !(cur >= 0 && npend <= G);
-        const bool ended = rcur >= 0 && cur < 0 && npend == 0;
-        const unsigned bm = __ballot_sync(FULL, blocked);
-        if (bm == 0u && !__any_sync(FULL, ended))
+        if (!__any_sync(FULL, blocked || (rcur >= 0 && cur < 0)))
             continue;
         __syncwarp();
-        // triangle phase: every group tests its pending leaves (up to G of them, lane i leaf i).  A single blocked group waits one
-        // round for company (more lanes per triangle phase); two blocked groups, or one that has waited, start it
-        const bool flush = bm != 0u && (__popc(bm) >= 2 * G || waited);
-        waited = bm != 0u && !flush;
-        if (flush) {
+        if (__any_sync(FULL, blocked)) { // triangle phase: every group tests its pending leaves (up to G of them, lane i leaf i)
             const int nb = npend < G ? npend : G;
             bool occluded = false;
             if (li < nb) {
@@ -296,7 +277,7 @@ __device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopPara
                 if ((__ballot_sync(FULL, occluded) >> gbase) & GM) {
                     if (li == 0)
                         S.hits[rcur].x = 0.f;
-                    cur = -1, npend = 0, sp = 0, bprim = -1;
+                    cur = -1, npend = 0, sp = 0;
                 }
             } else {
                 ht = __uint_as_float(group_min<G>(__float_as_uint(bt)));
@@ -305,21 +286,15 @@ __device__ __forceinline__ void coop_traverse(const DevScene &sc, const CoopPara
         const bool fin = rcur >= 0 && cur < 0 && npend == 0;
         if (__any_sync(FULL, fin)) { // retire finished rays, take the next ray of the chunk
             if constexpr (!ANYHIT) {
-                const bool cand = fin && (bprim >= 0 || bprim == kCoopRedo) && bt == ht;
+                const bool cand = fin && bprim >= 0 && bt == ht;
                 const unsigned cm = (__ballot_sync(FULL, cand) >> gbase) & GM;
                 bool win = cand;
-                if (cand && bprim == kCoopRedo) {
-                    win = li == 0;
-                } else if (cand && __popc(cm) > 1) { // equal distances in two lanes (rare): the reference keeps the first hit in its DFS order
+                if (cand && __popc(cm) > 1) { // equal distances in two lanes (rare): the reference keeps the first hit in its DFS order
                     const int key = sc.prim_orig ? __ldg(sc.prim_orig + bprim) : bprim;
                     win = key == __reduce_min_sync(cm << gbase, key);
                 }
                 if (win)
                     S.hits[rcur] = make_float4(bt, bu, bv, __int_as_float(bprim));
-            }
-            if constexpr (ANYHIT) {
-                if (fin && bprim == kCoopRedo && li == 0)
-                    S.hits[rcur].x = 2.f; // undecided: redone per thread
             }
             take(fin);
             if (__ballot_sync(FULL, rcur >= 0) == 0u)

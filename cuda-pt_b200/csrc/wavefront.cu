@@ -873,56 +873,40 @@ __global__ void __launch_bounds__(kCoopBlock)
     const CoopShared S = coop_setup(coop_smem, sc, cp, G, SLAB);
     const int lane = threadIdx.x & 31;
     const int count = *q_count;
-    for (int chunk = warp_next_chunk(work, lane); chunk * kCoopChunk < count; chunk = warp_next_chunk(work, lane)) {
-        // ---- prologue, one ray per lane and round: fetch, fp16 cached phase, ray record for the lane groups
-#pragma unroll 1
-        for (int j = 0; j < kCoopChunk / 32; j++) {
-            const int r = j * 32 + lane, i = chunk * kCoopChunk + r;
-            uint32_t slot = 0, tag = 0;
-            bool valid = i < count;
-            V3 o{0, 0, 0}, d{0, 0, 1};
-            int start = 0;
-            if (valid) {
-                slot = queue[i];
-                const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
-                o = xyz(ro), d = xyz(rd);
-                tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index
-                valid = (tag & TAG_ACTIVE) != 0;           // megakernel rules: k_shade may have ended the path
-            }
-            float4 h0 = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(-1));
-            bool coop_ray = valid;
-            const V3 inv_d = rcp3(d), o_div = o * inv_d;
-            if (valid && !coop_ray_ok(inv_d)) { // a (near-)zero direction component: per-thread traversal with the compare+select slab test
-                const Hit hh = closest_hit_ordered<true, false>(sc, S.cached, o, d);
-                h0 = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
-                coop_ray = false;
-            }
-            if (coop_ray)
-                start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
-            coop_store_ray(S, r, o, d, inv_d, o_div, start, coop_ray ? kMaxDist : -1.f, slot, valid ? tag : 0u);
-            S.hits[r] = h0;
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        uint32_t slot = 0, tag = 0;
+        bool valid = i < count;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        int start = 0;
+        if (valid) {
+            slot = queue[i];
+            const float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            o = xyz(ro), d = xyz(rd);
+            tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index
+            valid = (tag & TAG_ACTIVE) != 0;           // megakernel rules: k_shade may have ended the path
         }
+        float4 h0 = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(-1));
+        bool coop_ray = valid;
+        const V3 inv_d = rcp3(d), o_div = o * inv_d;
+        if (valid && !coop_ray_ok(inv_d)) { // a (near-)zero direction component: per-thread traversal with the compare+select slab test
+            const Hit hh = closest_hit_ordered<true, false>(sc, S.cached, o, d);
+            h0 = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
+            coop_ray = false;
+        }
+        if (coop_ray)
+            start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, kMaxDist, 0);
+        coop_store_ray(S, lane, o, d, inv_d, o_div, start, coop_ray ? kMaxDist : -1.f);
+        S.hits[lane] = h0;
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
         coop_traverse<G, false, SLAB>(sc, cp, S, lane);
-        // ---- epilogue, one ray per lane and round: interaction / miss, Russian roulette, compaction
-#pragma unroll 1
-        for (int j = 0; j < kCoopChunk / 32; j++) {
-            const int r = j * 32 + lane;
-            const float4 rd = S.rays[4 * r + 1];
-            const uint32_t slot = __float_as_uint(S.rays[4 * r + 2].w), tag = __float_as_uint(S.rays[4 * r + 3].w);
-            float4 h = S.hits[r];
-            if (__float_as_int(h.w) == kCoopRedo) { // deeper than the shared-memory stack (never on the bundled scenes)
-                const Hit hh = closest_hit_ordered<true, true>(sc, S.cached, xyz(S.rays[4 * r]), xyz(rd));
-                h = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
-            }
-            bool alive = false;
-            if (tag & TAG_ACTIVE)
-                alive = resolve_hit(sc, st, slot, tag, xyz(rd), h.x, h.y, h.z, __float_as_int(h.w), bounce, pt_rules);
-            warp_push(q_next, q_next_count, alive, slot, lane);
-        }
-        __syncwarp();
+        const float4 h = S.hits[lane];
+        bool alive = false;
+        if (valid)
+            alive = resolve_hit(sc, st, slot, tag, d, h.x, h.y, h.z, __float_as_int(h.w), bounce, pt_rules);
+        warp_push(q_next, q_next_count, alive, slot, lane);
     }
 }
 
@@ -933,51 +917,34 @@ __global__ void __launch_bounds__(kCoopBlock)
     const CoopShared S = coop_setup(coop_smem, sc, cp, G, SLAB);
     const int lane = threadIdx.x & 31;
     const int count = *sq_count;
-    for (int chunk = warp_next_chunk(work, lane); chunk * kCoopChunk < count; chunk = warp_next_chunk(work, lane)) {
-#pragma unroll 1
-        for (int j = 0; j < kCoopChunk / 32; j++) {
-            const int r = j * 32 + lane, i = chunk * kCoopChunk + r;
-            const bool valid = i < count;
-            uint32_t slot = 0;
-            V3 o{0, 0, 0}, d{0, 0, 1};
-            float range = -1.f;
-            int start = 0;
-            if (valid) {
-                slot = sq[i];
-                const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
-                o = xyz(a), d = xyz(b), range = a.w;
-            }
-            float vis0 = 1.f;
-            const V3 inv_d = rcp3(d), o_div = o * inv_d;
-            if (valid && !coop_ray_ok(inv_d)) { // per-thread traversal with the compare+select slab test
-                vis0 = unoccluded_ordered<true, false>(sc, S.cached, o, d, range) ? 1.f : 0.f;
-                range = -1.f;
-            }
-            if (range > 0.f)
-                start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, range, sc.num_nodes);
-            // a range <= 0 cannot be occluded (no t in (EPSILON, range)); user1 = 1: a ray of the queue sits in this slot
-            coop_store_ray(S, r, o, d, inv_d, o_div, start, range, slot, valid ? 1u : 0u);
-            S.hits[r] = make_float4(vis0, 0.f, 0.f, 0.f);
+    for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
+        const int i = chunk * 32 + lane;
+        const bool valid = i < count;
+        uint32_t slot = 0;
+        V3 o{0, 0, 0}, d{0, 0, 1};
+        float range = -1.f;
+        int start = 0;
+        if (valid) {
+            slot = sq[i];
+            const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
+            o = xyz(a), d = xyz(b), range = a.w;
         }
+        float vis0 = 1.f;
+        const V3 inv_d = rcp3(d), o_div = o * inv_d;
+        if (valid && !coop_ray_ok(inv_d)) { // per-thread traversal with the compare+select slab test
+            vis0 = unoccluded_ordered<true, false>(sc, S.cached, o, d, range) ? 1.f : 0.f;
+            range = -1.f;
+        }
+        if (range > 0.f)
+            start = cached_entry(S.cached, sc.num_cache, inv_d, o_div, range, sc.num_nodes);
+        coop_store_ray(S, lane, o, d, inv_d, o_div, start, range); // a range <= 0 cannot be occluded (no t in (EPSILON, range))
+        S.hits[lane] = make_float4(vis0, 0.f, 0.f, 0.f);
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
         coop_traverse<G, true, SLAB>(sc, cp, S, lane);
-#pragma unroll 1
-        for (int j = 0; j < kCoopChunk / 32; j++) {
-            const int r = j * 32 + lane;
-            const uint32_t slot = __float_as_uint(S.rays[4 * r + 2].w);
-            if (__float_as_uint(S.rays[4 * r + 3].w) == 0u)
-                continue;
-            float vis = S.hits[r].x;
-            if (vis == 2.f) { // deeper than the shared-memory stack: redone per thread
-                const float4 a = S.rays[4 * r], b = S.rays[4 * r + 1];
-                vis = unoccluded_ordered<true, true>(sc, S.cached, xyz(a), xyz(b), b.w) ? 1.f : 0.f;
-            }
-            if (vis != 0.f)
-                st.L[slot] = rb.hit[slot];
-        }
-        __syncwarp();
+        if (valid && S.hits[lane].x != 0.f)
+            st.L[slot] = rb.hit[slot];
     }
 }
 
@@ -1028,13 +995,9 @@ __global__ void __launch_bounds__(kCoopBlock)
         if (lane == 0)
             *S.next = 0;
         __syncwarp();
-        coop_traverse<G, false, SLAB, 32>(sc, cp, S, lane);
+        coop_traverse<G, false, SLAB>(sc, cp, S, lane);
         if (inside) {
-            float4 h = S.hits[lane];
-            if (__float_as_int(h.w) == kCoopRedo) {
-                const Hit hh = closest_hit_ordered<true, true>(sc, S.cached, o, d);
-                h = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
-            }
+            const float4 h = S.hits[lane];
             const int prim = __float_as_int(h.w);
             uint32_t tag = 0;
             V4 L = mk4(0, 0, 0, 1);
@@ -2001,7 +1964,8 @@ struct Renderer::Impl {
     size_t arena_nodes = 0, arena_wide = 0, l2_window_bytes = 0;
     int wide_width = 4, wide_nodes = 0, wide_max_stack = 0, wide_depth = 0;
     double wide_fill = 0;
-    int coop_blocks_per_sm = 0; // occupancy of the cooperative kernels with the current shared-memory carve-up
+    int coop_blocks_per_sm = 0; // occupancy of the cooperative kernels with the current shared-memory carve-up (smallest of the three)
+    int coop_blocks[3] = {0, 0, 0}; // k_trace_coop, k_shadow_apply_coop, k_raygen_coop: CTAs per SM each
     size_t coop_smem = 0;
     DevBuf<uint4> cache_nodes, uvs;
     DevBuf<int> obj_idxs, emitter_prims, prim_orig;
@@ -2402,8 +2366,6 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         coop_slab_ = std::max(0, atoi(e));
     if (const char *e = getenv("CPTB200_COOP_RAYGEN"))
         coop_raygen_ = atoi(e) != 0;
-    if (const char *e = getenv("CPTB200_COOP_STACK")) // shared-memory stack entries per lane group (tests: force the per-thread redo path)
-        coop_stack_ = std::min(kCoopStackMax, std::max(1, atoi(e)));
     set_coop(coop_flush_, coop_slab_);
     if (const char *e = getenv("CPTB200_TRAVERSAL"))
         set_traversal(atoi(e));
@@ -2452,7 +2414,7 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
     if (G == 8)
         coop_slab_ = 0; // the slab variant is instantiated for groups of 4 only
     for (;; coop_slab_ /= 2) { // shrink the slab until the carve-up fits
-        const int cap = std::min(coop_stack_, std::max(4, (m.wide_max_stack + 3) / 4 * 4));
+        const int cap = std::max(8, (m.wide_max_stack + 7) / 8 * 8);
         const CoopLayout L = coop_layout(m.dev.num_cache, coop_slab_, G, cap, kCoopBlock / 32);
         if (L.total <= max_optin) {
             m.coop_smem = size_t(L.total);
@@ -2467,13 +2429,13 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kCoopBlock, m.coop_smem));
         return nb;
     };
-    int nb;
     if (G == 8)
-        nb = std::min(std::min(prep(k_trace_coop<8, false>), prep(k_shadow_apply_coop<8, false>)), prep(k_raygen_coop<8, false>));
+        m.coop_blocks[0] = prep(k_trace_coop<8, false>), m.coop_blocks[1] = prep(k_shadow_apply_coop<8, false>), m.coop_blocks[2] = prep(k_raygen_coop<8, false>);
     else if (coop_slab_ > 0)
-        nb = std::min(std::min(prep(k_trace_coop<4, true>), prep(k_shadow_apply_coop<4, true>)), prep(k_raygen_coop<4, true>));
+        m.coop_blocks[0] = prep(k_trace_coop<4, true>), m.coop_blocks[1] = prep(k_shadow_apply_coop<4, true>), m.coop_blocks[2] = prep(k_raygen_coop<4, true>);
     else
-        nb = std::min(std::min(prep(k_trace_coop<4, false>), prep(k_shadow_apply_coop<4, false>)), prep(k_raygen_coop<4, false>));
+        m.coop_blocks[0] = prep(k_trace_coop<4, false>), m.coop_blocks[1] = prep(k_shadow_apply_coop<4, false>), m.coop_blocks[2] = prep(k_raygen_coop<4, false>);
+    const int nb = std::min(std::min(m.coop_blocks[0], m.coop_blocks[1]), m.coop_blocks[2]);
     m.coop_blocks_per_sm = nb;
     // preconditions of the ordered traversal, plus: the stack carve-up fits, and no leaf holds a clipped (SBVH) reference - the
     // reference's result on those depends on the order in which single leaves are tested (PairLayout::clipped_refs)
@@ -2568,10 +2530,11 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     // kernel (fused shading, volumetric path) keeps the ordered per-thread traversal
     const bool coop = traversal_ == 4 && coop_ok_ && rules_ != 2 && this->pipeline_ == 3;
     const int mode = traversal_ == 4 ? 2 : traversal_;
-    const int coop_grid = num_sms_ * std::max(1, m.coop_blocks_per_sm);
-    const CoopParams cpar{m.arena.p + m.arena_nodes, m.wide_width == 8 ? 0 : coop_slab_, std::min(coop_stack_, std::max(4, (m.wide_max_stack + 3) / 4 * 4))};
-#define LAUNCH_COOP(kernel, ...)                                                                                       \
+    int coop_grid = num_sms_; // set per kernel by LAUNCH_COOP
+    const CoopParams cpar{m.arena.p + m.arena_nodes, m.wide_width == 8 ? 0 : coop_slab_, std::max(8, (m.wide_max_stack + 7) / 8 * 8)};
+#define LAUNCH_COOP(which, kernel, ...)                                                                                \
     do {                                                                                                               \
+        coop_grid = num_sms_ * std::max(1, m.coop_blocks[which]);                                                      \
         if (m.wide_width == 8)                                                                                         \
             kernel<8, false><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                             \
         else if (coop_slab_ > 0)                                                                                       \
@@ -2744,7 +2707,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     }
     mark(0, 0);
     if (coop && coop_raygen_) // primary rays are coherent: the per-thread kernel runs them at 15 of 32 lanes and is the faster one
-        LAUNCH_COOP(k_raygen_coop, m.dev, cpar, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
+        LAUNCH_COOP(2, k_raygen_coop, m.dev, cpar, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
     else
         LAUNCH_MODE(k_raygen, m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
     ++wk;
@@ -2760,7 +2723,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             ++wk, ++launches;
             mark(4, b);
             if (pipeline_ == 3 && coop)
-                LAUNCH_COOP(k_shadow_apply_coop, m.dev, cpar, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+                LAUNCH_COOP(1, k_shadow_apply_coop, m.dev, cpar, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (pipeline_ == 3)
                 LAUNCH_MODE(k_shadow_apply, m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (dyn_minb_ >= 12)
@@ -2804,7 +2767,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             mark(2, b);
             k_resolve<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else if (coop) {
-            LAUNCH_COOP(k_trace_coop, m.dev, cpar, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+            LAUNCH_COOP(0, k_trace_coop, m.dev, cpar, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else {
             LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         }
@@ -2974,7 +2937,7 @@ std::string Renderer::info() const {
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
        << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : "cooperative"))))
        << ", wide layout " << impl_->wide_width << "-ary " << impl_->wide_nodes << " nodes (fill " << impl_->wide_fill << ", depth " << impl_->wide_depth
-       << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks_per_sm << " CTAs/SM x " << impl_->coop_smem
+       << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks[0] << "/" << impl_->coop_blocks[1] << "/" << impl_->coop_blocks[2] << " CTAs/SM (trace/shadow/raygen) x " << impl_->coop_smem
        << " B smem, slab " << coop_slab_ << " nodes, flush " << coop_flush_ << " lanes)"
        << ", pair depth " << impl_->pair_depth << ", nesting violations " << impl_->nesting_violations << " (max " << impl_->max_overshoot << "), clipped references " << impl_->clipped_refs
        << ", refined leaves " << impl_->refined_leaves

@@ -109,7 +109,6 @@ class Renderer {
     bool variance_on_ = false, kernel_timing_ = false;
     int pipeline_ = 3, row0_ = 0, row1_ = 0;
     bool ordered_ok_ = true, coop_ok_ = false, coop_raygen_ = false;
-    int coop_stack_ = 20; // kCoopStackMax
     int coop_flush_ = 1 /* unused since the triangle phase runs on demand */, coop_slab_ = 0;
     int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
     KernelTimes ktimes_;

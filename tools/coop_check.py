@@ -34,13 +34,6 @@ def parity():
             print(f"[parity] {scene} trav=4 (effective {eff}) opts={opts}: bit-exact pixels vs reference frame {ex * 100:.4f}%  rays {st['rays']}", flush=True)
             ok &= ex == 1.0
         print("   ", info, flush=True)
-    # the per-thread redo path of rays that outgrow the shared-memory stack, forced by a 3-entry stack (separate process: env)
-    if os.environ.get("CPTB200_COOP_STACK") is None:
-        import subprocess
-        env = dict(os.environ, CPTB200_COOP_STACK="3")
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), "parity_small"], env=env, capture_output=True, text=True)
-        print(out.stdout.strip().replace("[parity]", "[parity, stack=3]"), flush=True)
-        ok &= out.returncode == 0
     if os.path.exists(VADER):
         a, sa, _, _ = frame(VADER, 4, 2)
         b, sb, eff, info = frame(VADER, 4, 4)
@@ -92,12 +85,6 @@ def one(trav, spp=16):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "parity"
-    if what == "parity_small":
-        ref = np.fromfile(os.path.join(GOLD, "texroom_256_wfpt_f0064.bin"), dtype=np.float32).reshape(256, 256, 4)
-        out, st, eff, info = frame(os.path.join(GOLD, "texroom_256.cpts"), 64, 4)
-        ex = float((out.view(np.uint32) == ref.view(np.uint32)).all(-1).mean())
-        print(f"[parity] texroom_256.cpts trav=4 (effective {eff}): bit-exact pixels vs reference frame {ex * 100:.4f}%")
-        sys.exit(0 if ex == 1.0 and eff == 4 else 1)
     if what == "one":
         one(int(sys.argv[2]))
         sys.exit(0)
