@@ -46,6 +46,7 @@ METRIC = "Mrays/s (primary + closest-hit + shadow traversals), wavefront PT, 192
 
 WORKLOADS = {"c1": "vader_wfpt_1080p.xml",       # BASELINE config 1 (default): vader geometry, no image assets
              "c2": "vader_tex_wfpt_1080p.xml",    # texture-heavy stand-in: + 2K glossy/roughness/normal/albedo maps + envmap
+             "c3": "dispersion_cbox_wfpt_1080p.xml",  # BASELINE config 3 stand-in: cornell box with Diamond / Sapphire dispersion boxes, 7 bounces
              "vpt": "medium_cbox_vpt_1080p.xml",  # participating media (homogeneous), volumetric path tracer
              "grid": "grid_cbox_vpt_1080p.xml",   # BASELINE config 4 stand-in: grid (NanoVDB) medium, 304x512x304 voxels
              "fog": "vader_fog_vpt_1080p.xml",    # volumetric path on the 320k-triangle vader geometry inside a thin fog
@@ -229,6 +230,7 @@ def run_reference(args, scene, workload):
                      "the reference's whiskey scene, unmodified" if "whiskey" in workload else
                      "vader geometry bundled with the reference inside a homogeneous fog bounded by a cullable box" if "fog" in workload else
                      "cornell box geometry bundled with the reference + three homogeneous media" if "vpt" in workload else
+                     "cornell box bundled with the reference, boxes switched to the spectral dispersion BSDF (Diamond / Sapphire)" if "dispersion" in workload else
                      "vader geometry bundled with the reference; textures/envmap not shipped upstream, removed" if "tex" not in workload else
                      "vader geometry + seeded placeholder 2K textures and environment map (tools/make_assets.py)"),
             "config": {"workload": workload, "width": 1920, "height": 1080, "spp_per_step": S}}
@@ -260,6 +262,22 @@ def run_reference(args, scene, workload):
         if not errs:
             mains = [r["main"] for r, _ in allrec]
             rps = tbl.get("reference_scene_rays_per_sample", tbl["rays_per_sample"]) if tbl else None
+            if rps is None:
+                # no committed ray count for this workload: count them on the scene the reference's loader builds (`ref_dump dump`) with our
+                # renderer (8 spp; the per-bounce path counts on reference-built scenes are parity-checked).  Only the conversion factor
+                # Msamples/s -> Mrays/s comes from here, never a time
+                try:
+                    import cuda_pt_b200 as cpt
+                    tmpc = os.path.join(tempfile.gettempdir(), "bench_ref_count.cpts")
+                    subprocess.run([ref_dump, "dump", scene, tmpc], check=True, capture_output=True, timeout=900, cwd=ROOT)
+                    rc = cpt.WavefrontRenderer(tmpc, local_rank, 0)
+                    rc.render_batch(8, False)
+                    stc = rc.stats()
+                    rps = stc["rays"] / stc["samples"]
+                    rc.close()
+                    base["rays_per_sample_source"] = "counted now on the reference-built scene (8 spp)"
+                except Exception as e:
+                    base["rays_per_sample_error"] = str(e)[:200]
             px = mains[0]["width"] * mains[0]["height"]
             t_max = max(m["total_ms"] for m in mains)
             samples = sum(px * m["frames"] for m in mains)
@@ -557,6 +575,8 @@ def main():
                     if "vpt" in workload else
                     "vader geometry bundled with the reference + seeded placeholder 2K textures and environment map (tools/make_assets.py); fixed seeds"
                     if "tex" in workload else
+                    "cornell box bundled with the reference, boxes switched to the spectral dispersion BSDF (Diamond / Sapphire; BASELINE config 3 stand-in); fixed seeds"
+                    if "dispersion" in workload else
                     "vader geometry bundled with the reference (textures/envmap not shipped upstream, removed); fixed seeds"),
            "config": {"workload": workload, "width": W, "height": H, "spp_per_step": S, "max_depth": cfg["max_depth"],
                       "triangles": cfg["num_prims"], "parallelism": (f"{'row-band tile' if tiles else 'sample'}-split x{world}, 1 NCCL reduce of the fp32 accumulator to rank 0 per step, "

@@ -259,9 +259,9 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
         if (k == "samples_in_flight")
             r->impl->set_samples_in_flight(int(value));
         else if (k == "traversal") {
-            if (value < 0 || value > 4)
-                throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads), 3 (warp vote) or 4 "
-                                         "(warp-cooperative, wide layout)");
+            if (value < 0 || value > 5)
+                throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads), 3 (warp vote), 4 "
+                                         "(warp-cooperative, wide layout) or 5 (per thread, 4-ary wide layout)");
             r->impl->set_traversal(int(value)); // modes the scene does not allow are replaced (see Renderer::set_traversal)
         } else if (k == "coop_flush") {
             r->impl->set_coop(int(value), int(cpt_b200_get_option(r, "coop_slab")));

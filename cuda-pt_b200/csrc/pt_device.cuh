@@ -87,6 +87,7 @@ struct DevScene {
     const EmitterPOD *emitters;
     // re-laid-out ordered-traversal structure built at renderer construction
     const float4 *wnodes;      // 4 float4 per inner node (see bvh_relayout.cpp)
+    const float4 *wide;        // wide layout (scene_host.cpp build_wide_layout): 2 * width float4 per node, node 0 = root
     int num_nodes, num_cache, num_prims, num_emitters, envmap_id, wroot;
     const struct MediumPOD *media; // [0] = vacuum (volumetric path only)
     int num_media, cam_vol;

@@ -425,6 +425,115 @@ PT_DEV bool unoccluded_vote(const DevScene &sc, const uint4 *s_cached, V3 o, V3 
     return clear;
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-thread traversal of the 4-ary wide layout (traversal=5; scene_host.cpp build_wide_layout, the records the cooperative
+// kernels use): one ray per lane like the ordered mode, but every visit tests the four children of a node - half as many
+// dependent node fetches per ray as the pair layout (27 instead of 46 on vader), at about the same number of box tests.
+// The four results are sorted with a 5-exchange network, the nearest hit child is entered, the others are pushed far to near.
+// Same boxes, leaves, strict culls and tie rule as the ordered pair traversal.
+// ---------------------------------------------------------------------------------------------
+PT_DEV void load_wide_child(const float4 *__restrict__ p, float4 &lo, float4 &hi) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+#define CPTB_SORT2(ta, ra, tb, rb)                                                                                     \
+    {                                                                                                                  \
+        const bool sw = tb < ta;                                                                                       \
+        const float tt = sw ? tb : ta;                                                                                 \
+        const int rr = sw ? rb : ra;                                                                                   \
+        tb = sw ? ta : tb, rb = sw ? ra : rb, ta = tt, ra = rr;                                                        \
+    }
+template <bool FINITE, bool ANYHIT>
+PT_DEV Hit traverse_wide4(const DevScene &sc, const float4 *__restrict__ wide, const uint4 *s_cached, V3 o, V3 d, float t_max) {
+    Hit h{t_max, 0.f, 0.f, -1, 0};
+    const V3 inv_d = rcp3(d), o_div = o * inv_d;
+    const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, t_max, ANYHIT ? sc.num_nodes : 0);
+    if (ANYHIT && start >= sc.num_nodes)
+        return h;
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int sp = 0;
+    int cur = 0; // wide root
+    const float inf = __int_as_float(0x7f800000);
+    while (true) {
+        if (cur >= 0) {
+            const float4 *p = wide + cur * 8;
+            float4 l0, h0, l1, h1, l2, h2, l3, h3;
+            load_wide_child(p, l0, h0), load_wide_child(p + 2, l1, h1), load_wide_child(p + 4, l2, h2), load_wide_child(p + 6, l3, h3);
+            float t0, t1, t2, t3;
+            const bool b0 = slab_any<FINITE>(l0.x, l0.y, l0.z, h0.x, h0.y, h0.z, inv_d, o_div, t0) && t0 < h.t && __float_as_int(h0.w) > start;
+            const bool b1 = slab_any<FINITE>(l1.x, l1.y, l1.z, h1.x, h1.y, h1.z, inv_d, o_div, t1) && t1 < h.t && __float_as_int(h1.w) > start;
+            const bool b2 = slab_any<FINITE>(l2.x, l2.y, l2.z, h2.x, h2.y, h2.z, inv_d, o_div, t2) && t2 < h.t && __float_as_int(h2.w) > start;
+            const bool b3 = slab_any<FINITE>(l3.x, l3.y, l3.z, h3.x, h3.y, h3.z, inv_d, o_div, t3) && t3 < h.t && __float_as_int(h3.w) > start;
+            t0 = b0 ? t0 : inf, t1 = b1 ? t1 : inf, t2 = b2 ? t2 : inf, t3 = b3 ? t3 : inf;
+            int r0 = __float_as_int(l0.w), r1 = __float_as_int(l1.w), r2 = __float_as_int(l2.w), r3 = __float_as_int(l3.w);
+            const int n = int(b0) + int(b1) + int(b2) + int(b3);
+            if (n > 0) {
+                if (!ANYHIT || n > 1) { // ascending by entry distance (misses carry +inf and sink to the end)
+                    CPTB_SORT2(t0, r0, t1, r1)
+                    CPTB_SORT2(t2, r2, t3, r3)
+                    CPTB_SORT2(t0, r0, t2, r2)
+                    CPTB_SORT2(t1, r1, t3, r3)
+                    CPTB_SORT2(t1, r1, t2, r2)
+                }
+                if (n > 3)
+                    stack_ref[sp] = r3, stack_t[sp] = t3, ++sp;
+                if (n > 2)
+                    stack_ref[sp] = r2, stack_t[sp] = t2, ++sp;
+                if (n > 1)
+                    stack_ref[sp] = r1, stack_t[sp] = t1, ++sp;
+                cur = r0;
+                continue;
+            }
+        } else {
+            const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+            for (int idx = base; idx < base + cnt; idx++) {
+                float u, v;
+                const float dist = hit_triangle(sc.tris, idx, o, d, u, v, ANYHIT ? t_max : inf);
+                if constexpr (ANYHIT) {
+                    if (dist > kEps) {
+                        h.prim = idx;
+                        return h;
+                    }
+                } else {
+                    const bool valid = dist > kEps && (dist < h.t || (dist == h.t && prim_before(sc, idx, h.prim)));
+                    h.t = valid ? dist : h.t;
+                    h.u = valid ? u : h.u;
+                    h.v = valid ? v : h.v;
+                    h.prim = valid ? idx : h.prim;
+                }
+            }
+        }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (ANYHIT || stack_t[sp] < h.t) {
+                cur = stack_ref[sp];
+                found = true;
+                break;
+            }
+        }
+        if (!found)
+            break;
+    }
+    return h;
+}
+#undef CPTB_SORT2
+PT_DEV bool ray_is_finite(V3 d) {
+    const V3 inv = rcp3(d);
+    const float big = 1e28f;
+    return fabsf(inv.x) < big && fabsf(inv.y) < big && fabsf(inv.z) < big;
+}
+PT_DEV Hit closest_hit_wide4(const DevScene &sc, const float4 *wide, const uint4 *s_cached, V3 o, V3 d) {
+    return ray_is_finite(d) ? traverse_wide4<true, false>(sc, wide, s_cached, o, d, kMaxDist) : traverse_wide4<false, false>(sc, wide, s_cached, o, d, kMaxDist);
+}
+PT_DEV bool unoccluded_wide4(const DevScene &sc, const float4 *wide, const uint4 *s_cached, V3 o, V3 d, float max_dist) {
+    const Hit h = ray_is_finite(d) ? traverse_wide4<true, true>(sc, wide, s_cached, o, d, max_dist) : traverse_wide4<false, true>(sc, wide, s_cached, o, d, max_dist);
+    return h.prim < 0;
+}
+
+// MODE 5: per-thread traversal of the 4-ary wide layout (instantiated for k_raygen / k_shadow_apply / k_trace only).
 // MODE: 0 ordered (per-thread stack in local memory), 1 reference DFS order, 2 ordered with 256-bit node loads,
 // 3 ordered warp-vote scheduler.
 // `active` = this lane carries a ray; MODE 3 is warp-synchronous and must be called by all 32 lanes.
@@ -438,6 +547,8 @@ template <int MODE> PT_DEV Hit closest_hit(const DevScene &sc, const uint4 *s_ca
         return closest_hit_ordered<false, false>(sc, s_cached, o, d);
     else if constexpr (MODE == 1)
         return closest_hit_dfs(sc, s_cached, o, d);
+    else if constexpr (MODE == 5)
+        return closest_hit_wide4(sc, sc.wide, s_cached, o, d);
     else
     {
         const V3 inv = rcp3(d);
@@ -465,6 +576,8 @@ template <int MODE> PT_DEV bool unoccluded(const DevScene &sc, const uint4 *s_ca
         return unoccluded_ordered<false, false>(sc, s_cached, o, d, max_dist);
     else if constexpr (MODE == 1)
         return unoccluded_dfs(sc, s_cached, o, d, max_dist);
+    else if constexpr (MODE == 5)
+        return unoccluded_wide4(sc, sc.wide, s_cached, o, d, max_dist);
     else
     {
         const V3 inv = rcp3(d);

@@ -2243,6 +2243,7 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
     m.dev.mats = m.mats.p;
     m.dev.emitters = m.emitters.p;
     m.dev.wnodes = m.arena.p;
+    m.dev.wide = m.arena.p + m.arena_nodes;
     // L2 residency for the traversal arena (env CPTB200_L2_PERSIST=0 turns it off)
     {
         const char *e = getenv("CPTB200_L2_PERSIST");
@@ -2440,12 +2441,16 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
     // preconditions of the ordered traversal, plus: the stack carve-up fits, and no leaf holds a clipped (SBVH) reference - the
     // reference's result on those depends on the order in which single leaves are tested (PairLayout::clipped_refs)
     coop_ok_ = nb >= 1 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0;
+    // per-thread traversal of the same layout (traversal=5): 4-ary records, per-thread stack of kStackSize entries
+    wide4_ok_ = G == 4 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0 && m.wide_max_stack + 2 <= kStackSize;
 }
 
 void Renderer::set_traversal(int t) {
-    if (t < 0 || t > 4)
-        throw std::runtime_error("traversal must be 0..4");
+    if (t < 0 || t > 5)
+        throw std::runtime_error("traversal must be 0..5");
     if (t == 4 && !coop_ok_)
+        t = 2;
+    if (t == 5 && !wide4_ok_)
         t = 2;
     if (t != TRAVERSAL_DFS && !ordered_ok_)
         t = TRAVERSAL_DFS;
@@ -2529,7 +2534,8 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     // traversal=4: cooperative forms of k_raygen / k_shadow_apply / k_trace in the deferred-NEE surface pipeline; every other
     // kernel (fused shading, volumetric path) keeps the ordered per-thread traversal
     const bool coop = traversal_ == 4 && coop_ok_ && rules_ != 2 && this->pipeline_ == 3;
-    const int mode = traversal_ == 4 ? 2 : traversal_;
+    const int mode = (traversal_ == 4 || traversal_ == 5) ? 2 : traversal_;
+    const bool wide4 = traversal_ == 5 && wide4_ok_ && rules_ != 2 && this->pipeline_ == 3;
     int coop_grid = num_sms_; // set per kernel by LAUNCH_COOP
     const CoopParams cpar{m.arena.p + m.arena_nodes, m.wide_width == 8 ? 0 : coop_slab_, std::max(8, (m.wide_max_stack + 7) / 8 * 8)};
 #define LAUNCH_COOP(which, kernel, ...)                                                                                \
@@ -2542,7 +2548,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         else                                                                                                           \
             kernel<4, false><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                             \
     } while (0)
-    const int pipeline_ = (traversal_ == 1 || traversal_ == 3 || traversal_ == 4) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
+    const int pipeline_ = (traversal_ == 1 || traversal_ == 3 || traversal_ == 4 || traversal_ == 5) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
 #define LAUNCH_MODE(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (mode == 0)                                                                                                 \
@@ -2708,6 +2714,8 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     mark(0, 0);
     if (coop && coop_raygen_) // primary rays are coherent: the per-thread kernel runs them at 15 of 32 lanes and is the faster one
         LAUNCH_COOP(2, k_raygen_coop, m.dev, cpar, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
+    else if (wide4 && coop_raygen_)
+        k_raygen<5><<<grid, kBlock, smem, stream_>>>(m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
     else
         LAUNCH_MODE(k_raygen, m.dev, m.cam, st, bp, m.queue[0].p, q_counts, work + wk);
     ++wk;
@@ -2724,6 +2732,8 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             mark(4, b);
             if (pipeline_ == 3 && coop)
                 LAUNCH_COOP(1, k_shadow_apply_coop, m.dev, cpar, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+            else if (pipeline_ == 3 && wide4)
+                k_shadow_apply<5><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (pipeline_ == 3)
                 LAUNCH_MODE(k_shadow_apply, m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (dyn_minb_ >= 12)
@@ -2768,6 +2778,8 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             k_resolve<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else if (coop) {
             LAUNCH_COOP(0, k_trace_coop, m.dev, cpar, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+        } else if (wide4) {
+            k_trace<5><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else {
             LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         }
@@ -2935,7 +2947,7 @@ std::string Renderer::info() const {
     std::ostringstream os;
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
-       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : "cooperative"))))
+       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : "wide4 per thread")))))
        << ", wide layout " << impl_->wide_width << "-ary " << impl_->wide_nodes << " nodes (fill " << impl_->wide_fill << ", depth " << impl_->wide_depth
        << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks[0] << "/" << impl_->coop_blocks[1] << "/" << impl_->coop_blocks[2] << " CTAs/SM (trace/shadow/raygen) x " << impl_->coop_smem
        << " B smem, slab " << coop_slab_ << " nodes, flush " << coop_flush_ << " lanes)"

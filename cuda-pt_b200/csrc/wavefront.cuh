@@ -108,7 +108,7 @@ class Renderer {
     int s_max_ = 1, traversal_ = 2 /* ordered pair-node traversal with 256-bit node loads */, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
     bool variance_on_ = false, kernel_timing_ = false;
     int pipeline_ = 3, row0_ = 0, row1_ = 0;
-    bool ordered_ok_ = true, coop_ok_ = false, coop_raygen_ = false;
+    bool ordered_ok_ = true, coop_ok_ = false, coop_raygen_ = false, wide4_ok_ = false;
     int coop_flush_ = 1 /* unused since the triangle phase runs on demand */, coop_slab_ = 0;
     int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
     KernelTimes ktimes_;
