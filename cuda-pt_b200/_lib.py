@@ -91,6 +91,7 @@ def lib():
         "cpt_b200_get_option": (i64, [vp, cp]),
         "cpt_b200_stats": (i32, [vp, C.POINTER(u64)]),
         "cpt_b200_kernel_times": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)]),
+        "cpt_b200_queue_counts": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i32]),
         "cpt_b200_info": (i32, [vp, C.c_char_p, i32]),
         "cpt_b200_stream": (u64, [vp]),
         "cpt_b200_sync": (i32, [vp]),

@@ -354,6 +354,14 @@ int cpt_b200_kernel_times(cpt_b200_renderer *r, double *ms5, uint64_t *launches5
     return 0;
 }
 
+int cpt_b200_queue_counts(cpt_b200_renderer *r, int32_t *paths, int32_t *shadow, int n) {
+    if (!r || n < 0)
+        return -1;
+    int written = 0;
+    const int rc = guarded([&] { written = r->impl->queue_counts(paths, shadow, n); });
+    return rc ? -1 : written;
+}
+
 int cpt_b200_info(const cpt_b200_renderer *r, char *buf, int buf_len) {
     REQUIRE(r);
     REQUIRE(buf);

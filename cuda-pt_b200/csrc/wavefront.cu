@@ -2816,6 +2816,24 @@ void Renderer::collect_kernel_times(int samples) {
     }
 }
 
+int Renderer::queue_counts(int32_t *paths, int32_t *shadow, int n) {
+    Impl &m = *impl_;
+    CUDA_OK(cudaSetDevice(device_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    const int D = max_depth_, have = std::min(n, D + 1);
+    if (rules_ == 2 || int(m.counters.n) < 2 * (D + 2) || have <= 0)
+        return 0;
+    std::vector<int> h(size_t(2 * (D + 2)));
+    CUDA_OK(cudaMemcpy(h.data(), m.counters.p, h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < have; b++) {
+        if (paths)
+            paths[b] = h[size_t(b)];
+        if (shadow)
+            shadow[b] = h[size_t(D + 2 + b)];
+    }
+    return have;
+}
+
 const float *Renderer::render_raw(bool gamma) {
     launch_batch(accum_cnt_ + 1, 1, gamma, true, variance_on_);
     CUDA_OK(cudaStreamSynchronize(stream_));

@@ -87,6 +87,8 @@ class Renderer {
     int pipeline() const { return pipeline_; }
     int rules() const { return rules_; }
     KernelTimes kernel_times() const { return ktimes_; }
+    // queue sizes of the last batch (surface pipelines): shaded / extended segments and traversed shadow rays per bounce
+    int queue_counts(int32_t *paths, int32_t *shadow, int n);
 
     int width() const { return w_; }
     int height() const { return h_; }

@@ -15,7 +15,7 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import check, lib
+from ._lib import CptError, check, lib
 
 CFG = dict(width=0, height=1, spp=2, max_depth=3, max_diffuse=4, max_specular=5, max_transmit=6, gamma=7,
            renderer=8, num_bsdfs=9, num_emitters=10, envmap_id=11, num_objects=12, num_prims=13, num_nodes=14,
@@ -180,9 +180,17 @@ class WavefrontRenderer:
         return {k: {"ms": float(ms[i]), "launches": int(ln[i]), "units": int(un[i])}
                 for i, k in enumerate(["raygen", "shade", "trace", "splat", "shadow"])}
 
+    def queue_counts(self, n=64):
+        """(paths, shadow) per bounce of the last batch: segments shaded / extended and shadow rays traversed."""
+        a, b = (C.c_int32 * n)(), (C.c_int32 * n)()
+        k = lib().cpt_b200_queue_counts(self._h, a, b, n)
+        if k < 0:
+            raise CptError(lib().cpt_b200_last_error().decode("utf-8", "replace"))
+        return list(a[:k]), list(b[:k])
+
     def info(self):
-        buf = C.create_string_buffer(1024)
-        check(lib().cpt_b200_info(self._h, buf, 1024))
+        buf = C.create_string_buffer(2048)
+        check(lib().cpt_b200_info(self._h, buf, 2048))
         return buf.value.decode()
 
     def stream(self):

@@ -95,7 +95,10 @@ int cpt_b200_height(const cpt_b200_renderer *r);
 /* options: "rules" (0 wavefront termination rules, wavefront_pt.cu:186-195; 1 megakernel "pt" rules,
  * megakernel_pt.cu:159-180; 2 volumetric path tracer with participating media, megakernel_vpt.cu:203-456 - default
  * taken from the scene's <renderer type>), "samples_in_flight" (>=1),
- * "traversal" (0 ordered pair-node, 1 reference DFS order, 2/3 experimental loop shapes),
+ * "traversal" (0 / 2 / 3 ordered pair-node traversal: 128-bit loads / 256-bit loads (default) / warp-vote loop; 1 reference DFS
+ * order; 4 warp-cooperative traversal of the 4-ary wide layout; 5 per-thread traversal of that layout - a mode whose
+ * preconditions the scene does not meet is replaced, read the effective one back with cpt_b200_get_option),
+ * "coop_slab" (traversal 4: top nodes of the wide tree staged in shared memory by a TMA bulk copy, default 0),
  * "max_depth" (MaxDepthParams::max_depth, src/core/max_depth.h:26-42), "kernel_timing" (0/1: CUDA events
  * around every launch, read back with cpt_b200_kernel_times), "pipeline" (0: the NEE visibility ray is traced
  * inside the shading kernel; 1: in its own traversal kernel before shading; 2: dynamic-fetch traversal
@@ -117,6 +120,11 @@ int cpt_b200_stats(cpt_b200_renderer *r, uint64_t *stats8);
  * (NEE + BSDF), 2 trace (closest hit + RR + compaction), 3 splat, 4 shadow (NEE visibility kernel of the
  * split pipeline).  units = pixel-samples (0,3) or path segments (1,2,4) those launches processed. */
 int cpt_b200_kernel_times(cpt_b200_renderer *r, double *ms5, uint64_t *launches5, uint64_t *units5);
+/* queue sizes of the LAST batch, per bounce b = 0 .. n-1: paths[b] = path segments shaded at bounce b (= segments k_trace
+ * extended at bounce b), shadow[b] = shadow rays k_shadow_apply traversed at bounce b.  The unit counts of single launches:
+ * what an ncu capture of "the (b+1)-th launch of k_trace" processed (profiles/).  Replaces the reference's per-bounce
+ * `num_valid_ray` read-back (src/pt_impl/wf_path_tracer.cu:197-202).  Returns the number of entries written (<= n). */
+int cpt_b200_queue_counts(cpt_b200_renderer *r, int32_t *paths, int32_t *shadow, int n);
 /* PythonRenderer::info (python_render.cuh) — copies a one-line description */
 int cpt_b200_info(const cpt_b200_renderer *r, char *buf, int buf_len);
 /* the CUDA stream all work of this handle is issued on (as a cudaStream_t value) */

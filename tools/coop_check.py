@@ -87,6 +87,8 @@ def one(trav, spp=16):
     r.render_batch(spp, False)
     r.sync()
     print(r.info())
+    paths, shadow = r.queue_counts()
+    print("queue sizes of the batch (units of the b-th launch of k_trace / k_shadow_apply):", json.dumps({"paths": paths, "shadow": shadow}))
     r.close()
 
 
