@@ -713,7 +713,7 @@ void build_wide_layout(const PairLayout &pl, int width, WideLayout &out) {
 
     // breadth-first construction: queue of (pair node to collapse, wide node index, depth, stack need of the path so far)
     struct Item {
-        int pair_idx, wide_idx, depth, stack;
+        int pair_idx, wide_idx, depth, stack, stack_all;
     };
     std::vector<Item> queue;
     auto new_node = [&]() {
@@ -721,7 +721,7 @@ void build_wide_layout(const PairLayout &pl, int width, WideLayout &out) {
         out.nodes.resize(out.nodes.size() + 2 * size_t(width), F4{0, 0, 0, 0});
         return idx;
     };
-    queue.push_back(Item{pl.root, new_node(), 1, 0});
+    queue.push_back(Item{pl.root, new_node(), 1, 0, 0});
     size_t filled = 0;
     for (size_t qi = 0; qi < queue.size(); qi++) {
         const Item it = queue[qi];
@@ -760,6 +760,9 @@ void build_wide_layout(const PairLayout &pl, int width, WideLayout &out) {
             inner += as_int(c.lo.w) >= 0;
         const int need = it.stack + std::max(inner - 1, 0);
         out.max_stack = std::max(out.max_stack, need);
+        // a per-thread traversal that also pushes leaf children: all children but the one it enters
+        const int need_all = it.stack_all + std::max(int(kids.size()) - 1, 0);
+        out.max_stack_all = std::max(out.max_stack_all, need_all);
         filled += kids.size();
         for (int i = 0; i < width; i++) {
             Child c = i < int(kids.size()) ? kids[size_t(i)] : empty;
@@ -767,7 +770,7 @@ void build_wide_layout(const PairLayout &pl, int width, WideLayout &out) {
             if (i < int(kids.size())) {
                 if (ref >= 0) {
                     const int w = new_node();
-                    queue.push_back(Item{ref, w, it.depth + 1, need});
+                    queue.push_back(Item{ref, w, it.depth + 1, need, need_all});
                     c.lo.w = as_float(w);
                     out.inner_slots++;
                 } else {

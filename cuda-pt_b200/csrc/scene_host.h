@@ -115,6 +115,7 @@ struct WideLayout {
     int num_nodes = 0;
     int max_depth = 0;     // wide levels
     int max_stack = 0;     // worst-case number of deferred inner children along one root-to-leaf path
+    int max_stack_all = 0; // the same counting leaf children too (per-thread traversal that pushes every child it does not enter)
     double avg_children = 0; // filled slots per node
     int leaf_slots = 0, inner_slots = 0;
 };

@@ -432,6 +432,7 @@ PT_DEV bool unoccluded_vote(const DevScene &sc, const uint4 *s_cached, V3 o, V3 
 // The four results are sorted with a 5-exchange network, the nearest hit child is entered, the others are pushed far to near.
 // Same boxes, leaves, strict culls and tie rule as the ordered pair traversal.
 // ---------------------------------------------------------------------------------------------
+constexpr int kWideStack = 64; // per-thread stack of traverse_wide4 (every child that is not entered is pushed, leaves too)
 PT_DEV void load_wide_child(const float4 *__restrict__ p, float4 &lo, float4 &hi) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
@@ -451,8 +452,8 @@ PT_DEV Hit traverse_wide4(const DevScene &sc, const float4 *__restrict__ wide, c
     const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, t_max, ANYHIT ? sc.num_nodes : 0);
     if (ANYHIT && start >= sc.num_nodes)
         return h;
-    int stack_ref[kStackSize];
-    float stack_t[kStackSize];
+    int stack_ref[kWideStack];
+    float stack_t[kWideStack];
     int sp = 0;
     int cur = 0; // wide root
     const float inf = __int_as_float(0x7f800000);
@@ -470,13 +471,12 @@ PT_DEV Hit traverse_wide4(const DevScene &sc, const float4 *__restrict__ wide, c
             int r0 = __float_as_int(l0.w), r1 = __float_as_int(l1.w), r2 = __float_as_int(l2.w), r3 = __float_as_int(l3.w);
             const int n = int(b0) + int(b1) + int(b2) + int(b3);
             if (n > 0) {
-                if (!ANYHIT || n > 1) { // ascending by entry distance (misses carry +inf and sink to the end)
-                    CPTB_SORT2(t0, r0, t1, r1)
-                    CPTB_SORT2(t2, r2, t3, r3)
-                    CPTB_SORT2(t0, r0, t2, r2)
-                    CPTB_SORT2(t1, r1, t3, r3)
-                    CPTB_SORT2(t1, r1, t2, r2)
-                }
+                // ascending by entry distance (misses carry +inf and sink to the end)
+                CPTB_SORT2(t0, r0, t1, r1)
+                CPTB_SORT2(t2, r2, t3, r3)
+                CPTB_SORT2(t0, r0, t2, r2)
+                CPTB_SORT2(t1, r1, t3, r3)
+                CPTB_SORT2(t1, r1, t2, r2)
                 if (n > 3)
                     stack_ref[sp] = r3, stack_t[sp] = t3, ++sp;
                 if (n > 2)

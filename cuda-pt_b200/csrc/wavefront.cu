@@ -1962,7 +1962,7 @@ template <typename T> struct DevBuf {
 struct Renderer::Impl {
     DevBuf<float4> nodes, norms, arena; // arena = [pair nodes | wide nodes | triangles]
     size_t arena_nodes = 0, arena_wide = 0, l2_window_bytes = 0;
-    int wide_width = 4, wide_nodes = 0, wide_max_stack = 0, wide_depth = 0;
+    int wide_width = 4, wide_nodes = 0, wide_max_stack = 0, wide_max_stack_all = 0, wide_depth = 0;
     double wide_fill = 0;
     int coop_blocks_per_sm = 0; // occupancy of the cooperative kernels with the current shared-memory carve-up (smallest of the three)
     int coop_blocks[3] = {0, 0, 0}; // k_trace_coop, k_shadow_apply_coop, k_raygen_coop: CTAs per SM each
@@ -2133,7 +2133,7 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         build_wide_layout(pl, m.wide_width, wl);
         std::vector<float4> ww(wl.nodes.size());
         memcpy(ww.data(), wl.nodes.data(), ww.size() * sizeof(float4));
-        m.wide_nodes = wl.num_nodes, m.wide_max_stack = wl.max_stack, m.wide_depth = wl.max_depth, m.wide_fill = wl.avg_children;
+        m.wide_nodes = wl.num_nodes, m.wide_max_stack = wl.max_stack, m.wide_max_stack_all = wl.max_stack_all, m.wide_depth = wl.max_depth, m.wide_fill = wl.avg_children;
         // traversal arena: pair nodes, wide nodes and triangles in one allocation, so that one L2 access-policy window can pin
         // them all (the 4-5 GB path-state pool streams through L2 every bounce and would otherwise keep evicting them)
         m.arena.alloc(w4.size() + ww.size() + t4.size());
@@ -2442,7 +2442,7 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
     // reference's result on those depends on the order in which single leaves are tested (PairLayout::clipped_refs)
     coop_ok_ = nb >= 1 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0;
     // per-thread traversal of the same layout (traversal=5): 4-ary records, per-thread stack of kStackSize entries
-    wide4_ok_ = G == 4 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0 && m.wide_max_stack + 2 <= kStackSize;
+    wide4_ok_ = G == 4 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0 && m.wide_max_stack_all + 1 <= kWideStack;
 }
 
 void Renderer::set_traversal(int t) {

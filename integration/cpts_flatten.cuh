@@ -44,6 +44,7 @@ namespace {
 struct Writer {
     FILE *fp = nullptr;
     uint32_t n = 0;
+    bool in_memory = false; // open_memstream(): the caller patches the section count into the finished buffer
     explicit Writer(const std::string &path) : Writer(fopen(path.c_str(), "wb")) {}
     // any seekable stream: a file, or an open_memstream() buffer (the adapter's in-memory hand-over)
     explicit Writer(FILE *stream) : fp(stream) {
@@ -72,8 +73,10 @@ struct Writer {
         CptsHeader h{};
         memcpy(h.magic, CPTS_MAGIC, 8);
         h.n_sections = n;
-        fseek(fp, 0, SEEK_SET);
-        fwrite(&h, sizeof(h), 1, fp);
+        if (!in_memory) { // a memory stream cannot be patched through the FILE: its length follows the last write position
+            fseek(fp, 0, SEEK_SET);
+            fwrite(&h, sizeof(h), 1, fp);
+        }
         fclose(fp);
     }
 };
@@ -521,7 +524,12 @@ void dump_scene(const Scene &scene, const std::string &xml_path, const std::stri
 void flatten_scene_to_memory(const Scene &scene, const std::string &xml_path, char **data, size_t *bytes) {
     FILE *ms = open_memstream(data, bytes);
     Writer w(ms);
-    dump_scene(scene, xml_path, w);
+    w.in_memory = true;
+    dump_scene(scene, xml_path, w); // closes the stream: *data / *bytes are final
+    CptsHeader h{};
+    memcpy(h.magic, CPTS_MAGIC, 8);
+    h.n_sections = w.n;
+    memcpy(*data, &h, sizeof(h));
 }
 
 } // namespace

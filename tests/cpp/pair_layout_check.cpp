@@ -59,10 +59,14 @@ int main(int argc, char **argv) {
     }
     // wide layouts (build_wide_layout): every leaf record of the pair tree appears exactly once with the same box / reference /
     // DFS end, every inner slot points to a later node (breadth-first numbering, node 0 = root), the stack bound is a bound
-    int wide_errors = 0, wide_stack = 0;
+    int wide_errors = 0, wide_stack = 0, wide4_stack_all = 0;
     for (int width : {4, 8}) {
         WideLayout wl;
         build_wide_layout(pl, width, wl);
+        if (width == 4)
+            wide4_stack_all = wl.max_stack_all;
+        if (wl.max_stack_all < wl.max_stack)
+            wide_errors++;
         std::vector<int> wcov(P, 0);
         int leaves = 0;
         std::function<void(int, int)> wwalk = [&](int node, int stack) {
@@ -101,7 +105,7 @@ int main(int argc, char **argv) {
         wide_errors += wl.leaf_slots != leaf_records;
     }
     errors += wide_errors;
-    printf("prims %d leaf_records %d refined_leaves %d depth %d nesting_violations %d clipped_refs %d wide_errors %d wide_stack %d errors %d\n", P, leaf_records,
-           pl.refined_leaves, pl.max_depth, pl.nesting_violations, pl.clipped_refs, wide_errors, wide_stack, errors);
+    printf("prims %d leaf_records %d refined_leaves %d depth %d nesting_violations %d clipped_refs %d wide_errors %d wide_stack %d wide4_stack_all %d errors %d\n", P, leaf_records,
+           pl.refined_leaves, pl.max_depth, pl.nesting_violations, pl.clipped_refs, wide_errors, wide_stack, wide4_stack_all, errors);
     return errors ? 1 : 0;
 }
