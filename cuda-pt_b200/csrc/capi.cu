@@ -259,9 +259,9 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
         if (k == "samples_in_flight")
             r->impl->set_samples_in_flight(int(value));
         else if (k == "traversal") {
-            if (value < 0 || value > 5)
+            if (value < 0 || value > 6)
                 throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads), 3 (warp vote), 4 "
-                                         "(warp-cooperative, wide layout) or 5 (per thread, 4-ary wide layout)");
+                                         "(warp-cooperative, wide layout), 5 (per thread, 4-ary wide layout) or 6 (per thread, deferred leaves + lane refill)");
             r->impl->set_traversal(int(value)); // modes the scene does not allow are replaced (see Renderer::set_traversal)
         } else if (k == "coop_flush") {
             r->impl->set_coop(int(value), int(cpt_b200_get_option(r, "coop_slab")));
@@ -274,7 +274,7 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
         } else if (k == "split_shadow") {
             r->impl->set_pipeline(value != 0 ? 1 : 0);
         } else if (k == "pipeline") {
-            if (value < 0 || value > 5)
+            if (value < 0 || value > 6)
                 throw std::runtime_error("pipeline must be 0 (fused), 1 (split shadow kernel), 2 (dynamic-fetch traversal kernels), 3 (deferred NEE), "
                                          "4 (deferred NEE + dynamic-fetch traversal kernels) or 5 (deferred NEE over dense path records)");
             r->impl->set_pipeline(int(value));

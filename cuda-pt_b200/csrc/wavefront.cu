@@ -859,6 +859,172 @@ __global__ void __launch_bounds__(kBlock) k_trace(DevScene sc, PathState st, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// traversal=6: per-thread ordered traversal of the pair layout with DEFERRED LEAVES and LANE REFILL.
+// The lock-step model (tools/sim/trav_sim.cpp) says where the per-thread kernels lose their lanes: in ~97 % of
+// its iterations a warp pays for a leaf step (14 + 66 instructions per triangle) on behalf of ~3 lanes, and it idles the lanes
+// whose rays finished early.  Here a lane that reaches a leaf does not test it: the leaf goes to the lane's pending list (2
+// entries) and the lane pops on; the warp runs a triangle phase (every lane with a pending leaf tests one) only when enough
+// lanes have one or a lane cannot go on without it.  Lanes whose ray is done take the next rays of the queue as soon as
+// `refill` lanes are idle; the per-ray prologue (fetch, 1/d, fp16 cached phase) and epilogue (interaction, Russian roulette,
+// compaction) run then, for those lanes.  Same boxes, same tests, same tie rule as closest_hit_ordered; deferral only delays
+// updates of the closest distance (weaker culling, same result).
+// ------------------------------------------------------------------------------------------------
+#ifndef DQ_MIN_BLOCKS
+#define DQ_MIN_BLOCKS 10
+#endif
+template <bool SHADOW>
+__global__ void __launch_bounds__(kBlock, DQ_MIN_BLOCKS)
+    k_traverse_dq(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue, const int *__restrict__ q_count, int *work,
+                  uint32_t *q_next, int *q_next_count, int bounce, int pt_rules, int kRefill, int kFlush, int kSteps) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const int count = *q_count;
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int sp = 0, cur = kTraversalDone, start = 0, npend = 0, pend0 = 0, pend1 = 0, hprim = -1;
+    uint32_t slot = 0, tag = 0;
+    V3 o{0, 0, 0}, d{0, 0, 1}, inv_d{0, 0, 0}, o_div{0, 0, 0};
+    float ht = kMaxDist, hu = 0.f, hv = 0.f;
+    bool active = false, has_result = false, more = true;
+    int next = 0, end = 0;
+    const float inf = __int_as_float(0x7f800000);
+    while (true) {
+        unsigned act = __ballot_sync(0xffffffffu, active);
+        const int n_idle = 32 - __popc(act);
+        if ((more && n_idle >= kRefill) || act == 0u) {
+            // ---- epilogue of the rays that finished since the last refill
+            if constexpr (!SHADOW) {
+                bool alive = false;
+                if (has_result)
+                    alive = resolve_hit(sc, st, slot, tag, d, ht, hu, hv, hprim, bounce, pt_rules);
+                warp_push(q_next, q_next_count, alive, slot, lane);
+            } else {
+                if (has_result && hprim < 0) // unoccluded: the radiance k_shade<-2> prepared for that case
+                    st.L[slot] = rb.hit[slot];
+            }
+            has_result = false;
+            // ---- prologue of the next rays
+            if (more) {
+                int first = 0;
+                const int take = warp_take(work, count, lane, n_idle, next, end, more, first);
+                const int rank = __popc(~act & ((1u << lane) - 1u));
+                if (!active && rank < take) {
+                    slot = queue[first + rank];
+                    bool valid = true;
+                    if constexpr (SHADOW) {
+                        const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
+                        o = xyz(a), d = xyz(b), ht = a.w;
+                    } else {
+                        const float4 a = st.ray_o[slot], b = st.ray_d[slot];
+                        o = xyz(a), d = xyz(b), ht = kMaxDist;
+                        tag = __float_as_uint(b.w) & 0x50000000u; // reset(): clear hit flag and hit index
+                        valid = (tag & TAG_ACTIVE) != 0;         // megakernel rules: k_shade may have ended the path
+                    }
+                    if (valid) {
+                        inv_d = rcp3(d), o_div = o * inv_d;
+                        hu = hv = 0.f, hprim = -1, npend = 0, sp = 0;
+                        const float big = 1e28f;
+                        if (!(fabsf(inv_d.x) < big && fabsf(inv_d.y) < big && fabsf(inv_d.z) < big)) {
+                            // (near-)zero direction component: the compare+select slab form, per thread, right here
+                            if constexpr (SHADOW) {
+                                hprim = unoccluded_ordered<true, false>(sc, s_cached, o, d, ht) ? -1 : 0;
+                            } else {
+                                const Hit hh = closest_hit_ordered<true, false>(sc, s_cached, o, d);
+                                ht = hh.t, hu = hh.u, hv = hh.v, hprim = hh.prim;
+                            }
+                            has_result = true;
+                        } else {
+                            start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, ht, SHADOW ? sc.num_nodes : 0);
+                            if (SHADOW && start >= sc.num_nodes) { // no cached frontier node on the way: unoccluded (tracing_func.cuh:49)
+                                has_result = true;
+                            } else {
+                                cur = sc.wroot, active = true;
+                            }
+                        }
+                    }
+                }
+            }
+            act = __ballot_sync(0xffffffffu, active);
+            if (act == 0u) {
+                if (!more && !__any_sync(0xffffffffu, has_result))
+                    break;
+                continue; // results of rays that needed no traversal: handled by the next round
+            }
+        }
+#pragma unroll 1
+        for (int k = 0; k < kSteps; k++) {
+            if (active && cur != kTraversalDone && !(cur < 0 && npend == 2)) {
+                bool pop = false;
+                if (cur >= 0) {
+                    float4 a0, a1, b0, b1;
+                    load_pair_node<true>(sc.wnodes, cur, a0, a1, b0, b1);
+                    float t0, t1;
+                    const bool h0 = slab_test_finite(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < ht && __float_as_int(a1.w) > start;
+                    const bool h1 = slab_test_finite(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < ht && __float_as_int(b1.w) > start;
+                    const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+                    if (h0 && h1) {
+                        const bool swap = !SHADOW && t1 < t0;
+                        stack_ref[sp] = swap ? r0 : r1;
+                        stack_t[sp] = swap ? t0 : t1;
+                        ++sp;
+                        cur = swap ? r1 : r0;
+                    } else if (h0 || h1) {
+                        cur = h0 ? r0 : r1;
+                    } else {
+                        pop = true;
+                    }
+                } else { // a leaf: remember it, go on with the stack
+                    if (npend == 0)
+                        pend0 = cur;
+                    else
+                        pend1 = cur;
+                    ++npend;
+                    pop = true;
+                }
+                if (pop) {
+                    cur = kTraversalDone;
+                    while (sp > 0) {
+                        --sp;
+                        if (SHADOW || stack_t[sp] < ht) {
+                            cur = stack_ref[sp];
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- triangle phase: when enough lanes hold a pending leaf, or a lane cannot go on without it
+        const bool blocked = active && npend > 0 && (cur == kTraversalDone || (cur < 0 && npend == 2));
+        const unsigned have = __ballot_sync(0xffffffffu, active && npend > 0);
+        if (__popc(have) >= kFlush || __any_sync(0xffffffffu, blocked)) {
+            if (active && npend > 0) {
+                --npend;
+                const int packed = ~(npend == 1 ? pend1 : pend0), base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+                for (int idx = base; idx < base + cnt; idx++) {
+                    float u, v;
+                    const float dist = hit_triangle(sc.tris, idx, o, d, u, v, SHADOW ? ht : inf);
+                    if constexpr (SHADOW) {
+                        if (dist > kEps)
+                            hprim = idx, cur = kTraversalDone, npend = 0, sp = 0; // occluded: done
+                    } else {
+                        const bool better = dist > kEps && (dist < ht || (dist == ht && prim_before(sc, idx, hprim)));
+                        ht = better ? dist : ht;
+                        hu = better ? u : hu;
+                        hv = better ? v : hv;
+                        hprim = better ? idx : hprim;
+                    }
+                }
+            }
+        }
+        if (active && cur == kTraversalDone && npend == 0) { // this ray is done; its epilogue runs with the next refill
+            active = false;
+            has_result = true;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // warp-cooperative forms of the three traversal kernels of the default pipeline (traversal=4, traverse_coop.cuh):
 // same prologue / epilogue per path as k_raygen / k_shadow_apply / k_trace, one ray per lane; in between the warp's
 // 32 rays are traversed by lane groups over the wide layout.  Dynamic shared memory: coop_layout().
@@ -2376,6 +2542,8 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         dyn_steps_ = std::max(1, atoi(e));
     if (const char *e = getenv("CPTB200_DYN_MINB"))
         dyn_minb_ = atoi(e);
+    if (const char *e = getenv("CPTB200_DQ_FLUSH"))
+        dq_flush_ = std::min(32, std::max(1, atoi(e)));
     // default number of samples in flight: ~8M paths, at least 1, at most 64
     set_samples_in_flight(int(std::min<size_t>(64, std::max<size_t>(1, (size_t(8) << 20) / P))));
     CUDA_OK(cudaStreamSynchronize(stream_));
@@ -2446,8 +2614,10 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
 }
 
 void Renderer::set_traversal(int t) {
-    if (t < 0 || t > 5)
-        throw std::runtime_error("traversal must be 0..5");
+    if (t < 0 || t > 6)
+        throw std::runtime_error("traversal must be 0..6");
+    if (t == 6 && !ordered_ok_)
+        t = TRAVERSAL_DFS;
     if (t == 4 && !coop_ok_)
         t = 2;
     if (t == 5 && !wide4_ok_)
@@ -2534,7 +2704,8 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     // traversal=4: cooperative forms of k_raygen / k_shadow_apply / k_trace in the deferred-NEE surface pipeline; every other
     // kernel (fused shading, volumetric path) keeps the ordered per-thread traversal
     const bool coop = traversal_ == 4 && coop_ok_ && rules_ != 2 && this->pipeline_ == 3;
-    const int mode = (traversal_ == 4 || traversal_ == 5) ? 2 : traversal_;
+    const int mode = (traversal_ == 4 || traversal_ == 5 || traversal_ == 6) ? 2 : traversal_;
+    const bool dq = traversal_ == 6 && ordered_ok_ && rules_ != 2 && this->pipeline_ == 3;
     const bool wide4 = traversal_ == 5 && wide4_ok_ && rules_ != 2 && this->pipeline_ == 3;
     int coop_grid = num_sms_; // set per kernel by LAUNCH_COOP
     const CoopParams cpar{m.arena.p + m.arena_nodes, m.wide_width == 8 ? 0 : coop_slab_, std::max(8, (m.wide_max_stack + 7) / 8 * 8)};
@@ -2548,7 +2719,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         else                                                                                                           \
             kernel<4, false><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                             \
     } while (0)
-    const int pipeline_ = (traversal_ == 1 || traversal_ == 3 || traversal_ == 4 || traversal_ == 5) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
+    const int pipeline_ = (traversal_ == 1 || traversal_ == 3 || traversal_ == 4 || traversal_ == 5 || traversal_ == 6) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
 #define LAUNCH_MODE(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (mode == 0)                                                                                                 \
@@ -2734,6 +2905,9 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
                 LAUNCH_COOP(1, k_shadow_apply_coop, m.dev, cpar, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (pipeline_ == 3 && wide4)
                 k_shadow_apply<5><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
+            else if (pipeline_ == 3 && dq)
+                k_traverse_dq<true><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, nullptr, nullptr, b, rules_,
+                                                                     dyn_refill_, dq_flush_, dyn_steps_);
             else if (pipeline_ == 3)
                 LAUNCH_MODE(k_shadow_apply, m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (dyn_minb_ >= 12)
@@ -2780,6 +2954,9 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
             LAUNCH_COOP(0, k_trace_coop, m.dev, cpar, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else if (wide4) {
             k_trace<5><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+        } else if (dq) {
+            k_traverse_dq<false><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_,
+                                                                  dyn_refill_, dq_flush_, dyn_steps_);
         } else {
             LAUNCH_MODE(k_trace, m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         }
@@ -2965,7 +3142,7 @@ std::string Renderer::info() const {
     std::ostringstream os;
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
-       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : "wide4 per thread")))))
+       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : (traversal_ == 5 ? "wide4 per thread" : "deferred leaves + refill"))))))
        << ", wide layout " << impl_->wide_width << "-ary " << impl_->wide_nodes << " nodes (fill " << impl_->wide_fill << ", depth " << impl_->wide_depth
        << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks[0] << "/" << impl_->coop_blocks[1] << "/" << impl_->coop_blocks[2] << " CTAs/SM (trace/shadow/raygen) x " << impl_->coop_smem
        << " B smem, slab " << coop_slab_ << " nodes, flush " << coop_flush_ << " lanes)"

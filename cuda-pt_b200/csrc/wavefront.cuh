@@ -113,6 +113,7 @@ class Renderer {
     bool ordered_ok_ = true, coop_ok_ = false, coop_raygen_ = false, wide4_ok_ = false;
     int coop_flush_ = 1 /* unused since the triangle phase runs on demand */, coop_slab_ = 0;
     int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
+    int dq_flush_ = 16;                                  // traversal 6: lanes with a pending leaf that start a triangle phase
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);
     cudaStream_t stream_ = nullptr;

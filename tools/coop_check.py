@@ -36,7 +36,7 @@ def parity():
         print("   ", info, flush=True)
     if os.path.exists(VADER):
         a, sa, _, _ = frame(VADER, 4, 2)
-        for tr in (4, 5):
+        for tr in (4, 5, 6):
             b, sb, eff, info = frame(VADER, 4, tr)
             ex = float((a.view(np.uint32) == b.view(np.uint32)).all(-1).mean())
             print(f"[parity] vader 1080p 4 spp: trav {tr} (effective {eff}) vs trav 2 bit-exact pixels {ex * 100:.5f}%  rays {sb['rays']} vs {sa['rays']}", flush=True)
@@ -44,17 +44,18 @@ def parity():
         print("   ", info, flush=True)
         for scene, gold, spp in (("cbox_mats_256.cpts", "cbox_mats_256_wfpt_f0016.bin", 16), ("texroom_256.cpts", "texroom_256_wfpt_f0064.bin", 64)):
             ref = np.fromfile(os.path.join(GOLD, gold), dtype=np.float32).reshape(256, 256, 4)
-            out, st, eff, info = frame(os.path.join(GOLD, scene), spp, 5)
-            ex = float((out.view(np.uint32) == ref.view(np.uint32)).all(-1).mean())
-            print(f"[parity] {scene} trav=5 (effective {eff}): bit-exact pixels vs reference frame {ex * 100:.4f}%", flush=True)
-            ok &= ex == 1.0 and eff == 5
+            for tr in (5, 6):
+                out, st, eff, info = frame(os.path.join(GOLD, scene), spp, tr)
+                ex = float((out.view(np.uint32) == ref.view(np.uint32)).all(-1).mean())
+                print(f"[parity] {scene} trav={tr} (effective {eff}): bit-exact pixels vs reference frame {ex * 100:.4f}%", flush=True)
+                ok &= ex == 1.0 and eff == tr
     print("[parity] " + ("OK" if ok else "FAILED"), flush=True)
     return ok
 
 
 def bench(spp=32, sif=16):
     rows = []
-    configs = [(2, ()), (4, (("coop_slab", 0),)), (5, ())]
+    configs = [(2, ()), (4, (("coop_slab", 0),)), (5, ()), (6, ())]
     for trav, opts in configs:
         r = cpt.WavefrontRenderer(VADER, 0, 0)
         r.set_option("traversal", trav)

@@ -1016,6 +1016,11 @@ int main(int argc, char **argv) {
         show("coop G=8, chunk 32", model_coop(c8, cache_iters, cost, 8, 32));
         show("coop G=8, chunk 64", model_coop(c8, cache_iters, cost, 8, 64));
         show("coop G=8, chunk 256", model_coop(c8, cache_iters, cost, 8, 256));
+        for (int bufsz : {64, 128, 256, 1024}) {
+            const DefStats D = sim_thread_deferred(sc, rays, hits, cost, 4, 16, bufsz, 8);
+            printf("   per-thread deferred K=4 flush>=16 refill 8, chunk %4d: warp-inst/ray %7.1f lanes/inst %5.2f  visits/ray %5.1f tri-phases/ray %4.2f\n", bufsz,
+                   D.inst / D.rays, D.thread_inst / D.inst, D.visits / D.rays, D.tri_phases / D.rays);
+        }
         for (int K : {2, 4})
             for (int fl : {1, 8, 16, 24})
                 for (int rf : {0, 8}) {
