@@ -62,6 +62,24 @@ def test_cpts_roundtrip_and_reader(tmp_path):
     assert a["cie_xyz"].shape == (471, 4) and a["d65_spd"].shape == (531,)
 
 
+def test_scene_crosses_the_abi_in_memory(tmp_path):
+    """cpt_b200_scene_load_memory: the .cpts container handed over as a memory image (what the reference-side adapter
+    integration/b200_wavefront.cuh does with the Scene the reference's loader built) gives the scene the file gives; the image is
+    only read during the call; malformed images are refused like malformed files."""
+    src = os.path.join(GOLDEN, "texroom_256.cpts")
+    image = open(src, "rb").read()
+    a, b = cpt.Scene(src), cpt.Scene(image)
+    assert a.config == b.config and np.array_equal(a.camera, b.camera)
+    out = str(tmp_path / "from_memory.cpts")
+    b.save(out)
+    x, y = read_cpts(src), read_cpts(out)
+    assert set(x) == set(y) and all(x[k].tobytes() == y[k].tobytes() for k in x)
+    with pytest.raises(cpt.CptError, match="bad magic|empty"):
+        cpt.Scene(b"NOTASCENE" * 4)
+    with pytest.raises(cpt.CptError):
+        cpt.Scene(image[: len(image) // 3])
+
+
 def test_scene_errors(tmp_path):
     with pytest.raises(cpt.CptError, match="cannot open"):
         cpt.Scene(str(tmp_path / "missing.cpts"))
