@@ -54,7 +54,7 @@ def test_seed_offset_bit_exact_vs_reference():
     assert bit_exact_fraction(out[3][0], load_frame("cbox_wfpt_256_s7_wfpt_f0003.bin")) == 1.0
 
 
-@pytest.mark.parametrize("traversal", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("traversal", [0, 1, 2, 3, 4, 5, 6])
 def test_all_materials_bit_exact_vs_reference(traversal):
     """Lambert, specular, det-refraction, plastic, plastic-forward, GGX conductor (anisotropic), dispersion,
     area + point emitters, 8 bounces, Russian roulette."""
@@ -65,7 +65,7 @@ def test_all_materials_bit_exact_vs_reference(traversal):
     assert np.array_equal(out[16][1].view(np.uint32), var_ref.view(np.uint32))
 
 
-@pytest.mark.parametrize("traversal", [0, 1, 4])
+@pytest.mark.parametrize("traversal", [0, 1, 4, 5, 6])
 def test_textures_and_envmap_vs_reference(traversal):
     """Every texture slot (diffuse, specular, glossy/sigma_a, normal, roughness x/y, ior, emission) and a rotated
     lat-long environment map, on UV-mapped geometry; texels are the ones the reference decoded (scene dump)."""
@@ -545,7 +545,21 @@ def test_cooperative_traversal_is_used_where_allowed_and_replaced_where_not():
     s = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), 0, 0)
     s.set_option("traversal", 4)
     assert s.get_option("traversal") == 2 and "coop unavailable" in s.info()
+    s.set_option("traversal", 5)  # per thread over the wide layout: same precondition
+    assert s.get_option("traversal") == 2
     s.close()
+    # the wide / deferred forms on the benchmark geometry at reduced size (our loader's tree): identical to the ordered traversal
+    if have_vader():
+        frames = []
+        for trav in (2, 4, 5, 6):
+            v = cpt.WavefrontRenderer(os.path.join(SCENES, "vader_wfpt_256.xml"), 0, 0)
+            v.set_option("traversal", trav)
+            assert v.get_option("traversal") == trav
+            frames.append(v.render_to_host(4, False))
+            st = v.stats()
+            v.close()
+        for f in frames[1:]:
+            assert np.array_equal(frames[0].view(np.uint32), f.view(np.uint32))
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_DUMP) and have_vader()), reason="reference harness / vader mesh not on this box")
