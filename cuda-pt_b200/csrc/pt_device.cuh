@@ -78,7 +78,7 @@ struct DevScene {
     const uint4 *cache_nodes;  // fp16 near-root nodes
     const int *obj_idxs;       // per primitive object word
     const int *prim_orig;      // reference index of each primitive when refined leaves re-ordered them (nullptr: identity)
-    const float4 *tris;        // 3 float4 per primitive {v0,a20}{e1,a21}{e2,a22}
+    const float4 *tris;        // kTriStride float4 per primitive {v0,a20}{e1,a21}{e2,a22}[pad]
     const float4 *norms;       // 3 float4 per primitive
     const uint4 *uvs;          // 3 half2 per primitive (+pad)
     const ObjectPOD *objects;
@@ -173,9 +173,30 @@ PT_DEV void camera_ray(const CameraPOD &cam, int px, int py, Rng &rng, V3 &o, V3
 
 // ---- triangle test on the 48 B precomputed-adjoint layout
 // (reference: src/core/primitives.cuh:57-87, layout src/core/aos.cuh:113-164) ----
+// CPTB_TRI64 (default 1): a triangle record is padded from 48 to 64 bytes and read with two 256-bit loads instead of three
+// 128-bit ones - the traversal kernels are bound by L1 wavefronts (one per load instruction and line), not by bytes
+#ifndef CPTB_TRI64
+#define CPTB_TRI64 1
+#endif
+constexpr int kTriStride = CPTB_TRI64 ? 4 : 3;
+PT_DEV void load_triangle(const float4 *__restrict__ tris, int index, float4 &p0, float4 &v1, float4 &v2) {
+#if CPTB_TRI64
+    const float4 *p = tris + 4 * index;
+    float pad0, pad1, pad2, pad3;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(p0.x), "=f"(p0.y), "=f"(p0.z), "=f"(p0.w), "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w)
+                 : "l"(p));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v2.x), "=f"(v2.y), "=f"(v2.z), "=f"(v2.w), "=f"(pad0), "=f"(pad1), "=f"(pad2), "=f"(pad3)
+                 : "l"(p + 2));
+#else
+    p0 = __ldg(tris + 3 * index), v1 = __ldg(tris + 3 * index + 1), v2 = __ldg(tris + 3 * index + 2);
+#endif
+}
 PT_DEV float hit_triangle(const float4 *__restrict__ tris, int index, V3 o, V3 d, float &su, float &sv,
                           float max_range) {
-    const float4 p0 = __ldg(tris + 3 * index), v1 = __ldg(tris + 3 * index + 1), v2 = __ldg(tris + 3 * index + 2);
+    float4 p0, v1, v2;
+    load_triangle(tris, index, p0, v1, v2);
     V3 v = o - V3{p0.x, p0.y, p0.z};
     V3 t1 = V3{fmaf(v2.y, -d.z, d.y * v2.z), fmaf(-d.x, v2.z, v2.x * d.z), fmaf(v2.x, -d.y, d.x * v2.y)};
     V3 t2 = V3{fmaf(-d.y, v1.z, v1.y * d.z), fmaf(v1.x, -d.z, d.x * v1.z), fmaf(-d.x, v1.y, v1.x * d.y)};
@@ -694,7 +715,7 @@ PT_DEV V3 emitter_sample(const DevScene &sc, const EmitterPOD &e, V3 hit_pos, V3
         float ssum = uv.x + uv.y;
         if (!(ssum < 1.f))
             uv = V2{-uv.x + 1.f, -uv.y + 1.f};
-        const float4 p0 = __ldg(sc.tris + 3 * prim), e1 = __ldg(sc.tris + 3 * prim + 1), e2 = __ldg(sc.tris + 3 * prim + 2);
+        const float4 p0 = __ldg(sc.tris + kTriStride * prim), e1 = __ldg(sc.tris + kTriStride * prim + 1), e2 = __ldg(sc.tris + kTriStride * prim + 2);
         V3 sampled = V3{__fadd_rn(mad2(uv.x, e1.x, uv.y, e2.x), p0.x), __fadd_rn(mad2(uv.x, e1.y, uv.y, e2.y), p0.y),
                         __fadd_rn(mad2(uv.x, e1.z, uv.y, e2.z), p0.z)};
         const float4 na = __ldg(sc.norms + 3 * prim), nb = __ldg(sc.norms + 3 * prim + 1), nc = __ldg(sc.norms + 3 * prim + 2);

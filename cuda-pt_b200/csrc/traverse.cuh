@@ -176,13 +176,22 @@ PT_DEV void load_pair_node(const float4 *__restrict__ wnodes, int cur, float4 &a
 }
 
 // variant with one inner-or-leaf step per loop iteration (lanes alternate freely between the two paths)
+// CPTB_STACK64 (default 1): one 8-byte stack entry {ref, bits(t)} per push / pop (STL.64 / LDL.64) instead of two 4-byte arrays -
+// half the local-memory instructions and L1 wavefronts of the stack traffic (27 % of k_trace<2>'s L1 wavefronts, profiles/r02_*)
+#ifndef CPTB_STACK64
+#define CPTB_STACK64 1
+#endif
 template <bool WIDE, bool FINITE>
 PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, V3 d, float t_max = kMaxDist) {
     Hit h{t_max, 0.f, 0.f, -1, 0};
     const V3 inv_d = rcp3(d), o_div = o * inv_d;
     const int start = cached_entry(s_cached, sc.num_cache, inv_d, o_div, t_max, 0);
+#if CPTB_STACK64
+    uint2 stack[kStackSize];
+#else
     int stack_ref[kStackSize];
     float stack_t[kStackSize];
+#endif
     int sp = 0;
     int cur = sc.wroot;
     const float inf = __int_as_float(0x7f800000);
@@ -198,8 +207,12 @@ PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, 
             const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
             if (h0 && h1) {
                 const bool swap = t1 < t0;
+#if CPTB_STACK64
+                stack[sp] = make_uint2(uint32_t(swap ? r0 : r1), __float_as_uint(swap ? t0 : t1));
+#else
                 stack_ref[sp] = swap ? r0 : r1;
                 stack_t[sp] = swap ? t0 : t1;
+#endif
                 ++sp;
                 cur = swap ? r1 : r0;
                 continue;
@@ -224,11 +237,20 @@ PT_DEV Hit closest_hit_ordered(const DevScene &sc, const uint4 *s_cached, V3 o, 
         bool found = false;
         while (sp > 0) {
             --sp;
+#if CPTB_STACK64
+            const uint2 e = stack[sp];
+            if (__uint_as_float(e.y) < h.t) {
+                cur = int(e.x);
+                found = true;
+                break;
+            }
+#else
             if (stack_t[sp] < h.t) {
                 cur = stack_ref[sp];
                 found = true;
                 break;
             }
+#endif
         }
         if (!found)
             break;

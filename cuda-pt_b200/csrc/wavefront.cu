@@ -296,6 +296,8 @@ constexpr int kGrab = 128;  // rays a warp reserves per global atomic
 // kRefill (refill a warp when at least this many lanes are idle) and kSteps (traversal steps between refill
 // checks) are launch parameters: env CPTB200_DYN_REFILL (default 8) / CPTB200_DYN_STEPS (default 4)
 
+constexpr unsigned char kVisOddRay = 2; // stream traversal: shadow ray left to k_shadow_finish (see stream_fetch_stage)
+constexpr int kPrimOddRay = -2;          // same for an extension ray: hit record left to k_resolve
 struct RayBufs {
     float4 *sh_o; // shadow ray origin, w = range
     float4 *sh_d; // shadow ray direction, w = bits(start DFS index of the cached phase)
@@ -807,6 +809,8 @@ __global__ void __launch_bounds__(kBlock, MINB) k_intersect(DevScene sc, PathSta
 __global__ void __launch_bounds__(kBlock) k_resolve(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue,
                                                     const int *__restrict__ q_count, int *work, uint32_t *q_next,
                                                     int *q_next_count, int bounce, int pt_rules) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
     const int lane = threadIdx.x & 31;
     const int count = *q_count;
     for (int chunk = warp_next_chunk(work, lane); chunk * 32 < count; chunk = warp_next_chunk(work, lane)) {
@@ -818,7 +822,11 @@ __global__ void __launch_bounds__(kBlock) k_resolve(DevScene sc, PathState st, R
             const float4 rd = st.ray_d[slot];
             const uint32_t tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index
             if (tag & TAG_ACTIVE) {
-                const float4 h = rb.hit[slot];
+                float4 h = rb.hit[slot];
+                if (__float_as_int(h.w) == kPrimOddRay) { // stream traversal: a ray with a zero direction component, left to us
+                    const Hit hh = closest_hit_ordered<true, false>(sc, s_cached, xyz(st.ray_o[slot]), xyz(rd));
+                    h = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
+                }
                 alive = resolve_hit(sc, st, slot, tag, xyz(rd), h.x, h.y, h.z, __float_as_int(h.w), bounce, pt_rules);
             }
         }
@@ -1021,6 +1029,330 @@ __global__ void __launch_bounds__(kBlock, DQ_MIN_BLOCKS)
             active = false;
             has_result = true;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// traversal=7 ("stream"): traversal=6's walk (per-thread ordered traversal, leaves deferred into a 2-entry pending list, warp-wide
+// triangle phases, idle lanes refilled) with everything that made traversal=6 wait on memory taken out of the walk:
+//  * ray fetch is an asynchronous pipeline per warp.  One stage per pass through the main loop: reserve an aligned 32-ray
+//    chunk of the queue (atomic), read its slot ids, start `cp.async` gathers of the ray records into the warp's ring in shared
+//    memory, and - a pass later, when they have landed - run the per-ray prologue (1/d, the fp16 cached phase of
+//    tracing_func.cuh:124-142, rays that need no traversal answered on the spot) with one ray per lane at 32 of 32 lanes and
+//    compact the rays that do need a traversal to the ring's tail.  The walk never waits for global memory on behalf of a new
+//    ray: a lane whose ray is done takes the next one from shared memory.
+//  * no epilogue in the walk: a finished ray stores its hit record (closest hit) or one visibility byte (shadow ray) and is
+//    gone.  Interaction, Russian roulette and compaction run in k_resolve, the radiance swap in k_shadow_finish, both in queue
+//    order at 32 of 32 lanes - so the next bounce's queue keeps its slot order (traversal=6 lost it and k_shade paid).
+// Same boxes, same tests, same tie rule as closest_hit_ordered; deferral only delays updates of the closest distance.
+// Dynamic shared memory: cached nodes + per warp a ring of SQ_RING rays {o, tmax}{d, start} + id (36 B per ray).
+// ------------------------------------------------------------------------------------------------
+#ifndef SQ_MIN_BLOCKS
+#define SQ_MIN_BLOCKS 10
+#endif
+#ifndef SQ_RING
+#define SQ_RING 32
+#endif
+constexpr int kRing = SQ_RING; // ring entries per warp: a power of two, >= 32
+static_assert((kRing & (kRing - 1)) == 0 && kRing >= 32 && kRing <= 1024, "SQ_RING must be a power of two in [32, 1024]");
+constexpr int kLaneWords = 13; // per-lane words kept in shared memory: fetch register, o, d, id, hu, hv, hprim, pend0, pend1
+constexpr size_t kLaneBytes = size_t((kLaneWords * 32 * 4 + 15) / 16 * 16);
+constexpr size_t kRingBytes = kLaneBytes + size_t(kRing) * 36;
+enum { W_FREG = 0, W_OX, W_OY, W_OZ, W_DX, W_DY, W_DZ, W_ID, W_HU, W_HV, W_PRIM, W_PEND0, W_PEND1 };
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned s = unsigned(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const unsigned s = unsigned(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// warp-uniform state of a warp's fetch pipeline, packed so that it crosses the (out-of-line) stage function in two registers
+struct StreamFetch {
+    uint32_t ht;  // head | tail << 16: ring[head, tail) = rays ready to walk (16-bit wrapping counters, index & (kRing - 1))
+    uint32_t ctl; // stage (2 bits) | rays in the chunk in flight << 2 | queue exhausted << 8
+    __device__ int head() const { return int(ht & 0xffffu); }
+    __device__ int tail() const { return int(ht >> 16); }
+    __device__ int avail() const { return (tail() - head()) & 0xffff; }
+    __device__ int stage() const { return int(ctl & 3u); }
+    __device__ int fcount() const { return int((ctl >> 2) & 63u); }
+    __device__ bool more() const { return (ctl & 256u) == 0u; }
+};
+
+// One stage of the fetch pipeline (see k_traverse_stream).  Out of line on purpose: the per-ray prologue needs ~25 registers
+// of its own, and inlined into the walk it makes ptxas spill the walk's loop-carried state; across a call that state sits in
+// callee-saved registers.  Must be called by the full warp.
+template <bool SHADOW>
+__device__ __noinline__ StreamFetch stream_fetch_stage(StreamFetch f, int chunk, int num_cache, int num_nodes, const uint4 *s_cached, unsigned char *wbase,
+                                                       const float4 *__restrict__ src_o, const float4 *__restrict__ src_d, const uint32_t *__restrict__ queue,
+                                                       int count, unsigned char *__restrict__ vis, float4 *__restrict__ hit) {
+    const int lane = threadIdx.x & 31;
+    uint32_t *freg = reinterpret_cast<uint32_t *>(wbase) + W_FREG * 32 + lane;
+    float4 *ringA = reinterpret_cast<float4 *>(wbase + kLaneBytes); // o.xyz, tmax
+    float4 *ringB = ringA + kRing;                                  // d.xyz, bits(start)
+    uint32_t *ringS = reinterpret_cast<uint32_t *>(ringB + kRing);   // slot (closest hit) / queue position (shadow)
+    const int tail = f.tail(), stage = f.stage(), fcount = f.fcount();
+    if (stage == 3) { // the chunk's ray records have landed at ring[tail .. tail + fcount): prologue, one ray per lane
+        cp_async_wait_all();
+        __syncwarp();
+        const int pos = (tail + lane) & (kRing - 1);
+        bool trav = false;
+        float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 1, 0);
+        uint32_t rid = 0;
+        if (lane < fcount) {
+            a = ringA[pos], b = ringB[pos], rid = ringS[pos];
+            bool valid = true;
+            if constexpr (!SHADOW) {
+                valid = (__float_as_uint(b.w) & TAG_ACTIVE) != 0; // megakernel rules: k_shade may have ended the path
+                a.w = kMaxDist;
+            }
+            if (valid) {
+                const V3 po = xyz(a), pd = xyz(b);
+                const V3 pinv = rcp3(pd), podiv = po * pinv;
+                const float big = 1e28f;
+                if (!(fabsf(pinv.x) < big && fabsf(pinv.y) < big && fabsf(pinv.z) < big)) {
+                    // (near-)zero direction component: needs the compare+select slab form.  Rare; marked here and traced per thread by
+                    // the companion kernel that reads the result anyway (k_shadow_finish / k_resolve)
+                    if constexpr (SHADOW)
+                        vis[rid] = kVisOddRay;
+                    else
+                        hit[rid] = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(kPrimOddRay));
+                } else {
+                    const int st0 = cached_entry(s_cached, num_cache, pinv, podiv, a.w, SHADOW ? num_nodes : 0);
+                    if (SHADOW && st0 >= num_nodes) {
+                        vis[rid] = 1; // no cached frontier node on the way: unoccluded (tracing_func.cuh:49)
+                    } else {
+                        trav = true;
+                        b.w = __int_as_float(st0);
+                    }
+                }
+            }
+        }
+        __syncwarp(); // every lane has read its record before the compacted ones are written
+        const unsigned m = __ballot_sync(0xffffffffu, trav);
+        if (trav) {
+            const int p = (tail + __popc(m & ((1u << lane) - 1u))) & (kRing - 1);
+            ringA[p] = a, ringB[p] = b, ringS[p] = rid;
+        }
+        __syncwarp();
+        f.ht = (f.ht & 0xffffu) | (uint32_t((tail + __popc(m)) & 0xffff) << 16);
+        f.ctl &= ~255u; // stage 0
+    } else if (stage == 2) { // slot ids are here (shared memory): start the gathers of the ray records
+        cp_async_wait_all();
+        if (lane < fcount) {
+            const int pos = (tail + lane) & (kRing - 1);
+            const uint32_t slot = *freg;
+            cp_async16(ringA + pos, src_o + slot);
+            cp_async16(ringB + pos, src_d + slot);
+            if constexpr (!SHADOW)
+                ringS[pos] = slot;
+        }
+        cp_async_commit();
+        f.ctl |= 3u;
+    } else { // stage 1: the chunk number is here (lane 0 of `chunk`, reserved by the caller a pass ago): fetch the slot ids
+        const int fbase = __shfl_sync(0xffffffffu, chunk, 0) * 32;
+        if (fbase >= count) {
+            f.ctl = 256u; // queue exhausted, stage 0
+        } else {
+            const int n = min(32, count - fbase);
+            if (lane < n) {
+                cp_async4(freg, queue + fbase + lane);
+                if constexpr (SHADOW)
+                    ringS[(tail + lane) & (kRing - 1)] = uint32_t(fbase + lane);
+            }
+            cp_async_commit();
+            f.ctl = 2u | (uint32_t(n) << 2);
+        }
+    }
+    return f;
+}
+
+template <bool SHADOW>
+__global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
+    k_traverse_stream(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue, const int *__restrict__ q_count, int *work,
+                      unsigned char *__restrict__ vis, int kRefill, int kFlush, int kSteps) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_cached + sc.num_cache) + size_t(threadIdx.x >> 5) * kRingBytes;
+    // the walking ray's cold state, word w of lane l at lsf[w * 32] (conflict-free): what the box tests do not need stays out of
+    // the register file - o, d (triangle tests), id / hu / hv / hprim (retire), the two pending leaves
+    float *lsf = reinterpret_cast<float *>(wbase) + lane;
+    int *lsi = reinterpret_cast<int *>(lsf);
+    const float4 *ringA = reinterpret_cast<const float4 *>(wbase + kLaneBytes);
+    const float4 *ringB = ringA + kRing;
+    const uint32_t *ringS = reinterpret_cast<const uint32_t *>(ringB + kRing);
+    const int count = *q_count;
+    // ---- walk state, one ray per lane
+    uint2 stack[SHADOW ? 1 : kStackSize]; // closest hit: {ref, bits(t)}, one 8-byte access per push / pop
+    int stack_ref[SHADOW ? kStackSize : 1];
+    int sp = 0, cur = kTraversalDone, start = 0, npend = 0;
+    V3 inv_d{0, 0, 0}, o_div{0, 0, 0};
+    float ht = kMaxDist;
+    bool active = false; // (shadow rays: ht < 0 marks an occluded ray)
+    StreamFetch f{0u, 0u};
+    int pending = 0; // lane 0: the chunk number reserved for the fetch pipeline's next round
+    const float inf = __int_as_float(0x7f800000);
+    while (true) {
+        // ---------------- fetch pipeline: one stage per pass
+        if (f.stage() != 0) {
+            f = stream_fetch_stage<SHADOW>(f, pending, sc.num_cache, sc.num_nodes, s_cached, wbase, SHADOW ? rb.sh_o : st.ray_o, SHADOW ? rb.sh_d : st.ray_d, queue, count, vis, rb.hit);
+        } else if (f.more() && f.avail() <= kRing - 32) { // room for a chunk: reserve one; the number is used a pass later
+            if (lane == 0) // atom.inc, not atom.add: ptxas turns an add into its warp-aggregated form, whose shuffle waits for the result here
+                asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(pending) : "l"(work) : "memory");
+            f.ctl |= 1u;
+        }
+        // ---------------- refill idle lanes from the ring
+        unsigned act = __ballot_sync(0xffffffffu, active);
+        const int avail = f.avail();
+        if (avail > 0) {
+            const int n_idle = 32 - __popc(act);
+            if (n_idle >= kRefill || act == 0u || (!f.more() && f.stage() == 0 && n_idle > 0)) {
+                const int take = min(n_idle, avail);
+                const int rank = __popc(~act & lt_mask);
+                if (!active && rank < take) {
+                    const int p = (f.head() + rank) & (kRing - 1);
+                    const float4 a = ringA[p], b = ringB[p];
+                    lsi[W_ID * 32] = int(ringS[p]);
+                    lsf[W_OX * 32] = a.x, lsf[W_OY * 32] = a.y, lsf[W_OZ * 32] = a.z;
+                    lsf[W_DX * 32] = b.x, lsf[W_DY * 32] = b.y, lsf[W_DZ * 32] = b.z;
+                    if constexpr (!SHADOW)
+                        lsf[W_HU * 32] = 0.f, lsf[W_HV * 32] = 0.f, lsi[W_PRIM * 32] = -1;
+                    ht = a.w, start = __float_as_int(b.w);
+                    inv_d = rcp3(xyz(b)), o_div = xyz(a) * inv_d;
+                    npend = 0, sp = 0;
+                    cur = sc.wroot, active = true;
+                }
+                f.ht = (f.ht & 0xffff0000u) | uint32_t((f.head() + take) & 0xffff);
+                act = __ballot_sync(0xffffffffu, active);
+            }
+        }
+        if (act == 0u) {
+            if (!f.more() && f.stage() == 0 && f.avail() == 0)
+                break;
+            continue; // nothing to walk yet: let the fetch pipeline advance
+        }
+        // ---------------- walk
+#pragma unroll 1
+        for (int k = 0; k < kSteps; k++) {
+            if (active && cur != kTraversalDone && !(cur < 0 && npend == 2)) {
+                bool pop = false;
+                if (cur >= 0) {
+                    float4 a0, a1, b0, b1;
+                    load_pair_node<true>(sc.wnodes, cur, a0, a1, b0, b1);
+                    float t0, t1;
+                    const bool h0 = slab_test_finite(a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, inv_d, o_div, t0) && t0 < ht && __float_as_int(a1.w) > start;
+                    const bool h1 = slab_test_finite(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, inv_d, o_div, t1) && t1 < ht && __float_as_int(b1.w) > start;
+                    const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+                    if (h0 && h1) {
+                        const bool swap = !SHADOW && t1 < t0;
+                        if constexpr (SHADOW)
+                            stack_ref[sp] = r1;
+                        else
+                            stack[sp] = make_uint2(uint32_t(swap ? r0 : r1), __float_as_uint(swap ? t0 : t1));
+                        ++sp;
+                        cur = swap ? r1 : r0;
+                    } else if (h0 || h1) {
+                        cur = h0 ? r0 : r1;
+                    } else {
+                        pop = true;
+                    }
+                } else { // a leaf: remember it, go on with the stack
+                    lsi[(W_PEND0 + npend) * 32] = cur;
+                    ++npend;
+                    pop = true;
+                }
+                if (pop) {
+                    cur = kTraversalDone;
+                    while (sp > 0) {
+                        --sp;
+                        if constexpr (SHADOW) {
+                            cur = stack_ref[sp];
+                            break;
+                        } else {
+                            const uint2 e = stack[sp];
+                            if (__uint_as_float(e.y) < ht) {
+                                cur = int(e.x);
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---------------- triangle phase: when enough lanes hold a pending leaf, or a lane cannot go on without it
+        const bool blocked = active && npend > 0 && (cur == kTraversalDone || (cur < 0 && npend == 2));
+        const unsigned have = __ballot_sync(0xffffffffu, active && npend > 0);
+        if (__popc(have) >= kFlush || __any_sync(0xffffffffu, blocked)) {
+            if (active && npend > 0) {
+                --npend;
+                const int packed = ~lsi[(W_PEND0 + npend) * 32], base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+                const V3 o{lsf[W_OX * 32], lsf[W_OY * 32], lsf[W_OZ * 32]}, d{lsf[W_DX * 32], lsf[W_DY * 32], lsf[W_DZ * 32]};
+                if constexpr (SHADOW) {
+                    bool occl = false;
+                    for (int idx = base; idx < base + cnt; idx++) {
+                        float u, v;
+                        const float dist = hit_triangle(sc.tris, idx, o, d, u, v, ht);
+                        if (dist > kEps)
+                            occl = true;
+                    }
+                    if (occl) // occluded: done
+                        ht = -1.f, cur = kTraversalDone, npend = 0, sp = 0;
+                } else {
+                    float bu = 0.f, bv = 0.f;
+                    int hprim = lsi[W_PRIM * 32];
+                    bool changed = false;
+                    for (int idx = base; idx < base + cnt; idx++) {
+                        float u, v;
+                        const float dist = hit_triangle(sc.tris, idx, o, d, u, v, inf);
+                        const bool better = dist > kEps && (dist < ht || (dist == ht && prim_before(sc, idx, hprim)));
+                        ht = better ? dist : ht;
+                        bu = better ? u : bu;
+                        bv = better ? v : bv;
+                        hprim = better ? idx : hprim;
+                        changed |= better;
+                    }
+                    if (changed)
+                        lsf[W_HU * 32] = bu, lsf[W_HV * 32] = bv, lsi[W_PRIM * 32] = hprim;
+                }
+            }
+        }
+        // ---------------- retire
+        if (active && cur == kTraversalDone && npend == 0) {
+            active = false;
+            const uint32_t id = uint32_t(lsi[W_ID * 32]);
+            if constexpr (SHADOW)
+                vis[id] = ht < 0.f ? 0 : 1;
+            else
+                rb.hit[id] = make_float4(ht, lsf[W_HU * 32], lsf[W_HV * 32], __int_as_float(lsi[W_PRIM * 32]));
+        }
+    }
+}
+
+// the radiance swap of k_shadow_apply for the stream traversal: an unoccluded shadow ray takes the value k_shade<-2> prepared.
+// Rays the stream kernel marked kVisOddRay (zero direction component) are traced here, per thread, with the select-form slab test.
+__global__ void __launch_bounds__(256) k_shadow_finish(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ sq, const int *__restrict__ sq_count,
+                                                       const unsigned char *__restrict__ vis) {
+    extern __shared__ uint4 s_cached[];
+    stage_cached_nodes(sc, s_cached);
+    const int count = *sq_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const unsigned char v = vis[i];
+        if (v == 0)
+            continue;
+        const uint32_t slot = sq[i];
+        bool visible = true;
+        if (v == kVisOddRay) {
+            const float4 a = rb.sh_o[slot], b = rb.sh_d[slot];
+            visible = unoccluded_ordered<true, false>(sc, s_cached, xyz(a), xyz(b), a.w);
+        }
+        if (visible)
+            st.L[slot] = rb.hit[slot];
     }
 }
 
@@ -2154,6 +2486,8 @@ struct Renderer::Impl {
     int caps[3] = {16, 16, 16};
     DevBuf<uint32_t> queue[2], shadow_queue;
     DevBuf<float4> sh_o, sh_d, hit; // dynamic-fetch pipeline: shadow rays and hit records
+    DevBuf<unsigned char> vis;      // stream traversal: one visibility byte per shadow-queue entry
+    int stream_blocks[2] = {0, 0};  // stream traversal: resident CTAs per SM of k_traverse_stream<false / true>
     DevBuf<float4> vtr;             // volumetric wavefront: march results
     DevBuf<uint2> vstate;           // volumetric wavefront: nested-volume stack + event word
     DevBuf<uint32_t> queue3;        // volumetric wavefront: fourth queue (hit / trace ping-pong, shade, march)
@@ -2302,6 +2636,13 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         m.wide_nodes = wl.num_nodes, m.wide_max_stack = wl.max_stack, m.wide_max_stack_all = wl.max_stack_all, m.wide_depth = wl.max_depth, m.wide_fill = wl.avg_children;
         // traversal arena: pair nodes, wide nodes and triangles in one allocation, so that one L2 access-policy window can pin
         // them all (the 4-5 GB path-state pool streams through L2 every bounce and would otherwise keep evicting them)
+        if (kTriStride == 4) { // 64-byte triangle records (two 256-bit loads): {v0,a20}{e1,a21}{e2,a22}{0}
+            std::vector<float4> t64(t4.size() / 3 * 4, make_float4(0, 0, 0, 0));
+            for (size_t i = 0; i < t4.size() / 3; i++)
+                for (int k = 0; k < 3; k++)
+                    t64[4 * i + k] = t4[3 * i + k];
+            t4.swap(t64);
+        }
         m.arena.alloc(w4.size() + ww.size() + t4.size());
         CUDA_OK(cudaMemcpy(m.arena.p, w4.data(), w4.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpy(m.arena.p + w4.size(), ww.data(), ww.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -2542,6 +2883,14 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         dyn_steps_ = std::max(1, atoi(e));
     if (const char *e = getenv("CPTB200_DYN_MINB"))
         dyn_minb_ = atoi(e);
+    if (const char *e = getenv("CPTB200_SQ_REFILL"))
+        set_stream(atoi(e), -1, -1, -1);
+    if (const char *e = getenv("CPTB200_SQ_FLUSH"))
+        set_stream(-1, atoi(e), -1, -1);
+    if (const char *e = getenv("CPTB200_SQ_STEPS"))
+        set_stream(-1, -1, atoi(e), -1);
+    if (const char *e = getenv("CPTB200_SQ_BLOCKS"))
+        set_stream(-1, -1, -1, atoi(e));
     if (const char *e = getenv("CPTB200_DQ_FLUSH"))
         dq_flush_ = std::min(32, std::max(1, atoi(e)));
     // default number of samples in flight: ~8M paths, at least 1, at most 64
@@ -2611,13 +2960,28 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
     coop_ok_ = nb >= 1 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0;
     // per-thread traversal of the same layout (traversal=5): 4-ary records, per-thread stack of kStackSize entries
     wide4_ok_ = G == 4 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0 && m.wide_max_stack_all + 1 <= kWideStack;
+    // stream traversal (traversal=7): the pair layout per thread with deferred leaves - the same restriction on clipped references
+    stream_ok_ = ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0;
+}
+
+void Renderer::set_stream(int refill, int flush, int steps, int blocks) {
+    if (refill >= 0)
+        sq_refill_ = std::min(32, std::max(1, refill));
+    if (flush >= 0)
+        sq_flush_ = std::min(32, std::max(1, flush));
+    if (steps >= 0)
+        sq_steps_ = std::min(64, std::max(1, steps));
+    if (blocks >= 0)
+        sq_blocks_ = std::min(32, blocks);
 }
 
 void Renderer::set_traversal(int t) {
-    if (t < 0 || t > 6)
-        throw std::runtime_error("traversal must be 0..6");
+    if (t < 0 || t > 7)
+        throw std::runtime_error("traversal must be 0..7");
     if (t == 6 && !ordered_ok_)
         t = TRAVERSAL_DFS;
+    if (t == 7 && !stream_ok_)
+        t = 2;
     if (t == 4 && !coop_ok_)
         t = 2;
     if (t == 5 && !wide4_ok_)
@@ -2677,6 +3041,7 @@ void Renderer::ensure_capacity(int samples) {
         m.sh_o.alloc(slots);
         m.sh_d.alloc(slots);
         m.hit.alloc(slots);
+        m.vis.alloc(slots);
     }
     m.counters.alloc(size_t(8 * (max_depth_ + 2) + 8)); // D+2 queue sizes, D+2 shadow-queue sizes, then one work counter per launch (<= 5D+1)
     m.capacity_samples = std::max(samples, m.capacity_samples);
@@ -2704,9 +3069,19 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     // traversal=4: cooperative forms of k_raygen / k_shadow_apply / k_trace in the deferred-NEE surface pipeline; every other
     // kernel (fused shading, volumetric path) keeps the ordered per-thread traversal
     const bool coop = traversal_ == 4 && coop_ok_ && rules_ != 2 && this->pipeline_ == 3;
-    const int mode = (traversal_ == 4 || traversal_ == 5 || traversal_ == 6) ? 2 : traversal_;
+    const int mode = (traversal_ == 4 || traversal_ == 5 || traversal_ == 6 || traversal_ == 7) ? 2 : traversal_;
     const bool dq = traversal_ == 6 && ordered_ok_ && rules_ != 2 && this->pipeline_ == 3;
     const bool wide4 = traversal_ == 5 && wide4_ok_ && rules_ != 2 && this->pipeline_ == 3;
+    const bool sq = traversal_ == 7 && stream_ok_ && rules_ != 2 && this->pipeline_ == 3;
+    const size_t smem_sq = smem + size_t(kBlock / 32) * kRingBytes;
+    if (sq && m.stream_blocks[0] == 0) { // resident CTAs per SM of the two stream kernels with this scene's shared-memory size
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m.stream_blocks[0], k_traverse_stream<false>, kBlock, smem_sq));
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m.stream_blocks[1], k_traverse_stream<true>, kBlock, smem_sq));
+        if (m.stream_blocks[0] < 1 || m.stream_blocks[1] < 1)
+            throw std::runtime_error("cpt_b200: the stream traversal kernels do not fit on this device");
+    }
+    const int grid_sq[2] = {num_sms_ * (sq_blocks_ > 0 ? std::min(sq_blocks_, std::max(1, m.stream_blocks[0])) : std::max(1, m.stream_blocks[0])),
+                            num_sms_ * (sq_blocks_ > 0 ? std::min(sq_blocks_, std::max(1, m.stream_blocks[1])) : std::max(1, m.stream_blocks[1]))};
     int coop_grid = num_sms_; // set per kernel by LAUNCH_COOP
     const CoopParams cpar{m.arena.p + m.arena_nodes, m.wide_width == 8 ? 0 : coop_slab_, std::max(8, (m.wide_max_stack + 7) / 8 * 8)};
 #define LAUNCH_COOP(which, kernel, ...)                                                                                \
@@ -2719,7 +3094,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         else                                                                                                           \
             kernel<4, false><<<coop_grid, kCoopBlock, m.coop_smem, stream_>>>(__VA_ARGS__);                             \
     } while (0)
-    const int pipeline_ = (traversal_ == 1 || traversal_ == 3 || traversal_ == 4 || traversal_ == 5 || traversal_ == 6) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
+    const int pipeline_ = (traversal_ == 1 || traversal_ == 3 || traversal_ == 4 || traversal_ == 5 || traversal_ == 6 || traversal_ == 7) ? (this->pipeline_ == 2 ? 1 : (this->pipeline_ == 4 ? 3 : this->pipeline_)) : this->pipeline_; // dynamic fetch exists for the ordered traversal only
 #define LAUNCH_MODE(kernel, ...)                                                                                       \
     do {                                                                                                               \
         if (mode == 0)                                                                                                 \
@@ -2905,7 +3280,12 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
                 LAUNCH_COOP(1, k_shadow_apply_coop, m.dev, cpar, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (pipeline_ == 3 && wide4)
                 k_shadow_apply<5><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
-            else if (pipeline_ == 3 && dq)
+            else if (pipeline_ == 3 && sq) {
+                k_traverse_stream<true><<<grid_sq[1], kBlock, smem_sq, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, m.vis.p, sq_refill_,
+                                                                                    sq_flush_, sq_steps_);
+                k_shadow_finish<<<num_sms_ * 8, 256, smem, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, m.vis.p);
+                ++launches;
+            } else if (pipeline_ == 3 && dq)
                 k_traverse_dq<true><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, nullptr, nullptr, b, rules_,
                                                                      dyn_refill_, dq_flush_, dyn_steps_);
             else if (pipeline_ == 3)
@@ -2949,11 +3329,16 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
                 k_intersect<8><<<grid, kBlock, smem_dyn, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, dyn_refill_, dyn_steps_);
             ++wk, ++launches;
             mark(2, b);
-            k_resolve<<<grid, kBlock, 0, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+            k_resolve<<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else if (coop) {
             LAUNCH_COOP(0, k_trace_coop, m.dev, cpar, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else if (wide4) {
             k_trace<5><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+        } else if (sq) {
+            k_traverse_stream<false><<<grid_sq[0], kBlock, smem_sq, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, nullptr, sq_refill_, sq_flush_,
+                                                                                 sq_steps_);
+            ++wk, ++launches;
+            k_resolve<<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else if (dq) {
             k_traverse_dq<false><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_,
                                                                   dyn_refill_, dq_flush_, dyn_steps_);
@@ -3142,7 +3527,7 @@ std::string Renderer::info() const {
     std::ostringstream os;
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
-       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : (traversal_ == 5 ? "wide4 per thread" : "deferred leaves + refill"))))))
+       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : (traversal_ == 5 ? "wide4 per thread" : (traversal_ == 6 ? "deferred leaves + refill" : "stream")))))))
        << ", wide layout " << impl_->wide_width << "-ary " << impl_->wide_nodes << " nodes (fill " << impl_->wide_fill << ", depth " << impl_->wide_depth
        << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks[0] << "/" << impl_->coop_blocks[1] << "/" << impl_->coop_blocks[2] << " CTAs/SM (trace/shadow/raygen) x " << impl_->coop_smem
        << " B smem, slab " << coop_slab_ << " nodes, flush " << coop_flush_ << " lanes)"

@@ -71,6 +71,9 @@ class Renderer {
     int traversal() const { return traversal_; }
     // cooperative traversal knobs: triangle-phase threshold in lanes, treelet slab size in wide nodes
     void set_coop(int flush_lanes, int slab_nodes);
+    // stream traversal knobs (traversal 7); a negative value keeps the current setting
+    void set_stream(int refill, int flush, int steps, int blocks);
+    int stream_knob(int which) const { return which == 0 ? sq_refill_ : (which == 1 ? sq_flush_ : (which == 2 ? sq_steps_ : sq_blocks_)); }
     int coop_flush() const { return coop_flush_; }
     int coop_slab() const { return coop_slab_; }
     void enable_variance(bool on);
@@ -110,10 +113,11 @@ class Renderer {
     int s_max_ = 1, traversal_ = 2 /* ordered pair-node traversal with 256-bit node loads */, num_sms_ = 148, blocks_per_sm_ = 12, rules_ = 0;
     bool variance_on_ = false, kernel_timing_ = false;
     int pipeline_ = 3, row0_ = 0, row1_ = 0;
-    bool ordered_ok_ = true, coop_ok_ = false, coop_raygen_ = false, wide4_ok_ = false;
+    bool ordered_ok_ = true, coop_ok_ = false, coop_raygen_ = false, wide4_ok_ = false, stream_ok_ = false;
     int coop_flush_ = 1 /* unused since the triangle phase runs on demand */, coop_slab_ = 0;
     int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
     int dq_flush_ = 16;                                  // traversal 6: lanes with a pending leaf that start a triangle phase
+    int sq_refill_ = 8, sq_flush_ = 16, sq_steps_ = 4, sq_blocks_ = 0; // traversal 7 (stream): refill / triangle-phase thresholds in lanes, walk steps per pass, CTAs per SM (0: what fits)
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);
     cudaStream_t stream_ = nullptr;

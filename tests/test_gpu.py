@@ -54,7 +54,7 @@ def test_seed_offset_bit_exact_vs_reference():
     assert bit_exact_fraction(out[3][0], load_frame("cbox_wfpt_256_s7_wfpt_f0003.bin")) == 1.0
 
 
-@pytest.mark.parametrize("traversal", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("traversal", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_all_materials_bit_exact_vs_reference(traversal):
     """Lambert, specular, det-refraction, plastic, plastic-forward, GGX conductor (anisotropic), dispersion,
     area + point emitters, 8 bounces, Russian roulette."""
@@ -65,7 +65,7 @@ def test_all_materials_bit_exact_vs_reference(traversal):
     assert np.array_equal(out[16][1].view(np.uint32), var_ref.view(np.uint32))
 
 
-@pytest.mark.parametrize("traversal", [0, 1, 4, 5, 6])
+@pytest.mark.parametrize("traversal", [0, 1, 4, 5, 6, 7])
 def test_textures_and_envmap_vs_reference(traversal):
     """Every texture slot (diffuse, specular, glossy/sigma_a, normal, roughness x/y, ior, emission) and a rotated
     lat-long environment map, on UV-mapped geometry; texels are the ones the reference decoded (scene dump)."""
@@ -547,11 +547,26 @@ def test_cooperative_traversal_is_used_where_allowed_and_replaced_where_not():
     assert s.get_option("traversal") == 2 and "coop unavailable" in s.info()
     s.set_option("traversal", 5)  # per thread over the wide layout: same precondition
     assert s.get_option("traversal") == 2
+    s.set_option("traversal", 7)  # stream traversal (deferred leaves): same precondition
+    assert s.get_option("traversal") == 2
     s.close()
+    # stream traversal under the megakernel termination rules (k_resolve applies them) and at the extremes of its knobs
+    frames = []
+    for trav, opts in ((2, ()), (7, ()), (7, (("sq_refill", 1), ("sq_flush", 1), ("sq_steps", 1))), (7, (("sq_refill", 32), ("sq_flush", 32), ("sq_steps", 16), ("sq_blocks", 2)))):
+        m = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_mats_256.cpts"), 0, 0)
+        m.set_option("rules", 1)
+        m.set_option("traversal", trav)
+        for k, v in opts:
+            m.set_option(k, v)
+        assert m.get_option("traversal") == trav
+        frames.append(m.render_to_host(8, False))
+        m.close()
+    for f in frames[1:]:
+        assert np.array_equal(frames[0].view(np.uint32), f.view(np.uint32))
     # the wide / deferred forms on the benchmark geometry at reduced size (our loader's tree): identical to the ordered traversal
     if have_vader():
         frames = []
-        for trav in (2, 4, 5, 6):
+        for trav in (2, 4, 5, 6, 7):
             v = cpt.WavefrontRenderer(os.path.join(SCENES, "vader_wfpt_256.xml"), 0, 0)
             v.set_option("traversal", trav)
             assert v.get_option("traversal") == trav
