@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched by torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the unmodified reference on the same box
 
-A "step" is one pass of the hot path over one batch of paths: `--spp-per-step` (default 8) samples of the full
+A "step" is one pass of the hot path over one batch of paths: `--spp-per-step` (default 64) samples of the full
 1080p frame of `scenes/xml/vader_wfpt_1080p.xml` (BASELINE config 1: vader geometry, 320k triangles, 2 area
 lights, thin lens, 16 bounces; the textures / environment map of the upstream scene are not shipped and are
 removed).  rays = primary + closest-hit + shadow traversals, counted on the device.
@@ -328,12 +328,13 @@ def run_reference(args, scene, workload):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=16)  # x 64 samples per step = the 1024 spp of BASELINE config 1
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default=None)
-    ap.add_argument("--spp-per-step", type=int, default=16)
-    ap.add_argument("--traversal", type=int, default=None, help="traversal mode (default: the library's; modes the scene does not allow are replaced)")
+    ap.add_argument("--spp-per-step", type=int, default=64)
+    ap.add_argument("--traversal", type=int, default=None, help="traversal mode (default: the library's automatic choice between the ordered per-thread "
+                    "traversal, 2, and the stream traversal, 7, made from the device times of the warm-up steps; modes the scene does not allow are replaced)")
     ap.add_argument("--pipeline", type=int, default=None)
     ap.add_argument("--no-extras", action="store_true", help="skip the dropin / megakernel-rules legs (and the reference arm's megakernel run)")
     ap.add_argument("--no-balance", action="store_true", help="tile split with static row bands")
@@ -372,7 +373,7 @@ def main():
         r.set_option("traversal", args.traversal)
     if args.pipeline is not None:
         r.set_option("pipeline", args.pipeline)
-    traversal, pipeline = int(r.get_option("traversal")), int(r.get_option("pipeline"))
+    pipeline = int(r.get_option("pipeline"))
     r.set_option("kernel_timing", 1)
     from cuda_pt_b200.distributed import DistributedRenderer
     tiles = args.split == "tiles" and world > 1
@@ -410,6 +411,7 @@ def main():
     t_wall = time.perf_counter() - t_wall
     ms = e0.elapsed_time(e1)
     rows_final = list(dr.rows) if tiles else None
+    traversal, traversal_auto = int(r.get_option("traversal")), int(r.get_option("traversal_auto")) == 1  # (automatic: decided during the warm-up steps)
     clk = clocks.stop()
     st1, kt1 = r.stats(), r.kernel_times()
     rays = st1["rays"] - st0["rays"]
@@ -521,7 +523,7 @@ def main():
     if world == 1 and not args.no_extras and "vpt" not in workload:
         def leg(rr, steps):
             rr.set_option("samples_in_flight", S)
-            rr.render_batch(2 * S, False)
+            rr.render_batch(3 * S, False)  # warm-up; the automatic traversal choice needs three batches
             a = rr.stats()
             rr.render_batch(steps * S, False)
             rr.sync()
@@ -586,7 +588,9 @@ def main():
                       "steady_state_note": f"{K} steps x {step_spp} spp = {K * step_spp} spp timed (a steady-state rate; BASELINE's 1024 spp is the same loop run longer)",
                       "l2_note": f"path-state pool {S * W * H * 92 / 1e6:.0f} MB per step >> 126 MB L2 (no flush needed)",
                       "traversal": {0: "ordered pair-node", 1: "reference DFS order", 2: "ordered pair-node, 256-bit node loads", 3: "ordered, warp-vote",
-                                    4: "warp-cooperative, wide layout"}.get(traversal, str(traversal)),
+                                    4: "warp-cooperative, wide layout", 5: "per thread, 4-ary wide layout", 6: "per thread, deferred leaves + refill",
+                                    7: "stream (deferred leaves, async ray fetch, epilogue per chunk)"}.get(traversal, str(traversal))
+                                   + (" [chosen automatically from the warm-up steps]" if traversal_auto else ""),
                       "pipeline": ({0: "volumetric megakernel", 1: "volumetric wavefront over slot queues"}.get(pipeline, "volumetric wavefront, dense path records")
                                    if "vpt" in workload else
                                    {0: "fused", 1: "split shadow kernel", 2: "dynamic-fetch traversal", 3: "deferred NEE", 4: "deferred NEE + dynamic fetch",

@@ -259,8 +259,8 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
         if (k == "samples_in_flight")
             r->impl->set_samples_in_flight(int(value));
         else if (k == "traversal") {
-            if (value < 0 || value > 7)
-                throw std::runtime_error("traversal must be 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads), 3 (warp vote), 4 "
+            if (value < -1 || value > 7)
+                throw std::runtime_error("traversal must be -1 (automatic: 2 or 7, whichever is faster on the scene), 0 (ordered), 1 (reference dfs order), 2 (ordered, 256-bit node loads), 3 (warp vote), 4 "
                                          "(warp-cooperative, wide layout), 5 (per thread, 4-ary wide layout), 6 (per thread, deferred leaves + lane refill) "
                                          "or 7 (stream: 6 with an asynchronous ray-fetch pipeline and the epilogue in its own kernel)");
             r->impl->set_traversal(int(value)); // modes the scene does not allow are replaced (see Renderer::set_traversal)
@@ -272,6 +272,8 @@ int cpt_b200_set_option(cpt_b200_renderer *r, const char *key, int64_t value) {
             r->impl->set_stream(-1, -1, int(value), -1);
         } else if (k == "sq_blocks") {
             r->impl->set_stream(-1, -1, -1, int(value));
+        } else if (k == "sq_shadow") {
+            r->impl->set_stream_shadow(value != 0);
         } else if (k == "coop_flush") {
             r->impl->set_coop(int(value), int(cpt_b200_get_option(r, "coop_slab")));
         } else if (k == "coop_slab") {
@@ -322,6 +324,8 @@ int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key) {
         return r->impl->pipeline();
     if (k == "traversal")
         return r->impl->traversal();
+    if (k == "traversal_auto")
+        return r->impl->traversal_is_auto() ? 1 : 0;
     if (k == "sq_refill")
         return r->impl->stream_knob(0);
     if (k == "sq_flush")
@@ -330,6 +334,8 @@ int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key) {
         return r->impl->stream_knob(2);
     if (k == "sq_blocks")
         return r->impl->stream_knob(3);
+    if (k == "sq_shadow")
+        return r->impl->stream_shadow() ? 1 : 0;
     if (k == "coop_flush")
         return r->impl->coop_flush();
     if (k == "coop_slab")

@@ -173,10 +173,11 @@ PT_DEV void camera_ray(const CameraPOD &cam, int px, int py, Rng &rng, V3 &o, V3
 
 // ---- triangle test on the 48 B precomputed-adjoint layout
 // (reference: src/core/primitives.cuh:57-87, layout src/core/aos.cuh:113-164) ----
-// CPTB_TRI64 (default 1): a triangle record is padded from 48 to 64 bytes and read with two 256-bit loads instead of three
-// 128-bit ones - the traversal kernels are bound by L1 wavefronts (one per load instruction and line), not by bytes
+// CPTB_TRI64 (build knob, default 0): a triangle record padded from 48 to 64 bytes and read with two 256-bit loads instead of three
+// 128-bit ones.  Measured on vader 1080p (profiles/r02_stream_experiments.md): traversal kernels unchanged (3.31 -> 3.32 / 1.52 ->
+// 1.52 ms per sample), k_shade 0.95 -> 1.03 (its emitter sampling reads the records too, and the L2-pinned arena grows by 5 MB).
 #ifndef CPTB_TRI64
-#define CPTB_TRI64 1
+#define CPTB_TRI64 0
 #endif
 constexpr int kTriStride = CPTB_TRI64 ? 4 : 3;
 PT_DEV void load_triangle(const float4 *__restrict__ tris, int index, float4 &p0, float4 &v1, float4 &v2) {

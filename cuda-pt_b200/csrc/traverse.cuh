@@ -177,7 +177,8 @@ PT_DEV void load_pair_node(const float4 *__restrict__ wnodes, int cur, float4 &a
 
 // variant with one inner-or-leaf step per loop iteration (lanes alternate freely between the two paths)
 // CPTB_STACK64 (default 1): one 8-byte stack entry {ref, bits(t)} per push / pop (STL.64 / LDL.64) instead of two 4-byte arrays -
-// half the local-memory instructions and L1 wavefronts of the stack traffic (27 % of k_trace<2>'s L1 wavefronts, profiles/r02_*)
+// half the local-memory instructions of the stack traffic (27 % of k_trace<2>'s L1 wavefronts).  Measured: k_trace 3.31 -> 3.28 ms per
+// sample (profiles/r02_stream_experiments.md)
 #ifndef CPTB_STACK64
 #define CPTB_STACK64 1
 #endif

@@ -1036,29 +1036,48 @@ __global__ void __launch_bounds__(kBlock, DQ_MIN_BLOCKS)
 // traversal=7 ("stream"): traversal=6's walk (per-thread ordered traversal, leaves deferred into a 2-entry pending list, warp-wide
 // triangle phases, idle lanes refilled) with everything that made traversal=6 wait on memory taken out of the walk:
 //  * ray fetch is an asynchronous pipeline per warp.  One stage per pass through the main loop: reserve an aligned 32-ray
-//    chunk of the queue (atomic), read its slot ids, start `cp.async` gathers of the ray records into the warp's ring in shared
-//    memory, and - a pass later, when they have landed - run the per-ray prologue (1/d, the fp16 cached phase of
+//    chunk of the queue (atomic), `cp.async` its slot ids into shared memory, `cp.async`-gather the ray records into the warp's
+//    ring in shared memory, and - a pass later, when they have landed - run the per-ray prologue (1/d, the fp16 cached phase of
 //    tracing_func.cuh:124-142, rays that need no traversal answered on the spot) with one ray per lane at 32 of 32 lanes and
 //    compact the rays that do need a traversal to the ring's tail.  The walk never waits for global memory on behalf of a new
 //    ray: a lane whose ray is done takes the next one from shared memory.
-//  * no epilogue in the walk: a finished ray stores its hit record (closest hit) or one visibility byte (shadow ray) and is
-//    gone.  Interaction, Russian roulette and compaction run in k_resolve, the radiance swap in k_shadow_finish, both in queue
-//    order at 32 of 32 lanes - so the next bounce's queue keeps its slot order (traversal=6 lost it and k_shade paid).
+//  * the epilogue runs per CHUNK, in queue order, at 32 of 32 lanes: a finished ray stores its hit record and counts its chunk
+//    down; when the last ray of a chunk is done the warp runs interaction, Russian roulette and compaction for the chunk's 32
+//    queue entries (stream_resolve_chunk = k_trace's epilogue).  The next bounce's queue therefore keeps the slot order the
+//    shading kernel's gathers rely on (traversal=6 retired rays one by one and k_shade paid for it).  Shadow rays store one
+//    visibility byte; the radiance swap runs in k_shadow_finish.
 // Same boxes, same tests, same tie rule as closest_hit_ordered; deferral only delays updates of the closest distance.
-// Dynamic shared memory: cached nodes + per warp a ring of SQ_RING rays {o, tmax}{d, start} + id (36 B per ray).
+// The cold stages are out-of-line functions on purpose: inlined, their registers make ptxas spill the walk's loop-carried state.
+// Build knobs: SQ_REGSTATE (the walking ray's cold state in registers, 64 per thread, instead of shared memory), SQ_RING, SQ_MIN_BLOCKS,
+// SQ_INLINE_RESOLVE (0: hit records only, k_resolve does the epilogue as its own launch).
 // ------------------------------------------------------------------------------------------------
+#ifndef SQ_REGSTATE
+#define SQ_REGSTATE 1
+#endif
+#ifndef SQ_INLINE_RESOLVE
+#define SQ_INLINE_RESOLVE 1
+#endif
 #ifndef SQ_MIN_BLOCKS
-#define SQ_MIN_BLOCKS 10
+#define SQ_MIN_BLOCKS (SQ_REGSTATE ? 9 : 10)
 #endif
 #ifndef SQ_RING
 #define SQ_RING 32
 #endif
 constexpr int kRing = SQ_RING; // ring entries per warp: a power of two, >= 32
 static_assert((kRing & (kRing - 1)) == 0 && kRing >= 32 && kRing <= 1024, "SQ_RING must be a power of two in [32, 1024]");
-constexpr int kLaneWords = 13; // per-lane words kept in shared memory: fetch register, o, d, id, hu, hv, hprim, pend0, pend1
+#ifndef SQ_SMEM_STACK
+#define SQ_SMEM_STACK 12
+#endif
+#ifndef SQ_SHADOW_DEFER
+#define SQ_SHADOW_DEFER 1
+#endif
+constexpr int kSqSmemStack = SQ_SMEM_STACK; // closest-hit stack entries per lane kept in shared memory (the rest in local memory)
+constexpr int kChunkTab = 16;                      // chunks a warp may have open (rays walking or waiting in the ring)
+constexpr int kStartBits = 27, kStartMask = (1 << kStartBits) - 1; // ring word: cached-phase start index | chunk-table entry << 27
+constexpr int kLaneWords = SQ_REGSTATE ? 1 : 14;   // per-lane words kept in shared memory (enum below)
 constexpr size_t kLaneBytes = size_t((kLaneWords * 32 * 4 + 15) / 16 * 16);
-constexpr size_t kRingBytes = kLaneBytes + size_t(kRing) * 36;
-enum { W_FREG = 0, W_OX, W_OY, W_OZ, W_DX, W_DY, W_DZ, W_ID, W_HU, W_HV, W_PRIM, W_PEND0, W_PEND1 };
+constexpr size_t kRingBytes = kLaneBytes + size_t(kRing) * 36 + size_t(kChunkTab) * 8;
+enum { W_FREG = 0, W_OX, W_OY, W_OZ, W_DX, W_DY, W_DZ, W_ID, W_HU, W_HV, W_PRIM, W_PEND0, W_PEND1, W_CHUNK };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned s = unsigned(__cvta_generic_to_shared(smem_dst));
@@ -1071,35 +1090,73 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// warp-uniform state of a warp's fetch pipeline, packed so that it crosses the (out-of-line) stage function in two registers
+// what the out-of-line stages need, once per CTA in shared memory (passing the kernel's parameter struct by reference would make
+// nvcc copy it to local memory and route the walk's own accesses through that copy)
+struct StreamCtx {
+    DevScene sc;
+    PathState st;
+    RayBufs rb;
+    const uint32_t *queue;
+    uint32_t *q_next;
+    int *q_next_count;
+    unsigned char *vis;
+    int count, bounce, pt_rules, pad;
+};
+constexpr size_t kCtxBytes = (sizeof(StreamCtx) + 15) / 16 * 16;
+
+// warp-uniform state of a warp's fetch pipeline, packed so that it crosses the stage function in two registers
 struct StreamFetch {
     uint32_t ht;  // head | tail << 16: ring[head, tail) = rays ready to walk (16-bit wrapping counters, index & (kRing - 1))
-    uint32_t ctl; // stage (2 bits) | rays in the chunk in flight << 2 | queue exhausted << 8
+    uint32_t ctl; // stage (2 bits) | rays of the chunk in flight << 2 | queue exhausted << 8 | chunk-table entry << 9
     __device__ int head() const { return int(ht & 0xffffu); }
     __device__ int tail() const { return int(ht >> 16); }
     __device__ int avail() const { return (tail() - head()) & 0xffff; }
     __device__ int stage() const { return int(ctl & 3u); }
     __device__ int fcount() const { return int((ctl >> 2) & 63u); }
     __device__ bool more() const { return (ctl & 256u) == 0u; }
+    __device__ int entry() const { return int((ctl >> 9) & 15u); }
 };
 
-// One stage of the fetch pipeline (see k_traverse_stream).  Out of line on purpose: the per-ray prologue needs ~25 registers
-// of its own, and inlined into the walk it makes ptxas spill the walk's loop-carried state; across a call that state sits in
-// callee-saved registers.  Must be called by the full warp.
+// k_trace's epilogue for the 32 queue entries [fbase, fbase + 32) of one finished chunk (see k_resolve).  Full warp.
+__device__ __noinline__ void stream_resolve_chunk(const StreamCtx *ctx, const uint4 *s_cached, int fbase) {
+    const int lane = threadIdx.x & 31;
+    const int i = fbase + lane;
+    bool alive = false;
+    uint32_t slot = 0;
+    if (i < ctx->count) {
+        PathState st = ctx->st;
+        slot = ctx->queue[i];
+        const float4 rd = st.ray_d[slot];
+        const uint32_t tag = __float_as_uint(rd.w) & 0x50000000u; // reset(): clear hit flag and hit index
+        if (tag & TAG_ACTIVE) {
+            float4 h = ctx->rb.hit[slot];
+            if (__float_as_int(h.w) == kPrimOddRay) { // a ray with a zero direction component, left to us by the prologue
+                const Hit hh = closest_hit_ordered<true, false>(ctx->sc, s_cached, xyz(st.ray_o[slot]), xyz(rd));
+                h = make_float4(hh.t, hh.u, hh.v, __int_as_float(hh.prim));
+            }
+            alive = resolve_hit(ctx->sc, st, slot, tag, xyz(rd), h.x, h.y, h.z, __float_as_int(h.w), ctx->bounce, ctx->pt_rules);
+        }
+    }
+    warp_push(ctx->q_next, ctx->q_next_count, alive, slot, lane);
+}
+
+// One stage of the fetch pipeline.  Must be called by the full warp.  `chunk`: lane 0 holds the chunk number reserved a pass ago.
 template <bool SHADOW>
-__device__ __noinline__ StreamFetch stream_fetch_stage(StreamFetch f, int chunk, int num_cache, int num_nodes, const uint4 *s_cached, unsigned char *wbase,
-                                                       const float4 *__restrict__ src_o, const float4 *__restrict__ src_d, const uint32_t *__restrict__ queue,
-                                                       int count, unsigned char *__restrict__ vis, float4 *__restrict__ hit) {
+__device__ __noinline__ StreamFetch stream_fetch_stage(StreamFetch f, int chunk, const StreamCtx *ctx, const uint4 *s_cached, unsigned char *wbase) {
     const int lane = threadIdx.x & 31;
     uint32_t *freg = reinterpret_cast<uint32_t *>(wbase) + W_FREG * 32 + lane;
     float4 *ringA = reinterpret_cast<float4 *>(wbase + kLaneBytes); // o.xyz, tmax
-    float4 *ringB = ringA + kRing;                                  // d.xyz, bits(start)
+    float4 *ringB = ringA + kRing;                                  // d.xyz, bits(start | entry << 27)
     uint32_t *ringS = reinterpret_cast<uint32_t *>(ringB + kRing);   // slot (closest hit) / queue position (shadow)
+    int *tab_base = reinterpret_cast<int *>(ringS + kRing);
+    volatile int *tab_cnt = tab_base + kChunkTab;
     const int tail = f.tail(), stage = f.stage(), fcount = f.fcount();
+    constexpr bool kTable = !SHADOW && SQ_INLINE_RESOLVE;
     if (stage == 3) { // the chunk's ray records have landed at ring[tail .. tail + fcount): prologue, one ray per lane
         cp_async_wait_all();
         __syncwarp();
         const int pos = (tail + lane) & (kRing - 1);
+        const int num_cache = ctx->sc.num_cache, num_nodes = ctx->sc.num_nodes;
         bool trav = false;
         float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 1, 0);
         uint32_t rid = 0;
@@ -1116,18 +1173,18 @@ __device__ __noinline__ StreamFetch stream_fetch_stage(StreamFetch f, int chunk,
                 const float big = 1e28f;
                 if (!(fabsf(pinv.x) < big && fabsf(pinv.y) < big && fabsf(pinv.z) < big)) {
                     // (near-)zero direction component: needs the compare+select slab form.  Rare; marked here and traced per thread by
-                    // the companion kernel that reads the result anyway (k_shadow_finish / k_resolve)
+                    // the code that reads the result anyway (k_shadow_finish / the chunk epilogue)
                     if constexpr (SHADOW)
-                        vis[rid] = kVisOddRay;
+                        ctx->vis[rid] = kVisOddRay;
                     else
-                        hit[rid] = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(kPrimOddRay));
+                        ctx->rb.hit[rid] = make_float4(kMaxDist, 0.f, 0.f, __int_as_float(kPrimOddRay));
                 } else {
                     const int st0 = cached_entry(s_cached, num_cache, pinv, podiv, a.w, SHADOW ? num_nodes : 0);
                     if (SHADOW && st0 >= num_nodes) {
-                        vis[rid] = 1; // no cached frontier node on the way: unoccluded (tracing_func.cuh:49)
+                        ctx->vis[rid] = 1; // no cached frontier node on the way: unoccluded (tracing_func.cuh:49)
                     } else {
                         trav = true;
-                        b.w = __int_as_float(st0);
+                        b.w = __int_as_float(st0 | (kTable ? f.entry() << kStartBits : 0));
                     }
                 }
             }
@@ -1138,14 +1195,22 @@ __device__ __noinline__ StreamFetch stream_fetch_stage(StreamFetch f, int chunk,
             const int p = (tail + __popc(m & ((1u << lane) - 1u))) & (kRing - 1);
             ringA[p] = a, ringB[p] = b, ringS[p] = rid;
         }
+        if constexpr (kTable) {
+            const int e = f.entry();
+            if (lane == 0)
+                tab_cnt[e] = __popc(m); // 0: nothing of this chunk walks, its epilogue is due right away (the caller looks at the table)
+        }
         __syncwarp();
         f.ht = (f.ht & 0xffffu) | (uint32_t((tail + __popc(m)) & 0xffff) << 16);
         f.ctl &= ~255u; // stage 0
+        if (kTable && m == 0u)
+            f.ctl |= 0x2000u;
     } else if (stage == 2) { // slot ids are here (shared memory): start the gathers of the ray records
         cp_async_wait_all();
         if (lane < fcount) {
             const int pos = (tail + lane) & (kRing - 1);
             const uint32_t slot = *freg;
+            const float4 *src_o = SHADOW ? ctx->rb.sh_o : ctx->st.ray_o, *src_d = SHADOW ? ctx->rb.sh_d : ctx->st.ray_d;
             cp_async16(ringA + pos, src_o + slot);
             cp_async16(ringB + pos, src_d + slot);
             if constexpr (!SHADOW)
@@ -1153,55 +1218,134 @@ __device__ __noinline__ StreamFetch stream_fetch_stage(StreamFetch f, int chunk,
         }
         cp_async_commit();
         f.ctl |= 3u;
-    } else { // stage 1: the chunk number is here (lane 0 of `chunk`, reserved by the caller a pass ago): fetch the slot ids
+    } else { // stage 1: the chunk number is here: fetch the slot ids
         const int fbase = __shfl_sync(0xffffffffu, chunk, 0) * 32;
+        const int count = ctx->count;
         if (fbase >= count) {
             f.ctl = 256u; // queue exhausted, stage 0
         } else {
+            int e = 0;
+            if constexpr (kTable) { // an entry of the warp's chunk table; none free: try again next pass
+                const unsigned free_mask = __ballot_sync(0xffffffffu, lane < kChunkTab && tab_cnt[lane & (kChunkTab - 1)] < 0);
+                if (free_mask == 0u)
+                    return f;
+                e = __ffs(free_mask) - 1;
+                if (lane == 0)
+                    tab_base[e] = fbase, tab_cnt[e] = 1 << 20; // open; the prologue sets the number of walking rays
+            }
             const int n = min(32, count - fbase);
             if (lane < n) {
-                cp_async4(freg, queue + fbase + lane);
+                cp_async4(freg, ctx->queue + fbase + lane);
                 if constexpr (SHADOW)
                     ringS[(tail + lane) & (kRing - 1)] = uint32_t(fbase + lane);
             }
             cp_async_commit();
-            f.ctl = 2u | (uint32_t(n) << 2);
+            f.ctl = 2u | (uint32_t(n) << 2) | (uint32_t(e) << 9);
         }
     }
     return f;
 }
 
+// epilogues of the chunks in `done` (bit e = chunk-table entry e).  Heavy (uses the whole register file): the caller parks its
+// walk state in local memory around this call (see k_traverse_stream), so that ptxas keeps that state in registers elsewhere.
+__device__ __noinline__ void stream_resolve_done(unsigned done, const StreamCtx *ctx, const uint4 *s_cached, unsigned char *wbase) {
+    const int lane = threadIdx.x & 31;
+    int *tab_base = reinterpret_cast<int *>(wbase + kLaneBytes + size_t(kRing) * 36);
+    volatile int *tab_cnt = tab_base + kChunkTab;
+    while (done) {
+        const int e = __ffs(done) - 1;
+        done &= done - 1u;
+        stream_resolve_chunk(ctx, s_cached, tab_base[e]);
+        __syncwarp();
+        if (lane == 0)
+            tab_cnt[e] = -1;
+    }
+    __syncwarp();
+}
+
 template <bool SHADOW>
 __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
     k_traverse_stream(DevScene sc, PathState st, RayBufs rb, const uint32_t *__restrict__ queue, const int *__restrict__ q_count, int *work,
-                      unsigned char *__restrict__ vis, int kRefill, int kFlush, int kSteps) {
+                      unsigned char *__restrict__ vis, uint32_t *q_next, int *q_next_count, int bounce, int pt_rules, int kRefill, int kFlush, int kSteps) {
     extern __shared__ uint4 s_cached[];
-    stage_cached_nodes(sc, s_cached);
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_cached + sc.num_cache) + size_t(threadIdx.x >> 5) * kRingBytes;
-    // the walking ray's cold state, word w of lane l at lsf[w * 32] (conflict-free): what the box tests do not need stays out of
-    // the register file - o, d (triangle tests), id / hu / hv / hprim (retire), the two pending leaves
-    float *lsf = reinterpret_cast<float *>(wbase) + lane;
-    int *lsi = reinterpret_cast<int *>(lsf);
+    StreamCtx *ctx = reinterpret_cast<StreamCtx *>(s_cached + sc.num_cache);
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(ctx) + kCtxBytes + size_t(threadIdx.x >> 5) * kRingBytes;
+    if (threadIdx.x == 0) {
+        ctx->sc = sc, ctx->st = st, ctx->rb = rb, ctx->queue = queue, ctx->q_next = q_next, ctx->q_next_count = q_next_count, ctx->vis = vis;
+        ctx->count = *q_count, ctx->bounce = bounce, ctx->pt_rules = pt_rules, ctx->pad = 0;
+    }
     const float4 *ringA = reinterpret_cast<const float4 *>(wbase + kLaneBytes);
     const float4 *ringB = ringA + kRing;
     const uint32_t *ringS = reinterpret_cast<const uint32_t *>(ringB + kRing);
-    const int count = *q_count;
+    int *tab_base = reinterpret_cast<int *>(const_cast<uint32_t *>(ringS) + kRing);
+    volatile int *tab_cnt = tab_base + kChunkTab;
+    if (lane < kChunkTab)
+        tab_cnt[lane] = -1; // all entries free
+    stage_cached_nodes(sc, s_cached); // (ends with __syncthreads: the context and the tables are visible)
+    constexpr bool kTable = !SHADOW && SQ_INLINE_RESOLVE;
+    // the walking ray's cold state - what the box tests do not need: o, d (triangle tests), id / hu / hv / hprim / chunk (retire),
+    // the two pending leaves
+#if SQ_REGSTATE
+    V3 ro{0, 0, 0}, rd{0, 0, 1};
+    float rhu = 0.f, rhv = 0.f;
+    int rid = 0, rprim = -1, rpend0 = 0, rpend1 = 0, rchunk = 0;
+#else
+    // word w of lane l at lsf[w * 32] (conflict-free)
+    float *lsf = reinterpret_cast<float *>(wbase) + lane;
+    int *lsi = reinterpret_cast<int *>(lsf);
+#endif
     // ---- walk state, one ray per lane
-    uint2 stack[SHADOW ? 1 : kStackSize]; // closest hit: {ref, bits(t)}, one 8-byte access per push / pop
-    int stack_ref[SHADOW ? kStackSize : 1];
+    uint2 stack[SHADOW ? 1 : kStackSize - kSqSmemStack]; // closest hit: {ref, bits(t)}, one 8-byte access per push / pop
+    // SQ_SMEM_STACK: the first entries of every lane's stack in shared memory ([level][thread]: conflict-free, one or two wavefronts per
+    // warp instruction whatever the lanes' depths, and 32 walking lanes per warp no longer thrash L1 with their stacks)
+    uint2 *sstack = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(ctx) + kCtxBytes + size_t(kBlock / 32) * kRingBytes) + threadIdx.x;
+    int stack_ref[SHADOW ? kStackSize - kSqSmemStack : 1];
+    int *sstack_ref = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(ctx) + kCtxBytes + size_t(kBlock / 32) * kRingBytes) + threadIdx.x;
     int sp = 0, cur = kTraversalDone, start = 0, npend = 0;
     V3 inv_d{0, 0, 0}, o_div{0, 0, 0};
     float ht = kMaxDist;
     bool active = false; // (shadow rays: ht < 0 marks an occluded ray)
     StreamFetch f{0u, 0u};
     int pending = 0; // lane 0: the chunk number reserved for the fetch pipeline's next round
+    unsigned done = 0u; // chunk-table entries whose last ray retired in the previous pass
     const float inf = __int_as_float(0x7f800000);
     while (true) {
+        // ---------------- epilogues of the chunks that finished in the previous pass (about once per 32 rays)
+        if constexpr (kTable) {
+            if (done != 0u) {
+                // park the walk state in local memory around the call: the callee needs the whole register file, and values that
+                // live across it would be spilled by ptxas - with reloads inside the walk loop
+                volatile float park[24];
+                park[0] = inv_d.x, park[1] = inv_d.y, park[2] = inv_d.z, park[3] = o_div.x, park[4] = o_div.y, park[5] = o_div.z, park[6] = ht;
+                park[7] = __int_as_float(sp), park[8] = __int_as_float(cur), park[9] = __int_as_float(start);
+                park[10] = __int_as_float(npend | (active ? 4 : 0));
+#if SQ_REGSTATE
+                park[11] = ro.x, park[12] = ro.y, park[13] = ro.z, park[14] = rd.x, park[15] = rd.y, park[16] = rd.z, park[17] = rhu, park[18] = rhv;
+                park[19] = __int_as_float(rid), park[20] = __int_as_float(rprim), park[21] = __int_as_float(rpend0), park[22] = __int_as_float(rpend1);
+                park[23] = __int_as_float(rchunk);
+#endif
+                stream_resolve_done(done, ctx, s_cached, wbase);
+                done = 0u;
+                inv_d = V3{park[0], park[1], park[2]}, o_div = V3{park[3], park[4], park[5]}, ht = park[6];
+                sp = __float_as_int(park[7]), cur = __float_as_int(park[8]), start = __float_as_int(park[9]);
+                const int fl = __float_as_int(park[10]);
+                npend = fl & 3, active = (fl & 4) != 0;
+#if SQ_REGSTATE
+                ro = V3{park[11], park[12], park[13]}, rd = V3{park[14], park[15], park[16]}, rhu = park[17], rhv = park[18];
+                rid = __float_as_int(park[19]), rprim = __float_as_int(park[20]), rpend0 = __float_as_int(park[21]), rpend1 = __float_as_int(park[22]);
+                rchunk = __float_as_int(park[23]);
+#endif
+            }
+        }
         // ---------------- fetch pipeline: one stage per pass
         if (f.stage() != 0) {
-            f = stream_fetch_stage<SHADOW>(f, pending, sc.num_cache, sc.num_nodes, s_cached, wbase, SHADOW ? rb.sh_o : st.ray_o, SHADOW ? rb.sh_d : st.ray_d, queue, count, vis, rb.hit);
+            f = stream_fetch_stage<SHADOW>(f, pending, ctx, s_cached, wbase);
+            if (kTable && (f.ctl & 0x2000u)) { // a chunk without walking rays: its epilogue runs at the top of the next pass
+                f.ctl &= ~0x2000u;
+                done |= __ballot_sync(0xffffffffu, lane < kChunkTab && tab_cnt[lane & (kChunkTab - 1)] == 0);
+            }
         } else if (f.more() && f.avail() <= kRing - 32) { // room for a chunk: reserve one; the number is used a pass later
             if (lane == 0) // atom.inc, not atom.add: ptxas turns an add into its warp-aggregated form, whose shuffle waits for the result here
                 asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(pending) : "l"(work) : "memory");
@@ -1218,12 +1362,18 @@ __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
                 if (!active && rank < take) {
                     const int p = (f.head() + rank) & (kRing - 1);
                     const float4 a = ringA[p], b = ringB[p];
+                    const int sw = __float_as_int(b.w);
+#if SQ_REGSTATE
+                    rid = int(ringS[p]), ro = xyz(a), rd = xyz(b);
+                    rhu = rhv = 0.f, rprim = -1, rchunk = sw >> kStartBits;
+#else
                     lsi[W_ID * 32] = int(ringS[p]);
                     lsf[W_OX * 32] = a.x, lsf[W_OY * 32] = a.y, lsf[W_OZ * 32] = a.z;
                     lsf[W_DX * 32] = b.x, lsf[W_DY * 32] = b.y, lsf[W_DZ * 32] = b.z;
                     if constexpr (!SHADOW)
-                        lsf[W_HU * 32] = 0.f, lsf[W_HV * 32] = 0.f, lsi[W_PRIM * 32] = -1;
-                    ht = a.w, start = __float_as_int(b.w);
+                        lsf[W_HU * 32] = 0.f, lsf[W_HV * 32] = 0.f, lsi[W_PRIM * 32] = -1, lsi[W_CHUNK * 32] = sw >> kStartBits;
+#endif
+                    ht = a.w, start = sw & kStartMask;
                     inv_d = rcp3(xyz(b)), o_div = xyz(a) * inv_d;
                     npend = 0, sp = 0;
                     cur = sc.wroot, active = true;
@@ -1233,7 +1383,7 @@ __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
             }
         }
         if (act == 0u) {
-            if (!f.more() && f.stage() == 0 && f.avail() == 0)
+            if (!f.more() && f.stage() == 0 && f.avail() == 0 && done == 0u)
                 break;
             continue; // nothing to walk yet: let the fetch pipeline advance
         }
@@ -1251,10 +1401,19 @@ __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
                     const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
                     if (h0 && h1) {
                         const bool swap = !SHADOW && t1 < t0;
-                        if constexpr (SHADOW)
-                            stack_ref[sp] = r1;
-                        else
-                            stack[sp] = make_uint2(uint32_t(swap ? r0 : r1), __float_as_uint(swap ? t0 : t1));
+                        if constexpr (SHADOW) {
+                            if (kSqSmemStack > 0 && sp < kSqSmemStack)
+                                sstack_ref[sp * kBlock] = r1;
+                            else
+                                stack_ref[sp - kSqSmemStack] = r1;
+                        } else
+                        {
+                            const uint2 e = make_uint2(uint32_t(swap ? r0 : r1), __float_as_uint(swap ? t0 : t1));
+                            if (kSqSmemStack > 0 && sp < kSqSmemStack)
+                                sstack[sp * kBlock] = e;
+                            else
+                                stack[sp - kSqSmemStack] = e;
+                        }
                         ++sp;
                         cur = swap ? r1 : r0;
                     } else if (h0 || h1) {
@@ -1262,8 +1421,32 @@ __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
                     } else {
                         pop = true;
                     }
+                } else if (SHADOW && !SQ_SHADOW_DEFER) { // any-hit, leaves tested where they are found (an occluder ends the ray at once)
+#if SQ_REGSTATE
+                    const V3 o = ro, d = rd;
+#else
+                    const V3 o{lsf[W_OX * 32], lsf[W_OY * 32], lsf[W_OZ * 32]}, d{lsf[W_DX * 32], lsf[W_DY * 32], lsf[W_DZ * 32]};
+#endif
+                    const int packed = ~cur, base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+                    bool occl = false;
+                    for (int idx = base; idx < base + cnt; idx++) {
+                        float u, v;
+                        const float dist = hit_triangle(sc.tris, idx, o, d, u, v, ht);
+                        if (dist > kEps)
+                            occl = true;
+                    }
+                    if (occl)
+                        ht = -1.f, sp = 0;
+                    pop = true;
                 } else { // a leaf: remember it, go on with the stack
+#if SQ_REGSTATE
+                    if (npend == 0)
+                        rpend0 = cur;
+                    else
+                        rpend1 = cur;
+#else
                     lsi[(W_PEND0 + npend) * 32] = cur;
+#endif
                     ++npend;
                     pop = true;
                 }
@@ -1272,10 +1455,10 @@ __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
                     while (sp > 0) {
                         --sp;
                         if constexpr (SHADOW) {
-                            cur = stack_ref[sp];
+                            cur = (kSqSmemStack > 0 && sp < kSqSmemStack) ? sstack_ref[sp * kBlock] : stack_ref[sp - kSqSmemStack];
                             break;
                         } else {
-                            const uint2 e = stack[sp];
+                            const uint2 e = (kSqSmemStack > 0 && sp < kSqSmemStack) ? sstack[sp * kBlock] : stack[sp - kSqSmemStack];
                             if (__uint_as_float(e.y) < ht) {
                                 cur = int(e.x);
                                 break;
@@ -1291,8 +1474,13 @@ __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
         if (__popc(have) >= kFlush || __any_sync(0xffffffffu, blocked)) {
             if (active && npend > 0) {
                 --npend;
+#if SQ_REGSTATE
+                const int packed = ~(npend == 1 ? rpend1 : rpend0), base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
+                const V3 o = ro, d = rd;
+#else
                 const int packed = ~lsi[(W_PEND0 + npend) * 32], base = packed & kLeafBaseMask, cnt = packed >> kLeafCountShift;
                 const V3 o{lsf[W_OX * 32], lsf[W_OY * 32], lsf[W_OZ * 32]}, d{lsf[W_DX * 32], lsf[W_DY * 32], lsf[W_DZ * 32]};
+#endif
                 if constexpr (SHADOW) {
                     bool occl = false;
                     for (int idx = base; idx < base + cnt; idx++) {
@@ -1304,8 +1492,13 @@ __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
                     if (occl) // occluded: done
                         ht = -1.f, cur = kTraversalDone, npend = 0, sp = 0;
                 } else {
+#if SQ_REGSTATE
+                    float bu = rhu, bv = rhv;
+                    int hprim = rprim;
+#else
                     float bu = 0.f, bv = 0.f;
                     int hprim = lsi[W_PRIM * 32];
+#endif
                     bool changed = false;
                     for (int idx = base; idx < base + cnt; idx++) {
                         float u, v;
@@ -1317,19 +1510,43 @@ __global__ void __launch_bounds__(kBlock, SQ_MIN_BLOCKS)
                         hprim = better ? idx : hprim;
                         changed |= better;
                     }
+#if SQ_REGSTATE
+                    rhu = bu, rhv = bv, rprim = hprim;
+                    (void)changed;
+#else
                     if (changed)
                         lsf[W_HU * 32] = bu, lsf[W_HV * 32] = bv, lsi[W_PRIM * 32] = hprim;
+#endif
                 }
             }
         }
         // ---------------- retire
-        if (active && cur == kTraversalDone && npend == 0) {
+        const bool retire = active && cur == kTraversalDone && npend == 0;
+        if (retire) {
             active = false;
+#if SQ_REGSTATE
+            const uint32_t id = uint32_t(rid);
+            const float hu = rhu, hv = rhv;
+            const int hprim = rprim, chunk_e = rchunk;
+#else
             const uint32_t id = uint32_t(lsi[W_ID * 32]);
-            if constexpr (SHADOW)
+            const float hu = SHADOW ? 0.f : lsf[W_HU * 32], hv = SHADOW ? 0.f : lsf[W_HV * 32];
+            const int hprim = SHADOW ? 0 : lsi[W_PRIM * 32], chunk_e = SHADOW ? 0 : lsi[W_CHUNK * 32];
+#endif
+            if constexpr (SHADOW) {
                 vis[id] = ht < 0.f ? 0 : 1;
-            else
-                rb.hit[id] = make_float4(ht, lsf[W_HU * 32], lsf[W_HV * 32], __int_as_float(lsi[W_PRIM * 32]));
+            } else {
+                rb.hit[id] = make_float4(ht, hu, hv, __int_as_float(hprim));
+                if constexpr (kTable)
+                    atomicSub(const_cast<int *>(tab_cnt) + chunk_e, 1);
+            }
+            (void)hu, (void)hv, (void)hprim, (void)chunk_e;
+        }
+        if constexpr (kTable) {
+            if (__any_sync(0xffffffffu, retire)) { // chunks whose last ray just finished: their epilogue runs at the top of the next pass
+                __syncwarp();
+                done |= __ballot_sync(0xffffffffu, lane < kChunkTab && tab_cnt[lane & (kChunkTab - 1)] == 0);
+            }
         }
     }
 }
@@ -2488,6 +2705,7 @@ struct Renderer::Impl {
     DevBuf<float4> sh_o, sh_d, hit; // dynamic-fetch pipeline: shadow rays and hit records
     DevBuf<unsigned char> vis;      // stream traversal: one visibility byte per shadow-queue entry
     int stream_blocks[2] = {0, 0};  // stream traversal: resident CTAs per SM of k_traverse_stream<false / true>
+    bool auto_batch = false;        // the batch in flight takes part in the automatic traversal choice
     DevBuf<float4> vtr;             // volumetric wavefront: march results
     DevBuf<uint2> vstate;           // volumetric wavefront: nested-volume stack + event word
     DevBuf<uint32_t> queue3;        // volumetric wavefront: fourth queue (hit / trace ping-pong, shade, march)
@@ -2889,6 +3107,8 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         set_stream(-1, atoi(e), -1, -1);
     if (const char *e = getenv("CPTB200_SQ_STEPS"))
         set_stream(-1, -1, atoi(e), -1);
+    if (const char *e = getenv("CPTB200_SQ_SHADOW"))
+        sq_shadow_ = atoi(e) != 0;
     if (const char *e = getenv("CPTB200_SQ_BLOCKS"))
         set_stream(-1, -1, -1, atoi(e));
     if (const char *e = getenv("CPTB200_DQ_FLUSH"))
@@ -2961,7 +3181,7 @@ void Renderer::set_coop(int flush_lanes, int slab_nodes) {
     // per-thread traversal of the same layout (traversal=5): 4-ary records, per-thread stack of kStackSize entries
     wide4_ok_ = G == 4 && ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0 && m.wide_max_stack_all + 1 <= kWideStack;
     // stream traversal (traversal=7): the pair layout per thread with deferred leaves - the same restriction on clipped references
-    stream_ok_ = ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0;
+    stream_ok_ = ordered_ok_ && m.clipped_refs == 0 && m.nesting_violations == 0 && m.dev.num_nodes < (1 << kStartBits);
 }
 
 void Renderer::set_stream(int refill, int flush, int steps, int blocks) {
@@ -2975,9 +3195,29 @@ void Renderer::set_stream(int refill, int flush, int steps, int blocks) {
         sq_blocks_ = std::min(32, blocks);
 }
 
+void Renderer::auto_observe(float ms, int samples) {
+    // called after every synchronised batch: the first full-size batch warms up, the second is timed with the ordered traversal,
+    // the third with the stream traversal; from the fourth on the faster one runs (see launch_batch)
+    if (!impl_->auto_batch || auto_state_ >= 3 || samples <= 0)
+        return;
+    if (auto_state_ == 0 || samples != auto_samples_) {
+        auto_samples_ = samples, auto_state_ = 1;
+        return;
+    }
+    auto_ms_per_sample_[auto_state_ - 1] = ms / float(samples);
+    if (++auto_state_ == 3)
+        auto_choice_ = auto_ms_per_sample_[1] < 0.985f * auto_ms_per_sample_[0] ? 7 : 2;
+}
+
 void Renderer::set_traversal(int t) {
+    if (t == -1) {
+        auto_traversal_ = true, auto_state_ = 0, auto_choice_ = 2;
+        traversal_ = ordered_ok_ ? 2 : TRAVERSAL_DFS;
+        return;
+    }
     if (t < 0 || t > 7)
-        throw std::runtime_error("traversal must be 0..7");
+        throw std::runtime_error("traversal must be -1 (automatic) or 0..7");
+    auto_traversal_ = false;
     if (t == 6 && !ordered_ok_)
         t = TRAVERSAL_DFS;
     if (t == 7 && !stream_ok_)
@@ -2998,6 +3238,7 @@ void Renderer::set_samples_in_flight(int s) {
     if (P * size_t(s) >= (size_t(1) << 32))
         throw std::runtime_error("samples_in_flight * pixels exceeds the 32-bit slot index");
     s_max_ = s;
+    auto_state_ = 0;
 }
 
 void Renderer::enable_variance(bool on) {
@@ -3052,6 +3293,14 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     CUDA_OK(cudaSetDevice(device_));
     if (row_begin() >= row_end())
         throw std::runtime_error("cpt_b200: empty row range (row_begin >= row_end)");
+    // automatic traversal choice (set_traversal(-1), the default): this batch runs the mode the tuning state asks for
+    struct Restore {
+        int &ref, saved;
+        ~Restore() { ref = saved; }
+    } restore_traversal{traversal_, traversal_};
+    m.auto_batch = auto_traversal_ && stream_ok_ && traversal_ == 2 && rules_ != 2 && pipeline_ == 3;
+    if (m.auto_batch)
+        traversal_ = auto_state_ == 2 ? 7 : (auto_state_ >= 3 ? auto_choice_ : 2);
     ensure_capacity(samples);
     const int P = w_ * h_, D = max_depth_;
     PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p, m.lobes.p, m.vstate.p};
@@ -3073,7 +3322,7 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
     const bool dq = traversal_ == 6 && ordered_ok_ && rules_ != 2 && this->pipeline_ == 3;
     const bool wide4 = traversal_ == 5 && wide4_ok_ && rules_ != 2 && this->pipeline_ == 3;
     const bool sq = traversal_ == 7 && stream_ok_ && rules_ != 2 && this->pipeline_ == 3;
-    const size_t smem_sq = smem + size_t(kBlock / 32) * kRingBytes;
+    const size_t smem_sq = smem + kCtxBytes + size_t(kBlock / 32) * kRingBytes + size_t(kSqSmemStack) * kBlock * sizeof(uint2);
     if (sq && m.stream_blocks[0] == 0) { // resident CTAs per SM of the two stream kernels with this scene's shared-memory size
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m.stream_blocks[0], k_traverse_stream<false>, kBlock, smem_sq));
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m.stream_blocks[1], k_traverse_stream<true>, kBlock, smem_sq));
@@ -3280,9 +3529,9 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
                 LAUNCH_COOP(1, k_shadow_apply_coop, m.dev, cpar, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
             else if (pipeline_ == 3 && wide4)
                 k_shadow_apply<5><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk);
-            else if (pipeline_ == 3 && sq) {
-                k_traverse_stream<true><<<grid_sq[1], kBlock, smem_sq, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, m.vis.p, sq_refill_,
-                                                                                    sq_flush_, sq_steps_);
+            else if (pipeline_ == 3 && sq && sq_shadow_) {
+                k_traverse_stream<true><<<grid_sq[1], kBlock, smem_sq, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, work + wk, m.vis.p, nullptr, nullptr, b,
+                                                                                    rules_, sq_refill_, sq_flush_, sq_steps_);
                 k_shadow_finish<<<num_sms_ * 8, 256, smem, stream_>>>(m.dev, st, rb, m.shadow_queue.p, sq_counts + b, m.vis.p);
                 ++launches;
             } else if (pipeline_ == 3 && dq)
@@ -3335,10 +3584,12 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         } else if (wide4) {
             k_trace<5><<<grid, kBlock, smem, stream_>>>(m.dev, st, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
         } else if (sq) {
-            k_traverse_stream<false><<<grid_sq[0], kBlock, smem_sq, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, nullptr, sq_refill_, sq_flush_,
-                                                                                 sq_steps_);
+            k_traverse_stream<false><<<grid_sq[0], kBlock, smem_sq, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, nullptr, q_nxt, q_counts + b + 1, b, rules_,
+                                                                                 sq_refill_, sq_flush_, sq_steps_);
+#if !SQ_INLINE_RESOLVE
             ++wk, ++launches;
             k_resolve<<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_);
+#endif
         } else if (dq) {
             k_traverse_dq<false><<<grid, kBlock, smem, stream_>>>(m.dev, st, rb, q_cur, q_counts + b, work + wk, q_nxt, q_counts + b + 1, b, rules_,
                                                                   dyn_refill_, dq_flush_, dyn_steps_);
@@ -3403,6 +3654,7 @@ const float *Renderer::render_raw(bool gamma) {
     float ms = 0;
     cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
     host_stats_.device_ms += ms;
+    auto_observe(ms, 1);
     collect_kernel_times(1);
     return reinterpret_cast<const float *>(d_out_);
 }
@@ -3421,6 +3673,7 @@ const float *Renderer::render_batch(int spp, bool gamma) {
         float ms = 0;
         cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
         host_stats_.device_ms += ms;
+        auto_observe(ms, s);
         collect_kernel_times(s);
     }
     return reinterpret_cast<const float *>(d_out_);
@@ -3445,6 +3698,7 @@ void Renderer::render_offline(int num_iter, bool gamma, uint8_t *rgba8) {
         float ms = 0;
         cudaEventElapsedTime(&ms, impl_->ev0, impl_->ev1);
         host_stats_.device_ms += ms;
+        auto_observe(ms, s);
     }
     std::vector<float> host(size_t(w_) * h_ * 4);
     download_accumulator(host.data());
@@ -3527,7 +3781,7 @@ std::string Renderer::info() const {
     std::ostringstream os;
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
-       << " cached), traversal=" << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : (traversal_ == 5 ? "wide4 per thread" : (traversal_ == 6 ? "deferred leaves + refill" : "stream")))))))
+       << " cached), traversal=" << (auto_traversal_ ? (auto_state_ >= 3 ? (auto_choice_ == 7 ? "auto -> stream" : "auto -> ordered-256bit") : "auto (undecided)") : "") << (auto_traversal_ ? " / set: " : "") << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : (traversal_ == 5 ? "wide4 per thread" : (traversal_ == 6 ? "deferred leaves + refill" : "stream")))))))
        << ", wide layout " << impl_->wide_width << "-ary " << impl_->wide_nodes << " nodes (fill " << impl_->wide_fill << ", depth " << impl_->wide_depth
        << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks[0] << "/" << impl_->coop_blocks[1] << "/" << impl_->coop_blocks[2] << " CTAs/SM (trace/shadow/raygen) x " << impl_->coop_smem
        << " B smem, slab " << coop_slab_ << " nodes, flush " << coop_flush_ << " lanes)"

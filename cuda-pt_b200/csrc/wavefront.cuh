@@ -61,32 +61,38 @@ class Renderer {
     void reset();
     void set_seed_offset(int v) { seed_offset_ = v; }
     void update_camera(const float cam[CPTS_CAM_COUNT]);
-    void set_max_depth(int d) { max_depth_ = d; }
+    void set_max_depth(int d) { max_depth_ = d, auto_state_ = 0; }
     void set_samples_in_flight(int s);
     // 0 / 2 / 3: ordered pair traversal (128-bit / 256-bit loads / warp vote), 1: the reference's own DFS order, 4: warp-
     // cooperative traversal of the wide layout (traverse_coop.cuh).  A mode whose preconditions the scene does not meet
     // (ordered: stack depth and box nesting, checked at construction; cooperative: shared-memory stack) is replaced by the
     // best mode that is allowed - the constructor's fallback cannot be overridden from outside.
+    // -1: automatic (the default): the ordered per-thread traversal (2) or, where the scene allows it, the stream traversal (7) -
+    // whichever renders a batch faster on this scene; decided from the device times of the first batches (frames are bit-identical
+    // either way).  Any explicit mode turns the automatic choice off.
     void set_traversal(int t);
-    int traversal() const { return traversal_; }
+    int traversal() const { return (auto_traversal_ && auto_state_ >= 3) ? auto_choice_ : traversal_; }
+    bool traversal_is_auto() const { return auto_traversal_; }
     // cooperative traversal knobs: triangle-phase threshold in lanes, treelet slab size in wide nodes
     void set_coop(int flush_lanes, int slab_nodes);
     // stream traversal knobs (traversal 7); a negative value keeps the current setting
     void set_stream(int refill, int flush, int steps, int blocks);
+    void set_stream_shadow(bool on) { sq_shadow_ = on; }
+    bool stream_shadow() const { return sq_shadow_; }
     int stream_knob(int which) const { return which == 0 ? sq_refill_ : (which == 1 ? sq_flush_ : (which == 2 ? sq_steps_ : sq_blocks_)); }
     int coop_flush() const { return coop_flush_; }
     int coop_slab() const { return coop_slab_; }
     void enable_variance(bool on);
     void set_accum_count(int c) { accum_cnt_ = c; }
     void set_kernel_timing(bool on) { kernel_timing_ = on; }
-    void set_rules(int r) { rules_ = r; }
+    void set_rules(int r) { rules_ = r, auto_state_ = 0; }
     // tile split: only rows [row0,row1) of the frame are rendered and accumulated (row1 <= 0: to the bottom)
     void set_rows(int row0, int row1) { row0_ = row0, row1_ = row1; }
     int row_begin() const { return row0_; }
     int row_end() const { return row1_ > 0 ? (row1_ < h_ ? row1_ : h_) : h_; }
     // 0: NEE ray traced inside the shading kernel; 1: own shadow kernel; 2: dynamic-fetch traversal kernels;
     // 3: deferred NEE (shade first, trace only the shadow rays that can change the radiance)
-    void set_pipeline(int p) { pipeline_ = p; }
+    void set_pipeline(int p) { pipeline_ = p, auto_state_ = 0; }
     int pipeline() const { return pipeline_; }
     int rules() const { return rules_; }
     KernelTimes kernel_times() const { return ktimes_; }
@@ -117,6 +123,12 @@ class Renderer {
     int coop_flush_ = 1 /* unused since the triangle phase runs on demand */, coop_slab_ = 0;
     int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
     int dq_flush_ = 16;                                  // traversal 6: lanes with a pending leaf that start a triangle phase
+    // automatic traversal choice: 0 warm-up batch, 1 time traversal 2, 2 time traversal 7, 3 decided
+    bool auto_traversal_ = true;
+    int auto_state_ = 0, auto_samples_ = 0, auto_choice_ = 2;
+    float auto_ms_per_sample_[2] = {0.f, 0.f};
+    void auto_observe(float ms, int samples);
+    bool sq_shadow_ = false; // traversal 7: shadow rays through the stream kernel too (default: the ordered per-thread any-hit kernel)
     int sq_refill_ = 8, sq_flush_ = 16, sq_steps_ = 4, sq_blocks_ = 0; // traversal 7 (stream): refill / triangle-phase thresholds in lanes, walk steps per pass, CTAs per SM (0: what fits)
     KernelTimes ktimes_;
     void collect_kernel_times(int samples);
