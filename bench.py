@@ -506,13 +506,13 @@ def main():
     traffic = None
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(dom, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get("trace_stream" if (dom == "trace" and traversal == 7) else dom, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     vol = "vpt" in workload
     roofline = {"bound": "hbm", "kernel": {"vpt": "k_vpt", "raygen": "k_vptd_raygen" if vol else "k_raygen",
                                             "shade": "k_vptd_pre+k_vptd_post+k_vpt_march" if vol else "k_shade+k_shadow_apply",
-                                            "trace": "k_vptd_trace" if vol else "k_trace", "splat": "k_splat"}[dom],
+                                            "trace": "k_vptd_trace" if vol else ("k_traverse_stream<closest hit>" if traversal == 7 else "k_trace"), "splat": "k_splat"}[dom],
                 "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
                 "traffic": traffic, "peak_source": peak_src,
                 "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; BVH/triangle reads are L2-served "
@@ -523,7 +523,7 @@ def main():
     if world == 1 and not args.no_extras and "vpt" not in workload:
         def leg(rr, steps):
             rr.set_option("samples_in_flight", S)
-            rr.render_batch(3 * S, False)  # warm-up; the automatic traversal choice needs three batches
+            rr.render_batch(4 * S, False)  # warm-up; the automatic traversal choice needs four batches
             a = rr.stats()
             rr.render_batch(steps * S, False)
             rr.sync()
@@ -589,7 +589,7 @@ def main():
                       "l2_note": f"path-state pool {S * W * H * 92 / 1e6:.0f} MB per step >> 126 MB L2 (no flush needed)",
                       "traversal": {0: "ordered pair-node", 1: "reference DFS order", 2: "ordered pair-node, 256-bit node loads", 3: "ordered, warp-vote",
                                     4: "warp-cooperative, wide layout", 5: "per thread, 4-ary wide layout", 6: "per thread, deferred leaves + refill",
-                                    7: "stream (deferred leaves, async ray fetch, epilogue per chunk)"}.get(traversal, str(traversal))
+                                    7: "stream (deferred leaves, async ray fetch, epilogue per chunk)" + (", shadow rays too" if int(r.get_option("sq_shadow")) == 1 else "")}.get(traversal, str(traversal))
                                    + (" [chosen automatically from the warm-up steps]" if traversal_auto else ""),
                       "pipeline": ({0: "volumetric megakernel", 1: "volumetric wavefront over slot queues"}.get(pipeline, "volumetric wavefront, dense path records")
                                    if "vpt" in workload else

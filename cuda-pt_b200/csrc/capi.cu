@@ -335,7 +335,7 @@ int64_t cpt_b200_get_option(const cpt_b200_renderer *r, const char *key) {
     if (k == "sq_blocks")
         return r->impl->stream_knob(3);
     if (k == "sq_shadow")
-        return r->impl->stream_shadow() ? 1 : 0;
+        return r->impl->stream_shadow_effective() ? 1 : 0;
     if (k == "coop_flush")
         return r->impl->coop_flush();
     if (k == "coop_slab")

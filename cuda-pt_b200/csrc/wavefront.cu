@@ -3113,8 +3113,9 @@ Renderer::Renderer(const HostScene &scene, int device, int seed_offset)
         set_stream(-1, -1, -1, atoi(e));
     if (const char *e = getenv("CPTB200_DQ_FLUSH"))
         dq_flush_ = std::min(32, std::max(1, atoi(e)));
-    // default number of samples in flight: ~8M paths, at least 1, at most 64
-    set_samples_in_flight(int(std::min<size_t>(64, std::max<size_t>(1, (size_t(8) << 20) / P))));
+    // default number of samples in flight: ~32M paths (5 GB of path state at 160 B per path; the traversal kernels - the stream
+    // traversal above all - want long queues, and the pool is sized for 180 GB of HBM), at least 1, at most 64
+    set_samples_in_flight(int(std::min<size_t>(64, std::max<size_t>(1, (size_t(32) << 20) / P))));
     CUDA_OK(cudaStreamSynchronize(stream_));
 }
 
@@ -3197,21 +3198,25 @@ void Renderer::set_stream(int refill, int flush, int steps, int blocks) {
 
 void Renderer::auto_observe(float ms, int samples) {
     // called after every synchronised batch: the first full-size batch warms up, the second is timed with the ordered traversal,
-    // the third with the stream traversal; from the fourth on the faster one runs (see launch_batch)
-    if (!impl_->auto_batch || auto_state_ >= 3 || samples <= 0)
+    // the third with the stream traversal for the closest-hit rays, the fourth with shadow rays in the stream kernel too; from
+    // the fifth on the fastest of the three runs (see launch_batch)
+    if (!impl_->auto_batch || auto_state_ >= kAutoDecided || samples <= 0)
         return;
     if (auto_state_ == 0 || samples != auto_samples_) {
         auto_samples_ = samples, auto_state_ = 1;
         return;
     }
     auto_ms_per_sample_[auto_state_ - 1] = ms / float(samples);
-    if (++auto_state_ == 3)
-        auto_choice_ = auto_ms_per_sample_[1] < 0.985f * auto_ms_per_sample_[0] ? 7 : 2;
+    if (++auto_state_ == kAutoDecided) { // a more elaborate mode has to win by 1.5 %
+        const float t2 = auto_ms_per_sample_[0], t7 = auto_ms_per_sample_[1], t7s = auto_ms_per_sample_[2];
+        auto_choice_ = std::min(t7, t7s) < 0.985f * t2 ? 7 : 2;
+        auto_shadow_ = auto_choice_ == 7 && t7s < 0.985f * t7;
+    }
 }
 
 void Renderer::set_traversal(int t) {
     if (t == -1) {
-        auto_traversal_ = true, auto_state_ = 0, auto_choice_ = 2;
+        auto_traversal_ = true, auto_state_ = 0, auto_choice_ = 2, auto_shadow_ = false;
         traversal_ = ordered_ok_ ? 2 : TRAVERSAL_DFS;
         return;
     }
@@ -3298,9 +3303,15 @@ void Renderer::launch_batch(int first_accum, int samples, bool gamma, bool write
         int &ref, saved;
         ~Restore() { ref = saved; }
     } restore_traversal{traversal_, traversal_};
+    struct RestoreFlag {
+        bool &ref, saved;
+        ~RestoreFlag() { ref = saved; }
+    } restore_shadow{sq_shadow_, sq_shadow_};
     m.auto_batch = auto_traversal_ && stream_ok_ && traversal_ == 2 && rules_ != 2 && pipeline_ == 3;
-    if (m.auto_batch)
-        traversal_ = auto_state_ == 2 ? 7 : (auto_state_ >= 3 ? auto_choice_ : 2);
+    if (m.auto_batch) {
+        traversal_ = (auto_state_ == 2 || auto_state_ == 3) ? 7 : (auto_state_ >= kAutoDecided ? auto_choice_ : 2);
+        sq_shadow_ = auto_state_ == 3 || (auto_state_ >= kAutoDecided && auto_shadow_);
+    }
     ensure_capacity(samples);
     const int P = w_ * h_, D = max_depth_;
     PathState st{m.ray_o.p, m.ray_d.p, m.thp.p, m.L.p, m.isect.p, m.rng.p, m.pdf.p, m.lobes.p, m.vstate.p};
@@ -3781,7 +3792,7 @@ std::string Renderer::info() const {
     std::ostringstream os;
     os << "cpt_b200 wavefront renderer: " << w_ << "x" << h_ << ", max_depth " << max_depth_ << ", "
        << impl_->dev.num_prims << " primitives, " << impl_->dev.num_nodes << " BVH nodes (" << impl_->dev.num_cache
-       << " cached), traversal=" << (auto_traversal_ ? (auto_state_ >= 3 ? (auto_choice_ == 7 ? "auto -> stream" : "auto -> ordered-256bit") : "auto (undecided)") : "") << (auto_traversal_ ? " / set: " : "") << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : (traversal_ == 5 ? "wide4 per thread" : (traversal_ == 6 ? "deferred leaves + refill" : "stream")))))))
+       << " cached), traversal=" << (auto_traversal_ ? (auto_state_ >= kAutoDecided ? (auto_choice_ == 7 ? (auto_shadow_ ? "auto -> stream (closest hit + shadow rays)" : "auto -> stream (closest hit)") : "auto -> ordered-256bit") : "auto (undecided)") : "") << (auto_traversal_ ? " / set: " : "") << (traversal_ == 0 ? "ordered" : (traversal_ == 1 ? "dfs" : (traversal_ == 2 ? "ordered-256bit" : (traversal_ == 3 ? "ordered-vote" : (traversal_ == 4 ? "cooperative" : (traversal_ == 5 ? "wide4 per thread" : (traversal_ == 6 ? "deferred leaves + refill" : "stream")))))))
        << ", wide layout " << impl_->wide_width << "-ary " << impl_->wide_nodes << " nodes (fill " << impl_->wide_fill << ", depth " << impl_->wide_depth
        << ", stack " << impl_->wide_max_stack << "; coop " << (coop_ok_ ? "ok" : "unavailable") << ": " << impl_->coop_blocks[0] << "/" << impl_->coop_blocks[1] << "/" << impl_->coop_blocks[2] << " CTAs/SM (trace/shadow/raygen) x " << impl_->coop_smem
        << " B smem, slab " << coop_slab_ << " nodes, flush " << coop_flush_ << " lanes)"

@@ -67,11 +67,12 @@ class Renderer {
     // cooperative traversal of the wide layout (traverse_coop.cuh).  A mode whose preconditions the scene does not meet
     // (ordered: stack depth and box nesting, checked at construction; cooperative: shared-memory stack) is replaced by the
     // best mode that is allowed - the constructor's fallback cannot be overridden from outside.
-    // -1: automatic (the default): the ordered per-thread traversal (2) or, where the scene allows it, the stream traversal (7) -
-    // whichever renders a batch faster on this scene; decided from the device times of the first batches (frames are bit-identical
-    // either way).  Any explicit mode turns the automatic choice off.
+    // -1: automatic (the default): the ordered per-thread traversal (2) or, where the scene allows it, the stream traversal (7) for
+    // the closest-hit rays or for closest-hit and shadow rays - whichever renders a batch fastest on this scene; decided from the
+    // device times of the first batches (frames are bit-identical either way).  Any explicit mode turns the automatic choice off.
     void set_traversal(int t);
-    int traversal() const { return (auto_traversal_ && auto_state_ >= 3) ? auto_choice_ : traversal_; }
+    int traversal() const { return (auto_traversal_ && auto_state_ >= kAutoDecided) ? auto_choice_ : traversal_; }
+    bool stream_shadow_effective() const { return (auto_traversal_ && auto_state_ >= kAutoDecided) ? auto_shadow_ : sq_shadow_; }
     bool traversal_is_auto() const { return auto_traversal_; }
     // cooperative traversal knobs: triangle-phase threshold in lanes, treelet slab size in wide nodes
     void set_coop(int flush_lanes, int slab_nodes);
@@ -123,10 +124,12 @@ class Renderer {
     int coop_flush_ = 1 /* unused since the triangle phase runs on demand */, coop_slab_ = 0;
     int dyn_refill_ = 8, dyn_steps_ = 4, dyn_minb_ = 8; // tuning knobs of pipeline 2 (env CPTB200_DYN_*)
     int dq_flush_ = 16;                                  // traversal 6: lanes with a pending leaf that start a triangle phase
-    // automatic traversal choice: 0 warm-up batch, 1 time traversal 2, 2 time traversal 7, 3 decided
-    bool auto_traversal_ = true;
+    // automatic traversal choice: 0 warm-up batch, 1 time traversal 2, 2 time traversal 7, 3 time traversal 7 with the shadow rays
+    // in the stream kernel too, 4 decided
+    static constexpr int kAutoDecided = 4;
+    bool auto_traversal_ = true, auto_shadow_ = false;
     int auto_state_ = 0, auto_samples_ = 0, auto_choice_ = 2;
-    float auto_ms_per_sample_[2] = {0.f, 0.f};
+    float auto_ms_per_sample_[3] = {0.f, 0.f, 0.f};
     void auto_observe(float ms, int samples);
     bool sq_shadow_ = false; // traversal 7: shadow rays through the stream kernel too (default: the ordered per-thread any-hit kernel)
     int sq_refill_ = 8, sq_flush_ = 16, sq_steps_ = 4, sq_blocks_ = 0; // traversal 7 (stream): refill / triangle-phase thresholds in lanes, walk steps per pass, CTAs per SM (0: what fits)

@@ -95,9 +95,15 @@ int cpt_b200_height(const cpt_b200_renderer *r);
 /* options: "rules" (0 wavefront termination rules, wavefront_pt.cu:186-195; 1 megakernel "pt" rules,
  * megakernel_pt.cu:159-180; 2 volumetric path tracer with participating media, megakernel_vpt.cu:203-456 - default
  * taken from the scene's <renderer type>), "samples_in_flight" (>=1),
- * "traversal" (0 / 2 / 3 ordered pair-node traversal: 128-bit loads / 256-bit loads (default) / warp-vote loop; 1 reference DFS
- * order; 4 warp-cooperative traversal of the 4-ary wide layout; 5 per-thread traversal of that layout - a mode whose
- * preconditions the scene does not meet is replaced, read the effective one back with cpt_b200_get_option),
+ * "traversal" (-1 automatic, the default: 2 or 7 (closest-hit rays only, or shadow rays too), whichever renders the first batches of
+ * the scene fastest - frames are bit-identical either way; 0 / 2 / 3 ordered pair-node traversal: 128-bit loads / 256-bit loads /
+ * warp-vote loop; 1 reference DFS order; 4 warp-cooperative traversal of the 4-ary wide layout; 5 per-thread traversal of that
+ * layout; 6 per-thread with deferred leaves and lane refill; 7 stream traversal: 6 with an asynchronous ray-fetch pipeline per warp,
+ * the walk state in registers, the top of the stack in shared memory and the epilogue per finished 32-ray chunk - a mode whose
+ * preconditions the scene does not meet is replaced, read the effective one back with cpt_b200_get_option; "traversal_auto" reads
+ * whether the choice is automatic),
+ * "sq_refill" / "sq_flush" / "sq_steps" / "sq_blocks" / "sq_shadow" (traversal 7: idle lanes that trigger a refill, lanes with a
+ * pending leaf that start a triangle phase, walk steps per pass, CTAs per SM (0: what fits), shadow rays through the stream kernel),
  * "coop_slab" (traversal 4: top nodes of the wide tree staged in shared memory by a TMA bulk copy, default 0),
  * "max_depth" (MaxDepthParams::max_depth, src/core/max_depth.h:26-42), "kernel_timing" (0/1: CUDA events
  * around every launch, read back with cpt_b200_kernel_times), "pipeline" (0: the NEE visibility ray is traced

@@ -18,7 +18,7 @@ for scene in sys.argv[1:] or [VADER]:
         r.set_option("traversal", trav)
         for k, v in opts:
             r.set_option(k, v)
-        r.render_batch(3 * S, False)
+        r.render_batch(4 * S, False)
         ms, mr, kt = timed(r, 2 * S)
         print(json.dumps({"lib": tag, "scene": os.path.basename(scene), "mode": name, "effective": r.get_option("traversal"), "auto": r.get_option("traversal_auto"), "S": S,
                           "ms_per_spp": ms, "mrays": mr, "kernels": kt}), flush=True)

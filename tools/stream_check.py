@@ -103,7 +103,7 @@ def one(trav, spp=16):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if what == "one":
-        one(int(sys.argv[2]))
+        one(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 16)
     elif what == "parity":
         sys.exit(0 if parity() else 1)
     elif what == "sweep":
