@@ -503,10 +503,11 @@ def main():
         v["frac"] = v["achieved_gbs"] / peak
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    traffic = None
+    traffic, l1pipe, traffic_units = None, None, None
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("trace_stream" if (dom == "trace" and traversal == 7) else dom, {}).get("dram_bytes_per_launch")
+            ent = json.load(open(prof)).get("trace_stream" if (dom == "trace" and traversal == 7) else dom, {})
+            traffic, l1pipe, traffic_units = ent.get("dram_bytes_per_launch"), ent.get("l1tex_data_pipe_pct"), ent.get("units_in_this_launch")
         except Exception:
             traffic = None
     vol = "vpt" in workload
@@ -514,9 +515,12 @@ def main():
                                             "shade": "k_vptd_pre+k_vptd_post+k_vpt_march" if vol else "k_shade+k_shadow_apply",
                                             "trace": "k_vptd_trace" if vol else ("k_traverse_stream<closest hit>" if traversal == 7 else "k_trace"), "splat": "k_splat"}[dom],
                 "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
-                "traffic": traffic, "peak_source": peak_src,
-                "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; BVH/triangle reads are L2-served "
-                        "(scene fits the 126 MB L2) and traversal is latency/issue bound, so the HBM fraction is small by nature"}
+                "traffic": traffic, "traffic_units": traffic_units, "peak_source": peak_src,
+                "l1tex_data_pipe_pct_of_peak": l1pipe,
+                "note": "algorithmic bytes = SURVEY.md 8d per-unit figure x units per launch; `traffic` = dram bytes of ONE captured launch with "
+                        "`traffic_units` units (profiles/ncu_traffic.json).  BVH/triangle reads are L2-served (the arena is pinned in the 126 MB L2) "
+                        "and every step of a ray is a dependent fetch: the traversal kernels are bound by the L1/TEX pipe (`l1tex_data_pipe_pct_of_peak`, "
+                        "ncu), not by HBM, so the HBM fraction is small by nature (DESIGN.md 4c)"}
 
     # ---- extra legs (N=1): the reference megakernel's termination rules; the scene as the reference's loader builds it
     extras = {}

@@ -577,6 +577,32 @@ def test_cooperative_traversal_is_used_where_allowed_and_replaced_where_not():
             assert np.array_equal(frames[0].view(np.uint32), f.view(np.uint32))
 
 
+def test_automatic_traversal_choice_renders_the_same_bits():
+    """traversal=-1 (the default): warm-up batch, one batch each with the ordered per-thread kernels, the stream kernel for closest-hit
+    rays and the stream kernel for shadow rays too, then the fastest of the three - whatever it picks, the frame is the one the
+    ordered traversal renders, bit for bit; an explicit mode switches the choice off; scenes with clipped SBVH references stay ordered."""
+    r = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_mats_256.cpts"), 0, 0)
+    assert r.get_option("traversal_auto") == 1 and r.get_option("traversal") == 2
+    r.set_option("samples_in_flight", 2)
+    a = r.render_to_host(12, False)  # six batches: warm-up, three trials, two with the choice
+    assert r.get_option("traversal") in (2, 7) and "auto ->" in r.info()
+    r.set_option("traversal", 2)
+    assert r.get_option("traversal_auto") == 0
+    r.set_option("traversal", -1)
+    assert r.get_option("traversal_auto") == 1
+    r.close()
+    q = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_mats_256.cpts"), 0, 0)
+    q.set_option("traversal", 2)
+    q.set_option("samples_in_flight", 2)
+    assert np.array_equal(a.view(np.uint32), q.render_to_host(12, False).view(np.uint32))
+    q.close()
+    s = cpt.WavefrontRenderer(os.path.join(GOLDEN, "cbox_wfpt_256.cpts"), 0, 0)  # SBVH cornell box: 29 clipped references
+    s.set_option("samples_in_flight", 1)
+    s.render_to_host(8, False)
+    assert s.get_option("traversal") == 2 and s.get_option("sq_shadow") == 0
+    s.close()
+
+
 @pytest.mark.skipif(not (os.path.exists(REF_DUMP) and have_vader()), reason="reference harness / vader mesh not on this box")
 def test_benchmark_configuration_parity_vs_live_reference_1080p(tmp_path):
     """BASELINE config 1 as bench.py runs it - vader_wfpt_1080p.xml, 1920 x 1080, 16 bounces - against the unmodified
