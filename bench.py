@@ -412,6 +412,7 @@ def main():
     ms = e0.elapsed_time(e1)
     rows_final = list(dr.rows) if tiles else None
     traversal, traversal_auto = int(r.get_option("traversal")), int(r.get_option("traversal_auto")) == 1  # (automatic: decided during the warm-up steps)
+    stream_shadow = int(r.get_option("sq_shadow")) == 1
     clk = clocks.stop()
     st1, kt1 = r.stats(), r.kernel_times()
     rays = st1["rays"] - st0["rays"]
@@ -593,7 +594,7 @@ def main():
                       "l2_note": f"path-state pool {S * W * H * 92 / 1e6:.0f} MB per step >> 126 MB L2 (no flush needed)",
                       "traversal": {0: "ordered pair-node", 1: "reference DFS order", 2: "ordered pair-node, 256-bit node loads", 3: "ordered, warp-vote",
                                     4: "warp-cooperative, wide layout", 5: "per thread, 4-ary wide layout", 6: "per thread, deferred leaves + refill",
-                                    7: "stream (deferred leaves, async ray fetch, epilogue per chunk)" + (", shadow rays too" if int(r.get_option("sq_shadow")) == 1 else "")}.get(traversal, str(traversal))
+                                    7: "stream (deferred leaves, async ray fetch, epilogue per chunk)" + (", shadow rays too" if stream_shadow else "")}.get(traversal, str(traversal))
                                    + (" [chosen automatically from the warm-up steps]" if traversal_auto else ""),
                       "pipeline": ({0: "volumetric megakernel", 1: "volumetric wavefront over slot queues"}.get(pipeline, "volumetric wavefront, dense path records")
                                    if "vpt" in workload else
