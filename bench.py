@@ -9,6 +9,10 @@ A "step" is one pass of the hot path over one batch of paths: `--spp-per-step` (
 lights, thin lens, 16 bounces; the textures / environment map of the upstream scene are not shipped and are
 removed).  rays = primary + closest-hit + shadow traversals, counted on the device.
 
+The library chooses its traversal kernels by measurement during the first four batches of a renderer (warm-up, ordered
+per-thread kernels, stream kernel for closest-hit rays, stream kernels for both; frames are bit-identical either way), so `--warmup 4`
+keeps the trials out of the timed region; with `--warmup 3` the last trial is the first timed step.  `config.traversal` names the choice.
+
 One JSON line is printed by rank 0.  Keys beyond the base contract:
   roofline     dominant kernel, algorithmic bytes (SURVEY §8d figures) / CUDA-event time vs the measured HBM peak
   stages       the same for every kernel of the pipeline
