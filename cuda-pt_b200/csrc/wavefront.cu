@@ -1048,8 +1048,10 @@ __global__ void __launch_bounds__(kBlock, DQ_MIN_BLOCKS)
 //    visibility byte; the radiance swap runs in k_shadow_finish.
 // Same boxes, same tests, same tie rule as closest_hit_ordered; deferral only delays updates of the closest distance.
 // The cold stages are out-of-line functions on purpose: inlined, their registers make ptxas spill the walk's loop-carried state.
-// Build knobs: SQ_REGSTATE (the walking ray's cold state in registers, 64 per thread, instead of shared memory), SQ_RING, SQ_MIN_BLOCKS,
-// SQ_INLINE_RESOLVE (0: hit records only, k_resolve does the epilogue as its own launch).
+// Build knobs (measured one by one, profiles/r02_stream_experiments.md): SQ_REGSTATE (the walking ray's cold state in registers - 56
+// per thread at 9 CTAs per SM - instead of shared memory), SQ_SMEM_STACK (stack entries per lane in shared memory), SQ_RING, SQ_MIN_BLOCKS,
+// SQ_INLINE_RESOLVE (0: hit records only, k_resolve does the epilogue as its own launch), SQ_SHADOW_DEFER (0: any-hit rays test leaves
+// where they find them).
 // ------------------------------------------------------------------------------------------------
 #ifndef SQ_REGSTATE
 #define SQ_REGSTATE 1
