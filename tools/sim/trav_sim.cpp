@@ -140,6 +140,7 @@ struct Step {
     uint8_t kind;  // 0 inner, 1 leaf
     uint8_t cnt;   // leaf: triangles tested; inner(wide per-thread): children tested
     uint8_t pops;  // stack entries examined after this step (0 = descended without popping)
+    int32_t ref = 0; // pair traversal: node index (inner) / first primitive (leaf) - for the L1 line model
 };
 // cooperative traversal: one record per node visit of the lane group
 struct CStep {
@@ -178,7 +179,7 @@ static Hit trace_pair(const Scene &sc, const Ray &r, bool anyhit, Trace *tr, std
             const bool h0 = slab(a0, a1, inv_d, o_div, t0) && t0 < h.t && as_int(a1.w) > start;
             const bool h1 = slab(b0, b1, inv_d, o_div, t1) && t1 < h.t && as_int(b1.w) > start;
             const int r0 = as_int(a0.w), r1 = as_int(b0.w);
-            st.kind = 0, st.cnt = 2;
+            st.kind = 0, st.cnt = 2, st.ref = cur;
             if (h0 && h1) {
                 const bool swap = !anyhit && t1 < t0;
                 stack_ref[sp] = swap ? r0 : r1;
@@ -192,7 +193,7 @@ static Hit trace_pair(const Scene &sc, const Ray &r, bool anyhit, Trace *tr, std
             }
         } else {
             const int packed = ~cur, base = packed & ((1 << 26) - 1), cnt = packed >> 26;
-            st.kind = 1, st.cnt = uint8_t(cnt);
+            st.kind = 1, st.cnt = uint8_t(cnt), st.ref = base;
             for (int idx = base; idx < base + cnt; idx++) {
                 float u, v;
                 const float dist = hit_tri(sc, idx, r.o, r.d, u, v, anyhit ? r.tmax : INFINITY);
@@ -495,6 +496,89 @@ static Tally model_thread(const std::vector<const std::vector<Step> *> &rays, co
         }
     }
     return T;
+}
+
+// ------------------------------------------------------------------ L1 line model of the static per-thread kernel (round 2)
+// The per-thread traversal kernels are bound by the L1/TEX pipe: a warp-level load costs one wavefront per distinct 128-byte line its
+// active lanes touch.  This replays the pair traces of 32 rays in lock step (the static kernel) and counts, per ray, the wavefronts of
+// the node loads (2 x LDG.256 per visit: one 64-byte node = half a line) and of the triangle loads (3 x LDG.128 per triangle) - as a
+// function of WHICH rays share a warp.  `order` = the rays in the order they are handed to warps, 32 at a time.
+struct LineStats {
+    double node_wavefronts = 0, tri_wavefronts = 0, node_lane_loads = 0, tri_lane_loads = 0, iterations = 0, lane_iterations = 0;
+    size_t rays = 0;
+};
+static LineStats model_lines(const std::vector<const std::vector<Step> *> &rays, const std::vector<uint32_t> &order) {
+    LineStats L;
+    const size_t N = order.size();
+    for (size_t base = 0; base < N; base += 32) {
+        const size_t n = std::min<size_t>(32, N - base);
+        const std::vector<Step> *cur[32];
+        size_t pos[32];
+        int nact = 0;
+        for (size_t l = 0; l < 32; l++) {
+            cur[l] = l < n ? rays[order[base + l]] : nullptr, pos[l] = 0;
+            if (cur[l] && cur[l]->empty())
+                cur[l] = nullptr;
+            nact += cur[l] != nullptr;
+        }
+        L.rays += n;
+        while (nact > 0) {
+            int lines[32], nl = 0, n_in = 0, max_cnt = 0;
+            for (int l = 0; l < 32; l++) {
+                if (!cur[l])
+                    continue;
+                const Step &s = (*cur[l])[pos[l]];
+                if (s.kind == 0) {
+                    n_in++;
+                    const int line = s.ref >> 1; // two 64-byte pair nodes per 128-byte line
+                    bool seen = false;
+                    for (int k = 0; k < nl; k++)
+                        seen |= lines[k] == line;
+                    if (!seen)
+                        lines[nl++] = line;
+                } else
+                    max_cnt = std::max<int>(max_cnt, s.cnt);
+            }
+            L.node_wavefronts += 2.0 * nl, L.node_lane_loads += 2.0 * n_in;
+            for (int j = 0; j < max_cnt; j++) // the triangle loop: iteration j, loads k = 0..2 of 16 bytes at (first + j) * 48 + 16 k
+                for (int k = 0; k < 3; k++) {
+                    nl = 0;
+                    int lanes = 0;
+                    for (int l = 0; l < 32; l++) {
+                        if (!cur[l])
+                            continue;
+                        const Step &s = (*cur[l])[pos[l]];
+                        if (s.kind != 1 || s.cnt <= j)
+                            continue;
+                        lanes++;
+                        const int line = int((size_t(s.ref + j) * 48 + size_t(k) * 16) >> 7);
+                        bool seen = false;
+                        for (int q = 0; q < nl; q++)
+                            seen |= lines[q] == line;
+                        if (!seen)
+                            lines[nl++] = line;
+                    }
+                    L.tri_wavefronts += nl, L.tri_lane_loads += lanes;
+                }
+            L.iterations += 1, L.lane_iterations += nact;
+            for (int l = 0; l < 32; l++)
+                if (cur[l] && ++pos[l] >= cur[l]->size())
+                    cur[l] = nullptr, nact--;
+        }
+    }
+    return L;
+}
+// sort keys for "which rays share a warp": direction octant, then a 30-bit Morton code of the origin inside the scene's bounds
+static uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+    auto spread = [](uint32_t v) {
+        v &= 1023u;
+        v = (v | (v << 16)) & 0x030000FFu;
+        v = (v | (v << 8)) & 0x0300F00Fu;
+        v = (v | (v << 4)) & 0x030C30C3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1) | (spread(z) << 2);
 }
 
 // cooperative: G lanes per ray, 32/G groups per warp, flat loop, chunk of `buf` rays per warp
@@ -1005,6 +1089,54 @@ int main(int argc, char **argv) {
             p[i] = &tr[i].pair, t4[i] = &tr[i].w4t, t8[i] = &tr[i].w8t, c4[i] = &tr[i].c4, c8[i] = &tr[i].c8;
         auto show = [&](const char *name, const Tally &T) { printf("   %-34s warp-inst/ray %8.1f   lanes/inst %5.2f\n", name, T.inst / N, T.lanes()); };
         show("per-thread pair, static 32", model_thread(p, cache_iters, cost, 32, false));
+        { // L1 line model: wavefronts per ray of the static kernel for different assignments of rays to warps
+            V3 lo{1e30f, 1e30f, 1e30f}, hi{-1e30f, -1e30f, -1e30f};
+            for (const Ray &r : rays)
+                lo = V3{std::min(lo.x, r.o.x), std::min(lo.y, r.o.y), std::min(lo.z, r.o.z)}, hi = V3{std::max(hi.x, r.o.x), std::max(hi.y, r.o.y), std::max(hi.z, r.o.z)};
+            auto key = [&](size_t i, int mode) -> uint64_t {
+                const Ray &r = rays[i];
+                const uint32_t oct = (r.d.x < 0) | ((r.d.y < 0) << 1) | ((r.d.z < 0) << 2);
+                auto q = [&](float v, float a, float b) { return uint32_t(std::min(1023.f, std::max(0.f, (v - a) / std::max(b - a, 1e-20f) * 1023.f))); };
+                const uint32_t mo = morton3(q(r.o.x, lo.x, hi.x), q(r.o.y, lo.y, hi.y), q(r.o.z, lo.z, hi.z));
+                // finer direction cell: 6 x 8 x 8 cube-map cells
+                const float ax = std::fabs(r.d.x), ay = std::fabs(r.d.y), az = std::fabs(r.d.z);
+                int face;
+                float u, v;
+                if (ax >= ay && ax >= az)
+                    face = r.d.x < 0, u = r.d.y / ax, v = r.d.z / ax;
+                else if (ay >= az)
+                    face = 2 + (r.d.y < 0), u = r.d.x / ay, v = r.d.z / ay;
+                else
+                    face = 4 + (r.d.z < 0), u = r.d.x / az, v = r.d.y / az;
+                const uint32_t cell = uint32_t(face) * 64 + uint32_t(std::min(7.f, (u * 0.5f + 0.5f) * 8.f)) * 8 + uint32_t(std::min(7.f, (v * 0.5f + 0.5f) * 8.f));
+                if (mode == 1)
+                    return (uint64_t(oct) << 32) | mo;       // octant, then origin
+                if (mode == 2)
+                    return (uint64_t(mo >> 12) << 32) | (uint64_t(cell) << 20) | (mo & 0xfffu); // coarse origin cell (18 bits), direction cell, fine origin
+                return (uint64_t(cell) << 32) | mo;         // direction cell, then origin
+            };
+            auto report = [&](const char *name, const std::vector<uint32_t> &order) {
+                const LineStats S = model_lines(p, order);
+                printf("   L1 lines, %-44s node wavefronts/ray %6.1f (of %6.1f lane loads)  tri wavefronts/ray %5.1f (of %5.1f)  lanes/iteration %5.2f  warp iterations/ray %5.1f\n", name,
+                       S.node_wavefronts / S.rays, S.node_lane_loads / S.rays, S.tri_wavefronts / S.rays, S.tri_lane_loads / S.rays, S.lane_iterations / std::max(1.0, S.iterations),
+                       S.iterations / S.rays);
+            };
+            std::vector<uint32_t> order(N);
+            for (size_t i = 0; i < N; i++)
+                order[i] = uint32_t(i);
+            report("queue order (what k_trace<2> gets)", order);
+            for (int window : {256, 1024, 4096, 65536})
+                for (int mode : {1, 2, 3}) {
+                    std::vector<uint32_t> o2 = order;
+                    for (size_t b0 = 0; b0 < N; b0 += size_t(window)) {
+                        const size_t e0 = std::min(N, b0 + size_t(window));
+                        std::sort(o2.begin() + b0, o2.begin() + e0, [&](uint32_t a, uint32_t c) { return key(a, mode) < key(c, mode); });
+                    }
+                    char nm[96];
+                    snprintf(nm, sizeof nm, "sorted in windows of %d by %s", window, mode == 1 ? "octant | origin" : (mode == 2 ? "origin cell | dir cell" : "dir cell | origin"));
+                    report(nm, o2);
+                }
+        }
         show("per-thread pair, refill buf 128", model_thread(p, cache_iters, cost, 128, false, 4));
         show("per-thread pair, refill buf 512", model_thread(p, cache_iters, cost, 512, false, 4));
         show("per-thread pair, refill buf 4096", model_thread(p, cache_iters, cost, 4096, false, 4));
