@@ -3204,10 +3204,12 @@ void Renderer::auto_observe(float ms, int samples) {
     // the fifth on the fastest of the three runs (see launch_batch)
     if (!impl_->auto_batch || auto_state_ >= kAutoDecided || samples <= 0)
         return;
-    if (auto_state_ == 0 || samples != auto_samples_) {
+    if (auto_state_ == 0 || samples > auto_samples_) { // (a larger batch size than seen so far: start over with it)
         auto_samples_ = samples, auto_state_ = 1;
         return;
     }
+    if (samples < auto_samples_) // a remainder batch (spp not a multiple of the samples in flight): not comparable, this trial is
+        return;                  // repeated with the next full-size batch
     auto_ms_per_sample_[auto_state_ - 1] = ms / float(samples);
     if (++auto_state_ == kAutoDecided) { // a more elaborate mode has to win by 1.5 %
         const float t2 = auto_ms_per_sample_[0], t7 = auto_ms_per_sample_[1], t7s = auto_ms_per_sample_[2];
